@@ -1,0 +1,118 @@
+"""ctypes binding of libbk_kfac.so (include/bk_kfac.h).
+
+There is no CPU fallback: if the shared library is missing the import of any compute entry point
+raises, and every call checks its return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+from . import _build
+
+BK_PREC_BF16 = 1
+BK_PREC_BF16X3 = 3
+BK_SMALL_D_MAX = 160
+
+GEMM_SYRK_LOWER = 1
+GEMM_MIRROR = 2
+GEMM_TRI_A = 4
+GEMM_TRI_B = 8
+GEMM_RELU = 16
+
+_ERRORS = {
+    -2: "BK_ERR_ARG (bad argument or alignment)",
+    -3: "BK_ERR_DRIVER (cuTensorMapEncodeTiled unavailable)",
+    -4: "BK_ERR_TMAP (tensor-map encode failed)",
+    -5: "BK_ERR_CUDA (launch/runtime error)",
+    -6: "BK_ERR_WORKSPACE (workspace too small or misaligned)",
+    -7: "BK_ERR_ARCH (device is not compute capability 10.x)",
+}
+
+_p, _ll, _i, _f, _u, _ull, _sz = (C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint,
+                                  C.c_ulonglong, C.c_size_t)
+
+# name -> (restype, argtypes); mirrors include/bk_kfac.h declaration by declaration
+SIGNATURES = {
+    "bk_version": (C.c_char_p, []),
+    "bk_device_check": (_i, []),
+    "bk_gemm_nt": (_i, [_p, _p, _ll, _ll, _p, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _f,
+                        _p, _ll, _ll, _p, _ll, _p, _p, _ll, _ll, _p]),
+    "bk_transpose_split": (_i, [_p, _ll, _i, _i, _f, _i, _p, _p, _ll, _p]),
+    "bk_convert_split": (_i, [_p, _ll, _i, _i, _f, _i, _p, _p, _ll, _p]),
+    "bk_philox_normal": (_i, [_ull, _u, _u, _i, _i, _i, _p, _ll, _ll, _p, _p, _ll, _ll, _p]),
+    "bk_syrk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "bk_syrk_accum": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _f, _f, _f, _i, _p, _sz, _p]),
+    "bk_syrk_accum_staged": (_i, [_p, _ll, _p, _p, _ll, _i, _i, _f, _f, _i, _p]),
+    "bk_conv_a_accum": (_i, [_p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "bk_conv_g_accum": (_i, [_p, _ll, _p, _i, _i, _i, _f, _f, _f, _p]),
+    "bk_diag_accum": (_i, [_p, _p, _p, _i, _i, _f, _f, _p]),
+    "bk_diag_invert": (_i, [_p, _p, _ll, _f, _f, _p]),
+    "bk_diag_sample": (_i, [_p, _p, _ll, _i, _ull, _u, _u, _p, _p]),
+    "bk_diag_quadform": (_i, [_p, _p, _ll, _p, _ll, _i, _p]),
+    "bk_chol_inv_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
+    "bk_damp_chol_inv_batched": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
+                                      C.POINTER(_f), C.POINTER(_f), _i, _p, _sz, _p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class BkError(RuntimeError):
+    """A libbk_kfac entry point returned a negative status."""
+
+
+def lib_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True, strict: bool = True) -> C.CDLL:
+    """Load (building first if needed) the kernel library. Raises if it cannot be had.
+
+    strict=False (bring-up tools only) tolerates declared-but-missing symbols."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not path.exists():
+            if not build_if_missing:
+                raise BkError(f"{path} is missing: run `python -m bnn_kfac_b200._build`")
+            _build.build()
+        lib = C.CDLL(str(path))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name, None)
+            if fn is None:
+                if strict:
+                    raise BkError(f"{path} does not export {name} (declared in include/bk_kfac.h)")
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise BkError(f"{what} failed: {_ERRORS.get(rc, rc)}")
+    return rc
+
+
+def require_device() -> None:
+    """Fail loudly unless the current CUDA device can run the sm_100a kernels."""
+    import torch
+    if not torch.cuda.is_available():
+        raise BkError("bnn_kfac_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    check(load().bk_device_check(), "bk_device_check")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (or 0 for None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,204 @@
+// bk_api.cu — the exported C ABI (include/bk_kfac.h).  Argument validation + composition of the
+// kernel launchers; no torch types, no allocation, no hidden synchronisation except where the
+// header says so (bk_damp_chol_inv_batched returns a device-computed status).
+#include "../../include/bk_kfac.h"
+
+#include "bk_kernels.cuh"
+#include "bk_umma_gemm.cuh"
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline long long round8(long long v) { return (v + 7) / 8 * 8; }
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* bk_version(void) { return "bk_kfac 0.1 (sm_100a)"; }
+
+int bk_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return BK_ERR_CUDA;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return BK_ERR_CUDA;
+  return major == 10 ? BK_OK : BK_ERR_ARCH;
+}
+
+int bk_gemm_nt(const void* a_hi, const void* a_lo, long long lda, long long stride_a,
+               const void* b_hi, const void* b_lo, long long ldb, long long stride_b, int m, int n,
+               int k, int batch, int precision, int flags, float alpha, float beta, float* c,
+               long long ldc, long long stride_c, const float* bias, long long stride_bias,
+               void* o_hi, void* o_lo, long long ldo, long long stride_o, void* stream) {
+  if (precision != BK_PREC_BF16 && precision != BK_PREC_BF16X3) return BK_ERR_ARG;
+  bk::GemmArgs g;
+  g.A_hi = static_cast<const __nv_bfloat16*>(a_hi);
+  g.A_lo = static_cast<const __nv_bfloat16*>(a_lo);
+  g.B_hi = static_cast<const __nv_bfloat16*>(b_hi);
+  g.B_lo = static_cast<const __nv_bfloat16*>(b_lo);
+  g.lda = lda;
+  g.ldb = ldb;
+  g.strideA = stride_a;
+  g.strideB = stride_b;
+  g.M = m;
+  g.N = n;
+  g.K = k;
+  g.batch = batch;
+  g.nparts = precision;
+  g.flags = flags;
+  g.alpha = alpha;
+  g.beta = beta;
+  g.C = c;
+  g.ldc = ldc;
+  g.strideC = stride_c;
+  g.bias = bias;
+  g.strideBias = stride_bias;
+  g.O_hi = static_cast<__nv_bfloat16*>(o_hi);
+  g.O_lo = static_cast<__nv_bfloat16*>(o_lo);
+  g.ldo = ldo;
+  g.strideO = stride_o;
+  return bk::launch_umma_gemm(g, as_stream(stream));
+}
+
+int bk_transpose_split(const float* x, long long ldx, int rows, int cols, float scale, int ones_row,
+                       void* t_hi, void* t_lo, long long ldt, void* stream) {
+  if (x == nullptr || t_hi == nullptr || ldt < rows || ldx < cols) return BK_ERR_ARG;
+  return bk::launch_transpose_split(x, ldx, rows, cols, scale, ones_row,
+                                    static_cast<__nv_bfloat16*>(t_hi),
+                                    static_cast<__nv_bfloat16*>(t_lo), ldt, as_stream(stream));
+}
+
+int bk_convert_split(const float* x, long long ldx, int rows, int cols, float scale, int lower_only,
+                     void* o_hi, void* o_lo, long long ldo, void* stream) {
+  if (x == nullptr || o_hi == nullptr || ldo < cols || ldx < cols) return BK_ERR_ARG;
+  return bk::launch_convert_split(x, ldx, rows, cols, scale, lower_only,
+                                  static_cast<__nv_bfloat16*>(o_hi),
+                                  static_cast<__nv_bfloat16*>(o_lo), ldo, as_stream(stream));
+}
+
+int bk_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_id, int rows,
+                     int cols, int nsamples, float* zf, long long ldf, long long stride_f,
+                     void* z_hi, void* z_lo, long long ldz, long long stride_z, void* stream) {
+  if (zf == nullptr && z_hi == nullptr) return BK_ERR_ARG;
+  return bk::launch_philox_normal(seed, sample0, stream_id, rows, cols, nsamples, zf, ldf, stride_f,
+                                  static_cast<__nv_bfloat16*>(z_hi),
+                                  static_cast<__nv_bfloat16*>(z_lo), ldz, stride_z,
+                                  as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------ factor update
+size_t bk_syrk_workspace_bytes(int n, int d, int has_bias, int precision) {
+  const int dp = d + (has_bias ? 1 : 0);
+  if (dp <= BK_SMALL_D_MAX) return 0;
+  const size_t one = align_up(static_cast<size_t>(dp) * round8(n) * 2, 256);
+  return precision == BK_PREC_BF16X3 ? 2 * one : one;
+}
+
+int bk_syrk_accum_staged(float* state, long long ld_state, const void* xt_hi, const void* xt_lo,
+                         long long ldt, int n, int dprime, float alpha, float beta, int precision,
+                         void* stream) {
+  if (state == nullptr || xt_hi == nullptr || ld_state < dprime) return BK_ERR_ARG;
+  if (precision != BK_PREC_BF16 && precision != BK_PREC_BF16X3) return BK_ERR_ARG;
+  bk::GemmArgs g;
+  g.A_hi = g.B_hi = static_cast<const __nv_bfloat16*>(xt_hi);
+  g.A_lo = g.B_lo = static_cast<const __nv_bfloat16*>(xt_lo);
+  g.lda = g.ldb = ldt;
+  g.M = g.N = dprime;
+  g.K = n;
+  g.batch = 1;
+  g.nparts = precision;
+  g.flags = bk::kSyrkLower | bk::kMirror;
+  g.alpha = alpha;
+  g.beta = beta;
+  g.C = state;
+  g.ldc = ld_state;
+  return bk::launch_umma_gemm(g, as_stream(stream));
+}
+
+int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
+                  int has_bias, float in_scale, float alpha, float beta, int precision,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (state == nullptr || x == nullptr || n <= 0 || d <= 0) return BK_ERR_ARG;
+  const int dp = d + (has_bias ? 1 : 0);
+  if (ld_state < dp || ldx < d) return BK_ERR_ARG;
+  if (dp <= BK_SMALL_D_MAX) {
+    return bk::launch_small_syrk(state, ld_state, x, ldx, n, d, has_bias, in_scale, alpha, beta,
+                                 as_stream(stream));
+  }
+  if (precision != BK_PREC_BF16 && precision != BK_PREC_BF16X3) return BK_ERR_ARG;
+  const size_t need = bk_syrk_workspace_bytes(n, d, has_bias, precision);
+  if (workspace == nullptr || workspace_bytes < need ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return BK_ERR_WORKSPACE;
+  const long long ldt = round8(n);
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* lo = precision == BK_PREC_BF16X3
+                          ? reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(workspace) + need / 2)
+                          : nullptr;
+  int rc = bk::launch_transpose_split(x, ldx, n, d, in_scale, has_bias, hi, lo, ldt,
+                                      as_stream(stream));
+  if (rc) return rc;
+  return bk_syrk_accum_staged(state, ld_state, hi, lo, ldt, n, dp, alpha, beta, precision, stream);
+}
+
+int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int c, int h, int w,
+                    int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w, int has_bias,
+                    float alpha, float beta, void* stream) {
+  if (state == nullptr || x == nullptr) return BK_ERR_ARG;
+  return bk::launch_conv_a_syrk(state, ld_state, x, n, c, h, w, kh, kw, pad_h, pad_w, stride_h,
+                                stride_w, has_bias, alpha, beta, as_stream(stream));
+}
+
+int bk_conv_g_accum(float* state, long long ld_state, const float* g, int n, int o, int hw,
+                    float in_scale, float alpha, float beta, void* stream) {
+  if (state == nullptr || g == nullptr) return BK_ERR_ARG;
+  return bk::launch_conv_g_syrk(state, ld_state, g, n, o, hw, in_scale, alpha, beta,
+                                as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ diagonal
+int bk_diag_accum(float* state, const float* wgrad, const float* bgrad, int d_out, int d_in,
+                  float scale, float beta, void* stream) {
+  if (state == nullptr || wgrad == nullptr) return BK_ERR_ARG;
+  return bk::launch_diag_accum(state, wgrad, bgrad, d_out, d_in, scale, beta, as_stream(stream));
+}
+int bk_diag_invert(float* inv, const float* state, long long count, float add, float multiply,
+                   void* stream) {
+  if (inv == nullptr || state == nullptr) return BK_ERR_ARG;
+  return bk::launch_diag_invert(inv, state, count, add, multiply, as_stream(stream));
+}
+int bk_diag_sample(float* out, const float* inv, long long count, int nsamples,
+                   unsigned long long seed, unsigned sample0, unsigned stream_id,
+                   const float* z_or_null, void* stream) {
+  if (out == nullptr || inv == nullptr) return BK_ERR_ARG;
+  return bk::launch_diag_sample(out, inv, count, nsamples, seed, sample0, stream_id, z_or_null,
+                                as_stream(stream));
+}
+int bk_diag_quadform(float* out, const float* j, long long ldj, const float* h, long long count,
+                     int batch, void* stream) {
+  if (out == nullptr || j == nullptr || h == nullptr) return BK_ERR_ARG;
+  return bk::launch_diag_quadform(out, j, ldj, h, count, batch, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ inversion
+size_t bk_chol_inv_workspace_bytes(const int* dims_host, int count) {
+  if (dims_host == nullptr || count <= 0) return 0;
+  return bk::chol_inv_workspace_bytes(dims_host, count);
+}
+
+int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* outs_host,
+                             const int* dims_host, const float* add_host,
+                             const float* multiply_host, int count, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (factors_host == nullptr || outs_host == nullptr || dims_host == nullptr ||
+      add_host == nullptr || multiply_host == nullptr)
+    return BK_ERR_ARG;
+  return bk::chol_inv_batched(factors_host, outs_host, dims_host, add_host, multiply_host, count,
+                              workspace, workspace_bytes, as_stream(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

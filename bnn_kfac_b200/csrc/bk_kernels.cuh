@@ -1,0 +1,51 @@
+// bk_kernels.cuh — internal launcher declarations (one per kernel family). The exported C ABI in
+// bk_api.cu composes these; nothing here is visible outside the shared library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace bk {
+
+// ---- bk_prep.cu
+int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
+                           int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
+                           cudaStream_t stream);
+int launch_convert_split(const float* X, long long ldx, int rows, int cols, float scale,
+                         int lower_only, __nv_bfloat16* Ohi, __nv_bfloat16* Olo, long long ldo,
+                         cudaStream_t stream);
+int launch_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_id, int rows,
+                         int cols, int nsamples, float* Zf, long long ldf, long long stridef,
+                         __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, long long ldz, long long stridez,
+                         cudaStream_t stream);
+
+// ---- bk_factor_small.cu  (SIMT fp32 split-K SYRK for skinny factors; implicit im2col for conv)
+int launch_small_syrk(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
+                      int has_bias, float in_scale, float alpha, float beta, cudaStream_t stream);
+int launch_conv_a_syrk(float* state, long long ld_state, const float* x, int n, int c, int h, int w,
+                       int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w,
+                       int has_bias, float alpha, float beta, cudaStream_t stream);
+int launch_conv_g_syrk(float* state, long long ld_state, const float* g, int n, int o, int hw,
+                       float in_scale, float alpha, float beta, cudaStream_t stream);
+
+// ---- bk_diag.cu
+int launch_diag_accum(float* state, const float* wgrad, const float* bgrad, int d_out, int d_in,
+                      float scale, float beta, cudaStream_t stream);
+int launch_diag_invert(float* inv, const float* state, long long count, float add, float multiply,
+                       cudaStream_t stream);
+int launch_diag_sample(float* out, const float* inv, long long count, int nsamples,
+                       unsigned long long seed, unsigned sample0, unsigned stream_id,
+                       const float* z_or_null, cudaStream_t stream);
+int launch_diag_quadform(float* out, const float* J, long long ldj, const float* h, long long count,
+                         int batch, cudaStream_t stream);
+
+// ---- bk_chol.cu
+size_t chol_inv_workspace_bytes(const int* dims, int count);
+// Returns 0, the 1-based index of the first non-positive-definite factor, or a negative error.
+// Synchronises `stream` (the status is computed on the device).
+int chol_inv_batched(const float* const* factors, float* const* outs, const int* dims,
+                     const float* add, const float* multiply, int count, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace bk

@@ -1,0 +1,456 @@
+// bk_umma_gemm.cu — persistent, warp-specialised tcgen05 contraction core for sm_100a.
+//
+//   D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]
+//
+// Roles (256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0   TMA producer   : cp.async.bulk.tensor (128B swizzle) A 128x64 + B 256x64 per stage
+//   warp 1   MMA issuer     : one elected lane issues 4 x tcgen05.mma (128x256x16) per stage
+//   warp 2   TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double buffered)
+//   warps 4-7 epilogue      : tcgen05.ld -> smem transpose -> coalesced fused epilogue
+//                             (alpha/beta/bias/relu, fp32 and/or split-bf16 outputs,
+//                              SYRK lower-triangle masking + mirrored write)
+// Pipelines: smem full/empty ring (4 stages), TMEM full/empty (2 stages).
+//
+// Reference semantics served by this core (all /root/reference paths relative to the repo root):
+//   models/curvatures.py:349,356  first/second Kronecker factor  (SYRK mode, `state +=`)
+//   models/curvatures.py:404-405  matrix-normal sample L_A z L_G^T (triangular-A mode)
+//   models/wrapper.py:35-44       forward over weight samples      (bias + relu epilogue, batched)
+#include "bk_common.cuh"
+#include "bk_umma_gemm.cuh"
+
+#include <mutex>
+
+namespace bk {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UK = 16;  // K per tcgen05.mma for 16-bit inputs
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr uint32_t kBytesA = BM * BK * 2;  // 16 KiB
+constexpr uint32_t kBytesB = BN * BK * 2;  // 32 KiB
+constexpr uint32_t kStageBytes = kBytesA + kBytesB;
+constexpr uint32_t kEpiStageBytes = 32 * 33 * 4;  // per epilogue warp: 32x32 fp32, padded
+constexpr uint32_t kSmemBytes =
+    kStages * kStageBytes + 4 * kEpiStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr uint32_t kTmemCols = kAccStages * BN;  // 512
+
+struct KParams {
+  int M, N, K, batch, nparts, flags;
+  int tiles_m, tiles_n, tiles_per_batch, num_tiles;
+  int a_bmul, b_bmul;
+  float alpha, beta;
+  float* C;
+  long long ldc, strideC;
+  const float* bias;
+  long long strideBias;
+  __nv_bfloat16* Ohi;
+  __nv_bfloat16* Olo;
+  long long ldo, strideO;
+};
+
+__host__ __device__ inline int syrk_row_tiles(int mi, int tiles_n) {
+  int c = (mi * BM + BM - 1) / BN + 1;
+  return c < tiles_n ? c : tiles_n;
+}
+
+struct Tile {
+  int b, m0, n0, nkb;
+};
+
+__device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
+  Tile r;
+  r.b = t / p.tiles_per_batch;
+  int rem = t - r.b * p.tiles_per_batch;
+  int mi, nj;
+  if (p.flags & kSyrkLower) {
+    mi = 0;
+    int c = syrk_row_tiles(0, p.tiles_n);
+    while (rem >= c) {
+      rem -= c;
+      ++mi;
+      c = syrk_row_tiles(mi, p.tiles_n);
+    }
+    nj = rem;
+  } else {
+    // heaviest row blocks first when the k extent grows with m (triangular A)
+    mi = rem / p.tiles_n;
+    nj = rem - mi * p.tiles_n;
+    if (p.flags & kTriA) mi = p.tiles_m - 1 - mi;
+    if (p.flags & kTriB) nj = p.tiles_n - 1 - nj;
+  }
+  r.m0 = mi * BM;
+  r.n0 = nj * BN;
+  int kend = p.K;
+  if (p.flags & kTriA) kend = min(kend, r.m0 + BM);
+  if (p.flags & kTriB) kend = min(kend, r.n0 + BN);
+  r.nkb = (kend + BK - 1) / BK;
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024 B alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_epi = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 4 * kEpiStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + kStages;            // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;        // [kAccStages]
+  uint64_t* tempty_bar = tfull_bar + kAccStages;   // [kAccStages]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (p.nparts > 1) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(p, t);
+        const int iters = tl.nkb * p.nparts;
+        for (int it = 0; it < iters; ++it) {
+          const int part = it / tl.nkb;
+          const int kb = it - part * tl.nkb;
+          // part 0: hi*hi, part 1: hi*lo, part 2: lo*hi
+          const CUtensorMap* ma = (part == 2) ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = (part == 1) ? &tmB1 : &tmB0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          uint8_t* sa = smem + stage * kStageBytes;
+          tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tl.m0, tl.b * p.a_bmul);
+          tma_load_3d(sa + kBytesA, mb, &full_bar[stage], kb * BK, tl.n0, tl.b * p.b_bmul);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(p, t);
+        const int iters = tl.nkb * p.nparts;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = umma_smem_desc_k_sw128(sa);
+          const uint64_t db = umma_smem_desc_k_sw128(sa + kBytesA);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
+            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                         idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - kEpiWarp0;  // TMEM lane quadrant == warp % 4
+    float* stg = reinterpret_cast<float*>(smem_epi + q * kEpiStageBytes);
+    const bool syrk = (p.flags & kSyrkLower) != 0;
+    const bool mirror = (p.flags & kMirror) != 0;
+    const bool relu = (p.flags & kRelu) != 0;
+    const bool use_beta = p.beta != 0.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int r0 = tl.m0 + q * 32;        // first row of this warp's 32-row band
+      const int my_row = r0 + lane;         // row held by this thread in TMEM layout
+      float* Cb = p.C ? p.C + static_cast<long long>(tl.b) * p.strideC : nullptr;
+      const float* biasb = p.bias ? p.bias + static_cast<long long>(tl.b) * p.strideBias : nullptr;
+      __nv_bfloat16* Ohb = p.Ohi ? p.Ohi + static_cast<long long>(tl.b) * p.strideO : nullptr;
+      __nv_bfloat16* Olb = p.Olo ? p.Olo + static_cast<long long>(tl.b) * p.strideO : nullptr;
+      const uint32_t taddr0 =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int c0 = tl.n0 + ch * 32;
+        float v[32];
+        tmem_ld_32x32(taddr0 + static_cast<uint32_t>(ch * 32), v);
+        tmem_ld_wait();
+        if (ch == BN / 32 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        // band entirely outside the matrix, or (SYRK) entirely above the diagonal: nothing to do
+        if (r0 >= p.M || c0 >= p.N) continue;
+        if (syrk && c0 > r0 + 31) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+
+        // mirrored (transposed) write straight from registers: lanes = consecutive columns of
+        // the transposed block -> 128 B coalesced per instruction.
+        // All read-modify-writes below load a whole batch of 32 old values before the first store,
+        // so 32 independent loads are in flight per thread (a load-store-load chain would expose
+        // the full DRAM latency 32 times per chunk).
+        if (syrk && mirror && Cb != nullptr && my_row < p.M) {
+          const int jmax = my_row - c0;  // columns c0 + j < my_row (strictly below the diagonal)
+          float* dst0 = Cb + static_cast<long long>(c0) * p.ldc + my_row;
+          float old[32];
+          if (use_beta) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              old[j] = (j < jmax) ? __ldcg(dst0 + static_cast<long long>(j) * p.ldc) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = fmaf(p.beta, old[j], v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = v[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < jmax) __stcg(dst0 + static_cast<long long>(j) * p.ldc, old[j]);
+        }
+        // direct write: transpose through smem so that lanes = consecutive columns.
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int gc = c0 + lane;
+        const bool col_ok = gc < p.N;
+        const float bv = (biasb != nullptr && col_ok) ? biasb[gc] : 0.f;
+        // rows rr in [rlo, rhi) of this band are written by this lane
+        const int rhi = col_ok ? min(32, p.M - r0) : 0;
+        const int rlo = syrk ? max(0, gc - r0) : 0;
+        float x[32];
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) x[rr] = stg[rr * 33 + lane] + bv;
+        __syncwarp();
+        if (Cb != nullptr) {
+          float* dst0 = Cb + static_cast<long long>(r0) * p.ldc + gc;
+          if (use_beta) {
+            float old[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              old[rr] = (rr >= rlo && rr < rhi) ? __ldcg(dst0 + static_cast<long long>(rr) * p.ldc)
+                                                : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) x[rr] = fmaf(p.beta, old[rr], x[rr]);
+          }
+          if (relu) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) x[rr] = fmaxf(x[rr], 0.f);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            if (rr >= rlo && rr < rhi) __stcg(dst0 + static_cast<long long>(rr) * p.ldc, x[rr]);
+        } else if (relu) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) x[rr] = fmaxf(x[rr], 0.f);
+        }
+        if (Ohb != nullptr) {
+          __nv_bfloat16* o0 = Ohb + static_cast<long long>(r0) * p.ldo + gc;
+          __nv_bfloat16* l0 = Olb != nullptr ? Olb + static_cast<long long>(r0) * p.ldo + gc : nullptr;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr >= rlo && rr < rhi) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(x[rr]);
+              o0[static_cast<long long>(rr) * p.ldo] = h;
+              if (l0 != nullptr)
+                l0[static_cast<long long>(rr) * p.ldo] =
+                    __float2bfloat16_rn(x[rr] - __bfloat162float(h));
+            }
+          }
+        }
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+  });
+  return fn;
+}
+
+// K-major operand [batch][rows][K] bf16, row pitch ld, 128B-swizzled boxes of (64 x box_rows).
+int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int K, long long ld,
+                     long long stride, int batch, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -3;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0 || (stride % 8) != 0) return -2;
+  const bool shared = (stride == 0) || (batch == 1);
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(shared ? 1 : batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
+                           static_cast<cuuint64_t>(shared ? static_cast<long long>(rows) * ld
+                                                          : stride) *
+                               2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(static_cast<const void*>(base)), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -4;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = kNumSMsB200;
+  }
+  return n;
+}
+
+}  // namespace
+
+int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return 0;
+  if (a.K <= 0) return -2;
+  if (a.A_hi == nullptr || a.B_hi == nullptr) return -2;
+  if (a.nparts != 1 && a.nparts != 3) return -2;
+  if (a.nparts == 3 && (a.A_lo == nullptr || a.B_lo == nullptr)) return -2;
+  if ((a.flags & kSyrkLower) && a.M != a.N) return -2;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kSmemBytes));
+  });
+  if (attr_err != cudaSuccess) return -5;
+
+  KParams p{};
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.batch = a.batch;
+  p.nparts = a.nparts;
+  p.flags = a.flags;
+  p.tiles_m = (a.M + BM - 1) / BM;
+  p.tiles_n = (a.N + BN - 1) / BN;
+  if (a.flags & kSyrkLower) {
+    int tot = 0;
+    for (int mi = 0; mi < p.tiles_m; ++mi) tot += syrk_row_tiles(mi, p.tiles_n);
+    p.tiles_per_batch = tot;
+  } else {
+    p.tiles_per_batch = p.tiles_m * p.tiles_n;
+  }
+  p.num_tiles = p.tiles_per_batch * a.batch;
+  p.a_bmul = (a.strideA == 0 || a.batch == 1) ? 0 : 1;
+  p.b_bmul = (a.strideB == 0 || a.batch == 1) ? 0 : 1;
+  p.alpha = a.alpha;
+  p.beta = a.beta;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.strideC = a.strideC;
+  p.bias = a.bias;
+  p.strideBias = a.strideBias;
+  p.Ohi = a.O_hi;
+  p.Olo = a.O_lo;
+  p.ldo = a.ldo;
+  p.strideO = a.strideO;
+
+  CUtensorMap mA0, mA1, mB0, mB1;
+  int rc = make_operand_map(&mA0, a.A_hi, a.M, a.K, a.lda, a.strideA, a.batch, BM);
+  if (rc) return rc;
+  rc = make_operand_map(&mB0, a.B_hi, a.N, a.K, a.ldb, a.strideB, a.batch, BN);
+  if (rc) return rc;
+  if (a.nparts == 3) {
+    rc = make_operand_map(&mA1, a.A_lo, a.M, a.K, a.lda, a.strideA, a.batch, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&mB1, a.B_lo, a.N, a.K, a.ldb, a.strideB, a.batch, BN);
+    if (rc) return rc;
+  } else {
+    mA1 = mA0;
+    mB1 = mB0;
+  }
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  umma_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mA0, mA1, mB0, mB1, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+}  // namespace bk

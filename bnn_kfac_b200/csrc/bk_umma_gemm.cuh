@@ -1,0 +1,50 @@
+// bk_umma_gemm.cuh — host-side argument block for the tcgen05 "NT" contraction core.
+//
+//   D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]        (both operands K-major bf16, fp32 accumulate)
+//
+// Every dense contraction on the Kronecker-factored Laplace path is phrased in this form
+// (see DESIGN.md "Kernels"): factor SYRK (A == B, lower tiles + mirror), matrix-normal sampling
+// (triangular A), Monte-Carlo forward (bias + ReLU epilogue), kron-free quadratic forms.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bk {
+
+enum GemmFlags : int {
+  kSyrkLower = 1,   // A == B (square): only tiles touching the lower triangle, write c <= r only
+  kMirror = 2,      // with kSyrkLower: also write the transposed element (full symmetric result)
+  kTriA = 4,        // A[m][k] == 0 for k > m (lower-triangular A): skip those k-blocks
+  kTriB = 8,        // B[n][k] == 0 for k > n
+  kRelu = 16,       // max(x, 0) after alpha/beta/bias
+};
+
+struct GemmArgs {
+  // operands: hi parts mandatory; lo parts only for nparts == 3 (bf16x3 split precision:
+  // hi*hi + hi*lo + lo*hi, ~fp32-class accuracy).  ld in elements (multiple of 8), base 16 B aligned.
+  const __nv_bfloat16* A_hi = nullptr;
+  const __nv_bfloat16* A_lo = nullptr;
+  const __nv_bfloat16* B_hi = nullptr;
+  const __nv_bfloat16* B_lo = nullptr;
+  long long lda = 0, ldb = 0;
+  long long strideA = 0, strideB = 0;  // per-batch element strides; 0 = operand shared by all batches
+  int M = 0, N = 0, K = 0, batch = 1;
+  int nparts = 1;
+  int flags = 0;
+  // epilogue:  v = alpha * acc + beta * C + bias[n];  optional relu;  outputs: C (fp32) and/or
+  // O_hi[/O_lo] (bf16 [split]) — any may be null.
+  float alpha = 1.f, beta = 0.f;
+  float* C = nullptr;
+  long long ldc = 0, strideC = 0;
+  const float* bias = nullptr;
+  long long strideBias = 0;
+  __nv_bfloat16* O_hi = nullptr;
+  __nv_bfloat16* O_lo = nullptr;
+  long long ldo = 0, strideO = 0;
+};
+
+// Returns 0 on success, negative on argument / CUDA error (see include/bk_kfac.h error codes).
+int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace bk

@@ -1,0 +1,140 @@
+/* bk_kfac.h — C ABI of libbk_kfac.so, the sm_100a kernel library behind bnn_kfac_b200.
+ *
+ * Drop-in boundary: the reference (TianmingQiu/BNN_KFAC) has no FFI; its boundary is the Python class
+ * API of models/curvatures.py and models/wrapper.py.  bnn_kfac_b200/curvatures.py mirrors that API and
+ * is the only caller of the functions below.  Each entry point names the reference lines whose
+ * arithmetic it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless it says "host".
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - row-major matrices; `ld*` are row pitches in ELEMENTS.
+ *   - the caller owns every buffer, including workspaces (query the size first).
+ *   - return value: 0 ok; > 0 1-based index of the first factor that was not positive definite;
+ *     < 0 error (BK_ERR_*).  No global state besides cached function attributes.
+ *   - precision: BK_PREC_BF16 (bf16 operands, fp32 accumulate) or BK_PREC_BF16X3 (hi/lo split,
+ *     three tensor-core passes, ~fp32 accuracy).
+ */
+#ifndef BK_KFAC_H_
+#define BK_KFAC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_OK 0
+#define BK_ERR_ARG (-2)       /* bad argument / alignment */
+#define BK_ERR_DRIVER (-3)    /* cuTensorMapEncodeTiled entry point unavailable */
+#define BK_ERR_TMAP (-4)      /* tensor-map encode failed */
+#define BK_ERR_CUDA (-5)      /* launch or runtime error */
+#define BK_ERR_WORKSPACE (-6) /* workspace too small */
+#define BK_ERR_ARCH (-7)      /* device is not compute capability 10.x */
+
+#define BK_PREC_BF16 1
+#define BK_PREC_BF16X3 3
+
+/* flags for bk_gemm_nt (mirror bk::GemmFlags) */
+#define BK_GEMM_SYRK_LOWER 1
+#define BK_GEMM_MIRROR 2
+#define BK_GEMM_TRI_A 4
+#define BK_GEMM_TRI_B 8
+#define BK_GEMM_RELU 16
+
+const char* bk_version(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else BK_ERR_ARCH. */
+int bk_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Contraction core.  D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]; bf16 (uint16 storage) K-major
+ * operands, optional lo parts for BK_PREC_BF16X3; v = alpha*acc + beta*C + bias[n], optional relu;
+ * writes C (fp32) and/or O_hi/O_lo (bf16 split).  strideX == 0 shares the operand across batches.
+ * Replaces torch.mm / `@` at models/curvatures.py:349,356,405 and the per-sample forward GEMMs
+ * behind models/wrapper.py:35-44.
+ */
+int bk_gemm_nt(const void* a_hi, const void* a_lo, long long lda, long long stride_a,
+               const void* b_hi, const void* b_lo, long long ldb, long long stride_b,
+               int m, int n, int k, int batch, int precision, int flags,
+               float alpha, float beta,
+               float* c, long long ldc, long long stride_c,
+               const float* bias, long long stride_bias,
+               void* o_hi, void* o_lo, long long ldo, long long stride_o,
+               void* stream);
+
+/* fp32 [rows, cols] -> bf16 hi[/lo] [cols (+1 ones row), rows] (transposed, scaled).
+ * The ones row is the reference's bias augmentation, models/curvatures.py:346-348. */
+int bk_transpose_split(const float* x, long long ldx, int rows, int cols, float scale, int ones_row,
+                       void* t_hi, void* t_lo, long long ldt, void* stream);
+/* fp32 [rows, cols] -> bf16 hi[/lo] [rows, cols], optional lower-triangle mask. */
+int bk_convert_split(const float* x, long long ldx, int rows, int cols, float scale, int lower_only,
+                     void* o_hi, void* o_lo, long long ldo, void* stream);
+/* Counter-based N(0,1): element e of sample s of stream `stream_id` = Philox4x32-10(key = seed,
+ * counter = (e/4, sample0 + s, stream_id)) lane e%4, Box-Muller.  Replaces torch.randn at
+ * models/curvatures.py:404 and .normal_() at :207.  Any of zf / z_hi may be null. */
+int bk_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_id, int rows,
+                     int cols, int nsamples, float* zf, long long ldf, long long stride_f,
+                     void* z_hi, void* z_lo, long long ldz, long long stride_z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * KFAC factor accumulation (models/curvatures.py:345-349, 355-356, 359-363):
+ *   state = beta*state + alpha * [in_scale*x ; 1]^T [in_scale*x ; 1]      (x is [n, d] row-major)
+ * state is [d+has_bias, d+has_bias] fp32, written as a full symmetric matrix.  The reference's
+ * A = mm(fwd, fwd^T)/N is alpha = 1/N, in_scale = 1; its G with g = grad_output*N is in_scale = N.
+ * d + has_bias > BK_SMALL_D_MAX uses the tcgen05 SYRK and needs a workspace; smaller factors use the
+ * SIMT split-K kernel and need none.
+ */
+#define BK_SMALL_D_MAX 160
+size_t bk_syrk_workspace_bytes(int n, int d, int has_bias, int precision);
+int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
+                  int has_bias, float in_scale, float alpha, float beta, int precision,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* Same, operand already staged as K-major bf16 [d+has_bias, n] (e.g. by bk_transpose_split). */
+int bk_syrk_accum_staged(float* state, long long ld_state, const void* xt_hi, const void* xt_lo,
+                         long long ldt, int n, int dprime, float alpha, float beta, int precision,
+                         void* stream);
+
+/* Conv2d first factor with implicit im2col (models/curvatures.py:341-349): x is NCHW fp32,
+ * state [c*kh*kw + has_bias]^2;  alpha is applied to the un-normalised sum (reference: 1/(N*L)). */
+int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int c, int h, int w,
+                    int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w, int has_bias,
+                    float alpha, float beta, void* stream);
+/* Conv2d second factor (models/curvatures.py:353-356): g is [n, o, hw] fp32. */
+int bk_conv_g_accum(float* state, long long ld_state, const float* g, int n, int o, int hw,
+                    float in_scale, float alpha, float beta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Diagonal curvature (models/curvatures.py:155-207).
+ */
+/* state[o, i] = beta*state + scale * [wgrad | bgrad]^2  (Diagonal.update :165-172) */
+int bk_diag_accum(float* state, const float* wgrad, const float* bgrad, int d_out, int d_in,
+                  float scale, float beta, void* stream);
+/* inv = 1/sqrt(multiply*state + add)  (Diagonal.invert :202) */
+int bk_diag_invert(float* inv, const float* state, long long count, float add, float multiply,
+                   void* stream);
+/* out[s] = z[s] * inv  (Diagonal.sample :207); z from Philox unless z_or_null is given. */
+int bk_diag_sample(float* out, const float* inv, long long count, int nsamples,
+                   unsigned long long seed, unsigned sample0, unsigned stream_id,
+                   const float* z_or_null, void* stream);
+/* out[b] = sum_j J[b, j]^2 * h[j]  (classification_ll_diagonal.py:131, regression_ll_diagonal.py:139) */
+int bk_diag_quadform(float* out, const float* j, long long ldj, const float* h, long long count,
+                     int batch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Damped inversion (KFAC.invert, models/curvatures.py:381-392), batched over factors:
+ *   R = sqrt(multiply)*F + sqrt(add)*I;  R <- (R + R^T)/2;  out = cholesky_lower(inverse(R))
+ * computed as a reverse Cholesky + triangular inverse (no explicit inverse).  Host arrays of device
+ * pointers / dims; `info` is a device int (first failing 1-based factor index, 0 if none) that the
+ * call also returns after synchronising the stream.
+ */
+size_t bk_chol_inv_workspace_bytes(const int* dims_host, int count);
+int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* outs_host,
+                             const int* dims_host, const float* add_host,
+                             const float* multiply_host, int count, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BK_KFAC_H_ */
