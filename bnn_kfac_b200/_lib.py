@@ -51,6 +51,10 @@ SIGNATURES = {
     "bk_diag_invert": (_i, [_p, _p, _ll, _f, _f, _p]),
     "bk_diag_sample": (_i, [_p, _p, _ll, _i, _ull, _u, _u, _p, _p]),
     "bk_diag_quadform": (_i, [_p, _p, _ll, _p, _ll, _i, _p]),
+    "bk_sample_to_weights": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _ll, _p, _p]),
+    "bk_conv2d_relu_pool": (_i, [_p, _ll, _p, _p, _p] + [_i] * 14 + [_p]),
+    "bk_predictive_moments": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "bk_frob_dot": (_i, [_p, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
     "bk_chol_inv_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
     "bk_damp_chol_inv_batched": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
                                       C.POINTER(_f), C.POINTER(_f), _i, _p, _sz, _p]),

@@ -200,5 +200,40 @@ int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* out
                               workspace, workspace_bytes, as_stream(stream));
 }
 
+// ----------------------------------------------------------------------- predictive glue
+int bk_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b, int d_out,
+                         int d_in, int has_bias, int nsamples, float* w_f32, void* w_hi, void* w_lo,
+                         long long ldw, float* b_f32, void* stream) {
+  if (samples == nullptr || mean_w == nullptr) return BK_ERR_ARG;
+  if (has_bias && (mean_b == nullptr || b_f32 == nullptr)) return BK_ERR_ARG;
+  if (w_hi != nullptr && ldw < d_in) return BK_ERR_ARG;
+  return bk::launch_sample_to_weights(samples, mean_w, mean_b, d_out, d_in, has_bias ? 1 : 0,
+                                      nsamples, w_f32, static_cast<__nv_bfloat16*>(w_hi),
+                                      static_cast<__nv_bfloat16*>(w_lo), ldw, b_f32,
+                                      as_stream(stream));
+}
+
+int bk_conv2d_relu_pool(const float* in, long long in_sample_stride, const float* w, const float* b,
+                        float* out, int nsamples, int n, int c, int h, int wd, int o, int kh, int kw,
+                        int sh, int sw, int ph, int pw, int relu, int pool, void* stream) {
+  if (in == nullptr || w == nullptr || out == nullptr || sh <= 0 || sw <= 0) return BK_ERR_ARG;
+  return bk::launch_conv2d_relu_pool(in, in_sample_stride, w, b, out, nsamples, n, c, h, wd, o, kh,
+                                     kw, sh, sw, ph, pw, relu, pool, as_stream(stream));
+}
+
+int bk_predictive_moments(const float* logits, int nsamples, int batch, int classes, int mode,
+                          float* mean, float* meansq, void* stream) {
+  if (logits == nullptr || mean == nullptr) return BK_ERR_ARG;
+  return bk::launch_predictive_moments(logits, nsamples, batch, classes, mode, mean, meansq,
+                                       as_stream(stream));
+}
+
+int bk_frob_dot(float* out, const float* x, long long stride_x, const float* y, long long stride_y,
+                long long count, int batch, int absolute, int accumulate, void* stream) {
+  if (out == nullptr || x == nullptr || y == nullptr) return BK_ERR_ARG;
+  return bk::launch_frob_dot(out, x, stride_x, y, stride_y, count, batch, absolute, accumulate,
+                             as_stream(stream));
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

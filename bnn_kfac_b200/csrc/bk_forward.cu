@@ -1,0 +1,233 @@
+// bk_forward.cu — glue kernels of the Monte-Carlo / linearised predictive (HBM- or latency-bound;
+// the dense contractions themselves run in bk_umma_gemm.cu).
+//
+//   sample_to_weights   W_s = M + S_s[:, :-1], b_s = m_b + S_s[:, -1]     (Curvature._replace,
+//                       models/curvatures.py:67-82) for a whole batch of samples, emitted directly as
+//                       the bf16 (hi, lo) K-major operand of the forward GEMM (+ fp32 copies)
+//   conv2d_relu_pool    per-sample conv + bias + ReLU + 2x2 max-pool for the reference CNNs
+//                       (models/wrapper.py:53-101), weights differ per sample
+//   predictive_moments  mean over samples of softmax(logits) (sampling/classification_sampling.py:
+//                       74-79) or mean / mean-of-squares of raw outputs (regression_sampling.py:86-88)
+//   frob_dot            out[b] = |<X_b, Y_b>|  — last step of the kron-free quadratic form
+//                       (classification_ll_block.py:131-132 without materialising kron(Q, H))
+#include "bk_common.cuh"
+#include "bk_kernels.cuh"
+
+namespace bk {
+
+namespace {
+
+__global__ void sample_to_weights_kernel(const float* __restrict__ samples,
+                                         const float* __restrict__ mean_w,
+                                         const float* __restrict__ mean_b, int d_out, int d_in,
+                                         int has_bias, int nsamples, float* __restrict__ w_f32,
+                                         __nv_bfloat16* __restrict__ w_hi,
+                                         __nv_bfloat16* __restrict__ w_lo, long long ldw,
+                                         float* __restrict__ b_f32) {
+  const int dp = d_in + has_bias;
+  const long long per = static_cast<long long>(d_out) * dp;
+  const long long total = per * nsamples;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(e / per);
+    const long long r = e - static_cast<long long>(s) * per;
+    const int o = static_cast<int>(r / dp);
+    const int i = static_cast<int>(r - static_cast<long long>(o) * dp);
+    const float sv = samples[e];
+    if (i < d_in) {
+      const float v = mean_w[static_cast<long long>(o) * d_in + i] + sv;
+      if (w_f32 != nullptr) w_f32[(static_cast<long long>(s) * d_out + o) * d_in + i] = v;
+      if (w_hi != nullptr) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        const long long q = (static_cast<long long>(s) * d_out + o) * ldw + i;
+        w_hi[q] = h;
+        if (w_lo != nullptr) w_lo[q] = l;
+      }
+    } else {
+      b_f32[static_cast<long long>(s) * d_out + o] = mean_b[o] + sv;
+    }
+  }
+}
+
+// one CTA per (sample s, image n): weights of s and image n staged in shared memory
+__global__ void conv2d_relu_pool_kernel(const float* __restrict__ in, long long in_sample_stride,
+                                        const float* __restrict__ w, const float* __restrict__ b,
+                                        float* __restrict__ out, int N, int C, int H, int W, int O,
+                                        int KH, int KW, int SH, int SW, int PH, int PW, int relu,
+                                        int pool) {
+  extern __shared__ float sm[];
+  const int s = blockIdx.y, n = blockIdx.x;
+  const int OH = (H + 2 * PH - KH) / SH + 1, OW = (W + 2 * PW - KW) / SW + 1;
+  const int QH = pool ? OH / 2 : OH, QW = pool ? OW / 2 : OW;
+  float* ws = sm;                       // [O][C][KH][KW]
+  float* bs = ws + O * C * KH * KW;     // [O]
+  float* xs = bs + O;                   // [C][H][W]
+  const float* wsrc = w + static_cast<long long>(s) * O * C * KH * KW;
+  for (int i = threadIdx.x; i < O * C * KH * KW; i += blockDim.x) ws[i] = wsrc[i];
+  for (int i = threadIdx.x; i < O; i += blockDim.x) bs[i] = b ? b[static_cast<long long>(s) * O + i] : 0.f;
+  const float* xsrc = in + s * in_sample_stride + static_cast<long long>(n) * C * H * W;
+  for (int i = threadIdx.x; i < C * H * W; i += blockDim.x) xs[i] = xsrc[i];
+  __syncthreads();
+  float* dst = out + (static_cast<long long>(s) * N + n) * O * QH * QW;
+  for (int e = threadIdx.x; e < O * QH * QW; e += blockDim.x) {
+    const int o = e / (QH * QW);
+    const int r = e - o * QH * QW;
+    const int qy = r / QW, qx = r - qy * QW;
+    const int np = pool ? 2 : 1;
+    float best = -INFINITY;
+    for (int dy = 0; dy < np; ++dy)
+      for (int dx = 0; dx < np; ++dx) {
+        const int oy = qy * np + dy, ox = qx * np + dx;
+        float acc = bs[o];
+        for (int c = 0; c < C; ++c)
+          for (int ky = 0; ky < KH; ++ky) {
+            const int iy = oy * SH - PH + ky;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < KW; ++kx) {
+              const int ix = ox * SW - PW + kx;
+              if (ix < 0 || ix >= W) continue;
+              acc = fmaf(ws[((o * C + c) * KH + ky) * KW + kx], xs[(c * H + iy) * W + ix], acc);
+            }
+          }
+        best = fmaxf(best, acc);
+      }
+    dst[e] = relu ? fmaxf(best, 0.f) : best;  // relu and max-pool commute
+  }
+}
+
+// one warp per input row b.  mode 0: p = softmax(logits[s, b, :]); mode 1: p = logits[s, b, :].
+// mean[b, c] = (1/S) sum_s p ; meansq[b, c] = (1/S) sum_s p^2 (optional).  C <= 32 * kMaxPerLane.
+constexpr int kMaxPerLane = 32;
+__global__ void predictive_moments_kernel(const float* __restrict__ logits, int S, int B, int Cn,
+                                          int mode, float* __restrict__ mean,
+                                          float* __restrict__ meansq) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int per = (Cn + 31) / 32;
+  float m1[kMaxPerLane], m2[kMaxPerLane];
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) m1[k] = m2[k] = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
+    float v[kMaxPerLane];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = (k < per && c < Cn) ? row[c] : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+    if (mode == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) {
+        v[k] = (v[k] == -INFINITY) ? 0.f : expf(v[k] - mx);
+        sum += v[k];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) v[k] *= inv;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const float pv = (v[k] == -INFINITY) ? 0.f : v[k];
+      m1[k] += pv;
+      m2[k] = fmaf(pv, pv, m2[k]);
+    }
+  }
+  const float invS = 1.0f / static_cast<float>(S);
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (k < per && c < Cn) {
+      mean[static_cast<long long>(warp) * Cn + c] = m1[k] * invS;
+      if (meansq != nullptr) meansq[static_cast<long long>(warp) * Cn + c] = m2[k] * invS;
+    }
+  }
+}
+
+__global__ void frob_dot_kernel(float* __restrict__ out, const float* __restrict__ X,
+                                long long stride_x, const float* __restrict__ Y, long long stride_y,
+                                long long count, int absolute, int accumulate) {
+  const float* x = X + blockIdx.x * stride_x;
+  const float* y = Y + blockIdx.x * stride_y;
+  double acc = 0.0;
+  for (long long j = threadIdx.x; j < count; j += blockDim.x)
+    acc += static_cast<double>(x[j]) * static_cast<double>(y[j]);
+  __shared__ double part[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < 8) ? part[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      float r = static_cast<float>(absolute ? fabs(v) : v);
+      out[blockIdx.x] = accumulate ? out[blockIdx.x] + r : r;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b,
+                             int d_out, int d_in, int has_bias, int nsamples, float* w_f32,
+                             __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, long long ldw, float* b_f32,
+                             cudaStream_t stream) {
+  const long long total = static_cast<long long>(d_out) * (d_in + has_bias) * nsamples;
+  if (total <= 0) return 0;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(kNumSMsB200) * 8;
+  if (blocks > cap) blocks = cap;
+  sample_to_weights_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      samples, mean_w, mean_b, d_out, d_in, has_bias, nsamples, w_f32, w_hi, w_lo, ldw, b_f32);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_conv2d_relu_pool(const float* in, long long in_sample_stride, const float* w,
+                            const float* b, float* out, int S, int N, int C, int H, int W, int O,
+                            int KH, int KW, int SH, int SW, int PH, int PW, int relu, int pool,
+                            cudaStream_t stream) {
+  if (S <= 0 || N <= 0) return 0;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(O) * C * KH * KW + O +
+                                       static_cast<size_t>(C) * H * W);
+  if (smem > 200 * 1024) return -2;
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && smem > attr_set) {
+    if (cudaFuncSetAttribute(conv2d_relu_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return -5;
+    attr_set = smem;
+  }
+  conv2d_relu_pool_kernel<<<dim3(N, S), 256, smem, stream>>>(in, in_sample_stride, w, b, out, N, C, H,
+                                                             W, O, KH, KW, SH, SW, PH, PW, relu,
+                                                             pool);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_predictive_moments(const float* logits, int S, int B, int Cn, int mode, float* mean,
+                              float* meansq, cudaStream_t stream) {
+  if (S <= 0 || B <= 0 || Cn <= 0) return 0;
+  if (Cn > 32 * kMaxPerLane) return -2;
+  const int warps_per_block = 8;
+  const int blocks = (B + warps_per_block - 1) / warps_per_block;
+  predictive_moments_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(logits, S, B, Cn, mode, mean,
+                                                                         meansq);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_frob_dot(float* out, const float* X, long long stride_x, const float* Y,
+                    long long stride_y, long long count, int batch, int absolute, int accumulate,
+                    cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  frob_dot_kernel<<<batch, 256, 0, stream>>>(out, X, stride_x, Y, stride_y, count, absolute,
+                                             accumulate);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+}  // namespace bk

@@ -48,4 +48,20 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
                      const float* add, const float* multiply, int count, void* workspace,
                      size_t workspace_bytes, cudaStream_t stream);
 
+
+// ---- bk_forward.cu
+int launch_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b,
+                             int d_out, int d_in, int has_bias, int nsamples, float* w_f32,
+                             __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, long long ldw, float* b_f32,
+                             cudaStream_t stream);
+int launch_conv2d_relu_pool(const float* in, long long in_sample_stride, const float* w,
+                            const float* b, float* out, int S, int N, int C, int H, int W, int O,
+                            int KH, int KW, int SH, int SW, int PH, int PW, int relu, int pool,
+                            cudaStream_t stream);
+int launch_predictive_moments(const float* logits, int S, int B, int Cn, int mode, float* mean,
+                              float* meansq, cudaStream_t stream);
+int launch_frob_dot(float* out, const float* X, long long stride_x, const float* Y,
+                    long long stride_y, long long count, int batch, int absolute, int accumulate,
+                    cudaStream_t stream);
+
 }  // namespace bk

@@ -134,6 +134,32 @@ int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* out
                              const float* multiply_host, int count, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Predictive glue (the dense contractions of these stages are bk_gemm_nt calls).
+ */
+/* Curvature._replace for a batch of samples (models/curvatures.py:67-82):
+ *   W_s = mean_w + samples[s][:, :d_in],  b_s = mean_b + samples[s][:, d_in]
+ * samples is [nsamples, d_out, d_in + has_bias] fp32.  Outputs (any weight output may be null):
+ * w_f32 [nsamples, d_out, d_in], w_hi/w_lo bf16 split [nsamples, d_out, ldw], b_f32 [nsamples, d_out]. */
+int bk_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b, int d_out,
+                         int d_in, int has_bias, int nsamples, float* w_f32, void* w_hi, void* w_lo,
+                         long long ldw, float* b_f32, void* stream);
+/* Per-sample conv2d (+bias, optional ReLU, optional 2x2 max-pool) for the reference CNNs
+ * (models/wrapper.py:53-101): in [nsamples or 1, n, c, h, w] (in_sample_stride 0 = shared input),
+ * w [nsamples, o, c, kh, kw], b [nsamples, o] or null, out [nsamples, n, o, oh', ow']. */
+int bk_conv2d_relu_pool(const float* in, long long in_sample_stride, const float* w, const float* b,
+                        float* out, int nsamples, int n, int c, int h, int wd, int o, int kh, int kw,
+                        int sh, int sw, int ph, int pw, int relu, int pool, void* stream);
+/* Moments over posterior samples of logits [nsamples, batch, classes] (classes <= 1024):
+ * mode 0: p = softmax (sampling/classification_sampling.py:74-79); mode 1: p = raw output
+ * (sampling/regression_sampling.py:86-88).  mean = E_s[p]; meansq = E_s[p^2] (nullable). */
+int bk_predictive_moments(const float* logits, int nsamples, int batch, int classes, int mode,
+                          float* mean, float* meansq, void* stream);
+/* out[b] (+)= <x_b, y_b> (optionally absolute value): the last step of the kron-free
+ * J (Q (x) H) J^T = <V, Q V H^T> (sampling_free/classification/classification_ll_block.py:131-132). */
+int bk_frob_dot(float* out, const float* x, long long stride_x, const float* y, long long stride_y,
+                long long count, int batch, int absolute, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,176 @@
+"""Pins the CPU oracle (oracle/kfac_oracle.py) against outputs of the reference itself
+(tests/golden/reference_golden.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from models_for_tests import MLP, RegNet, load_params
+from oracle import kfac_oracle as O
+from bnn_kfac_b200.wrapper import BaseNet_750
+
+TOL64 = 1e-10   # fp64 restatement vs fp64 reference run: same algorithm, same LAPACK
+TOL32 = 2e-4    # fp32
+
+
+def _run_kfac(model, xs, ys):
+    est = O.OracleKFAC(model)
+    for x, y in zip(xs, ys):
+        O.fisher_backward(model, x, labels=y)
+        est.update()
+    return est
+
+
+@pytest.mark.parametrize("dtype,tag,tol", [(torch.float64, "mlp64", TOL64), (torch.float32, "mlp32", TOL32)])
+def test_mlp_factors_inverse_samples(golden, dtype, tag, tol):
+    model = load_params(MLP(), golden, "mlp", dtype)
+    xs = [torch.tensor(golden[f"mlp_x_{i}"]).to(dtype) for i in range(2)]
+    ys = [torch.tensor(golden[f"mlp_y_{i}"]) for i in range(2)]
+    est = _run_kfac(model, xs, ys)
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(est.layers):
+        assert relerr(est.state[layer][0], golden[f"{tag}_state_{li}_A"]) < tol
+        assert relerr(est.state[layer][1], golden[f"{tag}_state_{li}_G"]) < tol
+        # the inverse is conditioned ~1e3: allow cond * eps in fp32
+        itol = tol if dtype == torch.float64 else 5e-3
+        assert relerr(est.inv_state[layer][0], golden[f"{tag}_inv_{li}_A"]) < itol
+        assert relerr(est.inv_state[layer][1], golden[f"{tag}_inv_{li}_G"]) < itol
+        for s in range(2):
+            z = torch.tensor(golden[f"{tag}_z_{s}_{li}"])
+            ref_inv = (torch.tensor(golden[f"{tag}_inv_{li}_A"]), torch.tensor(golden[f"{tag}_inv_{li}_G"]))
+            assert relerr(O.kfac_sample(ref_inv[0], ref_inv[1], z), golden[f"{tag}_sample_{s}_{li}"]) < tol
+        # known-answer: bias augmentation makes A[-1, -1] == number of updates (curvatures.py:346-349)
+        assert abs(est.state[layer][0][-1, -1].item() - 2.0) < 1e-6
+
+
+def test_mlp_sample_and_replace_and_mc_mean(golden):
+    model = load_params(MLP(), golden, "mlp")
+    xs = [torch.tensor(golden[f"mlp_x_{i}"]).double() for i in range(2)]
+    ys = [torch.tensor(golden[f"mlp_y_{i}"]) for i in range(2)]
+    est = _run_kfac(model, xs, ys)
+    est.invert(0.04, 200.0)
+    noise = [[torch.tensor(golden[f"mlp64_sar_z_{s}_{li}"]) for li in range(2)] for s in range(3)]
+    for s in range(3):
+        est.sample_and_replace(noise[s])
+        for li, layer in enumerate(est.layers):
+            assert relerr(layer.weight.data, golden[f"mlp64_sar_w_{s}_{li}"]) < TOL64
+            assert relerr(layer.bias.data, golden[f"mlp64_sar_b_{s}_{li}"]) < TOL64
+    mean = O.mc_predict_classification(model, est, torch.tensor(golden["mlp_xtest"]), noise)
+    assert relerr(mean, golden["mlp64_mc_mean"]) < TOL64
+
+
+def test_per_layer_damping_lists(golden):
+    model = load_params(MLP(), golden, "mlp")
+    xs = [torch.tensor(golden[f"mlp_x_{i}"]).double() for i in range(2)]
+    ys = [torch.tensor(golden[f"mlp_y_{i}"]) for i in range(2)]
+    est = _run_kfac(model, xs, ys)
+    est.invert([1.0, 0.5], [200.0, 100.0])
+    for li, layer in enumerate(est.layers):
+        assert relerr(est.inv_state[layer][0], golden[f"mlp64_listinv_{li}_A"]) < TOL64
+        assert relerr(est.inv_state[layer][1], golden[f"mlp64_listinv_{li}_G"]) < TOL64
+
+
+def test_diagonal(golden):
+    model = load_params(MLP(), golden, "mlp")
+    est = O.OracleDiagonal(model)
+    for i in range(2):
+        x, y = torch.tensor(golden[f"mlp_x_{i}"]).double(), torch.tensor(golden[f"mlp_y_{i}"])
+        O.fisher_backward(model, x, labels=y)
+        est.update(batch_size=x.shape[0])
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(est.layers):
+        assert relerr(est.state[layer], golden[f"diag64_state_{li}"]) < TOL64
+        assert relerr(est.inv_state[layer], golden[f"diag64_inv_{li}"]) < TOL64
+        z = torch.tensor(golden[f"diag64_z_{li}"])
+        assert relerr(O.diag_sample(est.inv_state[layer], z), golden[f"diag64_sample_{li}"]) < TOL64
+    h = O.diag_flat_inverse(est.layers, est.inv_state)
+    xt = torch.tensor(golden["mlp_xtest"])
+    pred = torch.softmax(model(xt), dim=1)
+    J = O.params_jacobian_flat(pred, model, O.argmax_grad_outputs(pred))
+    assert relerr(J.detach(), golden["diag64_lin_J"]) < TOL64
+    assert abs(O.linearised_diag_variance(J.detach(), h) / float(golden["diag64_lin_var"]) - 1) < 1e-9
+
+
+def test_conv_factors_and_linearised_predictive(golden):
+    model = load_params(BaseNet_750(), golden, "cnn")
+    xs = [torch.tensor(golden[f"cnn_x_{i}"]).double() for i in range(2)]
+    ys = [torch.tensor(golden[f"cnn_y_{i}"]) for i in range(2)]
+    est = _run_kfac(model, xs, ys)
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(est.layers):
+        assert relerr(est.state[layer][0], golden[f"cnn64_state_{li}_A"]) < TOL64
+        assert relerr(est.state[layer][1], golden[f"cnn64_state_{li}_G"]) < TOL64
+        assert relerr(est.inv_state[layer][0], golden[f"cnn64_inv_{li}_A"]) < 1e-8
+        assert relerr(est.inv_state[layer][1], golden[f"cnn64_inv_{li}_G"]) < 1e-8
+        # upper triangle of the Cholesky factors is exactly zero
+        assert torch.triu(est.inv_state[layer][0], 1).abs().max().item() == 0.0
+    xt = torch.tensor(golden["cnn_xtest"])
+    for use_kron in (True, False):
+        pm, pstd, ent = O.linearised_classification_batch(model, est.layers, est.inv_state, xt, use_kron)
+        assert relerr(pm, golden["cnn64_lin_pred_mean"]) < TOL64
+        assert abs(pstd / float(golden["cnn64_lin_pred_std"]) - 1) < 1e-8
+        assert abs(ent - float(golden["cnn64_lin_entropy"])) < 1e-8
+    # per-layer terms, kron-free identity J (Q (x) H) J^T = <V, Q V H^T>  (quirk Q2 layout)
+    mods = list(model.modules())[1:]
+    for li, layer in enumerate(mods):
+        key = f"cnn64_lin_J_{li}"
+        if key in golden:
+            J = torch.tensor(golden[key])
+            Q, H = est.inv_state[layer]
+            assert abs(O.linearised_kfac_variance(J, Q, H) / float(golden[f"cnn64_lin_term_{li}"]) - 1) < 1e-8
+
+
+def test_regression_linearised(golden):
+    model = load_params(RegNet(30), golden, "reg", torch.float32)
+    layers = O.selected_layers(model)
+    state = {l: (torch.tensor(golden[f"reg_state_{i}_A"]), torch.tensor(golden[f"reg_state_{i}_G"]))
+             for i, l in enumerate(layers)}
+    xt = torch.tensor(golden["reg_xtest"])
+    for use_kron in (True, False):
+        stds = [O.linearised_regression_point(model, layers, state, x_j, 0.01, 30, 3, use_kron) for x_j in xt]
+        # fp32 pinverse of matrices conditioned ~1e4: compare the data-dependent part loosely
+        np.testing.assert_allclose(np.array(stds) - 3, golden["reg_pred_std"] - 3, rtol=5e-2, atol=1e-4)
+    assert relerr(model(xt).detach().squeeze(1), golden["reg_pred_mean"]) < 1e-6
+
+
+def test_kron_doctest_vector(golden):
+    """The reference's only executable check: models/utilities.py:400-407."""
+    out = O.kron(torch.tensor(golden["kron_a"]), torch.tensor(golden["kron_b"]))
+    assert np.array_equal(out.numpy(), golden["kron_out"])
+    assert np.array_equal(out.numpy(), np.array([[0, 5, 0, 10], [6, 7, 12, 14], [0, 15, 0, 20], [18, 21, 24, 28]]))
+
+
+def test_invert_identity_and_eigh():
+    torch.manual_seed(0)
+    x = torch.randn(40, 12, dtype=torch.float64)
+    F_ = x.t() @ x / 40
+    L = O.kfac_invert_factor(F_, 0.04, 200.0)
+    R = 200.0 ** 0.5 * F_ + 0.04 ** 0.5 * torch.eye(12, dtype=torch.float64)
+    assert relerr(L @ L.t() @ R, torch.eye(12)) < 1e-10
+    wa, va, wg, vg = O.factor_eigenvectors(F_, F_)
+    assert relerr(va @ torch.diag(wa) @ va.t(), 2 * F_) < 1e-10   # eigen-decomposition of F + F^T
+    ev = O.factor_eigenvalues(F_, F_)
+    assert ev.shape == (144,)
+
+
+def test_dense_fisher_and_dominance():
+    torch.manual_seed(1)
+    coords = O.kernel_block_coords_basenet15k()
+    assert coords[-1][1] == 15080 and len(coords) == 109   # hessian/utils.py:67-95
+    g = torch.randn(8, 50, dtype=torch.float64)
+    H = O.dense_fisher(g)
+    assert relerr(H, sum(torch.outer(r, r) for r in g) / 8) < 1e-12
+    dd, kd = O.dominance(H, [(0, 10), (10, 50)])
+    assert 0 < dd <= kd <= 1
+    J = torch.randn(1, 50, dtype=torch.float64)
+    assert O.dense_variance(J, O.dense_inverse(H, 0.04)) > 0
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    out = O.philox4x32_10(np.zeros((1, 4), dtype=np.uint32), (0, 0))
+    assert [hex(v) for v in out[0]] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    out = O.philox4x32_10(np.full((1, 4), 0xFFFFFFFF, dtype=np.uint32), (0xFFFFFFFF, 0xFFFFFFFF))
+    assert [hex(v) for v in out[0]] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    z = O.philox_normal(1234, 0, 7, 200000)
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.02
