@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — KFAC factor-update throughput (+ inversion latency and posterior-predictive
+throughput) on BASELINE.json's wide-MLP configuration.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --steps 20 --warmup 3    # the reference algorithm on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU (weak scaling)
+
+Workload (config.workload = "cfg5_wide_mlp"): MLP 4096-4096-4096-4096-10, batch 4096 per GPU,
+synthetic bf16-representable activations N(0,1) and output gradients N(0,1)/N (BASELINE.md §3,
+config 5).  A *step* is one `KFAC.update` over one batch: first and second Kronecker factor of all
+four Linear layers (A 4097^2 x4, G 4096^2 x3 + 10^2), accumulated into the running state
+(models/curvatures.py:325-365 of the reference).  Model forward/backward is not part of the step
+(the metric is "factor-update samples/s": samples whose (a, g) are folded into all factors per second).
+
+  value : samples/s with the step's (a, g) already resident in HBM (device-timed, max over ranks)
+  e2e   : same metric through the public API with HOST buffers: per step the (a, g) tensors are copied
+          from pinned host memory, `KFAC.update` runs, and a per-factor checksum is read back
+  roofline     : the tcgen05 SYRK kernel, algorithmic flops d'(d'+1)N per launch / event-timed launch
+  cpu_baseline : oracle/ (CPU restatement of the reference's update) on a bounded sample, rank 0 only
+
+Multi-GPU: the batch axis shards (each rank owns its own 4096-sample batches, weak scaling); the
+factors are plain sums (curvatures.py:359-361), so the only exchange is ONE all-reduce of the factor
+states after the K accumulation steps (it is what `invert()` needs); it is inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTHS = [4096, 4096, 4096, 4096, 10]
+BATCH = 4096
+REF_SAMPLE_ROWS = 1024
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def synth_batch(gen, batch, widths):
+    """Per layer (a [batch, d_in], g [batch, d_out]) fp32, bf16-representable (BASELINE config 5)."""
+    out = []
+    for d_in, d_out in zip(widths[:-1], widths[1:]):
+        a = torch.randn(batch, d_in, generator=gen).bfloat16().float()
+        g = (torch.randn(batch, d_out, generator=gen) / batch).bfloat16().float()
+        out.append((a, g))
+    return out
+
+
+def algorithmic_flops_per_sample(widths):
+    """d_in'(d_in'+1) + d_out(d_out+1) per sample per Linear layer."""
+    return sum((a + 1) * (a + 2) + b * (b + 1) for a, b in zip(widths[:-1], widths[1:]))
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own update arithmetic (oracle port, torch CPU fp32, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import kfac_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(1234)
+    data = synth_batch(gen, REF_SAMPLE_ROWS, WIDTHS)
+    state = [None] * len(data)
+
+    def step():
+        for i, (a, g) in enumerate(data):
+            f1, f2 = O.kfac_linear_factors(a, g * a.shape[0], True)
+            if state[i] is None:
+                state[i] = [f1, f2]
+            else:  # models/curvatures.py:359-361
+                state[i][0] += f1
+                state[i][1] += f2
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = REF_SAMPLE_ROWS * args.steps / dt
+    sample = f"{REF_SAMPLE_ROWS} of {BATCH} rows per step, all 4 layers, fp32 torch CPU"
+    line = {"impl": "reference", "metric": "kfac_factor_update_samples_per_s", "value": value,
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5_wide_mlp", "widths": WIDTHS, "batch_per_gpu": BATCH},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_leg(max_seconds=20.0):
+    from oracle import kfac_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(1234)
+    data = synth_batch(gen, REF_SAMPLE_ROWS, WIDTHS)
+
+    def step():
+        for a, g in data:
+            O.kfac_linear_factors(a, g * a.shape[0], True)
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        if time.perf_counter() - t0 > max_seconds or n >= 8:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": REF_SAMPLE_ROWS * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of {REF_SAMPLE_ROWS} of {BATCH} rows, all 4 layers, fp32 torch CPU"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip inversion / predictive extras")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bnn_kfac_b200 import _lib
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.distributed import allreduce_state
+    from bnn_kfac_b200.wrapper import MLP
+    L = _lib.load()
+    _lib.require_device()
+
+    torch.manual_seed(0)
+    model = MLP(WIDTHS).to(dev)
+    est = KFAC(model, precision=args.precision)
+    layers = [l for _, l in est._selected_layers()]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = [(a.pin_memory(), g.pin_memory()) for a, g in synth_batch(gen, BATCH, WIDTHS)]
+    resident = [(a.to(dev), g.to(dev)) for a, g in host]
+    staging = [(torch.empty_like(a), torch.empty_like(g)) for a, g in resident]
+    h2d_bytes = sum(a.numel() * 4 + g.numel() * 4 for a, g in host)
+    checksum_host = torch.empty(2 * len(layers), dtype=torch.float32).pin_memory()
+
+    def step_device(bufs):
+        for layer, (a, g) in zip(layers, bufs):
+            est.record[layer] = [a, g]
+        est.update(BATCH)
+
+    def step_e2e():
+        for (ha, hg), (da, dg) in zip(host, staging):
+            da.copy_(ha, non_blocking=True)
+            dg.copy_(hg, non_blocking=True)
+        step_device(staging)
+        cs = torch.stack([est.state[l][k].diagonal().sum() for l in layers for k in range(2)])
+        checksum_host.copy_(cs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return checksum_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, after=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if after is not None:
+            after()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    reduce_after = (lambda: allreduce_state(est)) if world > 1 else None
+    for _ in range(args.warmup):
+        step_device(resident)
+    with ClockSampler(local_rank) as clocks:
+        ms_dev = timed(lambda: step_device(resident), args.steps, reduce_after)
+    for _ in range(args.warmup):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps, reduce_after)
+
+    total_samples = BATCH * args.steps * world
+    value = total_samples / (ms_dev * 1e-3)
+    e2e_value = total_samples / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 SYRK), timed alone on its own launches
+    peaks = load_peaks()
+    prec = {"bf16": 1, "bf16x3": 3, "fp32": 1}[args.precision]
+    n, d = BATCH, WIDTHS[0]
+    ldt = n
+    hi = torch.empty(d + 1, ldt, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty_like(hi)
+    L.bk_transpose_split(resident[0][0].data_ptr(), d, n, d, 1.0, 1, hi.data_ptr(), lo.data_ptr(), ldt,
+                         _lib.stream_ptr())
+    scratch = torch.zeros(d + 1, d + 1, device=dev)
+    reps = 20
+
+    def syrk():
+        L.bk_syrk_accum_staged(scratch.data_ptr(), d + 1, hi.data_ptr(), lo.data_ptr(), ldt, n, d + 1,
+                               1.0 / n, 1.0, prec, _lib.stream_ptr())
+    for _ in range(3):
+        syrk()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        syrk()
+    e1.record()
+    torch.cuda.synchronize()
+    syrk_ms = e0.elapsed_time(e1) / reps
+    syrk_flops = (d + 1) * (d + 2) * n          # one multiply-add per lower-triangle entry per sample
+    achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "umma_gemm_kernel (SYRK 4097x4097x4096, lower+mirror)",
+                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)",
+                "us_per_launch": syrk_ms * 1e3, "traffic": None}
+    prof = os.path.join(ROOT, "profiles", "syrk_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    line = {"metric": "kfac_factor_update_samples_per_s", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "cfg5_wide_mlp", "widths": WIDTHS, "batch_per_gpu": BATCH,
+                       "parallelism": f"batch-sharded x{world}, one factor all-reduce per timed region",
+                       "l2": "inputs_larger_than_l2 (0.47 GB of activations + 0.4 GB of factor state per step)"},
+            "algorithmic_tflops": value * algorithmic_flops_per_sample(WIDTHS) / 1e12,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": checksum_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": None, "roofline": roofline, "clocks": clocks.summary()}
+
+    # kernels launched by this library inside the device-timed region (counted by the library itself)
+    c0 = L.bk_launch_count()
+    step_device(resident)
+    torch.cuda.synchronize()
+    line["gpu_launches"] = int(L.bk_launch_count() - c0) * args.steps
+
+    if not args.no_extras:
+        line["extras"] = extras(est, model, layers, dev, world, rank)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(est, model, layers, dev, world, rank):
+    """Inversion latency and posterior-predictive throughput on the same workload (device-timed)."""
+    import torch.distributed as dist
+    from bnn_kfac_b200.predictive import mc_moments
+    out = {}
+
+    def ev_ms(fn, reps=1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    est.invert(1.0, 200.0)      # warm-up (workspace allocation)
+    out["invert_ms_all_layers"] = ev_ms(lambda: est.invert(1.0, 200.0))
+    # posterior predictive: S weight samples per rank (sample ids sharded over ranks), 1024 test inputs
+    S, B = 4, 1024
+    x = torch.randn(B, WIDTHS[0], device=dev)
+    mc_moments(est, x, S, sample0=rank * S)
+    ms = ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S))
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["posterior_predictive"] = {"value": S * world * B / (t.item() * 1e-3),
+                                   "unit": "(weight samples x test inputs)/s",
+                                   "weight_samples_per_s": S * world / (t.item() * 1e-3),
+                                   "config": {"samples_per_gpu": S, "test_inputs": B}}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

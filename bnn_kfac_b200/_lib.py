@@ -11,9 +11,10 @@ from pathlib import Path
 
 from . import _build
 
+BK_PREC_FP32 = 0
 BK_PREC_BF16 = 1
 BK_PREC_BF16X3 = 3
-BK_SMALL_D_MAX = 160
+BK_SMALL_D_MAX = 176
 
 GEMM_SYRK_LOWER = 1
 GEMM_MIRROR = 2
@@ -37,6 +38,7 @@ _p, _ll, _i, _f, _u, _ull, _sz = (C.c_void_p, C.c_longlong, C.c_int, C.c_float, 
 SIGNATURES = {
     "bk_version": (C.c_char_p, []),
     "bk_device_check": (_i, []),
+    "bk_launch_count": (_ull, []),
     "bk_gemm_nt": (_i, [_p, _p, _ll, _ll, _p, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _f,
                         _p, _ll, _ll, _p, _ll, _p, _p, _ll, _ll, _p]),
     "bk_transpose_split": (_i, [_p, _ll, _i, _i, _f, _i, _p, _p, _ll, _p]),

@@ -14,10 +14,19 @@ inline long long round8(long long v) { return (v + 7) / 8 * 8; }
 
 }  // namespace
 
+#include <atomic>
+
+namespace bk {
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+}  // namespace bk
+
 #pragma GCC visibility push(default)
 extern "C" {
 
 const char* bk_version(void) { return "bk_kfac 0.1 (sm_100a)"; }
+
+unsigned long long bk_launch_count(void) { return bk::g_launches.load(); }
 
 int bk_device_check(void) {
   int dev = 0;
@@ -92,7 +101,7 @@ int bk_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_
 // ------------------------------------------------------------------------------ factor update
 size_t bk_syrk_workspace_bytes(int n, int d, int has_bias, int precision) {
   const int dp = d + (has_bias ? 1 : 0);
-  if (dp <= BK_SMALL_D_MAX) return 0;
+  if (dp <= BK_SMALL_D_MAX || precision == BK_PREC_FP32) return 0;
   const size_t one = align_up(static_cast<size_t>(dp) * round8(n) * 2, 256);
   return precision == BK_PREC_BF16X3 ? 2 * one : one;
 }
@@ -127,6 +136,10 @@ int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ld
   if (dp <= BK_SMALL_D_MAX) {
     return bk::launch_small_syrk(state, ld_state, x, ldx, n, d, has_bias, in_scale, alpha, beta,
                                  as_stream(stream));
+  }
+  if (precision == BK_PREC_FP32) {
+    return bk::launch_syrk_fp32(state, ld_state, x, ldx, n, d, has_bias, in_scale, alpha, beta,
+                                as_stream(stream));
   }
   if (precision != BK_PREC_BF16 && precision != BK_PREC_BF16X3) return BK_ERR_ARG;
   const size_t need = bk_syrk_workspace_bytes(n, d, has_bias, precision);

@@ -334,26 +334,33 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   const dim3 tb(32, 8);
   const dim3 tg((max_pad + 31) / 32, (max_pad + 31) / 32, count);
   damp_flip_kernel<<<tg, tb, 0, stream>>>(d_tab);
+  note_launch();
   for (int k = 0; k < max_nb; ++k) {
     potrf_diag_kernel<<<count, 256, 0, stream>>>(d_tab, k, d_info);
+  note_launch();
     const int m = max_pad - (k + 1) * NB;
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
       rank64_kernel<<<dim3(tm, count), 256, smem, stream>>>(d_tab, k, kPanel);
+  note_launch();
       rank64_kernel<<<dim3(tm * (tm + 1) / 2, count), 256, smem, stream>>>(d_tab, k, kTrail);
+  note_launch();
     }
   }
   for (int k = 0; k < max_nb; ++k) {
     const int n = (k + 1) * NB;
     const int tn = (n + TN - 1) / TN;
     rank64_kernel<<<dim3(tn, count), 256, smem, stream>>>(d_tab, k, kRowScale);
+  note_launch();
     const int m = max_pad - (k + 1) * NB;
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
       rank64_kernel<<<dim3(tm * tn, count), 256, smem, stream>>>(d_tab, k, kXUpdate);
+  note_launch();
     }
   }
   flip_out_kernel<<<tg, tb, 0, stream>>>(d_tab);
+  note_launch();
   if (cudaGetLastError() != cudaSuccess) return -5;
 
   int* h_info = new int[count];

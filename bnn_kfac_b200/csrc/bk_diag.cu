@@ -104,6 +104,7 @@ int launch_diag_accum(float* state, const float* wgrad, const float* bgrad, int 
   if (total <= 0) return 0;
   diag_accum_kernel<<<grid_for(total), kBlock, 0, stream>>>(state, wgrad, bgrad, d_out, d_in, scale,
                                                             beta);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -111,6 +112,7 @@ int launch_diag_invert(float* inv, const float* state, long long count, float ad
                        cudaStream_t stream) {
   if (count <= 0) return 0;
   diag_invert_kernel<<<grid_for(count), kBlock, 0, stream>>>(inv, state, count, add, multiply);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -120,6 +122,7 @@ int launch_diag_sample(float* out, const float* inv, long long count, int nsampl
   if (count <= 0 || nsamples <= 0) return 0;
   diag_sample_kernel<<<grid_for(((count + 3) / 4) * nsamples), kBlock, 0, stream>>>(
       out, inv, count, nsamples, seed, sample0, stream_id, z_or_null);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -127,6 +130,7 @@ int launch_diag_quadform(float* out, const float* J, long long ldj, const float*
                          int batch, cudaStream_t stream) {
   if (batch <= 0) return 0;
   diag_quadform_kernel<<<batch, kBlock, 0, stream>>>(out, J, ldj, h, count);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

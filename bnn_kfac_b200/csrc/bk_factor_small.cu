@@ -1,4 +1,4 @@
-// bk_factor_small.cu — SIMT fp32 split-K SYRK for skinny Kronecker factors (d' <= 160).
+// bk_factor_small.cu — SIMT fp32 split-K SYRK for skinny Kronecker factors (d' <= 176).
 //
 // These factors (conv layers, small Linear layers: 5..161 wide) have a tiny output and a long
 // reduction axis (conv1 of BaseNet_15k: 26 x 26 output over 147 456 patch columns), so they are
@@ -138,10 +138,11 @@ template <class Loader>
 int run_small_syrk(float* state, long long ld_state, Loader load, long long nrows, int d,
                    int has_bias, float alpha, float beta, cudaStream_t stream) {
   const int dp = d + has_bias;
-  if (dp <= 0 || dp > 160) return -2;
+  if (dp <= 0 || dp > 176) return -2;
   if (beta != 1.f) {
     dim3 g((dp + 127) / 128, dp), b(128);
     scale_square_kernel<<<g, b, 0, stream>>>(state, ld_state, dp, beta);
+    note_launch();
   }
   if (nrows <= 0) return cudaGetLastError() == cudaSuccess ? 0 : -5;
   // split the reduction axis: at most 4 CTAs per SM, at least 4 staged tiles per CTA
@@ -158,13 +159,15 @@ int run_small_syrk(float* state, long long ld_state, Loader load, long long nrow
     const size_t smem = sizeof(float) * kRowsPerTile * ((TT) * 16 + 1);                          \
     small_syrk_kernel<TT, Loader><<<static_cast<int>(ctas), kTX * kTY, smem, stream>>>(          \
         state, ld_state, load, nrows, d, has_bias, alpha, per);                                  \
+    note_launch();                                                                               \
   }
   if (T <= 1) BK_LAUNCH_T(1)
   else if (T == 2) BK_LAUNCH_T(2)
   else if (T <= 4) BK_LAUNCH_T(4)
   else if (T <= 6) BK_LAUNCH_T(6)
   else if (T <= 8) BK_LAUNCH_T(8)
-  else BK_LAUNCH_T(10)
+  else if (T <= 10) BK_LAUNCH_T(10)
+  else BK_LAUNCH_T(11)
 #undef BK_LAUNCH_T
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

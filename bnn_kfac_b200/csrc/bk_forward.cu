@@ -186,6 +186,7 @@ int launch_sample_to_weights(const float* samples, const float* mean_w, const fl
   if (blocks > cap) blocks = cap;
   sample_to_weights_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       samples, mean_w, mean_b, d_out, d_in, has_bias, nsamples, w_f32, w_hi, w_lo, ldw, b_f32);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -207,6 +208,7 @@ int launch_conv2d_relu_pool(const float* in, long long in_sample_stride, const f
   conv2d_relu_pool_kernel<<<dim3(N, S), 256, smem, stream>>>(in, in_sample_stride, w, b, out, N, C, H,
                                                              W, O, KH, KW, SH, SW, PH, PW, relu,
                                                              pool);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -218,6 +220,7 @@ int launch_predictive_moments(const float* logits, int S, int B, int Cn, int mod
   const int blocks = (B + warps_per_block - 1) / warps_per_block;
   predictive_moments_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(logits, S, B, Cn, mode, mean,
                                                                          meansq);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -227,6 +230,7 @@ int launch_frob_dot(float* out, const float* X, long long stride_x, const float*
   if (batch <= 0) return 0;
   frob_dot_kernel<<<batch, 256, 0, stream>>>(out, X, stride_x, Y, stride_y, count, absolute,
                                              accumulate);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

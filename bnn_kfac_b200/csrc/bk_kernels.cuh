@@ -29,6 +29,10 @@ int launch_conv_a_syrk(float* state, long long ld_state, const float* x, int n, 
 int launch_conv_g_syrk(float* state, long long ld_state, const float* g, int n, int o, int hw,
                        float in_scale, float alpha, float beta, cudaStream_t stream);
 
+// ---- bk_syrk_fp32.cu  (full-fp32 SIMT SYRK, any d; parity mode for ill-conditioned factors)
+int launch_syrk_fp32(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
+                     int has_bias, float in_scale, float alpha, float beta, cudaStream_t stream);
+
 // ---- bk_diag.cu
 int launch_diag_accum(float* state, const float* wgrad, const float* bgrad, int d_out, int d_in,
                       float scale, float beta, cudaStream_t stream);

@@ -75,6 +75,7 @@ int launch_transpose_split(const float* X, long long ldx, int rows, int cols, fl
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_split_kernel<<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, ones_row, Thi, Tlo,
                                                      ldt);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -87,6 +88,7 @@ int launch_convert_split(const float* X, long long ldx, int rows, int cols, floa
   dim3 grid(bx, rows), block(256);
   convert_split_kernel<<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, lower_only, Ohi, Olo,
                                                    ldo);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
@@ -144,6 +146,7 @@ int launch_philox_normal(unsigned long long seed, unsigned sample0, unsigned str
   if (blocks > cap) blocks = cap;
   philox_normal_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       seed, sample0, stream_id, rows, cols, nsamples, Zf, ldf, stridef, Zhi, Zlo, ldz, stridez);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

@@ -450,6 +450,7 @@ int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   umma_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mA0, mA1, mB0, mB1, p);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 

@@ -37,7 +37,13 @@ from torch.nn import Module, Sequential
 
 from . import _lib
 
-_PRECISIONS = {"bf16": _lib.BK_PREC_BF16, "bf16x3": _lib.BK_PREC_BF16X3}
+_PRECISIONS = {"fp32": _lib.BK_PREC_FP32, "bf16": _lib.BK_PREC_BF16, "bf16x3": _lib.BK_PREC_BF16X3}
+
+
+def gemm_precision(name: str) -> int:
+    """Precision of the tensor-core contractions (sampling, forward, quadratic forms): "fp32" only
+    changes the factor SYRK; everything downstream then runs split-bf16 (bf16x3)."""
+    return _lib.BK_PREC_BF16 if name == "bf16" else _lib.BK_PREC_BF16X3
 
 
 def _round8(v: int) -> int:
@@ -173,6 +179,20 @@ class Curvature(ABC):
 
     def _invalidate_caches(self):
         pass
+
+    # The estimator is reachable from the pickled model through its hooks (bound methods), exactly as
+    # in the reference; the ctypes handle and the scratch buffer are process-local and are dropped.
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d.pop("_lib", None)
+        d["_ws"] = None
+        d["_staged"] = dict()
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._lib = _lib.load()
+        self._ws = _Workspace()
 
     def _next_sample_id(self) -> int:
         sid = self._sample_counter
@@ -407,7 +427,7 @@ class KFAC(Curvature):
             self._sample_counter += n_samples
         layer_id = [l for _, l in self._selected_layers()].index(layer)
         return matrix_normal_samples(stA, stG, first.shape[0], second.shape[0], n_samples,
-                                     precision=_PRECISIONS[self.precision], seed=self.seed,
+                                     precision=gemm_precision(self.precision), seed=self.seed,
                                      sample0=sample0, stream_id=layer_id, z=z, ws=self._ws)
 
 

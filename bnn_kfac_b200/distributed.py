@@ -1,0 +1,240 @@
+"""Multi-GPU layer: one process per GPU, `torch.distributed` (NCCL over NVLink 5 / NVSwitch).
+
+The reference is single-device (no collective exists in it), so this module defines
+the sharding of its hot path and nothing else:
+
+  factor update   the batch axis is sharded; every rank accumulates the per-batch MEAN factors of its
+                  own shard exactly like a single-device run (models/curvatures.py:349,356,359-363).
+                  Because `state` is a plain sum of batch means, the exchange is deferred: ONE
+                  reduction of the accumulated state, not one per mini-batch.  The global batch mean is
+                  the average of the equally sized per-rank means, so the reduced state is SUM / world.
+  inversion       factors are owned round-robin by cost (d^3, longest-processing-time first); each
+                  owner receives the reduced factor (`reduce` to the owner == reduce-scatter over
+                  whole factors), inverts it with the batched Cholesky kernels, and broadcasts L.
+  MC predictive   posterior samples are sharded; sample s always uses Philox subsequence s, so the
+                  result is independent of the number of GPUs; (sum p, sum p^2) are all-reduced.
+  linearised      test inputs are sharded; the per-input variances are all-gathered.
+  Diagonal        `Diagonal.update` squares the batch-MEAN gradient (curvatures.py:165-168), so the
+                  mean gradient is all-reduced BEFORE squaring to match a single-device run.
+
+Every function takes `group=None` (default process group) and works with any backend that supports the
+tensors it is given: the host-side logic (ownership plan, reduce / broadcast choreography, sample
+partition) is exercised in tests/ on CPU tensors with gloo and world_size 2; the arithmetic between the
+collectives is always the CUDA library.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank(group=None) -> int:
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+# ------------------------------------------------------------------------------------- planning
+def plan_owners(dims: Sequence[int], world: int) -> List[int]:
+    """Owner rank of each factor: longest-processing-time-first on cost d^3 (ties: lowest rank).
+    Deterministic, identical on every rank."""
+    load = [0.0] * world
+    owners = [0] * len(dims)
+    for i in sorted(range(len(dims)), key=lambda i: (-dims[i], i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owners[i] = r
+        load[r] += float(dims[i]) ** 3
+    return owners
+
+
+def sample_slice(n_samples: int, world: int, r: int) -> Tuple[int, int]:
+    """Contiguous block [s0, s1) of global posterior-sample ids handled by rank r."""
+    base, rem = divmod(n_samples, world)
+    s0 = r * base + min(r, rem)
+    return s0, s0 + base + (1 if r < rem else 0)
+
+
+def row_slice(n_rows: int, world: int, r: int) -> Tuple[int, int]:
+    return sample_slice(n_rows, world, r)
+
+
+# ----------------------------------------------------------------------------- factor exchange
+def _flat_views(tensors: Sequence[Tensor]) -> Tuple[Tensor, List[Tensor]]:
+    """One contiguous buffer holding copies of `tensors` + views into it (a single collective
+    instead of one per factor: launch-latency bound otherwise for the small nets)."""
+    total = sum(t.numel() for t in tensors)
+    flat = torch.empty(total, dtype=tensors[0].dtype, device=tensors[0].device)
+    views, off = [], 0
+    for t in tensors:
+        v = flat[off:off + t.numel()].view_as(t)
+        v.copy_(t)
+        views.append(v)
+        off += t.numel()
+    return flat, views
+
+
+def allreduce_state(est, group=None, average: bool = True) -> None:
+    """In-place all-reduce of an estimator's accumulated `state` (KFAC: [A, G] per layer; Diagonal:
+    one tensor per layer).  average=True divides by the world size (global-batch mean, see module
+    docstring).  Large states are reduced in place factor by factor; small ones are coalesced."""
+    w = world_size(group)
+    if w == 1:
+        return
+    tensors: List[Tensor] = []
+    for v in est.state.values():
+        tensors += list(v) if isinstance(v, (list, tuple)) else [v]
+    if not tensors:
+        return
+    small = [t for t in tensors if t.numel() * t.element_size() < (1 << 20)]
+    large = [t for t in tensors if t.numel() * t.element_size() >= (1 << 20)]
+    works = []
+    for t in large:
+        works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    if small:
+        flat, views = _flat_views(small)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        for t, v in zip(small, views):
+            t.copy_(v)
+    for wk in works:
+        wk.wait()
+    if average:
+        for t in tensors:
+            t.mul_(1.0 / w)
+
+
+def reduce_to_owners(tensors: Sequence[Tensor], owners: Sequence[int], group=None,
+                     average: bool = True) -> None:
+    """`reduce` every factor to its owner (reduce-scatter at whole-factor granularity).  After the
+    call tensors[i] holds the global value on rank owners[i]; on other ranks its content is
+    unspecified (NCCL leaves partial sums there)."""
+    w = world_size(group)
+    if w == 1:
+        return
+    me = rank(group)
+    works = [dist.reduce(t, dst=dist.get_global_rank(group, o) if group is not None else o,
+                         op=dist.ReduceOp.SUM, group=group, async_op=True)
+             for t, o in zip(tensors, owners)]
+    for wk in works:
+        wk.wait()
+    if average:
+        for t, o in zip(tensors, owners):
+            if o == me:
+                t.mul_(1.0 / w)
+
+
+def broadcast_from_owners(tensors: Sequence[Tensor], owners: Sequence[int], group=None) -> None:
+    w = world_size(group)
+    if w == 1:
+        return
+    works = [dist.broadcast(t, src=dist.get_global_rank(group, o) if group is not None else o,
+                            group=group, async_op=True)
+             for t, o in zip(tensors, owners)]
+    for wk in works:
+        wk.wait()
+
+
+def invert_sharded(est, add=0., multiply=1., group=None,
+                   inverter: Optional[Callable[[List[Tensor], List[float], List[float]], List[Tensor]]] = None,
+                   keep_state_replicated: bool = False) -> None:
+    """`KFAC.invert` across ranks (models/curvatures.py:367-398 per factor): reduce each accumulated
+    factor to its owner, invert owned factors, broadcast the Cholesky factors of the inverses.
+    `est.inv_state` ends up identical on every rank.  keep_state_replicated=True additionally
+    all-reduces `est.state` first (callers that read `.state` afterwards, as
+    regression_ll_block.py:127-129 does)."""
+    from .curvatures import invert_factors
+    assert est.state, "State dict is empty. Did you call 'update' prior to this?"
+    inverter = inverter or (lambda fs, a, m: invert_factors(fs, a, m, getattr(est, "_ws", None)))
+    w, me = world_size(group), rank(group)
+    layers = list(est.state.keys())
+    factors, adds, mults = [], [], []
+    for index, layer in enumerate(layers):
+        if not isinstance(add, (float, int)) and not isinstance(multiply, (float, int)):
+            assert len(add) == len(multiply) == len(layers)
+            n, s = add[index], multiply[index]
+        else:
+            n, s = float(add), float(multiply)
+        first, second = est.state[layer]
+        factors += [first, second]
+        adds += [float(n)] * 2
+        mults += [float(s)] * 2
+    owners = plan_owners([f.shape[0] for f in factors], w)
+    if keep_state_replicated:
+        allreduce_state(est, group)
+        reduced = factors
+    else:
+        # reduce into scratch copies so that the local partial `state` stays a valid accumulator
+        reduced = [f.clone() for f in factors]
+        reduce_to_owners(reduced, owners, group)
+    mine = [i for i, o in enumerate(owners) if o == me]
+    outs: List[Optional[Tensor]] = [None] * len(factors)
+    if mine:
+        res = inverter([reduced[i] for i in mine], [adds[i] for i in mine], [mults[i] for i in mine])
+        for i, r in zip(mine, res):
+            outs[i] = r
+    for i, f in enumerate(factors):
+        if outs[i] is None:
+            outs[i] = torch.empty_like(f)
+    broadcast_from_owners(outs, owners, group)
+    for li, layer in enumerate(layers):
+        est.inv_state[layer] = (outs[2 * li], outs[2 * li + 1])
+    if hasattr(est, "_invalidate_caches"):
+        est._invalidate_caches()
+
+
+# -------------------------------------------------------------------------------- predictive
+def mc_predict_sharded(est, x: Tensor, n_samples: int, mode: str = "classification", group=None,
+                       program=None,
+                       moments_fn: Optional[Callable[..., Tuple[Tensor, Tensor]]] = None):
+    """MC predictive with the S posterior samples sharded over ranks
+    (sampling/classification_sampling.py:71-80, sampling/regression_sampling.py:81-88).
+    Returns the same value on every rank and for every world size (Philox subsequence = sample id)."""
+    if moments_fn is None:
+        from .predictive import mc_moments
+        moments_fn = mc_moments
+    w, me = world_size(group), rank(group)
+    if n_samples < w:  # same decision on every rank, before any collective
+        raise ValueError(f"n_samples ({n_samples}) must be >= the number of ranks ({w})")
+    s0, s1 = sample_slice(n_samples, w, me)
+    mean, meansq = moments_fn(est, x, s1 - s0, sample0=s0, mode=mode, program=program)
+    acc = torch.stack([mean * (s1 - s0), meansq * (s1 - s0)])
+    if w > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    mean, meansq = acc[0] / n_samples, acc[1] / n_samples
+    if mode == "classification":
+        return mean
+    var = (meansq - mean * mean).clamp_min(0.0)
+    return mean.squeeze(1), var.sqrt().squeeze(1)
+
+
+def gather_rows(local: Tensor, n_rows: int, group=None) -> Tensor:
+    """All-gather of per-test-input results computed on `row_slice` shards (linearised predictive)."""
+    w = world_size(group)
+    if w == 1:
+        return local
+    sizes = [row_slice(n_rows, w, r) for r in range(w)]
+    parts = [torch.empty((b - a,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+             for a, b in sizes]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts, dim=0)
+
+
+# ---------------------------------------------------------------------------------- diagonal
+def allreduce_mean_grads(model: torch.nn.Module, group=None) -> None:
+    """Average `.grad` across ranks BEFORE `Diagonal.update` squares it (curvatures.py:165-168 squares
+    the batch-mean gradient; squaring per-shard means is a different estimator)."""
+    w = world_size(group)
+    if w == 1:
+        return
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat, views = _flat_views(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / w)
+    for g, v in zip(grads, views):
+        g.copy_(v)

@@ -1,0 +1,333 @@
+"""Posterior predictive: Monte-Carlo over weight samples and the sampling-free linearised form.
+
+The reference keeps these loops in scripts; they are first-class functions here, with semantics
+pinned to the cited script lines (paths relative to /root/reference):
+
+  mc_predict            sampling/classification_sampling.py:71-80 (mean of softmax over S samples),
+                        sampling/regression_sampling.py:81-88 (per-input mean / std, ddof = 0);
+                        each sample = Curvature.sample_and_replace + forward (models/wrapper.py:35-44)
+  linearised_kfac       sampling_free/classification/classification_ll_block.py:114-135,
+                        sampling_free/regression/regression_ll_block.py:120-140
+  linearised_diag       sampling_free/classification/classification_ll_diagonal.py:104-131,
+                        sampling_free/regression/regression_ll_diagonal.py:116-139
+
+`mc_predict` never writes sampled weights back into the model: all S weight samples of a layer are
+drawn in one batched launch, turned into bf16 GEMM operands by one fused kernel, and the S forward
+passes run as ONE batched tcgen05 GEMM per Linear layer (bias + ReLU in the epilogue) / one SIMT
+launch per conv layer.  Sample s always uses Philox subsequence s, so sharding samples over GPUs does
+not change the result.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+from torch.nn import Module
+
+from . import _lib
+from .curvatures import KFAC, Diagonal, _round8, gemm_precision, invert_factors, stage_operand
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Op:
+    kind: str                 # "conv" | "linear" | "flatten"
+    layer: Optional[Module] = None
+    relu: bool = False
+    pool: bool = False
+
+
+def program_for(model: Module) -> List[Op]:
+    """Forward program of the supported architectures (reference CNNs, LeNet-5, MLP stacks)."""
+    name = model.__class__.__name__
+    if name == "BaseNet_15k":
+        return [Op("conv", model.conv1, True, True), Op("conv", model.conv2, True, True), Op("flatten"),
+                Op("linear", model.fc1, True), Op("linear", model.fc2, False)]
+    if name == "BaseNet_750":
+        return [Op("conv", model.conv1, True, True), Op("conv", model.conv2, True, True), Op("flatten"),
+                Op("linear", model.fc1, False)]
+    if name == "LeNet5":
+        return [Op("conv", model.conv1, True, True), Op("conv", model.conv2, True, True), Op("flatten"),
+                Op("linear", model.fc1, True), Op("linear", model.fc2, True), Op("linear", model.fc3, False)]
+    if name == "MLP" and hasattr(model, "layers"):
+        n = len(model.layers)
+        return [Op("flatten")] + [Op("linear", l, i + 1 < n) for i, l in enumerate(model.layers)]
+    # generic: attribute-ordered Linear layers fc1..fcK with ReLU between (reference regression nets)
+    fcs = [m for m in model.children() if m.__class__.__name__ == "Linear"]
+    if fcs and len(fcs) == len(list(model.children())):
+        return [Op("linear", l, i + 1 < len(fcs)) for i, l in enumerate(fcs)]
+    raise NotImplementedError(f"no forward program for {name}; pass program=[Op(...), ...]")
+
+
+def _linear_forward(lib, act, act_shared: bool, rows: int, d_in: int, w_hi, w_lo, ldw: int, bias, S: int,
+                    d_out: int, relu: bool, last: bool, prec: int):
+    """act: (hi, lo, ld) bf16 staged [S or 1, rows, ld].  Returns fp32 [S, rows, d_out] when `last`,
+    else the next layer's staged (hi, lo, ld)."""
+    a_hi, a_lo, lda = act
+    x3 = prec == _lib.BK_PREC_BF16X3
+    dev = a_hi.device
+    flags = _lib.GEMM_RELU if relu else 0
+    if last:
+        out = torch.empty(S, rows, d_out, device=dev, dtype=torch.float32)
+        c_ptr, o_hi, o_lo, ldo = out.data_ptr(), None, None, 0
+    else:
+        ldo = _round8(d_out)
+        o_hi = torch.zeros(S, rows, ldo, dtype=torch.bfloat16, device=dev)
+        o_lo = torch.zeros_like(o_hi) if x3 else None
+        out, c_ptr = None, 0
+    _lib.check(lib.bk_gemm_nt(a_hi.data_ptr(), a_lo.data_ptr() if x3 else 0, lda,
+                              0 if act_shared else rows * lda,
+                              w_hi.data_ptr(), w_lo.data_ptr() if x3 else 0, ldw, d_out * ldw,
+                              rows, d_out, d_in, S, prec, flags, 1.0, 0.0,
+                              c_ptr, d_out, rows * d_out,
+                              bias.data_ptr(), d_out,
+                              _lib.ptr(o_hi), _lib.ptr(o_lo), ldo, rows * ldo, _lib.stream_ptr()),
+               "bk_gemm_nt(forward)")
+    return out if last else (o_hi, o_lo, ldo)
+
+
+def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
+              program: Optional[Sequence[Op]] = None, noise: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """Outputs of the network under `n_samples` posterior weight samples: [S, B, C] fp32.
+
+    noise: optional per-layer external noise, noise[layer_index] = [S, d_in', d_out] (parity mode)."""
+    lib = _lib.load()
+    prog = list(program) if program is not None else program_for(est.model)
+    prec = gemm_precision(est.precision)
+    x3 = prec == _lib.BK_PREC_BF16X3
+    S = n_samples
+    st = _lib.stream_ptr()
+    dev = x.device
+    layer_index = {l: i for i, l in est._selected_layers()}
+    cur = x.float().contiguous()       # fp32 activation, [B, ...] (shared) or [S, B, ...]
+    shared = True
+    staged = None                      # bf16 operand of the next Linear (hi, lo, ld)
+    B = x.shape[0]
+    n_ops = len(prog)
+    for oi, op in enumerate(prog):
+        if op.kind == "flatten":
+            if staged is None:
+                cur = cur.reshape(cur.shape[0], -1) if shared else cur.reshape(S, B, -1)
+            continue
+        layer = op.layer
+        li = layer_index[layer]
+        z = None if noise is None else noise[li]
+        smp = est.sample_batch(layer, S, z=z, sample0=sample0)        # [S, d_out, d_in']
+        has_bias = layer.bias is not None
+        d_out = smp.shape[1]
+        d_in = smp.shape[2] - int(has_bias)
+        mean_w = layer.weight.detach().float().reshape(d_out, d_in).contiguous()
+        mean_b = layer.bias.detach().float().contiguous() if has_bias else None
+        b_s = torch.zeros(S, d_out, device=dev, dtype=torch.float32)
+        if op.kind == "conv":
+            w_s = torch.empty(S, d_out, d_in, device=dev, dtype=torch.float32)
+            _lib.check(lib.bk_sample_to_weights(smp.data_ptr(), mean_w.data_ptr(), _lib.ptr(mean_b), d_out,
+                                                d_in, int(has_bias), S, w_s.data_ptr(), 0, 0, 0,
+                                                b_s.data_ptr(), st), "bk_sample_to_weights")
+            n, c, h, w = (cur.shape if shared else cur.shape[1:])
+            kh, kw = layer.kernel_size
+            sh, sw = layer.stride
+            ph, pw = layer.padding
+            oh = (h + 2 * ph - kh) // sh + 1
+            ow = (w + 2 * pw - kw) // sw + 1
+            qh, qw = (oh // 2, ow // 2) if op.pool else (oh, ow)
+            out = torch.empty(S, n, d_out, qh, qw, device=dev, dtype=torch.float32)
+            _lib.check(lib.bk_conv2d_relu_pool(cur.data_ptr(), 0 if shared else n * c * h * w, w_s.data_ptr(),
+                                               b_s.data_ptr(), out.data_ptr(), S, n, c, h, w, d_out, kh, kw,
+                                               sh, sw, ph, pw, int(op.relu), int(op.pool), st),
+                       "bk_conv2d_relu_pool")
+            cur, shared = out, False
+            continue
+        # ---- linear
+        ldw = _round8(d_in)
+        w_hi = torch.zeros(S, d_out, ldw, dtype=torch.bfloat16, device=dev)
+        w_lo = torch.zeros_like(w_hi) if x3 else None
+        _lib.check(lib.bk_sample_to_weights(smp.data_ptr(), mean_w.data_ptr(), _lib.ptr(mean_b), d_out, d_in,
+                                            int(has_bias), S, 0, w_hi.data_ptr(), _lib.ptr(w_lo), ldw,
+                                            b_s.data_ptr(), st), "bk_sample_to_weights")
+        if staged is None:
+            flat = cur.reshape(-1, d_in)                              # [B, d_in] or [S*B, d_in]
+            hi, lo, ld = stage_operand(flat)
+            staged = (hi, lo if x3 else hi, ld)
+        last = all(o.kind == "flatten" for o in prog[oi + 1:])
+        res = _linear_forward(lib, staged, shared, B, d_in, w_hi, w_lo, ldw, b_s, S, d_out, op.relu, last,
+                              prec)
+        if last:
+            return res
+        staged, shared = res, False
+    raise RuntimeError("forward program must end with a Linear layer")
+
+
+def mc_moments(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0, mode: str = "classification",
+               program=None, noise=None) -> Tuple[Tensor, Tensor]:
+    """(E_s[p], E_s[p^2]) over `n_samples` samples starting at global sample id `sample0`;
+    p = softmax(logits) (classification) or the raw output (regression)."""
+    lib = _lib.load()
+    logits = mc_logits(est, x, n_samples, sample0, program, noise)
+    S, B, Cn = logits.shape
+    mean = torch.empty(B, Cn, device=x.device, dtype=torch.float32)
+    meansq = torch.empty_like(mean)
+    _lib.check(lib.bk_predictive_moments(logits.data_ptr(), S, B, Cn, 0 if mode == "classification" else 1,
+                                         mean.data_ptr(), meansq.data_ptr(), _lib.stream_ptr()),
+               "bk_predictive_moments")
+    return mean, meansq
+
+
+def mc_predict(est: KFAC, x: Tensor, n_samples: int = 30, mode: str = "classification", program=None,
+               noise=None, sample0: int = 0):
+    """classification: mean softmax [B, C].  regression: (mean [B], std [B]) with ddof = 0."""
+    mean, meansq = mc_moments(est, x, n_samples, sample0, mode, program, noise)
+    if mode == "classification":
+        return mean
+    var = (meansq - mean * mean).clamp_min(0.0)
+    return mean.squeeze(1), var.sqrt().squeeze(1)
+
+
+# ------------------------------------------------------------------------------------------------
+def kron_quadform(V: Tensor, Q: Tensor, H: Tensor, *, precision: int = _lib.BK_PREC_BF16X3,
+                  triangular: bool = False, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """|<V_b, Q V_b H^T>| for a batch of V_b [d_in', d_out]  ==  |J_b (Q (x) H) J_b^T| with
+    V_b = J_b.view(d_in', d_out) — the Kronecker product is never formed.
+    `triangular=True`: Q and H are lower-triangular (Cholesky factors, reference quirk Q1) and the
+    zero k-blocks are skipped."""
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    x3 = precision == _lib.BK_PREC_BF16X3
+    Bn, dinp, dout = V.shape
+    dev = V.device
+    V = V.float().contiguous()
+    q_hi, q_lo, ldq = stage_operand(Q, lower_only=triangular)
+    h_hi, h_lo, ldh = stage_operand(H, lower_only=triangular)
+    ldv = _round8(dinp)
+    vt_hi = torch.zeros(Bn, dout, ldv, dtype=torch.bfloat16, device=dev)
+    vt_lo = torch.zeros_like(vt_hi)
+    for b in range(Bn):
+        _lib.check(lib.bk_transpose_split(V[b].data_ptr(), dout, dinp, dout, 1.0, 0, vt_hi[b].data_ptr(),
+                                          vt_lo[b].data_ptr(), ldv, st), "bk_transpose_split")
+    ldu = _round8(dout)
+    u_hi = torch.zeros(Bn, dinp, ldu, dtype=torch.bfloat16, device=dev)
+    u_lo = torch.zeros_like(u_hi)
+    # U_b = Q V_b
+    _lib.check(lib.bk_gemm_nt(q_hi.data_ptr(), q_lo.data_ptr() if x3 else 0, ldq, 0,
+                              vt_hi.data_ptr(), vt_lo.data_ptr() if x3 else 0, ldv, dout * ldv,
+                              dinp, dout, dinp, Bn, precision, _lib.GEMM_TRI_A if triangular else 0, 1.0, 0.0,
+                              0, 0, 0, 0, 0, u_hi.data_ptr(), u_lo.data_ptr() if x3 else 0, ldu, dinp * ldu,
+                              st), "bk_gemm_nt(QV)")
+    # W_b = U_b H^T
+    Wm = torch.empty(Bn, dinp, dout, device=dev, dtype=torch.float32)
+    _lib.check(lib.bk_gemm_nt(u_hi.data_ptr(), u_lo.data_ptr() if x3 else 0, ldu, dinp * ldu,
+                              h_hi.data_ptr(), h_lo.data_ptr() if x3 else 0, ldh, 0,
+                              dinp, dout, dout, Bn, precision, _lib.GEMM_TRI_B if triangular else 0, 1.0, 0.0,
+                              Wm.data_ptr(), dout, dinp * dout, 0, 0, 0, 0, 0, 0, st), "bk_gemm_nt(UH^T)")
+    if out is None:
+        out = torch.zeros(Bn, device=dev, dtype=torch.float32)
+        accumulate = False
+    _lib.check(lib.bk_frob_dot(out.data_ptr(), V.data_ptr(), dinp * dout, Wm.data_ptr(), dinp * dout,
+                               dinp * dout, Bn, 1, int(accumulate), st), "bk_frob_dot")
+    return out
+
+
+def _layer_jacobian(out: Tensor, layer: Module, grad_outputs: Optional[Tensor]) -> Tensor:
+    """J_i = cat(flatten(d out / d p) for p in layer.parameters()) (classification_ll_block.py:128-130).
+    Autograd is host plumbing exactly as in the reference script."""
+    g = [torch.flatten(torch.autograd.grad(out, [p], grad_outputs=grad_outputs, retain_graph=True,
+                                           allow_unused=True)[0]) for p in layer.parameters()]
+    return torch.cat(g, dim=0)
+
+
+def argmax_grad_outputs(pred_mean: Tensor) -> Tensor:
+    """grad_outputs[:, idx] = 1 with a vector idx (reference quirk Q3, classification_ll_block.py:119-121)."""
+    idx = torch.argmax(pred_mean.detach(), dim=1)
+    go = torch.zeros_like(pred_mean)
+    go[:, idx] = 1
+    return go
+
+
+def linearised_kfac_classification(est: KFAC, x: Tensor) -> Tuple[Tensor, float, float]:
+    """One test batch of the sampling-free KFAC predictive: (pred_mean [B, C], pred_std, entropy).
+    classification_ll_block.py:114-135, including its quirks (Cholesky factors used as Q_i / H_i, flat
+    Jacobian reinterpreted row-major, gradient summed over the batch)."""
+    pred_mean = torch.softmax(est.model(x), dim=1)
+    go = argmax_grad_outputs(pred_mean)
+    total = torch.zeros(1, device=x.device, dtype=torch.float32)
+    prec = gemm_precision(est.precision)
+    for layer in list(est.model.modules())[1:]:
+        if layer in est.state:
+            Q_i, H_i = est.inv_state[layer]
+            J_i = _layer_jacobian(pred_mean, layer, go).detach()
+            V = J_i.reshape(1, Q_i.shape[0], H_i.shape[0])
+            kron_quadform(V, Q_i, H_i, precision=prec, triangular=True, out=total, accumulate=True)
+    pred_std = float(total.item())
+    entropy = 0.5 * np.log2(2 * np.e * np.pi * pred_std)
+    return pred_mean.detach(), pred_std, float(entropy)
+
+
+def linearised_kfac_regression(est: KFAC, x_test: Tensor, tau: float, N: float, sigma: float) -> Tensor:
+    """Predictive std per test point: sqrt(sum_layers |J (q_inv (x) h_inv) J^T|) + sigma with
+    q_inv = (N (A + tau I))^-1, h_inv = (N (G + tau I))^-1 taken from `state`.
+    regression_ll_block.py:120-140.  The inverses are computed ONCE (the script recomputes them per
+    test point) as L L^T from the batched Cholesky kernel (R = N F + N tau I is SPD, so the
+    pseudo-inverse of the script is the inverse)."""
+    lib = _lib.load()
+    layers = [l for l in list(est.model.modules())[1:] if l in est.state]
+    factors, adds, mults = [], [], []
+    for l in layers:
+        factors += list(est.state[l])
+        adds += [(N * tau) ** 2] * 2
+        mults += [float(N) ** 2] * 2
+    chol = invert_factors(factors, adds, mults, est._ws)
+    invs = [inverse_from_chol(Lc) for Lc in chol]
+    preds = est.model(x_test)
+    P = preds.shape[0]
+    total = torch.zeros(P, device=x_test.device, dtype=torch.float32)
+    prec = gemm_precision(est.precision)
+    for i, l in enumerate(layers):
+        q_inv, h_inv = invs[2 * i], invs[2 * i + 1]
+        Js = []
+        for j in range(P):
+            Js.append(_layer_jacobian(preds[j], l, torch.ones_like(preds[j])).detach())
+        V = torch.stack(Js).reshape(P, q_inv.shape[0], h_inv.shape[0])
+        kron_quadform(V, q_inv, h_inv, precision=prec, out=total, accumulate=True)
+    return total.sqrt() + sigma
+
+
+def inverse_from_chol(Lc: Tensor, precision: int = _lib.BK_PREC_BF16X3) -> Tensor:
+    """R^-1 = L L^T from the Cholesky factor of the inverse (one triangular-aware tensor-core GEMM)."""
+    lib = _lib.load()
+    d = Lc.shape[0]
+    hi, lo, ld = stage_operand(Lc, lower_only=True)
+    out = torch.empty(d, d, device=Lc.device, dtype=torch.float32)
+    x3 = precision == _lib.BK_PREC_BF16X3
+    _lib.check(lib.bk_gemm_nt(hi.data_ptr(), lo.data_ptr() if x3 else 0, ld, 0,
+                              hi.data_ptr(), lo.data_ptr() if x3 else 0, ld, 0,
+                              d, d, d, 1, precision, _lib.GEMM_TRI_A | _lib.GEMM_TRI_B, 1.0, 0.0,
+                              out.data_ptr(), d, 0, 0, 0, 0, 0, 0, 0, _lib.stream_ptr()), "bk_gemm_nt(LL^T)")
+    return out
+
+
+def diag_flat_inverse(est: Diagonal) -> Tensor:
+    """h = cat(flatten(inv_state[layer])) in model.modules() order (classification_ll_diagonal.py:108-113)."""
+    return torch.cat([torch.flatten(est.inv_state[l]) for l in list(est.model.modules())[1:]
+                      if l in est.state], dim=0)
+
+
+def linearised_diag(est: Diagonal, J: Tensor, h: Optional[Tensor] = None) -> Tensor:
+    """var_b = sum_j J[b, j]^2 h_j for Jacobian rows J [B, P] over net.parameters() order
+    (classification_ll_diagonal.py:127-131; regression_ll_diagonal.py:135-139)."""
+    lib = _lib.load()
+    h = diag_flat_inverse(est) if h is None else h
+    J = J.float().contiguous()
+    out = torch.empty(J.shape[0], device=J.device, dtype=torch.float32)
+    _lib.check(lib.bk_diag_quadform(out.data_ptr(), J.data_ptr(), J.stride(0), h.data_ptr(), h.numel(),
+                                    J.shape[0], _lib.stream_ptr()), "bk_diag_quadform")
+    return out
+
+
+def params_jacobian(out: Tensor, model: Module, grad_outputs: Optional[Tensor]) -> Tensor:
+    """Flat Jacobian row over net.parameters() (classification_ll_diagonal.py:127-130)."""
+    g = [torch.flatten(torch.autograd.grad(out, [p], grad_outputs=grad_outputs, retain_graph=True,
+                                           allow_unused=True)[0]) for p in model.parameters()]
+    return torch.cat(g, dim=0).unsqueeze(0)

@@ -33,6 +33,7 @@ extern "C" {
 #define BK_ERR_WORKSPACE (-6) /* workspace too small */
 #define BK_ERR_ARCH (-7)      /* device is not compute capability 10.x */
 
+#define BK_PREC_FP32 0 /* bk_syrk_accum only: full-fp32 SIMT SYRK (parity on ill-conditioned factors) */
 #define BK_PREC_BF16 1
 #define BK_PREC_BF16X3 3
 
@@ -44,6 +45,8 @@ extern "C" {
 #define BK_GEMM_RELU 16
 
 const char* bk_version(void);
+/* Total number of kernels this library has launched in this process (monotonic counter). */
+unsigned long long bk_launch_count(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), else BK_ERR_ARCH. */
 int bk_device_check(void);
 
@@ -85,7 +88,7 @@ int bk_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_
  * d + has_bias > BK_SMALL_D_MAX uses the tcgen05 SYRK and needs a workspace; smaller factors use the
  * SIMT split-K kernel and need none.
  */
-#define BK_SMALL_D_MAX 160
+#define BK_SMALL_D_MAX 176
 size_t bk_syrk_workspace_bytes(int n, int d, int has_bias, int precision);
 int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
                   int has_bias, float in_scale, float alpha, float beta, int precision,

@@ -1,0 +1,392 @@
+"""GPU parity tests: the CUDA path (through the public Python API -> C ABI -> sm_100a kernels)
+against (a) the committed outputs of the reference itself and (b) the CPU oracle on identical seeded
+inputs.  Tolerances are BASELINE.json's: factors 1e-3 relative Frobenius, inverses 1e-3, predictive
+mean / variance 1e-3 under shared noise.  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from models_for_tests import MLP, RegNet, load_params
+from oracle import kfac_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from bnn_kfac_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda:0")
+
+
+def _fisher_step(model, x, y):
+    loss = torch.nn.functional.cross_entropy(model(x), y)
+    model.zero_grad()
+    loss.backward()
+
+
+def _gpu_kfac_mlp(golden, dev, precision="bf16x3"):
+    from bnn_kfac_b200.curvatures import KFAC
+    model = load_params(MLP(), golden, "mlp", torch.float32).to(dev)
+    est = KFAC(model, precision=precision)
+    for i in range(2):
+        x = torch.tensor(golden[f"mlp_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"mlp_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        est.update(batch_size=x.shape[0])
+    return model, est
+
+
+def _layers(est):
+    return [l for _, l in est._selected_layers()]
+
+
+def test_mlp_vs_reference_golden(golden, dev):
+    model, est = _gpu_kfac_mlp(golden, dev)
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(_layers(est)):
+        A, G = est.state[layer]
+        assert relerr(A.cpu(), golden[f"mlp64_state_{li}_A"]) < TOL
+        assert relerr(G.cpu(), golden[f"mlp64_state_{li}_G"]) < TOL
+        assert abs(A[-1, -1].item() - 2.0) < 1e-5          # ones row: one per update
+        LA, LG = est.inv_state[layer]
+        assert isinstance(est.state[layer], list) and isinstance(est.inv_state[layer], tuple)
+        assert relerr(LA.cpu(), golden[f"mlp64_inv_{li}_A"]) < TOL
+        assert relerr(LG.cpu(), golden[f"mlp64_inv_{li}_G"]) < TOL
+        assert torch.triu(LA, 1).abs().max().item() == 0.0
+        for s in range(2):
+            z = torch.tensor(golden[f"mlp64_z_{s}_{li}"]).float().to(dev)
+            smp = est.sample(layer, z=z)
+            assert smp.shape == (LG.shape[0], LA.shape[0])
+            assert relerr(smp.cpu(), golden[f"mlp64_sample_{s}_{li}"]) < TOL
+
+
+def test_mlp_bf16_single_pass_within_factor_tolerance(golden, dev):
+    """Throughput mode (one bf16 pass): factors must still meet the 1e-3 factor tolerance on
+    ReLU/image-like (non-negative) activations."""
+    model, est = _gpu_kfac_mlp(golden, dev, precision="bf16")
+    for li, layer in enumerate(_layers(est)):
+        A, G = est.state[layer]
+        assert relerr(A.cpu(), golden[f"mlp64_state_{li}_A"]) < TOL
+
+
+def test_mlp_per_layer_damping_lists(golden, dev):
+    model, est = _gpu_kfac_mlp(golden, dev)
+    est.invert([1.0, 0.5], [200.0, 100.0])
+    for li, layer in enumerate(_layers(est)):
+        assert relerr(est.inv_state[layer][0].cpu(), golden[f"mlp64_listinv_{li}_A"]) < TOL
+        assert relerr(est.inv_state[layer][1].cpu(), golden[f"mlp64_listinv_{li}_G"]) < TOL
+
+
+def test_mlp_mc_predictive_vs_reference_golden(golden, dev):
+    """Shared-noise MC predictive: the batched path consumes the reference's recorded z."""
+    from bnn_kfac_b200.predictive import Op, mc_predict
+    model, est = _gpu_kfac_mlp(golden, dev)
+    est.invert(0.04, 200.0)
+    noise = [torch.stack([torch.tensor(golden[f"mlp64_sar_z_{s}_{li}"]).float() for s in range(3)]).to(dev)
+             for li in range(2)]
+    prog = [Op("linear", model.fc1, True), Op("linear", model.fc2, False)]
+    xt = torch.tensor(golden["mlp_xtest"]).float().to(dev)
+    mean = mc_predict(est, xt, 3, program=prog, noise=noise)
+    assert relerr(mean.cpu(), golden["mlp64_mc_mean"]) < TOL
+    # and the reference's own sequential API: sample() + _replace reproduce the perturbed weights
+    for s in range(3):
+        model.load_state_dict(est.model_state)
+        for li, layer in enumerate(_layers(est)):
+            est._replace(est.sample(layer, z=noise[li][s]), layer.weight, layer.bias)
+            assert relerr(layer.weight.data.cpu(), golden[f"mlp64_sar_w_{s}_{li}"]) < TOL
+            assert relerr(layer.bias.data.cpu(), golden[f"mlp64_sar_b_{s}_{li}"]) < TOL
+    model.load_state_dict(est.model_state)
+
+
+def test_diagonal_vs_reference_golden(golden, dev):
+    from bnn_kfac_b200.curvatures import Diagonal
+    from bnn_kfac_b200.predictive import argmax_grad_outputs, linearised_diag, params_jacobian
+    model = load_params(MLP(), golden, "mlp", torch.float32).to(dev)
+    est = Diagonal(model)
+    for i in range(2):
+        x = torch.tensor(golden[f"mlp_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"mlp_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        est.update(batch_size=x.shape[0])
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(_layers(est)):
+        assert relerr(est.state[layer].cpu(), golden[f"diag64_state_{li}"]) < 1e-5
+        assert relerr(est.inv_state[layer].cpu(), golden[f"diag64_inv_{li}"]) < 1e-5
+        z = torch.tensor(golden[f"diag64_z_{li}"]).float().to(dev)
+        assert relerr(est.sample(layer, z=z).cpu(), golden[f"diag64_sample_{li}"]) < 1e-5
+        s1 = est.sample(layer)
+        assert s1.shape == est.inv_state[layer].shape and torch.isfinite(s1).all()
+    xt = torch.tensor(golden["mlp_xtest"]).float().to(dev)
+    pred = torch.softmax(model(xt), dim=1)
+    J = params_jacobian(pred, model, argmax_grad_outputs(pred)).detach()
+    assert relerr(J.cpu(), golden["diag64_lin_J"]) < 1e-4
+    var = linearised_diag(est, J)
+    assert abs(var.item() / float(golden["diag64_lin_var"]) - 1) < TOL
+
+
+def test_conv_vs_reference_golden(golden, dev):
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.predictive import linearised_kfac_classification
+    from bnn_kfac_b200.wrapper import BaseNet_750
+    model = load_params(BaseNet_750(), golden, "cnn", torch.float32).to(dev)
+    est = KFAC(model)
+    for i in range(2):
+        x = torch.tensor(golden[f"cnn_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"cnn_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        est.update(batch_size=x.shape[0])
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(_layers(est)):
+        assert relerr(est.state[layer][0].cpu(), golden[f"cnn64_state_{li}_A"]) < TOL
+        assert relerr(est.state[layer][1].cpu(), golden[f"cnn64_state_{li}_G"]) < TOL
+        assert relerr(est.inv_state[layer][0].cpu(), golden[f"cnn64_inv_{li}_A"]) < TOL
+        assert relerr(est.inv_state[layer][1].cpu(), golden[f"cnn64_inv_{li}_G"]) < TOL
+        z = torch.tensor(golden[f"cnn64_z_0_{li}"]).float().to(dev)
+        assert relerr(est.sample(layer, z=z).cpu(), golden[f"cnn64_sample_0_{li}"]) < TOL
+    xt = torch.tensor(golden["cnn_xtest"]).float().to(dev)
+    pm, pstd, ent = linearised_kfac_classification(est, xt)
+    assert relerr(pm.cpu(), golden["cnn64_lin_pred_mean"]) < 1e-4
+    assert abs(pstd / float(golden["cnn64_lin_pred_std"]) - 1) < TOL
+    assert abs(ent - float(golden["cnn64_lin_entropy"])) < 1e-3
+
+
+def test_regression_linearised_vs_reference_golden(golden, dev):
+    """regression_ll_block.py:120-140.  The factors of this toy problem are conditioned ~1e5-1e6, so
+    fp32 (the reference's and ours) resolves the data-dependent part of the std to cond*eps ~ 5e-2;
+    the test states that tolerance instead of the 1e-3 that applies to well-conditioned factors."""
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.predictive import linearised_kfac_regression
+    model = load_params(RegNet(30), golden, "reg", torch.float32).to(dev)
+    est = KFAC(model)
+    for i, l in enumerate(_layers(est)):
+        est.state[l] = [torch.tensor(golden[f"reg_state_{i}_A"]).to(dev),
+                        torch.tensor(golden[f"reg_state_{i}_G"]).to(dev)]
+    xt = torch.tensor(golden["reg_xtest"]).to(dev)
+    std = linearised_kfac_regression(est, xt, tau=0.01, N=30, sigma=3)
+    np.testing.assert_allclose(std.cpu().numpy() - 3, golden["reg_pred_std"] - 3, rtol=5e-2, atol=1e-3)
+
+
+# ------------------------------------------------------------------ oracle comparisons at config sizes
+def _oracle_vs_gpu(model_ctor, x, dev, add, mult, n_updates=2, seed=0, precision="bf16x3"):
+    from bnn_kfac_b200.curvatures import KFAC
+    torch.manual_seed(seed)
+    cpu_model = model_ctor().double()
+    cpu_model.weight_init_uniform(0.2)
+    gpu_model = model_ctor()
+    gpu_model.load_state_dict({k: v.float() for k, v in cpu_model.state_dict().items()})
+    gpu_model = gpu_model.to(dev)
+    oest = O.OracleKFAC(cpu_model)
+    gest = KFAC(gpu_model, precision=precision)
+    gen = torch.Generator().manual_seed(1234)
+    for u in range(n_updates):
+        xb = x[u]
+        labels = O.fisher_backward(cpu_model, xb.double(), generator=gen)
+        oest.update()
+        _fisher_step(gpu_model, xb.float().to(dev), labels.to(dev))
+        gest.update(batch_size=xb.shape[0])
+    oest.invert(add, mult)
+    gest.invert(add, mult)
+    return cpu_model, gpu_model, oest, gest
+
+
+@pytest.mark.parametrize("damping", [(0.04, 200.0), (1.0, 200.0)])
+def test_cfg1_mlp_784_1024_1024_10_vs_oracle(dev, damping):
+    """BASELINE config 1 (builder-defined MLP): batch 256, U(0,1) images, weights U(-0.2, 0.2)."""
+    from bnn_kfac_b200.predictive import mc_predict
+    from bnn_kfac_b200.wrapper import MLP as WMLP
+    g = torch.Generator().manual_seed(1234)
+    x = [torch.rand(256, 1, 28, 28, generator=g) for _ in range(2)]
+    # The damped first-layer factor of image inputs is conditioned ~2e4 at (0.04, 200): the inverse
+    # amplifies factor differences by that much, so END-TO-END parity of the inverse at 1e-3 needs
+    # fp32-class factors (precision="fp32", the reference's own arithmetic class).  Stage-wise parity
+    # (each stage fed the other side's previous stage) is checked for the default bf16x3 path too.
+    cm, gm, oest, gest = _oracle_vs_gpu(lambda: WMLP([784, 1024, 1024, 10]), x, dev, *damping,
+                                        precision="fp32")
+    for ol, gl in zip(oest.layers, _layers(gest)):
+        assert relerr(gest.state[gl][0].cpu(), oest.state[ol][0]) < TOL
+        assert relerr(gest.state[gl][1].cpu(), oest.state[ol][1]) < TOL
+        assert relerr(gest.inv_state[gl][0].cpu(), oest.inv_state[ol][0]) < TOL
+        assert relerr(gest.inv_state[gl][1].cpu(), oest.inv_state[ol][1]) < TOL
+    _, _, o3, g3 = _oracle_vs_gpu(lambda: WMLP([784, 1024, 1024, 10]), x, dev, *damping)
+    for ol, gl in zip(o3.layers, _layers(g3)):
+        for k in range(2):
+            assert relerr(g3.state[gl][k].cpu(), o3.state[ol][k]) < 1e-5        # factor stage
+            stage = O.kfac_invert_factor(g3.state[gl][k].double().cpu(), *damping)  # inversion stage
+            assert relerr(g3.inv_state[gl][k].cpu(), stage) < TOL
+    # shared-noise MC predictive, 4 samples
+    S = 4
+    zs = [[torch.randn(oest.inv_state[l][0].shape[0], oest.inv_state[l][1].shape[0], generator=g,
+                       dtype=torch.float64) for l in oest.layers] for _ in range(S)]
+    xt = torch.rand(64, 1, 28, 28, generator=g)
+    ref = O.mc_predict_classification(cm, oest, xt.double(), zs)
+    noise = [torch.stack([zs[s][li] for s in range(S)]).float().to(dev) for li in range(len(oest.layers))]
+    got = mc_predict(gest, xt.to(dev), S, noise=noise)
+    assert relerr(got.cpu(), ref) < TOL
+
+
+def test_cfg4_basenet15k_vs_oracle(dev):
+    """Conv KFAC with implicit-im2col factors + batched MC forward through the conv kernels."""
+    from bnn_kfac_b200.predictive import mc_predict
+    from bnn_kfac_b200.wrapper import BaseNet_15k
+    g = torch.Generator().manual_seed(1234)
+    x = [torch.rand(64, 1, 28, 28, generator=g) for _ in range(2)]
+    cm, gm, oest, gest = _oracle_vs_gpu(BaseNet_15k, x, dev, 0.04, 200.0)
+    for ol, gl in zip(oest.layers, _layers(gest)):
+        for k in range(2):
+            assert relerr(gest.state[gl][k].cpu(), oest.state[ol][k]) < TOL
+            assert relerr(gest.inv_state[gl][k].cpu(), oest.inv_state[ol][k]) < TOL
+    S = 5
+    zs = [[torch.randn(oest.inv_state[l][0].shape[0], oest.inv_state[l][1].shape[0], generator=g,
+                       dtype=torch.float64) for l in oest.layers] for _ in range(S)]
+    xt = torch.rand(32, 1, 28, 28, generator=g)
+    ref = O.mc_predict_classification(cm, oest, xt.double(), zs)
+    noise = [torch.stack([zs[s][li] for s in range(S)]).float().to(dev) for li in range(len(oest.layers))]
+    got = mc_predict(gest, xt.to(dev), S, noise=noise)
+    assert relerr(got.cpu(), ref) < TOL
+
+
+def test_lenet5_factor_shapes(dev):
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.wrapper import LeNet5
+    torch.manual_seed(0)
+    model = LeNet5().to(dev)
+    est = KFAC(model)
+    x = torch.rand(16, 1, 28, 28, device=dev)
+    _fisher_step(model, x, torch.randint(0, 10, (16,), device=dev))
+    est.update(16)
+    shapes = [(tuple(v[0].shape), tuple(v[1].shape)) for v in est.state.values()]
+    assert shapes == [((26, 26), (6, 6)), ((151, 151), (16, 16)), ((401, 401), (120, 120)),
+                      ((121, 121), (84, 84)), ((85, 85), (10, 10))]
+    est.invert(0.04, 200.0)
+    for (LA, LG) in est.inv_state.values():
+        assert torch.isfinite(LA).all() and torch.isfinite(LG).all()
+
+
+# ------------------------------------------------------------------ full-size properties (config 5)
+def test_cfg5_wide_factor_properties(dev):
+    """4096-wide layer, batch 4096: size-independent properties at BASELINE.json's full size."""
+    from bnn_kfac_b200.curvatures import KFAC, invert_factors
+    lin = torch.nn.Linear(4096, 4096).to(dev)
+    model = torch.nn.Sequential(lin)
+    est = KFAC(model, precision="bf16")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    # bf16-representable activations (BASELINE config 5): the bf16 pass is then exact on the inputs
+    x = torch.randn(4096, 4096, generator=g).bfloat16().float().to(dev)
+    out = model(x)
+    gout = (torch.randn(4096, 4096, generator=g) / 4096).bfloat16().float().to(dev)
+    out.backward(gout)
+    est.update(4096)
+    A, G = est.state[lin]
+    assert A.shape == (4097, 4097) and G.shape == (4096, 4096)
+    assert abs(A[-1, -1].item() - 1.0) < 1e-6
+    assert (A - A.t()).abs().max().item() == 0.0 and (G - G.t()).abs().max().item() == 0.0
+    xa = torch.cat([x, torch.ones(4096, 1, device=dev)], 1).double()
+    assert relerr(A.cpu(), (xa.t() @ xa / 4096).cpu()) < 1e-5
+    gs = (gout * 4096).double()
+    assert relerr(G.cpu(), (gs.t() @ gs / 4096).cpu()) < 1e-5
+    # linearity of the accumulation: a second identical update doubles the state
+    A1 = A.clone()
+    out = model(x)
+    out.backward(gout)
+    est.update(4096)
+    assert relerr(est.state[lin][0].cpu(), (2 * A1).cpu()) < 1e-6
+    # inversion round trip: L L^T R == I
+    (L,) = invert_factors([A1], [1.0], [200.0])
+    R = (200.0 ** 0.5 * A1.double() + torch.eye(4097, device=dev, dtype=torch.float64))
+    R = (R + R.t()) / 2
+    eye = L.double() @ (L.double().t() @ R)
+    assert relerr(eye.cpu(), torch.eye(4097)) < TOL
+    assert torch.triu(L, 1).abs().max().item() == 0.0
+
+
+def test_sampling_statistics_and_shard_invariance(dev):
+    """Fused-Philox mode: E[vec(S) vec(S)^T] -> R_A^-1 (x) R_G^-1 (checked on marginal variances),
+    and sample s is the same tensor whether drawn in one call or in shards."""
+    from bnn_kfac_b200.curvatures import KFAC
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(12, 7).to(dev)
+    model = torch.nn.Sequential(lin)
+    est = KFAC(model, seed=99)
+    x = torch.rand(64, 12, device=dev)
+    _fisher_step(model, x, torch.randint(0, 7, (64,), device=dev))
+    est.update(64)
+    est.invert(0.5, 10.0)
+    S = 4096
+    allS = est.sample_batch(lin, S, sample0=0)
+    part = torch.cat([est.sample_batch(lin, 1000, sample0=0), est.sample_batch(lin, S - 1000, sample0=1000)])
+    assert torch.equal(allS, part)
+    LA, LG = est.inv_state[lin]
+    var_ref = torch.outer(torch.diag(LG @ LG.t()), torch.diag(LA @ LA.t()))   # [d_out, d_in']
+    var = allS.var(dim=0, unbiased=False)
+    assert relerr(var.cpu(), var_ref.cpu()) < 0.1
+    assert allS.mean(dim=0).abs().max().item() < 5 * var_ref.max().sqrt().item() / S ** 0.5
+
+
+def test_philox_device_matches_oracle(dev):
+    from bnn_kfac_b200.sampling import philox_normal_t
+    z = philox_normal_t(1234, 3, 7, 50, 20, 2, dev).cpu().numpy()     # [2, 20, 50]
+    for s in range(2):
+        ref = O.philox_normal(1234, 3 + s, 7, 1000)
+        np.testing.assert_allclose(z[s].reshape(-1), ref, atol=2e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------ API / edge cases
+def test_api_errors_and_edge_cases(dev):
+    from bnn_kfac_b200.curvatures import KFAC, Diagonal
+    model = MLP().to(dev)
+    with pytest.raises(TypeError):
+        KFAC(model, layer_types=3)
+    with pytest.raises(AssertionError):
+        KFAC(model, layer_types="Conv1d")
+    est = KFAC(model)
+    with pytest.raises(AssertionError):
+        est.invert()
+    with pytest.raises(AssertionError):
+        est.sample(model.fc1)
+    d = Diagonal(model)
+    with pytest.raises(AssertionError):
+        d.invert()
+    # layer_types as str / [] / filter
+    assert KFAC(model, layer_types=[]).layer_types == ['Linear', 'Conv2d', 'MultiheadAttention']
+    only = KFAC(MLP().to(dev), layer_types="Conv2d")
+    assert len(only.record) == 0
+    # batch of one, no-bias layer
+    nb = torch.nn.Sequential(torch.nn.Linear(9, 4, bias=False)).to(dev)
+    e2 = KFAC(nb)
+    x = torch.rand(1, 9, device=dev)
+    _fisher_step(nb, x, torch.tensor([2], device=dev))
+    e2.update(1)
+    assert e2.state[nb[0]][0].shape == (9, 9)
+    assert relerr(e2.state[nb[0]][0].cpu(), (x.t() @ x).cpu()) < 1e-5
+    e2.invert(1.0, 1.0)
+    s = e2.sample(nb[0])
+    assert s.shape == (4, 9)
+    e2.sample_and_replace()
+    # non positive definite factor -> RuntimeError (reference: caught and retried in NumPy)
+    e2.state[nb[0]][0].fill_(0.0)
+    e2.state[nb[0]][0][3, 3] = -1.0
+    with pytest.raises(RuntimeError):
+        e2.invert(0.0, 1.0)
+
+
+def test_save_load_roundtrip(dev, tmp_path):
+    from bnn_kfac_b200.curvatures import KFAC
+    model = MLP().to(dev)
+    est = KFAC(model)
+    x = torch.rand(8, 20, device=dev)
+    _fisher_step(model, x, torch.randint(0, 5, (8,), device=dev))
+    est.update(8)
+    est.invert(0.04, 200.0)
+    fn = str(tmp_path / "kfac.dat")
+    est.save(fn)
+    est2 = KFAC(MLP().to(dev))
+    est2.load(fn)
+    for (k1, v1), (k2, v2) in zip(est.state.items(), est2.state.items()):
+        assert torch.equal(v1[0], v2[0]) and torch.equal(v1[1], v2[1])
+    blob = torch.load(fn, weights_only=False)
+    assert set(blob["state_by_name"].keys()) == {"fc1", "fc2"}
