@@ -175,7 +175,7 @@ def invert_sharded(est, add=0., multiply=1., group=None,
     if mine:
         res = inverter([reduced[i] for i in mine], [adds[i] for i in mine], [mults[i] for i in mine])
         for i, r in zip(mine, res):
-            outs[i] = r
+            outs[i] = r.contiguous()    # collectives ship the storage: it must be dense row-major
     for i, f in enumerate(factors):
         if outs[i] is None:
             outs[i] = torch.empty_like(f)
@@ -216,11 +216,14 @@ def gather_rows(local: Tensor, n_rows: int, group=None) -> Tensor:
     w = world_size(group)
     if w == 1:
         return local
-    sizes = [row_slice(n_rows, w, r) for r in range(w)]
-    parts = [torch.empty((b - a,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-             for a, b in sizes]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts, dim=0)
+    sizes = [b - a for a, b in (row_slice(n_rows, w, r) for r in range(w))]
+    # equal-sized all-gather (every backend supports it): pad the local block to the largest shard
+    pad = max(sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]].copy_(local)
+    parts = [torch.empty_like(buf) for _ in range(w)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
 
 
 # ---------------------------------------------------------------------------------- diagonal

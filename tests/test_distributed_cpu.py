@@ -1,0 +1,147 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic in bnn_kfac_b200/distributed.py:
+ownership plan, deferred factor reduction, reduce-to-owner / broadcast choreography of the sharded
+inversion, sample sharding of the MC predictive, row gather, mean-gradient all-reduce.
+The arithmetic between the collectives is injected (oracle functions stand in for the CUDA library),
+so these tests check exactly what a second GPU adds: who owns what, and what is exchanged when."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from bnn_kfac_b200 import distributed as D  # noqa: E402
+
+
+def test_plan_owners_balances_cubic_cost():
+    dims = [4097, 4096, 4097, 4096, 4097, 4096, 4097, 10]
+    for world in (1, 2, 4, 8):
+        owners = D.plan_owners(dims, world)
+        assert len(owners) == len(dims) and all(0 <= o < world for o in owners)
+        load = [sum(d ** 3 for d, o in zip(dims, owners) if o == r) for r in range(world)]
+        assert max(load) <= sum(load) / world + max(dims) ** 3     # LPT bound
+    assert D.plan_owners([5, 3], 4) == [0, 1]
+    assert D.plan_owners([], 2) == []
+
+
+def test_sample_slice_partitions_exactly():
+    for n, w in [(100, 8), (30, 4), (7, 2), (8, 8), (5, 1)]:
+        got = [D.sample_slice(n, w, r) for r in range(w)]
+        assert got[0][0] == 0 and got[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+        sizes = [b - a for a, b in got]
+        assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeEst:
+    """The attributes distributed.py touches on an estimator."""
+
+    def __init__(self, state):
+        self.state = state
+        self.inv_state = {}
+        self.invalidated = 0
+
+    def _invalidate_caches(self):
+        self.invalidated += 1
+
+
+def _spd(d, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(3 * d, d, generator=g, dtype=torch.float64)
+    return x.t() @ x / (3 * d)
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import kfac_oracle as O
+        dims = [(6, 4), (9, 5), (3, 2)]
+        layers = [torch.nn.Linear(a - 1, b) for a, b in dims]
+        # per-rank partial factors (what each rank's batch shard produced)
+        part = {l: [_spd(a, 10 * i + rank), _spd(b, 100 + 10 * i + rank)] for i, (l, (a, b)) in enumerate(zip(layers, dims))}
+        full = {l: [sum(_spd(a, 10 * i + r) for r in range(world)) / world,
+                    sum(_spd(b, 100 + 10 * i + r) for r in range(world)) / world]
+                for i, (l, (a, b)) in enumerate(zip(layers, dims))}
+
+        # 1) deferred all-reduce of the state == mean over ranks
+        est = _FakeEst({l: [t.clone() for t in v] for l, v in part.items()})
+        D.allreduce_state(est)
+        for l in layers:
+            for k in range(2):
+                assert torch.allclose(est.state[l][k], full[l][k], atol=1e-12)
+
+        # 2) sharded inversion: reduce to owners, invert owned, broadcast
+        calls = []
+
+        def inverter(fs, adds, mults):
+            calls.append([f.shape[0] for f in fs])
+            return [O.kfac_invert_factor(f, a, m) for f, a, m in zip(fs, adds, mults)]
+
+        est = _FakeEst({l: [t.clone() for t in v] for l, v in part.items()})
+        D.invert_sharded(est, [0.5, 1.0, 2.0], [10.0, 20.0, 30.0], inverter=inverter)
+        adds, mults = [0.5, 1.0, 2.0], [10.0, 20.0, 30.0]
+        for i, l in enumerate(layers):
+            for k in range(2):
+                ref = O.kfac_invert_factor(full[l][k], adds[i], mults[i])
+                assert torch.allclose(est.inv_state[l][k], ref, atol=1e-10), (rank, i, k)
+                # the local partial accumulator is untouched (update() can continue)
+                assert torch.equal(est.state[l][k], part[l][k])
+            assert isinstance(est.inv_state[l], tuple)
+        owners = D.plan_owners([d for ab in dims for d in ab], world)
+        mine = sorted(d for d, o in zip([d for ab in dims for d in ab], owners) if o == rank)
+        assert sorted(sum(calls, [])) == mine            # each rank inverted exactly what it owns
+        assert est.invalidated == 1
+
+        # 3) MC predictive: samples sharded, result independent of the world size
+        def moments_fn(est_, x, n, sample0=0, mode="classification", program=None):
+            ids = torch.arange(sample0, sample0 + n, dtype=torch.float64)
+            p = torch.softmax(x.double() * (1 + ids.view(-1, 1, 1) / 10), dim=-1)   # sample id -> value
+            return p.mean(0), (p * p).mean(0)
+
+        x = torch.linspace(-1, 1, 12).view(4, 3)
+        S = 7
+        got = D.mc_predict_sharded(None, x, S, group=None, moments_fn=moments_fn)
+        ref = moments_fn(None, x, S)[0]
+        assert torch.allclose(got, ref, atol=1e-12)
+        mean, std = D.mc_predict_sharded(None, x[:, :1], S, mode="regression", moments_fn=(
+            lambda e, xx, n, sample0=0, mode="regression", program=None: (
+                (xx.double() * torch.arange(sample0, sample0 + n, dtype=torch.float64).view(-1, 1, 1)).mean(0),
+                ((xx.double() * torch.arange(sample0, sample0 + n, dtype=torch.float64).view(-1, 1, 1)) ** 2).mean(0))))
+        vals = x[:, :1].double() * torch.arange(S, dtype=torch.float64).view(-1, 1, 1)
+        assert torch.allclose(mean, vals.mean(0).squeeze(1), atol=1e-12)
+        assert torch.allclose(std, vals.std(0, unbiased=False).squeeze(1), atol=1e-9)
+        with pytest.raises(ValueError):
+            D.mc_predict_sharded(None, x, 1, moments_fn=moments_fn)
+
+        # 4) row gather of sharded linearised-predictive results
+        n_rows = 5
+        a, b = D.row_slice(n_rows, world, rank)
+        local = torch.arange(a, b, dtype=torch.float32) * 2
+        assert torch.equal(D.gather_rows(local, n_rows), torch.arange(n_rows, dtype=torch.float32) * 2)
+
+        # 5) Diagonal: mean gradient all-reduced before squaring
+        m = torch.nn.Linear(3, 2)
+        for p in m.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))
+        D.allreduce_mean_grads(m)
+        for p in m.parameters():
+            assert torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2))
+        Path(tmp, f"ok{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
