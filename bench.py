@@ -272,20 +272,23 @@ def main():
     value = total_samples / (ms_dev * 1e-3)
     e2e_value = total_samples / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (tcgen05 SYRK), timed alone on its own launches
+    # ---- roofline of the dominant kernel (tcgen05 SYRK on the d x d block; the bias row / column of
+    # the first factor is produced from column sums by the staging kernel), timed on its own launches
+    # with the same operand shapes and state pitch as the step uses
     peaks = load_peaks()
     prec = {"bf16": 1, "bf16x3": 3, "fp32": 1}[args.precision]
     n, d = BATCH, WIDTHS[0]
     ldt = n
-    hi = torch.empty(d + 1, ldt, dtype=torch.bfloat16, device=dev)
+    hi = torch.empty(d, ldt, dtype=torch.bfloat16, device=dev)
     lo = torch.empty_like(hi)
-    L.bk_transpose_split(resident[0][0].data_ptr(), d, n, d, 1.0, 1, hi.data_ptr(), lo.data_ptr(), ldt,
+    L.bk_transpose_split(resident[0][0].data_ptr(), d, n, d, 1.0, 0, hi.data_ptr(), lo.data_ptr(), ldt,
                          _lib.stream_ptr())
-    scratch = torch.zeros(d + 1, d + 1, device=dev)
+    ld_state = est.state[layers[0]][0].stride(0)
+    scratch = torch.zeros(d + 1, ld_state, device=dev)
     reps = 20
 
     def syrk():
-        L.bk_syrk_accum_staged(scratch.data_ptr(), d + 1, hi.data_ptr(), lo.data_ptr(), ldt, n, d + 1,
+        L.bk_syrk_accum_staged(scratch.data_ptr(), ld_state, hi.data_ptr(), lo.data_ptr(), ldt, n, d,
                                1.0 / n, 1.0, prec, _lib.stream_ptr())
     for _ in range(3):
         syrk()
@@ -297,9 +300,10 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     syrk_ms = e0.elapsed_time(e1) / reps
-    syrk_flops = (d + 1) * (d + 2) * n          # one multiply-add per lower-triangle entry per sample
+    syrk_flops = d * (d + 1) * n          # one multiply-add per lower-triangle entry per sample
     achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "umma_gemm_kernel (SYRK 4097x4097x4096, lower+mirror)",
+    roofline = {"bound": "tensor",
+                "kernel": "umma_gemm_kernel<cta_group 2, TMA-reduce epilogue> (SYRK 4096x4096x4096, lower+mirror)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)",
                 "us_per_launch": syrk_ms * 1e3, "traffic": None}

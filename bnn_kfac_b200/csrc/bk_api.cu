@@ -37,6 +37,8 @@ int bk_device_check(void) {
   return major == 10 ? BK_OK : BK_ERR_ARCH;
 }
 
+void bk_set_cta_group(int cta_group) { bk::set_umma_cta_group(cta_group); }
+
 int bk_gemm_nt(const void* a_hi, const void* a_lo, long long lda, long long stride_a,
                const void* b_hi, const void* b_lo, long long ldb, long long stride_b, int m, int n,
                int k, int batch, int precision, int flags, float alpha, float beta, float* c,
@@ -99,11 +101,15 @@ int bk_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_
 }
 
 // ------------------------------------------------------------------------------ factor update
+// Workspace layout of the tensor-core path: [X^T hi : d x ldt bf16][X^T lo (bf16x3 only)][colsum : d fp32]
+// The bias row of ones is NOT staged: the SYRK runs on the d x d block and row / column d of the
+// factor come from exact fp32 column sums (one extra 256-row tile row of the SYRK saved at d = 4096).
 size_t bk_syrk_workspace_bytes(int n, int d, int has_bias, int precision) {
   const int dp = d + (has_bias ? 1 : 0);
   if (dp <= BK_SMALL_D_MAX || precision == BK_PREC_FP32) return 0;
   const size_t one = align_up(static_cast<size_t>(dp) * round8(n) * 2, 256);
-  return precision == BK_PREC_BF16X3 ? 2 * one : one;
+  const size_t sums = has_bias ? align_up(static_cast<size_t>(d) * 4, 256) : 0;
+  return (precision == BK_PREC_BF16X3 ? 2 * one : one) + sums;
 }
 
 int bk_syrk_accum_staged(float* state, long long ld_state, const void* xt_hi, const void* xt_lo,
@@ -147,14 +153,35 @@ int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ld
       (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return BK_ERR_WORKSPACE;
   const long long ldt = round8(n);
-  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(workspace);
-  __nv_bfloat16* lo = precision == BK_PREC_BF16X3
-                          ? reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(workspace) + need / 2)
-                          : nullptr;
-  int rc = bk::launch_transpose_split(x, ldx, n, d, in_scale, has_bias, hi, lo, ldt,
-                                      as_stream(stream));
+  const size_t one = align_up(static_cast<size_t>(dp) * ldt * 2, 256);
+  char* base = static_cast<char*>(workspace);
+  if (has_bias && ((ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0)) {
+    // unaligned rows: generic staging kernel with an explicit row of ones, SYRK on d + 1 rows
+    __nv_bfloat16* hi1 = reinterpret_cast<__nv_bfloat16*>(base);
+    __nv_bfloat16* lo1 =
+        precision == BK_PREC_BF16X3 ? reinterpret_cast<__nv_bfloat16*>(base + one) : nullptr;
+    int rc1 = bk::launch_transpose_split(x, ldx, n, d, in_scale, 1, hi1, lo1, ldt, as_stream(stream));
+    if (rc1) return rc1;
+    return bk_syrk_accum_staged(state, ld_state, hi1, lo1, ldt, n, dp, alpha, beta, precision,
+                                stream);
+  }
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* lo =
+      precision == BK_PREC_BF16X3 ? reinterpret_cast<__nv_bfloat16*>(base + one) : nullptr;
+  float* colsum = has_bias
+                      ? reinterpret_cast<float*>(base + (precision == BK_PREC_BF16X3 ? 2 : 1) * one)
+                      : nullptr;
+  cudaStream_t st = as_stream(stream);
+  if (colsum != nullptr &&
+      cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, st) != cudaSuccess)
+    return BK_ERR_CUDA;
+  int rc = bk::launch_transpose_split(x, ldx, n, d, in_scale, 0, hi, lo, ldt, st, colsum);
   if (rc) return rc;
-  return bk_syrk_accum_staged(state, ld_state, hi, lo, ldt, n, dp, alpha, beta, precision, stream);
+  rc = bk_syrk_accum_staged(state, ld_state, hi, lo, ldt, n, d, alpha, beta, precision, stream);
+  if (rc) return rc;
+  if (has_bias)
+    rc = bk::launch_bias_border(state, ld_state, d, colsum, alpha, beta, static_cast<float>(n), st);
+  return rc;
 }
 
 int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int c, int h, int w,

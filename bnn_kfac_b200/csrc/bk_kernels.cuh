@@ -9,9 +9,13 @@
 namespace bk {
 
 // ---- bk_prep.cu
+// colsum (optional, fp32 [cols], pre-zeroed): receives sum_n scale * X[n, j] (bias row of A).
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
-                           cudaStream_t stream);
+                           cudaStream_t stream, float* colsum = nullptr);
+// Row / column d of a bias-augmented factor from the column sums (see bk_prep.cu).
+int launch_bias_border(float* state, long long ld, int d, const float* colsum, float alpha,
+                       float beta, float n, cudaStream_t stream);
 int launch_convert_split(const float* X, long long ldx, int rows, int cols, float scale,
                          int lower_only, __nv_bfloat16* Ohi, __nv_bfloat16* Olo, long long ldo,
                          cudaStream_t stream);

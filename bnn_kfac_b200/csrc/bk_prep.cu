@@ -52,6 +52,100 @@ __global__ void transpose_split_kernel(const float* __restrict__ X, long long ld
   }
 }
 
+// Fast path (ldx % 4 == 0, 16 B aligned rows): 64 samples x 64 features per CTA, float4 loads,
+// bf16x2 stores (one full 128 B line per warp instruction), optional per-feature column sums
+// (sum_n scale * x[n, j], exact fp32) for the bias row of the first Kronecker factor: the caller then
+// runs the SYRK on the d x d block only and fills row/column d from these sums
+// (models/curvatures.py:346-349 without materialising the row of ones).
+__global__ void __launch_bounds__(256)
+transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
+                         __nv_bfloat16* __restrict__ Thi, __nv_bfloat16* __restrict__ Tlo,
+                         long long ldt, float* __restrict__ colsum) {
+  __shared__ float tile[64][65];  // [sample][feature]
+  const int c0 = blockIdx.x * 64;
+  const int r0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  {
+    const int f4 = (tid & 15) * 4;  // feature offset of this thread's float4
+    const int sr = tid >> 4;        // 16 sample rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int s = sr + 16 * pass;
+      const int r = r0 + s, c = c0 + f4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        const float* src = X + static_cast<long long>(r) * ldx + c;
+        if (c + 3 < cols) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          if (c < cols) v.x = src[0];
+          if (c + 1 < cols) v.y = src[1];
+          if (c + 2 < cols) v.z = src[2];
+        }
+      }
+      tile[s][f4 + 0] = v.x * scale;
+      tile[s][f4 + 1] = v.y * scale;
+      tile[s][f4 + 2] = v.z * scale;
+      tile[s][f4 + 3] = v.w * scale;
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int oc = r0 + 2 * lane;  // sample pair written by this lane
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const int f = warp + 8 * pass;
+    const int orow = c0 + f;
+    if (orow >= cols) continue;
+    const float a = tile[2 * lane][f], b = tile[2 * lane + 1][f];
+    __nv_bfloat16 ah, al, bh, bl;
+    split_bf16(a, ah, al);
+    split_bf16(b, bh, bl);
+    __nv_bfloat16* dh = Thi + static_cast<long long>(orow) * ldt + oc;
+    if (oc + 1 < rows) {
+      *reinterpret_cast<__nv_bfloat162*>(dh) = __halves2bfloat162(ah, bh);
+      if (Tlo != nullptr)
+        *reinterpret_cast<__nv_bfloat162*>(Tlo + static_cast<long long>(orow) * ldt + oc) =
+            __halves2bfloat162(al, bl);
+    } else if (oc < rows) {
+      dh[0] = ah;
+      if (Tlo != nullptr) Tlo[static_cast<long long>(orow) * ldt + oc] = al;
+    }
+  }
+  if (colsum != nullptr && tid < 64 && c0 + tid < cols) {
+    float sacc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) sacc += tile[k][tid];  // rows beyond `rows` hold zeros
+    atomicAdd(&colsum[c0 + tid], sacc);
+  }
+}
+
+__global__ void fill_ones_row_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                     int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    hi[i] = __float2bfloat16_rn(1.f);
+    if (lo != nullptr) lo[i] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// state[d][j] = state[j][d] = beta*old + alpha*colsum[j];  state[d][d] = beta*old + alpha*n.
+__global__ void bias_border_kernel(float* __restrict__ state, long long ld, int d,
+                                   const float* __restrict__ colsum, float alpha, float beta,
+                                   float n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < d) {
+    float* row = state + static_cast<long long>(d) * ld + j;
+    float* col = state + static_cast<long long>(j) * ld + d;
+    const float v = (beta == 0.f ? 0.f : beta * *row) + alpha * colsum[j];
+    *row = v;
+    *col = v;
+  } else if (j == d) {
+    float* c = state + static_cast<long long>(d) * ld + d;
+    *c = (beta == 0.f ? 0.f : beta * *c) + alpha * n;
+  }
+}
+
 __global__ void convert_split_kernel(const float* __restrict__ X, long long ldx, int rows, int cols,
                                      float scale, int lower_only, __nv_bfloat16* __restrict__ Ohi,
                                      __nv_bfloat16* __restrict__ Olo, long long ldo) {
@@ -70,11 +164,35 @@ __global__ void convert_split_kernel(const float* __restrict__ X, long long ldx,
 
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, float* colsum) {
   if (rows <= 0 || cols <= 0) return 0;
+  const bool fast = (ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (ldt % 2 == 0) &&
+                    (reinterpret_cast<uintptr_t>(Thi) % 4 == 0) &&
+                    (Tlo == nullptr || reinterpret_cast<uintptr_t>(Tlo) % 4 == 0);
+  if (colsum != nullptr && !fast) return -2;  // callers only request sums on the aligned path
+  if (fast) {
+    dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+    transpose_split64_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo, ldt,
+                                                       colsum);
+    note_launch();
+    if (ones_row) {  // generic operand with an explicit row of ones (bk_transpose_split ABI)
+      fill_ones_row_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
+          Thi + static_cast<long long>(cols) * ldt,
+          Tlo != nullptr ? Tlo + static_cast<long long>(cols) * ldt : nullptr, rows);
+      note_launch();
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+  }
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_split_kernel<<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, ones_row, Thi, Tlo,
                                                      ldt);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_bias_border(float* state, long long ld, int d, const float* colsum, float alpha,
+                       float beta, float n, cudaStream_t stream) {
+  bias_border_kernel<<<(d + 1 + 255) / 256, 256, 0, stream>>>(state, ld, d, colsum, alpha, beta, n);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

@@ -2,14 +2,24 @@
 //
 //   D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]
 //
-// Roles (256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
-//   warp 0   TMA producer   : cp.async.bulk.tensor (128B swizzle) A 128x64 + B 256x64 per stage
-//   warp 1   MMA issuer     : one elected lane issues 4 x tcgen05.mma (128x256x16) per stage
-//   warp 2   TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double buffered)
+// Two instantiations of one kernel (template parameter CG = tcgen05 cta_group):
+//   CG = 1  one CTA per SM, 128 x 256 output tile, 4-stage ring of (A 128x64 + B 256x64) bf16.
+//           Shared memory carries 48 KB in + 48 KB out per k-block = 192 B/cycle at the tensor-core
+//           floor against 128 B/cycle available, so this variant tops out near 0.6 of the floor; it
+//           serves the small / skinny problems.
+//   CG = 2  CTA PAIR (cluster of 2 on one TPC), 256 x 256 output tile: each CTA stages its own 128
+//           rows of A and only HALF of the B rows (32 KB per stage, 6-stage ring), the leader CTA
+//           issues tcgen05.mma.cta_group::2 (M = 256) and releases both CTAs' ring slots with a
+//           multicast commit; each CTA's epilogue drains its own 128 accumulator rows.  Halves the
+//           shared-memory and L2 traffic per flop: this is the throughput path for wide layers.
+// Roles (256 threads per CTA, persistent, static round-robin tile schedule over clusters):
+//   warp 0   TMA producer   : cp.async.bulk.tensor (128B swizzle) into the stage ring
+//   warp 1   MMA issuer     : one elected lane issues 4 x tcgen05.mma (M x 256 x 16) per stage
+//   warp 2   TMEM allocator : 512 columns = two M x 256 fp32 accumulators (double buffered)
 //   warps 4-7 epilogue      : tcgen05.ld -> smem transpose -> coalesced fused epilogue
 //                             (alpha/beta/bias/relu, fp32 and/or split-bf16 outputs,
 //                              SYRK lower-triangle masking + mirrored write)
-// Pipelines: smem full/empty ring (4 stages), TMEM full/empty (2 stages).
+// Pipelines: smem full/empty ring, TMEM full/empty (2 stages).
 //
 // Reference semantics served by this core (all /root/reference paths relative to the repo root):
 //   models/curvatures.py:349,356  first/second Kronecker factor  (SYRK mode, `state +=`)
@@ -24,26 +34,34 @@ namespace bk {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;  // accumulator rows per CTA (TMEM lanes)
 constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UK = 16;  // K per tcgen05.mma for 16-bit inputs
-constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr uint32_t kBytesA = BM * BK * 2;  // 16 KiB
-constexpr uint32_t kBytesB = BN * BK * 2;  // 32 KiB
-constexpr uint32_t kStageBytes = kBytesA + kBytesB;
-constexpr uint32_t kEpiStageBytes = 32 * 33 * 4;  // per epilogue warp: 32x32 fp32, padded
-constexpr uint32_t kSmemBytes =
-    kStages * kStageBytes + 4 * kEpiStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+// per epilogue warp: two 32x32 fp32 tiles (direct + mirrored) in 128B-swizzled TMA layout, 1024 B
+// aligned; the register-path epilogue uses the first 32x33 floats of it as a padded transpose buffer
+constexpr uint32_t kEpiStageBytes = 2 * 32 * 32 * 4;
 constexpr uint32_t kTmemCols = kAccStages * BN;  // 512
+
+template <int CG>
+struct Cfg {
+  static constexpr int kTileM = BM * CG;                      // output rows per cluster tile
+  static constexpr int kRowsB = BN / CG;                      // B rows staged by each CTA
+  static constexpr uint32_t kBytesB = kRowsB * BK * 2;        // 32 / 16 KiB
+  static constexpr uint32_t kStageBytes = kBytesA + kBytesB;  // 48 / 32 KiB
+  static constexpr int kStages = CG == 1 ? 4 : 6;
+  static constexpr uint32_t kSmemBytes =
+      kStages * kStageBytes + 4 * kEpiStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+};
 
 struct KParams {
   int M, N, K, batch, nparts, flags;
   int tiles_m, tiles_n, tiles_per_batch, num_tiles;
-  int a_bmul, b_bmul;
+  int a_bmul, b_bmul, c_bmul;
   float alpha, beta;
   float* C;
   long long ldc, strideC;
@@ -54,8 +72,8 @@ struct KParams {
   long long ldo, strideO;
 };
 
-__host__ __device__ inline int syrk_row_tiles(int mi, int tiles_n) {
-  int c = (mi * BM + BM - 1) / BN + 1;
+__host__ __device__ inline int syrk_row_tiles(int mi, int tiles_n, int tile_m) {
+  int c = (mi * tile_m + tile_m - 1) / BN + 1;
   return c < tiles_n ? c : tiles_n;
 }
 
@@ -63,18 +81,20 @@ struct Tile {
   int b, m0, n0, nkb;
 };
 
+template <int CG>
 __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
+  constexpr int kTileM = Cfg<CG>::kTileM;
   Tile r;
   r.b = t / p.tiles_per_batch;
   int rem = t - r.b * p.tiles_per_batch;
   int mi, nj;
   if (p.flags & kSyrkLower) {
     mi = 0;
-    int c = syrk_row_tiles(0, p.tiles_n);
+    int c = syrk_row_tiles(0, p.tiles_n, kTileM);
     while (rem >= c) {
       rem -= c;
       ++mi;
-      c = syrk_row_tiles(mi, p.tiles_n);
+      c = syrk_row_tiles(mi, p.tiles_n, kTileM);
     }
     nj = rem;
   } else {
@@ -84,37 +104,47 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
     if (p.flags & kTriA) mi = p.tiles_m - 1 - mi;
     if (p.flags & kTriB) nj = p.tiles_n - 1 - nj;
   }
-  r.m0 = mi * BM;
+  r.m0 = mi * kTileM;
   r.n0 = nj * BN;
   int kend = p.K;
-  if (p.flags & kTriA) kend = min(kend, r.m0 + BM);
+  if (p.flags & kTriA) kend = min(kend, r.m0 + kTileM);
   if (p.flags & kTriB) kend = min(kend, r.n0 + BN);
   r.nkb = (kend + BK - 1) / BK;
   return r;
 }
 
+template <int CG, bool kTmaEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                 const KParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const KParams p) {
+  constexpr int kStages = Cfg<CG>::kStages;
+  constexpr uint32_t kStageBytes = Cfg<CG>::kStageBytes;
+  constexpr int kTileM = Cfg<CG>::kTileM;
+  constexpr int kRowsB = Cfg<CG>::kRowsB;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operand tiles need 1024 B alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_epi = smem + kStages * kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 4 * kEpiStageBytes);
-  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* full_bar = bars;                       // [kStages]   (CG=2: the leader's are used)
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;        // [kAccStages]
-  uint64_t* tempty_bar = tfull_bar + kAccStages;   // [kAccStages]
+  uint64_t* tempty_bar = tfull_bar + kAccStages;   // [kAccStages] (CG=2: the leader's are used)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (leader) issues the MMAs; both CTAs load, and drain their own 128 rows.
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int first_tile = (CG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = (CG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
+    if (kTmaEpi) tma_prefetch_desc(&tmC);
     if (p.nparts > 1) {
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmB1);
@@ -127,13 +157,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], 4 * CG);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == 2) {
+    if (CG == 2) tmem_alloc_2sm(tmem_ptr, kTmemCols);
+    else tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -142,9 +176,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const Tile tl = decode_tile(p, t);
+      for (int t = first_tile; t < p.num_tiles; t += tile_step) {
+        const Tile tl = decode_tile<CG>(p, t);
         const int iters = tl.nkb * p.nparts;
+        // this CTA's slice of the cluster tile: its own 128 rows of A, its share of the B rows
+        const int a_row = tl.m0 + static_cast<int>(cta_rank) * BM;
+        const int b_row = tl.n0 + static_cast<int>(cta_rank) * kRowsB;
         for (int it = 0; it < iters; ++it) {
           const int part = it / tl.nkb;
           const int kb = it - part * tl.nkb;
@@ -152,10 +189,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const CUtensorMap* ma = (part == 2) ? &tmA1 : &tmA0;
           const CUtensorMap* mb = (part == 1) ? &tmB1 : &tmB0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           uint8_t* sa = smem + stage * kStageBytes;
-          tma_load_3d(sa, ma, &full_bar[stage], kb * BK, tl.m0, tl.b * p.a_bmul);
-          tma_load_3d(sa + kBytesA, mb, &full_bar[stage], kb * BK, tl.n0, tl.b * p.b_bmul);
+          if (CG == 2) {
+            // both CTAs' bytes complete on the LEADER's full barrier, which expects 2 stages' worth
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            tma_load_3d_2sm(sa, ma, lbar, kb * BK, a_row, tl.b * p.a_bmul);
+            tma_load_3d_2sm(sa + kBytesA, mb, lbar, kb * BK, b_row, tl.b * p.b_bmul);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_3d(sa, ma, &full_bar[stage], kb * BK, a_row, tl.b * p.a_bmul);
+            tma_load_3d(sa + kBytesA, mb, &full_bar[stage], kb * BK, b_row, tl.b * p.b_bmul);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -165,14 +210,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const Tile tl = decode_tile(p, t);
+      for (int t = first_tile; t < p.num_tiles; t += tile_step) {
+        const Tile tl = decode_tile<CG>(p, t);
         const int iters = tl.nkb * p.nparts;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -186,16 +231,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-            umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                         idesc, (it | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(k * 2),
+                               db + static_cast<uint64_t>(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2),
+                           db + static_cast<uint64_t>(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) umma_commit_2sm(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_2sm(&tfull_bar[acc], 3);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
@@ -212,11 +265,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const bool use_beta = p.beta != 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const Tile tl = decode_tile(p, t);
+    const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
+    for (int t = first_tile; t < p.num_tiles; t += tile_step) {
+      const Tile tl = decode_tile<CG>(p, t);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int r0 = tl.m0 + q * 32;        // first row of this warp's 32-row band
+      // first row of this warp's 32-row band (the peer CTA of a pair holds rows 128..255)
+      const int r0 = tl.m0 + static_cast<int>(cta_rank) * BM + q * 32;
       const int my_row = r0 + lane;         // row held by this thread in TMEM layout
       float* Cb = p.C ? p.C + static_cast<long long>(tl.b) * p.strideC : nullptr;
       const float* biasb = p.bias ? p.bias + static_cast<long long>(tl.b) * p.strideBias : nullptr;
@@ -234,13 +289,56 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(tempty_leader0 + static_cast<uint32_t>(acc) * 8u);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
         }
         // band entirely outside the matrix, or (SYRK) entirely above the diagonal: nothing to do
         if (r0 >= p.M || c0 >= p.N) continue;
         if (syrk && c0 > r0 + 31) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+
+        if (kTmaEpi) {
+          // ---- accumulate through the TMA: C[tile] += alpha*acc as an L2-side reduction.  The warp
+          // never loads C, so nothing here waits on DRAM; out-of-range rows / columns are clipped by
+          // the tensor map.  SYRK: chunks on the diagonal (c0 == r0) are masked to c <= r (direct)
+          // and c < r (mirrored) by writing zeros; chunks below it are stored whole, twice.
+          uint8_t* sd = reinterpret_cast<uint8_t*>(stg);  // direct tile   [32 rows][32 cols]
+          uint8_t* sm = sd + 32 * 32 * 4;                 // mirrored tile [32 cols][32 rows]
+          const bool diag = syrk && c0 == r0;
+          const bool do_mirror = syrk && mirror;
+          if (lane == 0) tma_store_wait_read0();  // previous chunk's stores have drained the buffer
+          __syncwarp();
+          // direct: lane = row, eight 16 B chunks per row at swizzled position (chunk ^ (row & 7))
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 o;
+            o.x = (!diag || c4 * 4 + 0 <= lane) ? v[c4 * 4 + 0] : 0.f;
+            o.y = (!diag || c4 * 4 + 1 <= lane) ? v[c4 * 4 + 1] : 0.f;
+            o.z = (!diag || c4 * 4 + 2 <= lane) ? v[c4 * 4 + 2] : 0.f;
+            o.w = (!diag || c4 * 4 + 3 <= lane) ? v[c4 * 4 + 3] : 0.f;
+            *reinterpret_cast<float4*>(sd + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = o;
+          }
+          if (do_mirror) {
+            // mirrored: tile row j = original column, element (j, lane); lanes -> consecutive floats
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float o = (!diag || j < lane) ? v[j] : 0.f;
+              *reinterpret_cast<float*>(sm + j * 128 + ((((lane >> 2) ^ (j & 7)) << 4) |
+                                                        ((lane & 3) << 2))) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_3d(&tmC, sd, c0, r0, tl.b * p.c_bmul);
+            if (do_mirror) tma_reduce_add_3d(&tmC, sm, r0, c0, tl.b * p.c_bmul);
+            tma_store_commit();
+          }
+          continue;
+        }
 
         // mirrored (transposed) write straight from registers: lanes = consecutive columns of
         // the transposed block -> 128 B coalesced per instruction.
@@ -323,11 +421,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   }
 
+  if (kTmaEpi && warp >= kEpiWarp0 && lane == 0) tma_store_wait_read0();  // smem outlives stores
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still be reading its TMEM / receiving commits
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -374,6 +475,28 @@ int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int 
   return r == CUDA_SUCCESS ? 0 : -4;
 }
 
+// fp32 output [batch][rows][cols], row pitch ld elements: 128B-swizzled boxes of 32 x 32.
+int make_output_map(CUtensorMap* map, float* base, int rows, int cols, long long ld,
+                    long long stride, int batch) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -3;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4,
+                           static_cast<cuuint64_t>(batch == 1 ? static_cast<long long>(rows) * ld
+                                                              : stride) *
+                               4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, static_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -4;
+}
+
+// bring-up / A-B timing switch for the TMA-reduce epilogue (1 = allowed)
+int g_allow_tma_epilogue = 1;
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -385,24 +508,19 @@ int sm_count() {
   return n;
 }
 
-}  // namespace
-
-int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
-  if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return 0;
-  if (a.K <= 0) return -2;
-  if (a.A_hi == nullptr || a.B_hi == nullptr) return -2;
-  if (a.nparts != 1 && a.nparts != 3) return -2;
-  if (a.nparts == 3 && (a.A_lo == nullptr || a.B_lo == nullptr)) return -2;
-  if ((a.flags & kSyrkLower) && a.M != a.N) return -2;
-
+// kTmaEpi: epilogue = TMA reduce-add of alpha*acc into C (see tma_epilogue_ok()).
+template <int CG, bool kTmaEpi>
+int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(kSmemBytes));
+    attr_err = cudaFuncSetAttribute(umma_gemm_kernel<CG, kTmaEpi>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(Cfg<CG>::kSmemBytes));
   });
   if (attr_err != cudaSuccess) return -5;
 
+  constexpr int kTileM = Cfg<CG>::kTileM;
   KParams p{};
   p.M = a.M;
   p.N = a.N;
@@ -410,11 +528,11 @@ int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.batch = a.batch;
   p.nparts = a.nparts;
   p.flags = a.flags;
-  p.tiles_m = (a.M + BM - 1) / BM;
+  p.tiles_m = (a.M + kTileM - 1) / kTileM;
   p.tiles_n = (a.N + BN - 1) / BN;
   if (a.flags & kSyrkLower) {
     int tot = 0;
-    for (int mi = 0; mi < p.tiles_m; ++mi) tot += syrk_row_tiles(mi, p.tiles_n);
+    for (int mi = 0; mi < p.tiles_m; ++mi) tot += syrk_row_tiles(mi, p.tiles_n, kTileM);
     p.tiles_per_batch = tot;
   } else {
     p.tiles_per_batch = p.tiles_m * p.tiles_n;
@@ -422,6 +540,7 @@ int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.num_tiles = p.tiles_per_batch * a.batch;
   p.a_bmul = (a.strideA == 0 || a.batch == 1) ? 0 : 1;
   p.b_bmul = (a.strideB == 0 || a.batch == 1) ? 0 : 1;
+  p.c_bmul = (a.batch == 1) ? 0 : 1;
   p.alpha = a.alpha;
   p.beta = a.beta;
   p.C = a.C;
@@ -434,24 +553,86 @@ int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.ldo = a.ldo;
   p.strideO = a.strideO;
 
+  // Each CTA loads boxes of its own 128 A rows and of its share (256 / CG) of the B rows.
   CUtensorMap mA0, mA1, mB0, mB1;
   int rc = make_operand_map(&mA0, a.A_hi, a.M, a.K, a.lda, a.strideA, a.batch, BM);
   if (rc) return rc;
-  rc = make_operand_map(&mB0, a.B_hi, a.N, a.K, a.ldb, a.strideB, a.batch, BN);
+  rc = make_operand_map(&mB0, a.B_hi, a.N, a.K, a.ldb, a.strideB, a.batch, Cfg<CG>::kRowsB);
   if (rc) return rc;
   if (a.nparts == 3) {
     rc = make_operand_map(&mA1, a.A_lo, a.M, a.K, a.lda, a.strideA, a.batch, BM);
     if (rc) return rc;
-    rc = make_operand_map(&mB1, a.B_lo, a.N, a.K, a.ldb, a.strideB, a.batch, BN);
+    rc = make_operand_map(&mB1, a.B_lo, a.N, a.K, a.ldb, a.strideB, a.batch, Cfg<CG>::kRowsB);
     if (rc) return rc;
   } else {
     mA1 = mA0;
     mB1 = mB0;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  umma_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mA0, mA1, mB0, mB1, p);
+  // beta == 0 with the accumulating epilogue: zero-fill C first.
+  CUtensorMap mC = mA0;
+  if (kTmaEpi) {
+    rc = make_output_map(&mC, a.C, a.M, a.N, a.ldc, a.strideC, a.batch);
+    if (rc) return rc;
+    if (a.beta == 0.f) {
+      for (int b = 0; b < a.batch; ++b)
+        if (cudaMemset2DAsync(a.C + static_cast<long long>(b) * a.strideC,
+                              static_cast<size_t>(a.ldc) * 4, 0, static_cast<size_t>(a.N) * 4,
+                              static_cast<size_t>(a.M), stream) != cudaSuccess)
+          return -5;
+    }
+  }
+  const int clusters_max = sm_count() / CG;
+  const int clusters = p.num_tiles < clusters_max ? p.num_tiles : clusters_max;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<CG>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<CG, kTmaEpi>, mA0, mA1, mB0, mB1,
+                                             mC, p);
   note_launch();
-  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+  return (err == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -5;
+}
+
+}  // namespace
+
+// cta_group override for bring-up / A-B timing: 0 = automatic, 1 or 2 = forced; +16 disables the
+// TMA-reduce epilogue (register read-modify-write epilogue everywhere).
+static int g_force_cta_group = 0;
+void set_umma_cta_group(int cg) {
+  g_allow_tma_epilogue = (cg & 16) ? 0 : 1;
+  cg &= 15;
+  g_force_cta_group = (cg == 1 || cg == 2) ? cg : 0;
+}
+
+int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return 0;
+  if (a.K <= 0) return -2;
+  if (a.A_hi == nullptr || a.B_hi == nullptr) return -2;
+  if (a.nparts != 1 && a.nparts != 3) return -2;
+  if (a.nparts == 3 && (a.A_lo == nullptr || a.B_lo == nullptr)) return -2;
+  if ((a.flags & kSyrkLower) && a.M != a.N) return -2;
+  // CTA pairs (256-row tiles) pay off once the 256-row quantisation wastes little: at least one
+  // full pair tile of rows and a full 256-column tile.
+  int cg = (a.M >= 192 && a.N >= 129) ? 2 : 1;
+  if (g_force_cta_group) cg = g_force_cta_group;
+  // Accumulating epilogue through the TMA (see the kernel): needs a 16 B aligned, 16 B pitched C,
+  // no fused bias / relu / bf16 outputs, and beta in {0, 1}.
+  const bool tma_epi =
+      g_allow_tma_epilogue && a.C != nullptr && a.bias == nullptr && a.O_hi == nullptr &&
+      !(a.flags & kRelu) && (a.beta == 1.f || a.beta == 0.f) && (a.ldc % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.batch == 1 || (a.strideC % 4) == 0) &&
+      (!(a.flags & kSyrkLower) || (a.flags & kMirror));
+  if (cg == 2)
+    return tma_epi ? launch_cg<2, true>(a, stream) : launch_cg<2, false>(a, stream);
+  return tma_epi ? launch_cg<1, true>(a, stream) : launch_cg<1, false>(a, stream);
 }
 
 }  // namespace bk

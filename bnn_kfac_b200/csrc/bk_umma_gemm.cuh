@@ -46,5 +46,7 @@ struct GemmArgs {
 
 // Returns 0 on success, negative on argument / CUDA error (see include/bk_kfac.h error codes).
 int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream);
+// Tuning / bring-up knob: force the tcgen05 cta_group of the contraction core (1 or 2; 0 = automatic).
+void set_umma_cta_group(int cg);
 
 }  // namespace bk

@@ -50,6 +50,17 @@ def _round8(v: int) -> int:
     return (v + 7) // 8 * 8
 
 
+def _alloc_factor(d: int, device) -> Tensor:
+    """fp32 [d, d] factor.  Wide factors get a row pitch that is a multiple of 4 elements (16 B) so
+    that the accumulating TMA epilogue of the tensor-core SYRK can address them (d' = d_in + 1 is odd
+    for every power-of-two layer width); the returned tensor is then a [d, d] view of a [d, pitch]
+    buffer — same shape and values as the reference's factor, different stride(0)."""
+    if d > _lib.BK_SMALL_D_MAX and d % 4:
+        pitch = (d + 3) // 4 * 4
+        return torch.empty(d, pitch, device=device, dtype=torch.float32)[:, :d]
+    return torch.empty(d, d, device=device, dtype=torch.float32)
+
+
 class _Workspace:
     """Grow-only device scratch buffer (256 B aligned) reused across kernel calls."""
 
@@ -330,8 +341,8 @@ class KFAC(Curvature):
                 first, second = self.state[layer]
                 beta = 1.0
             else:
-                first = torch.empty(d_a, d_a, device=forward.device, dtype=torch.float32)
-                second = torch.empty(d_g, d_g, device=forward.device, dtype=torch.float32)
+                first = _alloc_factor(d_a, forward.device)
+                second = _alloc_factor(d_g, forward.device)
                 self.state[layer] = [first, second]
                 beta = 0.0
             if module_class == 'Conv2d':

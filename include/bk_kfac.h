@@ -50,6 +50,11 @@ unsigned long long bk_launch_count(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), else BK_ERR_ARCH. */
 int bk_device_check(void);
 
+/* Tuning knob (process-wide): force the tcgen05 cta_group of the contraction core.  1 = one CTA per
+ * SM (128 x 256 tiles), 2 = CTA pairs (256 x 256 tiles, tcgen05.mma.cta_group::2), 0 = automatic
+ * (pairs whenever the problem has at least 192 rows and 129 columns).  Results do not depend on it. */
+void bk_set_cta_group(int cta_group);
+
 /* ---------------------------------------------------------------------------------------------
  * Contraction core.  D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]; bf16 (uint16 storage) K-major
  * operands, optional lo parts for BK_PREC_BF16X3; v = alpha*acc + beta*C + bias[n], optional relu;
