@@ -58,6 +58,11 @@ SIGNATURES = {
     "bk_conv2d_relu_pool": (_i, [_p, _ll, _p, _p, _p] + [_i] * 14 + [_p]),
     "bk_predictive_moments": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "bk_frob_dot": (_i, [_p, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
+    "bk_eigh_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
+    "bk_eigh_batched": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
+                             _i, _f, _i, _p, _sz, _p]),
+    "bk_kron": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
+    "bk_dominance": (_i, [_p, _ll, _i, _f, _p, _p, _i, _p, _p]),
     "bk_chol_inv_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
     "bk_damp_chol_inv_batched": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
                                       C.POINTER(_f), C.POINTER(_f), _i, _p, _sz, _p]),

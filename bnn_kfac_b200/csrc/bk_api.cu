@@ -240,6 +240,35 @@ int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* out
                               workspace, workspace_bytes, as_stream(stream));
 }
 
+// ------------------------------------------------------------------------- eigen / dense Fisher
+size_t bk_eigh_workspace_bytes(const int* dims_host, int count) {
+  if (dims_host == nullptr || count <= 0) return 0;
+  return bk::eigh_workspace_bytes(dims_host, count);
+}
+
+int bk_eigh_batched(const float* const* factors_host, const long long* ld_host,
+                    float* const* evals_host, float* const* evecs_host, const int* dims_host,
+                    int count, float sym_scale, int max_sweeps, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (factors_host == nullptr || ld_host == nullptr || evals_host == nullptr || dims_host == nullptr)
+    return BK_ERR_ARG;
+  return bk::eigh_batched(factors_host, ld_host, evals_host, evecs_host, dims_host, count, sym_scale,
+                          max_sweeps, workspace, workspace_bytes, as_stream(stream));
+}
+
+int bk_dominance(const float* h, long long ld, int p, float tau, const int* block_begin,
+                 const int* block_end, int nblocks, double* out3, void* stream) {
+  if (h == nullptr || out3 == nullptr || ld < p) return BK_ERR_ARG;
+  if (nblocks > 0 && (block_begin == nullptr || block_end == nullptr)) return BK_ERR_ARG;
+  return bk::launch_dominance(h, ld, p, tau, block_begin, block_end, nblocks, out3,
+                              as_stream(stream));
+}
+
+int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream) {
+  if (a == nullptr || b == nullptr || out == nullptr) return BK_ERR_ARG;
+  return bk::launch_kron(a, m, n, b, p, q, out, as_stream(stream));
+}
+
 // ----------------------------------------------------------------------- predictive glue
 int bk_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b, int d_out,
                          int d_in, int has_bias, int nsamples, float* w_f32, void* w_hi, void* w_lo,

@@ -57,6 +57,21 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
                      size_t workspace_bytes, cudaStream_t stream);
 
 
+// ---- bk_eigh.cu  (batched one-sided Jacobi eigensolver)
+size_t eigh_workspace_bytes(const int* dims, int count);
+// Returns 0, the 1-based index of the first factor that did not converge, or a negative error.
+// Synchronises `stream` once per sweep when a factor is wider than the shared-memory path.
+int eigh_batched(const float* const* factors, const long long* ldf, float* const* evals,
+                 float* const* evecs, const int* dims, int count, float sym_scale, int max_sweeps,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// ---- bk_dense.cu
+int launch_dominance(const float* H, long long ld, int P, float tau, const int* block_begin,
+                     const int* block_end, int nblocks, double* out3, cudaStream_t stream);
+
+int launch_kron(const float* a, int m, int n, const float* b, int p, int q, float* out,
+                cudaStream_t stream);
+
 // ---- bk_forward.cu
 int launch_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b,
                              int d_out, int d_in, int has_bias, int nsamples, float* w_f32,

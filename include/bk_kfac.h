@@ -143,6 +143,33 @@ int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* out
                              size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Symmetric eigendecomposition, batched over factors (models/utilities.py:144-159 get_eigenvectors:
+ * symeig of F + F^T; :120-141 get_eigenvalues: symeig of F): S = sym_scale * (F + F^T), one-sided
+ * Jacobi with warp-shuffle rotations.  evals[i]: [d] ascending; evecs[i]: [d, d] row-major with the
+ * eigenvectors as COLUMNS (symeig / linalg.eigh layout), may be null (host array or entries).
+ * Returns 0, > 0 = 1-based index of the first factor not converged after max_sweeps (<= 0: 30),
+ * < 0 error.  Host arrays of device pointers / leading dimensions / dims (count <= 64).
+ */
+size_t bk_eigh_workspace_bytes(const int* dims_host, int count);
+int bk_eigh_batched(const float* const* factors_host, const long long* ld_host,
+                    float* const* evals_host, float* const* evecs_host, const int* dims_host,
+                    int count, float sym_scale, int max_sweeps, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense Fisher (hessian/classification_ll_dense_kernel_diag.py:68-91, hessian/utils.py:4-23).
+ * out3 (device, fp64) = { sum |diag(H + tau I)|, sum |H + tau I|, sum over the diagonal blocks
+ * [block_begin[b], block_end[b]) of |H + tau I| }; blocks disjoint and ascending (device int arrays).
+ * H itself is accumulated with bk_syrk_accum on the stacked flat gradients; its damped inverse is
+ * bk_damp_chol_inv_batched(add = tau^2, multiply = 1).
+ */
+int bk_dominance(const float* h, long long ld, int p, float tau, const int* block_begin,
+                 const int* block_end, int nblocks, double* out3, void* stream);
+/* Kronecker product out[m*p, n*q] = a[m, n] (x) b[p, q], all contiguous fp32
+ * (models/utilities.py:387-409, sampling_free/utils.py:279-290). */
+int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Predictive glue (the dense contractions of these stages are bk_gemm_nt calls).
  */
 /* Curvature._replace for a batch of samples (models/curvatures.py:67-82):

@@ -432,3 +432,117 @@ def test_save_load_roundtrip(dev, tmp_path):
         assert torch.equal(v1[0], v2[0]) and torch.equal(v1[1], v2[1])
     blob = torch.load(fn, weights_only=False)
     assert set(blob["state_by_name"].keys()) == {"fc1", "fc2"}
+
+
+# ------------------------------------------------------------------ eigendecomposition (a17)
+def _psd(d, n, g, dev):
+    x = torch.relu(torch.randn(n, d, generator=g))
+    return (x.t() @ x / n).to(dev)
+
+
+def test_eigh_jacobi_vs_linalg(dev):
+    """bk_eigh_batched (one-sided Jacobi) against torch.linalg.eigh in fp64: eigenvalues, the
+    reconstruction V diag(w) V^T and orthogonality - never raw eigenvectors (sign / basis ambiguity).
+    Sizes cover the shared-memory path (<= 164), the streamed path, odd sizes, rank deficiency
+    (n < d) and an indefinite matrix."""
+    from bnn_kfac_b200.utilities import eigh_factors
+    g = torch.Generator().manual_seed(11)
+    mats = [_psd(d, n, g, dev) for d, n in [(1, 4), (5, 64), (30, 64), (126, 512), (161, 64), (165, 400),
+                                           (300, 512), (785, 256)]]
+    ind = torch.randn(97, 97, generator=g).to(dev)
+    mats.append(ind + ind.t())
+    vals, vecs = eigh_factors(mats, sym_scale=0.5)
+    for m, w, v in zip(mats, vals, vecs):
+        d = m.shape[0]
+        S = (0.5 * (m + m.t())).double().cpu()
+        wref = torch.linalg.eigvalsh(S)
+        scale = wref.abs().max().item()
+        assert (w.double().cpu() - wref).abs().max().item() < TOL * scale, d
+        assert torch.all(w[1:] >= w[:-1])
+        vd = v.double().cpu()
+        assert relerr(vd @ torch.diag(w.double().cpu()) @ vd.t(), S) < TOL, d
+        assert relerr(vd.t() @ vd, torch.eye(d, dtype=torch.float64)) < 5e-4, d
+
+
+def test_get_eigenvectors_eigenvalues_kron_api(golden, dev):
+    """models/utilities.py:120-159, 387-409 surface on the factors of the golden MLP."""
+    from bnn_kfac_b200.utilities import get_eigenvalues, get_eigenvectors, kron
+    model, est = _gpu_kfac_mlp(golden, dev)
+    vecs = get_eigenvectors(est.state)
+    flat = get_eigenvalues([est.state[l] for l in _layers(est)])
+    ref_flat = []
+    for layer in _layers(est):
+        A, G = [t.double().cpu() for t in est.state[layer]]
+        wa, va, wg, vg = O.factor_eigenvectors(A, G)
+        UA, UG = [t.double().cpu() for t in vecs[layer]]
+        # same eigenbasis: U diag(w) U^T reconstructs F + F^T with the oracle's eigenvalues
+        assert relerr(UA @ torch.diag(wa) @ UA.t(), A + A.t()) < TOL
+        assert relerr(UG @ torch.diag(wg) @ UG.t(), G + G.t()) < TOL
+        ref_flat.append(O.factor_eigenvalues(A, G))
+    ref_flat = torch.cat(ref_flat)
+    assert flat.shape == ref_flat.shape
+    assert (flat.double().cpu() - ref_flat).abs().max().item() < TOL * ref_flat.abs().max().item()
+    a = torch.tensor([[1., 2.], [3., 4.]], device=dev)
+    b = torch.tensor([[0., 5.], [6., 7.]], device=dev)
+    want = torch.tensor([[0, 5, 0, 10], [6, 7, 12, 14], [0, 15, 0, 20], [18, 21, 24, 28]], dtype=torch.float32)
+    assert torch.equal(kron(a, b).cpu(), want)                    # the reference's doctest vector
+    x, y = torch.randn(7, 3, device=dev), torch.randn(4, 9, device=dev)
+    assert relerr(kron(x, y).cpu(), O.kron(x.cpu(), y.cpu())) < 1e-6
+
+
+# ------------------------------------------------------------------ dense Fisher (a16, config 3)
+def test_cfg3_dense_fisher_basenet15k(dev):
+    """hessian/classification_ll_dense_kernel_diag.py:68-91 on MNIST-shaped synthetic data: flat
+    gradients of BaseNet_15k (P = 15 080) for batch-size-1 steps with labels sampled from the model,
+    H = sum g g^T / n (one SYRK), dominance reductions, damped inverse and |J H^-1 J^T| on the
+    last-layer sub-block (P = 810, where the CPU oracle's pinv is affordable), and the full-size
+    inverse through its residual."""
+    from bnn_kfac_b200 import dense as DN
+    from bnn_kfac_b200.wrapper import BaseNet_15k
+    torch.manual_seed(0)
+    cpu_model = BaseNet_15k().double()
+    cpu_model.weight_init_uniform(0.2)
+    gpu_model = BaseNet_15k()
+    gpu_model.load_state_dict({k: v.float() for k, v in cpu_model.state_dict().items()})
+    gpu_model = gpu_model.to(dev)
+    gen = torch.Generator().manual_seed(1234)
+    n = 48
+    x = torch.rand(n, 1, 28, 28, generator=gen)
+    g_cpu, g_gpu = [], []
+    for b in range(n):
+        labels = O.fisher_backward(cpu_model, x[b:b + 1].double(), generator=gen)
+        g_cpu.append(O.flat_gradient(cpu_model))
+        _fisher_step(gpu_model, x[b:b + 1].to(dev), labels.to(dev))
+        g_gpu.append(DN.flat_gradient(gpu_model))
+    Gc, Gg = torch.stack(g_cpu), torch.stack(g_gpu)
+    assert Gg.shape == (n, 15080)
+    assert relerr(Gg.cpu(), Gc) < 1e-4
+    H = DN.dense_fisher(Gg)
+    Href = O.dense_fisher(Gc)
+    assert H.shape == (15080, 15080)
+    assert relerr(H.cpu(), Href) < TOL
+    # accumulation in two chunks == one shot
+    H2 = DN.dense_fisher(Gg[:20], normalise=n)
+    H2 = DN.dense_fisher(Gg[20:], state=H2, normalise=n)
+    assert relerr(H2.cpu(), Href) < TOL
+    coords = DN.kernel_block_coords_basenet15k()
+    assert coords == O.kernel_block_coords_basenet15k() and coords[-1][1] == 15080
+    dd, db = DN.dominance(H, coords, tau=1e-5)
+    rd, rb = O.dominance(Href, coords, tau=1e-5)
+    assert abs(dd / rd - 1) < TOL and abs(db / rb - 1) < TOL
+    # last-layer block (fc2: 800 weights + 10 biases): damped inverse and predictive variance
+    tau = 0.04
+    Hl = H[-810:, -810:].contiguous()
+    Hl_ref = Href[-810:, -810:]
+    inv = DN.dense_inverse(Hl, tau)
+    inv_ref = O.dense_inverse(Hl_ref, tau)
+    assert relerr(inv.cpu(), inv_ref) < TOL
+    J = torch.randn(16, 810, generator=gen)
+    var = DN.dense_variance(J.to(dev), inv)
+    ref = torch.tensor([O.dense_variance(J[i:i + 1].double(), inv_ref) for i in range(16)])
+    assert relerr(var.cpu(), ref) < TOL
+    # full size: (H + tau I) inv == I through the batched Cholesky path
+    inv_full = DN.dense_inverse(H, tau)
+    R = H.double() + tau * torch.eye(15080, device=dev, dtype=torch.float64)
+    probe = torch.randn(15080, 8, generator=gen, dtype=torch.float64).to(dev)
+    assert relerr((inv_full.double() @ (R @ probe)).cpu(), probe.cpu()) < TOL
