@@ -21,6 +21,13 @@ GEMM_MIRROR = 2
 GEMM_TRI_A = 4
 GEMM_TRI_B = 8
 GEMM_RELU = 16
+GEMM_TRI_B_UPPER = 32
+
+
+def gemm_tri_koff(koff: int) -> int:
+    """Flag bits for BK_GEMM_TRI_KOFF(koff) (include/bk_kfac.h)."""
+    assert koff % 8 == 0
+    return (koff // 8) << 8
 
 _ERRORS = {
     -2: "BK_ERR_ARG (bad argument or alignment)",

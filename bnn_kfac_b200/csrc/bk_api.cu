@@ -59,7 +59,8 @@ int bk_gemm_nt(const void* a_hi, const void* a_lo, long long lda, long long stri
   g.K = k;
   g.batch = batch;
   g.nparts = precision;
-  g.flags = flags;
+  g.flags = flags & 0xFF;
+  g.tri_koff = ((flags >> 8) & 0xFFFFFF) * 8;
   g.alpha = alpha;
   g.beta = beta;
   g.C = c;

@@ -212,40 +212,61 @@ int launch_convert_split(const float* X, long long ldx, int rows, int cols, floa
 
 namespace {
 
-// Element e (row-major index into the [rows, cols] output, int64) belongs to Philox counter
-// (e / 4, sample, stream_id) under key = seed; lane e % 4 of the 4 normals that counter yields.
-__global__ void philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_id,
-                                     int rows, int cols, int nsamples, float* __restrict__ Zf,
-                                     long long ldf, long long stridef,
-                                     __nv_bfloat16* __restrict__ Zhi,
-                                     __nv_bfloat16* __restrict__ Zlo, long long ldz,
-                                     long long stridez) {
-  const long long per = static_cast<long long>(rows) * cols;
-  const long long groups = (per + 3) / 4;
-  const long long total = groups * nsamples;
-  for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < total;
-       g += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int s = static_cast<int>(g / groups);
-    const long long gi = g - static_cast<long long>(s) * groups;
-    uint32_t c[4] = {static_cast<uint32_t>(gi), static_cast<uint32_t>(gi >> 32), sample0 + s,
-                     stream_id};
-    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-    float z[4];
-    box_muller(c[0], c[1], z[0], z[1]);
-    box_muller(c[2], c[3], z[2], z[3]);
+// Matrix element (r, c) of sample s is lane c % 4 of the Philox block with counter
+// (c / 4, r, sample0 + s, stream_id) under key = seed: one thread produces 4 consecutive columns of one
+// row (one Philox call, two Box-Muller pairs) and stores them as one 8-byte bf16x4 (rows are 16 B
+// aligned because ldz % 8 == 0).  No 64-bit index arithmetic, no dependence on the launch geometry.
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_id, int rows,
+                     int cols, int nsamples, float* __restrict__ Zf, long long ldf,
+                     long long stridef, __nv_bfloat16* __restrict__ Zhi,
+                     __nv_bfloat16* __restrict__ Zlo, long long ldz, long long stridez) {
+  const int groups = (cols + 3) >> 2;  // column groups per row
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const bool vec = (Zhi != nullptr) && ((ldz & 3) == 0) && ((stridez & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(Zhi) & 7) == 0) &&
+                   (Zlo == nullptr || (reinterpret_cast<uintptr_t>(Zlo) & 7) == 0);
+  // grid: x -> column groups, y -> rows (grid-stride), z -> samples (grid-stride)
+  for (int s = blockIdx.z; s < nsamples; s += gridDim.z) {
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+      for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        uint32_t c[4] = {static_cast<uint32_t>(g), static_cast<uint32_t>(r), sample0 + s, stream_id};
+        philox4x32_10(c, k0, k1);
+        float z[4];
+        box_muller(c[0], c[1], z[0], z[1]);
+        box_muller(c[2], c[3], z[2], z[3]);
+        const int c0 = g << 2;
+        const int nv = min(4, cols - c0);
+        if (Zf != nullptr) {
+          float* dst = Zf + s * stridef + static_cast<long long>(r) * ldf + c0;
+          for (int j = 0; j < nv; ++j) dst[j] = z[j];
+        }
+        if (Zhi != nullptr) {
+          __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const long long e = gi * 4 + j;
-      if (e >= per) break;
-      const int r = static_cast<int>(e / cols);
-      const int cc = static_cast<int>(e - static_cast<long long>(r) * cols);
-      if (Zf != nullptr) Zf[s * stridef + static_cast<long long>(r) * ldf + cc] = z[j];
-      if (Zhi != nullptr) {
-        __nv_bfloat16 h, l;
-        split_bf16(z[j], h, l);
-        const long long o = s * stridez + static_cast<long long>(r) * ldz + cc;
-        Zhi[o] = h;
-        if (Zlo != nullptr) Zlo[o] = l;
+          for (int j = 0; j < 4; ++j) split_bf16(z[j], h[j], l[j]);
+          const long long o = s * stridez + static_cast<long long>(r) * ldz + c0;
+          if (vec && c0 + 3 < ldz) {
+            // the padding columns [cols, ldz) of the operand are written as zeros
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j >= nv) h[j] = l[j] = __float2bfloat16_rn(0.f);
+            uint2 ph, pl;
+            ph.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
+            ph.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16) | __bfloat16_as_ushort(h[2]);
+            *reinterpret_cast<uint2*>(Zhi + o) = ph;
+            if (Zlo != nullptr) {
+              pl.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
+              pl.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[3])) << 16) | __bfloat16_as_ushort(l[2]);
+              *reinterpret_cast<uint2*>(Zlo + o) = pl;
+            }
+          } else {
+            for (int j = 0; j < nv; ++j) {
+              Zhi[o + j] = h[j];
+              if (Zlo != nullptr) Zlo[o + j] = l[j];
+            }
+          }
+        }
       }
     }
   }
@@ -258,12 +279,10 @@ int launch_philox_normal(unsigned long long seed, unsigned sample0, unsigned str
                          __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, long long ldz, long long stridez,
                          cudaStream_t stream) {
   if (rows <= 0 || cols <= 0 || nsamples <= 0) return 0;
-  const long long total = ((static_cast<long long>(rows) * cols + 3) / 4) * nsamples;
-  long long blocks = (total + 255) / 256;
-  const long long cap = static_cast<long long>(kNumSMsB200) * 16;
-  if (blocks > cap) blocks = cap;
-  philox_normal_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-      seed, sample0, stream_id, rows, cols, nsamples, Zf, ldf, stridef, Zhi, Zlo, ldz, stridez);
+  const int groups = (cols + 3) / 4;
+  dim3 grid((groups + 255) / 256, rows < 4096 ? rows : 4096, nsamples < 16 ? nsamples : 16);
+  philox_normal_kernel<<<grid, 256, 0, stream>>>(seed, sample0, stream_id, rows, cols, nsamples, Zf,
+                                                 ldf, stridef, Zhi, Zlo, ldz, stridez);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

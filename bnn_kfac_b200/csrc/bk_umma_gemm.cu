@@ -62,6 +62,7 @@ struct KParams {
   int M, N, K, batch, nparts, flags;
   int tiles_m, tiles_n, tiles_per_batch, num_tiles;
   int a_bmul, b_bmul, c_bmul;
+  int tri_koff;  // kTriB: B[n][k] == 0 for k > tri_koff + n
   float alpha, beta;
   float* C;
   long long ldc, strideC;
@@ -78,7 +79,7 @@ __host__ __device__ inline int syrk_row_tiles(int mi, int tiles_n, int tile_m) {
 }
 
 struct Tile {
-  int b, m0, n0, nkb;
+  int b, m0, n0, kb0, nkb;  // k-blocks [kb0, kb0 + nkb) carry non-zero operand data
 };
 
 template <int CG>
@@ -108,8 +109,9 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
   r.n0 = nj * BN;
   int kend = p.K;
   if (p.flags & kTriA) kend = min(kend, r.m0 + kTileM);
-  if (p.flags & kTriB) kend = min(kend, r.n0 + BN);
-  r.nkb = (kend + BK - 1) / BK;
+  if (p.flags & kTriB) kend = min(kend, p.tri_koff + r.n0 + BN);
+  r.kb0 = (p.flags & kTriBUpper) ? min(r.n0, p.K) / BK : 0;
+  r.nkb = max((kend + BK - 1) / BK - r.kb0, 0);
   return r;
 }
 
@@ -184,7 +186,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int b_row = tl.n0 + static_cast<int>(cta_rank) * kRowsB;
         for (int it = 0; it < iters; ++it) {
           const int part = it / tl.nkb;
-          const int kb = it - part * tl.nkb;
+          const int kb = tl.kb0 + it - part * tl.nkb;
           // part 0: hi*hi, part 1: hi*lo, part 2: lo*hi
           const CUtensorMap* ma = (part == 2) ? &tmA1 : &tmA0;
           const CUtensorMap* mb = (part == 1) ? &tmB1 : &tmB0;
@@ -541,6 +543,7 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.a_bmul = (a.strideA == 0 || a.batch == 1) ? 0 : 1;
   p.b_bmul = (a.strideB == 0 || a.batch == 1) ? 0 : 1;
   p.c_bmul = (a.batch == 1) ? 0 : 1;
+  p.tri_koff = a.tri_koff;
   p.alpha = a.alpha;
   p.beta = a.beta;
   p.C = a.C;

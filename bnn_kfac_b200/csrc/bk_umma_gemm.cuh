@@ -16,8 +16,9 @@ enum GemmFlags : int {
   kSyrkLower = 1,   // A == B (square): only tiles touching the lower triangle, write c <= r only
   kMirror = 2,      // with kSyrkLower: also write the transposed element (full symmetric result)
   kTriA = 4,        // A[m][k] == 0 for k > m (lower-triangular A): skip those k-blocks
-  kTriB = 8,        // B[n][k] == 0 for k > n
+  kTriB = 8,        // B[n][k] == 0 for k > tri_koff + n
   kRelu = 16,       // max(x, 0) after alpha/beta/bias
+  kTriBUpper = 32,  // B[n][k] == 0 for k < n (B is the transpose of a lower-triangular matrix)
 };
 
 struct GemmArgs {
@@ -32,6 +33,7 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0, batch = 1;
   int nparts = 1;
   int flags = 0;
+  int tri_koff = 0;  // with kTriB: B[n][k] == 0 for k > tri_koff + n (dense columns [0, tri_koff))
   // epilogue:  v = alpha * acc + beta * C + bias[n];  optional relu;  outputs: C (fp32) and/or
   // O_hi[/O_lo] (bf16 [split]) — any may be null.
   float alpha = 1.f, beta = 0.f;

@@ -419,6 +419,40 @@ class KFAC(Curvature):
             self._staged[layer] = tuple(stage_operand(L, lower_only=True) for L in self.inv_state[layer])
         return self._staged[layer]
 
+    def _implicit_operands(self, layer):
+        """Staged bf16 operands of the implicit MC forward (predictive._implicit_linear), cached per
+        layer until the next invert(): L_A^T (upper triangular) and the K-concatenated
+        [M~ | 0 | L_G] with M~ = [W | b] in columns [0, d_in') and L_G (lower) from column kx on."""
+        key = ("implicit", layer)
+        if key not in self._staged:
+            lib = self._lib
+            LA, LG = self.inv_state[layer]
+            d = LA.shape[0]
+            kx = _round8(d)
+            t_hi = torch.zeros(d, kx, dtype=torch.bfloat16, device=LA.device)
+            t_lo = torch.zeros_like(t_hi)
+            la = LA.float().contiguous()
+            _lib.check(lib.bk_transpose_split(la.data_ptr(), la.stride(0), d, d, 1.0, 0, t_hi.data_ptr(),
+                                              t_lo.data_ptr(), kx, _lib.stream_ptr()), "bk_transpose_split")
+            d_out = LG.shape[0]
+            m = layer.weight.detach().float().reshape(d_out, -1)
+            if layer.bias is not None:
+                m = torch.cat([m, layer.bias.detach().float().reshape(d_out, 1)], dim=1)
+            m = m.contiguous()
+            lg = LG.float().contiguous()
+            ldcat = kx + _round8(d_out)
+            c_hi = torch.zeros(d_out, ldcat, dtype=torch.bfloat16, device=LA.device)
+            c_lo = torch.zeros_like(c_hi)
+            st = _lib.stream_ptr()
+            _lib.check(lib.bk_convert_split(m.data_ptr(), m.stride(0), d_out, m.shape[1], 1.0, 0,
+                                            c_hi.data_ptr(), c_lo.data_ptr(), ldcat, st), "bk_convert_split")
+            _lib.check(lib.bk_convert_split(lg.data_ptr(), lg.stride(0), d_out, d_out, 1.0, 1,
+                                            c_hi.data_ptr() + 2 * kx, c_lo.data_ptr() + 2 * kx, ldcat, st),
+                       "bk_convert_split")
+            self._staged[key] = {"LAT": (t_hi, t_lo, kx), "MLG": (c_hi, c_lo, ldcat), "kx": kx,
+                                 "la_dd": LA[d - 1, d - 1].reshape(1)}
+        return self._staged[key]
+
     def sample(self, layer: Module, z: Optional[Tensor] = None) -> Tensor:
         """(L_A z L_G^T)^T -> [d_out, d_in'] with z ~ N(0,1)^{d_in' x d_out} (curvatures.py:400-405).
         `z` (shape [d_in', d_out]) replaces the internal Philox draw."""

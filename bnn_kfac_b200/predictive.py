@@ -89,24 +89,147 @@ def _linear_forward(lib, act, act_shared: bool, rows: int, d_in: int, w_hi, w_lo
     return out if last else (o_hi, o_lo, ldo)
 
 
-def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
-              program: Optional[Sequence[Op]] = None, noise: Optional[Sequence[Tensor]] = None) -> Tensor:
-    """Outputs of the network under `n_samples` posterior weight samples: [S, B, C] fp32.
+def _gemm(lib, a, sa, b, sb, m, n, k, batch, prec, flags=0, alpha=1.0, beta=0.0, c=None, ldc=0, sc=0,
+          o=None, so=0, what="bk_gemm_nt"):
+    """bk_gemm_nt on staged operands: a / b / o are (hi, lo, ld) triples, c an fp32 tensor."""
+    x3 = prec == _lib.BK_PREC_BF16X3
+    a_hi, a_lo, lda = a
+    b_hi, b_lo, ldb = b
+    o_hi, o_lo, ldo = o if o is not None else (None, None, 0)
+    _lib.check(lib.bk_gemm_nt(a_hi.data_ptr(), a_lo.data_ptr() if x3 else 0, lda, sa,
+                              b_hi.data_ptr(), b_lo.data_ptr() if x3 else 0, ldb, sb,
+                              m, n, k, batch, prec, flags, alpha, beta,
+                              _lib.ptr(c), ldc, sc, 0, 0,
+                              _lib.ptr(o_hi), _lib.ptr(o_lo) if x3 else 0, ldo, so, _lib.stream_ptr()), what)
 
-    noise: optional per-layer external noise, noise[layer_index] = [S, d_in', d_out] (parity mode)."""
+
+def _stage_activation(lib, x2d: Tensor, x3: bool, ones_col: bool):
+    """fp32 [rows, d] -> bf16 (hi, lo, ld) with an optional trailing column of ones (the reference's
+    bias augmentation, models/curvatures.py:346-348, on the activation side)."""
+    rows, d = x2d.shape
+    ld = _round8(d + int(ones_col))
+    hi = torch.zeros(rows, ld, dtype=torch.bfloat16, device=x2d.device)
+    lo = torch.zeros_like(hi) if x3 else hi
+    xc = x2d.float().contiguous()
+    _lib.check(lib.bk_convert_split(xc.data_ptr(), xc.stride(0), rows, d, 1.0, 0, hi.data_ptr(),
+                                    lo.data_ptr() if x3 else 0, ld, _lib.stream_ptr()), "bk_convert_split")
+    if ones_col:
+        hi[:, d] = 1.0
+    return hi, lo, ld
+
+
+def _ptr(t: Optional[Tensor], off_elems: int = 0) -> int:
+    return 0 if t is None else t.data_ptr() + 2 * off_elems
+
+
+def _gemm_raw(lib, a_hi, a_lo, lda, sa, b_hi, b_lo, ldb, sb, m, n, k, batch, prec, flags, c, ldc, sc,
+              o_hi, o_lo, ldo, so, what, beta=0.0):
+    x3 = prec == _lib.BK_PREC_BF16X3
+    _lib.check(lib.bk_gemm_nt(a_hi, a_lo if x3 else 0, lda, sa, b_hi, b_lo if x3 else 0, ldb, sb,
+                              m, n, k, batch, prec, flags, 1.0, beta, c, ldc, sc, 0, 0,
+                              o_hi, o_lo if x3 else 0, ldo, so, _lib.stream_ptr()), what)
+
+
+def _new_cat(S: int, B: int, kx: int, d_out: int, x3: bool, dev):
+    """K-concatenated activation buffer [S, B, kx + round8(d_out)] of a Linear layer (zero-filled:
+    padding columns must stay zero)."""
+    ldcat = kx + _round8(d_out)
+    hi = torch.zeros(S, B, ldcat, dtype=torch.bfloat16, device=dev)
+    lo = torch.zeros_like(hi) if x3 else None
+    return hi, lo, ldcat
+
+
+def _implicit_linear(lib, est: KFAC, layer: Module, li: int, cat, x_shared: bool, B: int, S: int,
+                     sample0: int, z: Optional[Tensor], relu: bool, last: bool, prec: int, nxt):
+    """One Linear layer of the MC forward WITHOUT materialising the sampled weights.
+
+    With x~ = [x, 1] and the sample (L_A Z L_G^T)^T added to M~ = [W | b] (models/curvatures.py:
+    67-82, 403-405):   x~ W_s~^T = x~ M~^T + ((x~ L_A) Z_s) L_G^T  =  [x~ | Y2_s] [M~ | L_G]^T.
+    Three tensor-core contractions per layer with the B test inputs as the row dimension (~6 B d^2
+    flops instead of the 2 d^3 of forming W_s), the same numbers for the same Z_s:
+        Y1   = x~ L_A[:, :d_in]       (L_A^T upper: leading zero k-blocks skipped; the last column of
+                                       x~ L_A is the constant L_A[d_in, d_in] and is filled, not computed)
+        Y2_s = Y1 Z_s                 (Z_s^T comes straight from the Philox kernel in operand layout and
+                                       lands in the right half of the K-concatenated buffer)
+        out  = act([x~ | Y2_s] [M~ | L_G]^T)   (one GEMM over K = d_in' + d_out, bias through the ones
+                                       column, ReLU and the next layer's bf16 operand in the epilogue)
+    cat: (hi, lo, ldcat) buffer [S, B, ldcat] whose left part holds x~_s (ones column included).
+    nxt: the next layer's cat buffer (the epilogue writes activations into its left part) or None."""
+    x3 = prec == _lib.BK_PREC_BF16X3
+    LA, LG = est.inv_state[layer]
+    dinp, dout = LA.shape[0], LG.shape[0]
+    d_in = dinp - 1
+    dev = LA.device
+    ops = est._implicit_operands(layer)
+    kx = ops["kx"]
+    c_hi, c_lo, ldcat = cat
+    Sx = 1 if x_shared else S
+    # 1. Y1 = x~ L_A
+    ld1 = kx
+    y1_hi = torch.zeros(Sx, B, ld1, dtype=torch.bfloat16, device=dev)
+    y1_lo = torch.zeros_like(y1_hi) if x3 else None
+    t_hi, t_lo, ldt = ops["LAT"]
+    _gemm_raw(lib, _ptr(c_hi), _ptr(c_lo), ldcat, B * ldcat, _ptr(t_hi), _ptr(t_lo), ldt, 0,
+              B, d_in, dinp, Sx, prec, _lib.GEMM_TRI_B_UPPER, 0, 0, 0,
+              _ptr(y1_hi), _ptr(y1_lo), ld1, B * ld1, "bk_gemm_nt(x L_A)")
+    dd = ops["la_dd"]
+    dd_hi = dd.to(torch.bfloat16)
+    y1_hi[:, :, d_in] = dd_hi
+    if x3:
+        y1_lo[:, :, d_in] = (dd - dd_hi.float()).to(torch.bfloat16)
+    # 2. Y2_s = Y1 Z_s  ->  right half of the concatenated buffer
+    ldz = kx
+    zt_hi = torch.empty(S, dout, ldz, dtype=torch.bfloat16, device=dev)
+    zt_lo = torch.empty_like(zt_hi) if x3 else None
+    if z is None:
+        _lib.check(lib.bk_philox_normal(est.seed, sample0, li, dout, dinp, S, 0, 0, 0, zt_hi.data_ptr(),
+                                        _lib.ptr(zt_lo), ldz, dout * ldz, _lib.stream_ptr()), "bk_philox_normal")
+    else:
+        zz = z.to(dev, torch.float32).contiguous()
+        assert zz.shape == (S, dinp, dout), "noise must be [S, d_in', d_out]"
+        if ldz != dinp:
+            zt_hi.zero_()
+            if x3:
+                zt_lo.zero_()
+        for s_ in range(S):
+            _lib.check(lib.bk_transpose_split(zz[s_].data_ptr(), dout, dinp, dout, 1.0, 0, zt_hi[s_].data_ptr(),
+                                              zt_lo[s_].data_ptr() if x3 else 0, ldz, _lib.stream_ptr()),
+                       "bk_transpose_split")
+    _gemm_raw(lib, _ptr(y1_hi), _ptr(y1_lo), ld1, 0 if x_shared else B * ld1,
+              _ptr(zt_hi), _ptr(zt_lo), ldz, dout * ldz, B, dout, dinp, S, prec, 0, 0, 0, 0,
+              _ptr(c_hi, kx), _ptr(c_lo, kx), ldcat, B * ldcat, "bk_gemm_nt(Y1 Z)")
+    # 3. out_s = act([x~ | Y2_s] [M~ | L_G]^T)
+    m_hi, m_lo, ldm = ops["MLG"]
+    flags = _lib.GEMM_TRI_B | _lib.gemm_tri_koff(kx) | (_lib.GEMM_RELU if relu else 0)
+    K = kx + dout
+    if last:
+        ldc = (dout + 3) // 4 * 4
+        out = torch.empty(S, B, ldc, device=dev, dtype=torch.float32)
+        _gemm_raw(lib, _ptr(c_hi), _ptr(c_lo), ldcat, B * ldcat, _ptr(m_hi), _ptr(m_lo), ldm, 0,
+                  B, dout, K, S, prec, flags, out.data_ptr(), ldc, B * ldc, 0, 0, 0, 0,
+                  "bk_gemm_nt([x|Y2][M|L_G]^T)")
+        return out[:, :, :dout]
+    n_hi, n_lo, ldn = nxt
+    _gemm_raw(lib, _ptr(c_hi), _ptr(c_lo), ldcat, B * ldcat, _ptr(m_hi), _ptr(m_lo), ldm, 0,
+              B, dout, K, S, prec, flags, 0, 0, 0, _ptr(n_hi), _ptr(n_lo), ldn, B * ldn,
+              "bk_gemm_nt([x|Y2][M|L_G]^T)")
+    n_hi[:, :, dout] = 1.0           # ones column of the next layer's x~
+    return nxt
+
+
+def _mc_logits_chunk(est: KFAC, x: Tensor, S: int, sample0: int, prog, noise, implicit: Optional[bool]):
     lib = _lib.load()
-    prog = list(program) if program is not None else program_for(est.model)
     prec = gemm_precision(est.precision)
     x3 = prec == _lib.BK_PREC_BF16X3
-    S = n_samples
     st = _lib.stream_ptr()
     dev = x.device
     layer_index = {l: i for i, l in est._selected_layers()}
     cur = x.float().contiguous()       # fp32 activation, [B, ...] (shared) or [S, B, ...]
     shared = True
     staged = None                      # bf16 operand of the next Linear (hi, lo, ld)
+    staged_ones = False                # does `staged` carry the trailing ones column?
+    cat = None                         # K-concatenated buffer of the next implicit Linear layer
     B = x.shape[0]
-    n_ops = len(prog)
     for oi, op in enumerate(prog):
         if op.kind == "flatten":
             if staged is None:
@@ -115,10 +238,49 @@ def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
         layer = op.layer
         li = layer_index[layer]
         z = None if noise is None else noise[li]
-        smp = est.sample_batch(layer, S, z=z, sample0=sample0)        # [S, d_out, d_in']
         has_bias = layer.bias is not None
-        d_out = smp.shape[1]
-        d_in = smp.shape[2] - int(has_bias)
+        LA, LG = est.inv_state[layer]
+        d_out = LG.shape[0]
+        d_in = LA.shape[0] - int(has_bias)
+        last = all(o.kind == "flatten" for o in prog[oi + 1:])
+        use_implicit = implicit
+        if use_implicit is None:   # forming W_s costs ~2 d^3 per sample, the implicit form ~6 B d^2
+            use_implicit = 2 * B < min(d_in + 1, d_out) and min(d_in, d_out) >= 64
+        if op.kind == "linear" and use_implicit and has_bias:
+            kx = _round8(d_in + 1)
+            if cat is None:
+                # first implicit layer: stage x~ once (fp32 activations, shared or per sample)
+                cat = _new_cat(S, B, kx, d_out, x3, dev)
+                if staged is not None:   # bf16 operand left by a materialised Linear layer
+                    s_hi, s_lo, s_ld = staged
+                    rows = s_hi.numel() // (B * s_ld)
+                    cat[0][:, :, :d_in].copy_(s_hi.view(rows, B, s_ld)[:, :, :d_in].expand(S, B, d_in))
+                    if x3:
+                        cat[1][:, :, :d_in].copy_(s_lo.view(rows, B, s_ld)[:, :, :d_in].expand(S, B, d_in))
+                    cat[0][:, :, d_in] = 1.0
+                    shared = shared and rows == 1
+                else:
+                    flat = cur.reshape(-1, d_in)
+                    hi, lo, ld = _stage_activation(lib, flat, x3, True)
+                    rows = flat.shape[0] // B
+                    cat[0][:, :, :ld].copy_(hi.view(rows, B, ld).expand(S, B, ld))
+                    if x3:
+                        cat[1][:, :, :ld].copy_(lo.view(rows, B, ld).expand(S, B, ld))
+            # the epilogue of this layer writes straight into the next implicit layer's buffer
+            nxt = None
+            if not last:
+                nl = next(o.layer for o in prog[oi + 1:] if o.kind != "flatten")
+                nxt = _new_cat(S, B, _round8(d_out + 1), est.inv_state[nl][1].shape[0], x3, dev)
+            res = _implicit_linear(lib, est, layer, li, cat, shared, B, S, sample0, z, op.relu, last, prec,
+                                   nxt)
+            if last:
+                return res
+            # does the next layer also run implicitly?  otherwise hand over a plain staged activation
+            cat, shared = res, False
+            staged, staged_ones = (cat[0], cat[1] if x3 else cat[0], cat[2]), True
+            continue
+        cat = None
+        smp = est.sample_batch(layer, S, z=z, sample0=sample0)        # [S, d_out, d_in']
         mean_w = layer.weight.detach().float().reshape(d_out, d_in).contiguous()
         mean_b = layer.bias.detach().float().contiguous() if has_bias else None
         b_s = torch.zeros(S, d_out, device=dev, dtype=torch.float32)
@@ -141,7 +303,7 @@ def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
                        "bk_conv2d_relu_pool")
             cur, shared = out, False
             continue
-        # ---- linear
+        # ---- linear, materialised weights
         ldw = _round8(d_in)
         w_hi = torch.zeros(S, d_out, ldw, dtype=torch.bfloat16, device=dev)
         w_lo = torch.zeros_like(w_hi) if x3 else None
@@ -152,13 +314,34 @@ def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
             flat = cur.reshape(-1, d_in)                              # [B, d_in] or [S*B, d_in]
             hi, lo, ld = stage_operand(flat)
             staged = (hi, lo if x3 else hi, ld)
-        last = all(o.kind == "flatten" for o in prog[oi + 1:])
+            staged_ones = False
         res = _linear_forward(lib, staged, shared, B, d_in, w_hi, w_lo, ldw, b_s, S, d_out, op.relu, last,
                               prec)
         if last:
             return res
-        staged, shared = res, False
+        staged, shared, staged_ones = res, False, False
     raise RuntimeError("forward program must end with a Linear layer")
+
+
+def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
+              program: Optional[Sequence[Op]] = None, noise: Optional[Sequence[Tensor]] = None,
+              implicit: Optional[bool] = None, max_chunk_bytes: int = 6 << 30) -> Tensor:
+    """Outputs of the network under `n_samples` posterior weight samples: [S, B, C] fp32.
+
+    noise: optional per-layer external noise, noise[layer_index] = [S, d_in', d_out] (parity mode).
+    implicit: None = choose per layer (see _implicit_linear), True / False = force.
+    Samples are processed in chunks whose noise operands fit `max_chunk_bytes`."""
+    prog = list(program) if program is not None else program_for(est.model)
+    x3 = gemm_precision(est.precision) == _lib.BK_PREC_BF16X3
+    per_sample = max(int(est.inv_state[op.layer][0].shape[0]) * int(est.inv_state[op.layer][1].shape[0])
+                     for op in prog if op.layer is not None) * (4 if x3 else 2) * 3
+    chunk = max(1, min(n_samples, max_chunk_bytes // max(per_sample, 1)))
+    outs = []
+    for s0 in range(0, n_samples, chunk):
+        sc = min(chunk, n_samples - s0)
+        nz = None if noise is None else [None if t is None else t[s0:s0 + sc] for t in noise]
+        outs.append(_mc_logits_chunk(est, x, sc, sample0 + s0, prog, nz, implicit))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
 
 def mc_moments(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0, mode: str = "classification",
@@ -166,7 +349,7 @@ def mc_moments(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0, mode: str
     """(E_s[p], E_s[p^2]) over `n_samples` samples starting at global sample id `sample0`;
     p = softmax(logits) (classification) or the raw output (regression)."""
     lib = _lib.load()
-    logits = mc_logits(est, x, n_samples, sample0, program, noise)
+    logits = mc_logits(est, x, n_samples, sample0, program, noise).contiguous()
     S, B, Cn = logits.shape
     mean = torch.empty(B, Cn, device=x.device, dtype=torch.float32)
     meansq = torch.empty_like(mean)

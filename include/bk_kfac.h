@@ -43,6 +43,9 @@ extern "C" {
 #define BK_GEMM_TRI_A 4
 #define BK_GEMM_TRI_B 8
 #define BK_GEMM_RELU 16
+#define BK_GEMM_TRI_B_UPPER 32 /* B[n][k] == 0 for k < n */
+/* with BK_GEMM_TRI_B: B[n][k] == 0 only for k > koff + n (koff dense leading columns, multiple of 8) */
+#define BK_GEMM_TRI_KOFF(koff) (((koff) / 8) << 8)
 
 const char* bk_version(void);
 /* Total number of kernels this library has launched in this process (monotonic counter). */
@@ -78,9 +81,10 @@ int bk_transpose_split(const float* x, long long ldx, int rows, int cols, float 
 /* fp32 [rows, cols] -> bf16 hi[/lo] [rows, cols], optional lower-triangle mask. */
 int bk_convert_split(const float* x, long long ldx, int rows, int cols, float scale, int lower_only,
                      void* o_hi, void* o_lo, long long ldo, void* stream);
-/* Counter-based N(0,1): element e of sample s of stream `stream_id` = Philox4x32-10(key = seed,
- * counter = (e/4, sample0 + s, stream_id)) lane e%4, Box-Muller.  Replaces torch.randn at
- * models/curvatures.py:404 and .normal_() at :207.  Any of zf / z_hi may be null. */
+/* Counter-based N(0,1) matrices [rows, cols]: element (r, c) of sample s of stream `stream_id` =
+ * Philox4x32-10(key = seed, counter = (c/4, r, sample0 + s, stream_id)) lane c%4, Box-Muller.
+ * Replaces torch.randn at models/curvatures.py:404.  Any of zf / z_hi may be null; the padding
+ * columns [cols, ldz) of the bf16 outputs are zero-filled when ldz is a multiple of 4. */
 int bk_philox_normal(unsigned long long seed, unsigned sample0, unsigned stream_id, int rows,
                      int cols, int nsamples, float* zf, long long ldf, long long stride_f,
                      void* z_hi, void* z_lo, long long ldz, long long stride_z, void* stream);

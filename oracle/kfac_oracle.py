@@ -432,6 +432,25 @@ def philox4x32_10(counter: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
     return c.astype(np.uint32)
 
 
+def philox_normal_matrix(seed: int, sample: int, stream_id: int, rows: int, cols: int) -> np.ndarray:
+    """The [rows, cols] normal matrix of (seed, sample, stream) as bk_philox_normal defines it
+    (include/bk_kfac.h): element (r, c) = lane c % 4 of counter (c // 4, r, sample, stream_id);
+    Box-Muller on 24-bit uniforms, evaluated in fp64 (agrees with the device's fast-math fp32 to ~1e-5)."""
+    groups = (cols + 3) // 4
+    g, r = np.meshgrid(np.arange(groups, dtype=np.uint64), np.arange(rows, dtype=np.uint64))
+    ctr = np.stack([g.reshape(-1), r.reshape(-1), np.full(rows * groups, sample, dtype=np.uint64),
+                    np.full(rows * groups, stream_id, dtype=np.uint64)], axis=1)
+    u = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).astype(np.float64)
+    out = np.empty((rows * groups, 4))
+    for a, b, o in ((0, 1, 0), (2, 3, 2)):
+        u1 = (np.floor(u[:, a] / 256.0) + 1.0) / 16777216.0
+        u2 = np.floor(u[:, b] / 256.0) / 16777216.0
+        rad = np.sqrt(-2.0 * np.log(u1))
+        out[:, o] = rad * np.cos(2.0 * math.pi * u2)
+        out[:, o + 1] = rad * np.sin(2.0 * math.pi * u2)
+    return out.reshape(rows, groups * 4)[:, :cols]
+
+
 def philox_normal(seed: int, sample: int, stream_id: int, count: int) -> np.ndarray:
     """The first `count` normals of (seed, sample, stream): element e uses counter (e // 4, sample,
     stream_id), lane e % 4; Box-Muller on 24-bit uniforms (bk_philox_normal in include/bk_kfac.h).
