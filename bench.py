@@ -363,11 +363,13 @@ def extras(est, model, layers, dev, world, rank):
 
     est.invert(1.0, 200.0)      # warm-up (workspace allocation)
     out["invert_ms_all_layers"] = ev_ms(lambda: est.invert(1.0, 200.0))
+    out["invert_config"] = "8 factors (4 x 4097^2, 3 x 4096^2, 10^2), add=1, multiply=200, one batched launch sequence"
     # posterior predictive: S weight samples per rank (sample ids sharded over ranks), 1024 test inputs
-    S, B = 4, 1024
+    S, B = 16, 1024
     x = torch.randn(B, WIDTHS[0], device=dev)
-    mc_moments(est, x, S, sample0=rank * S)
-    ms = ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S))
+    for _ in range(2):
+        mc_moments(est, x, S, sample0=rank * S)
+    ms = ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=3)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -268,8 +268,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    // one 32x32 -> 64 multiply (IMAD.WIDE) yields both halves
+    const unsigned long long p0 = static_cast<unsigned long long>(M0) * c[0];
+    const unsigned long long p1 = static_cast<unsigned long long>(M1) * c[2];
+    const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
     const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
     c[0] = n0;
     c[1] = n1;
@@ -284,7 +287,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
   const float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
   const float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);           // [0, 1)
-  const float r = sqrtf(-2.0f * __logf(u1));
+  const float t = -2.0f * __logf(u1);   // >= 0
+  const float r = t * rsqrtf(fmaxf(t, 1e-30f));  // sqrt(t) from one MUFU.RSQ (t == 0 -> 0)
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c;

@@ -134,13 +134,17 @@ def _new_cat(S: int, B: int, kx: int, d_out: int, x3: bool, dev):
     """K-concatenated activation buffer [S, B, kx + round8(d_out)] of a Linear layer (zero-filled:
     padding columns must stay zero)."""
     ldcat = kx + _round8(d_out)
-    hi = torch.zeros(S, B, ldcat, dtype=torch.bfloat16, device=dev)
-    lo = torch.zeros_like(hi) if x3 else None
+    hi = torch.empty(S, B, ldcat, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty_like(hi) if x3 else None
+    for t in (hi, lo):
+        if t is not None and ldcat != kx + d_out:
+            t[:, :, kx + d_out:].zero_()
     return hi, lo, ldcat
 
 
 def _implicit_linear(lib, est: KFAC, layer: Module, li: int, cat, x_shared: bool, B: int, S: int,
-                     sample0: int, z: Optional[Tensor], relu: bool, last: bool, prec: int, nxt):
+                     sample0: int, z: Optional[Tensor], relu: bool, last: bool, prec: int, nxt,
+                     prefetched=None):
     """One Linear layer of the MC forward WITHOUT materialising the sampled weights.
 
     With x~ = [x, 1] and the sample (L_A Z L_G^T)^T added to M~ = [W | b] (models/curvatures.py:
@@ -166,8 +170,12 @@ def _implicit_linear(lib, est: KFAC, layer: Module, li: int, cat, x_shared: bool
     Sx = 1 if x_shared else S
     # 1. Y1 = x~ L_A
     ld1 = kx
-    y1_hi = torch.zeros(Sx, B, ld1, dtype=torch.bfloat16, device=dev)
-    y1_lo = torch.zeros_like(y1_hi) if x3 else None
+    y1_hi = torch.empty(Sx, B, ld1, dtype=torch.bfloat16, device=dev)
+    y1_lo = torch.empty_like(y1_hi) if x3 else None
+    if ld1 != dinp:
+        y1_hi[:, :, dinp:].zero_()
+        if x3:
+            y1_lo[:, :, dinp:].zero_()
     t_hi, t_lo, ldt = ops["LAT"]
     _gemm_raw(lib, _ptr(c_hi), _ptr(c_lo), ldcat, B * ldcat, _ptr(t_hi), _ptr(t_lo), ldt, 0,
               B, d_in, dinp, Sx, prec, _lib.GEMM_TRI_B_UPPER, 0, 0, 0,
@@ -179,9 +187,16 @@ def _implicit_linear(lib, est: KFAC, layer: Module, li: int, cat, x_shared: bool
         y1_lo[:, :, d_in] = (dd - dd_hi.float()).to(torch.bfloat16)
     # 2. Y2_s = Y1 Z_s  ->  right half of the concatenated buffer
     ldz = kx
-    zt_hi = torch.empty(S, dout, ldz, dtype=torch.bfloat16, device=dev)
-    zt_lo = torch.empty_like(zt_hi) if x3 else None
-    if z is None:
+    pre = None if prefetched is None else prefetched.get(li)
+    if pre is not None:
+        zt_hi, zt_lo, ev = pre
+        torch.cuda.current_stream().wait_event(ev)
+    else:
+        zt_hi = torch.empty(S, dout, ldz, dtype=torch.bfloat16, device=dev)
+        zt_lo = torch.empty_like(zt_hi) if x3 else None
+    if pre is not None:
+        pass
+    elif z is None:
         _lib.check(lib.bk_philox_normal(est.seed, sample0, li, dout, dinp, S, 0, 0, 0, zt_hi.data_ptr(),
                                         _lib.ptr(zt_lo), ldz, dout * ldz, _lib.stream_ptr()), "bk_philox_normal")
     else:
@@ -213,8 +228,53 @@ def _implicit_linear(lib, est: KFAC, layer: Module, li: int, cat, x_shared: bool
     _gemm_raw(lib, _ptr(c_hi), _ptr(c_lo), ldcat, B * ldcat, _ptr(m_hi), _ptr(m_lo), ldm, 0,
               B, dout, K, S, prec, flags, 0, 0, 0, _ptr(n_hi), _ptr(n_lo), ldn, B * ldn,
               "bk_gemm_nt([x|Y2][M|L_G]^T)")
-    n_hi[:, :, dout] = 1.0           # ones column of the next layer's x~
+    # ones column of the next layer's x~ (hi = 1, lo = 0) and zero padding up to its kx
+    kxn = _round8(dout + 1)
+    n_hi[:, :, dout:kxn].zero_()
+    n_hi[:, :, dout] = 1.0
+    if n_lo is not None:
+        n_lo[:, :, dout:kxn].zero_()
     return nxt
+
+
+_noise_stream = {}
+
+
+def _prefetch_noise(lib, est: KFAC, prog, layer_index, B, S, sample0, x3, implicit, dev):
+    """Philox noise operands Z_s^T of every implicit Linear layer, generated on a side stream so that
+    the (SIMT, shared-memory-free) generator runs underneath the tensor-core GEMMs of earlier layers.
+    The noise does not depend on activations: element (o, i) of sample s of layer l is a pure function
+    of (seed, sample id, layer id, o, i).  Returns {layer index: (z_hi, z_lo, ready event)}."""
+    main = torch.cuda.current_stream()
+    side = _noise_stream.get(dev)
+    if side is None:
+        side = _noise_stream[dev] = torch.cuda.Stream(device=dev)
+    out = {}
+    side.wait_stream(main)
+    for op in prog:
+        if op.kind != "linear" or op.layer.bias is None:
+            continue
+        LA, LG = est.inv_state[op.layer]
+        dinp, dout = LA.shape[0], LG.shape[0]
+        use = implicit
+        if use is None:
+            use = 2 * B < min(dinp, dout) and min(dinp - 1, dout) >= 64
+        if not use:
+            continue
+        li = layer_index[op.layer]
+        ldz = _round8(dinp)
+        with torch.cuda.stream(side):
+            z_hi = torch.empty(S, dout, ldz, dtype=torch.bfloat16, device=dev)
+            z_lo = torch.empty_like(z_hi) if x3 else None
+            _lib.check(lib.bk_philox_normal(est.seed, sample0, li, dout, dinp, S, 0, 0, 0, z_hi.data_ptr(),
+                                            _lib.ptr(z_lo), ldz, dout * ldz, side.cuda_stream), "bk_philox_normal")
+            ev = torch.cuda.Event()
+            ev.record(side)
+        z_hi.record_stream(main)
+        if z_lo is not None:
+            z_lo.record_stream(main)
+        out[li] = (z_hi, z_lo, ev)
+    return out
 
 
 def _mc_logits_chunk(est: KFAC, x: Tensor, S: int, sample0: int, prog, noise, implicit: Optional[bool]):
@@ -230,6 +290,7 @@ def _mc_logits_chunk(est: KFAC, x: Tensor, S: int, sample0: int, prog, noise, im
     staged_ones = False                # does `staged` carry the trailing ones column?
     cat = None                         # K-concatenated buffer of the next implicit Linear layer
     B = x.shape[0]
+    prefetched = _prefetch_noise(lib, est, prog, layer_index, B, S, sample0, x3, implicit, dev) if noise is None else None
     for oi, op in enumerate(prog):
         if op.kind == "flatten":
             if staged is None:
@@ -272,7 +333,7 @@ def _mc_logits_chunk(est: KFAC, x: Tensor, S: int, sample0: int, prog, noise, im
                 nl = next(o.layer for o in prog[oi + 1:] if o.kind != "flatten")
                 nxt = _new_cat(S, B, _round8(d_out + 1), est.inv_state[nl][1].shape[0], x3, dev)
             res = _implicit_linear(lib, est, layer, li, cat, shared, B, S, sample0, z, op.relu, last, prec,
-                                   nxt)
+                                   nxt, prefetched)
             if last:
                 return res
             # does the next layer also run implicitly?  otherwise hand over a plain staged activation
