@@ -272,24 +272,41 @@ def main():
     value = total_samples / (ms_dev * 1e-3)
     e2e_value = total_samples / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (tcgen05 SYRK on the d x d block; the bias row / column of
-    # the first factor is produced from column sums by the staging kernel), timed on its own launches
-    # with the same operand shapes and state pitch as the step uses
+    # ---- roofline of the dominant kernel: the grouped tcgen05 SYRK launch of one step (all 7 wide
+    # factors: 4 x A on the 4096 x 4096 block + 3 x G; the bias row / column of A comes from column
+    # sums in the staging kernel), timed on its own launches with the operand shapes and state
+    # pitches the step uses
+    import ctypes as C
     peaks = load_peaks()
     prec = {"bf16": 1, "bf16x3": 3, "fp32": 1}[args.precision]
-    n, d = BATCH, WIDTHS[0]
-    ldt = n
-    hi = torch.empty(d, ldt, dtype=torch.bfloat16, device=dev)
-    lo = torch.empty_like(hi)
-    L.bk_transpose_split(resident[0][0].data_ptr(), d, n, d, 1.0, 0, hi.data_ptr(), lo.data_ptr(), ldt,
-                         _lib.stream_ptr())
-    ld_state = est.state[layers[0]][0].stride(0)
-    scratch = torch.zeros(d + 1, ld_state, device=dev)
+    n = BATCH
+    grp = []      # (state, ld, hi, lo, d)
+    for layer, (a, g) in zip(layers, resident):
+        for x, st_t in ((a, est.state[layer][0]), (g, est.state[layer][1])):
+            d = x.shape[1]
+            if d <= 176:
+                continue
+            hi = torch.empty(d, n, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty_like(hi)
+            L.bk_transpose_split(x.data_ptr(), d, n, d, 1.0, 0, hi.data_ptr(), lo.data_ptr(), n,
+                                 _lib.stream_ptr())
+            scratch = torch.zeros(st_t.shape[0], st_t.stride(0), device=dev)
+            grp.append((scratch, st_t.stride(0), hi, lo, d))
+    cnt = len(grp)
+    a_states = (C.c_void_p * cnt)(*[t[0].data_ptr() for t in grp])
+    a_lds = (C.c_longlong * cnt)(*[t[1] for t in grp])
+    a_hi = (C.c_void_p * cnt)(*[t[2].data_ptr() for t in grp])
+    a_lo = (C.c_void_p * cnt)(*[t[3].data_ptr() for t in grp])
+    a_ldt = (C.c_longlong * cnt)(*[n] * cnt)
+    a_ns = (C.c_int * cnt)(*[n] * cnt)
+    a_ds = (C.c_int * cnt)(*[t[4] for t in grp])
+    a_al = (C.c_float * cnt)(*[1.0 / n] * cnt)
+    a_be = (C.c_float * cnt)(*[1.0] * cnt)
     reps = 20
 
     def syrk():
-        L.bk_syrk_accum_staged(scratch.data_ptr(), ld_state, hi.data_ptr(), lo.data_ptr(), ldt, n, d,
-                               1.0 / n, 1.0, prec, _lib.stream_ptr())
+        _lib.check(L.bk_syrk_accum_staged_grouped(a_states, a_lds, a_hi, a_lo, a_ldt, a_ns, a_ds, a_al, a_be,
+                                                  cnt, prec, _lib.stream_ptr()), "bk_syrk_accum_staged_grouped")
     for _ in range(3):
         syrk()
     torch.cuda.synchronize()
@@ -300,13 +317,14 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     syrk_ms = e0.elapsed_time(e1) / reps
-    syrk_flops = d * (d + 1) * n          # one multiply-add per lower-triangle entry per sample
+    syrk_flops = sum(t[4] * (t[4] + 1) * n for t in grp)   # one multiply-add per lower-triangle entry per sample
     achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor",
-                "kernel": "umma_gemm_kernel<cta_group 2, TMA-reduce epilogue> (SYRK 4096x4096x4096, lower+mirror)",
+                "kernel": f"umma_syrk_grouped_kernel (cta_group::2, TMA-reduce epilogue; {cnt} SYRKs 4096x4096x4096 "
+                          "lower+mirror in one launch)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)",
-                "us_per_launch": syrk_ms * 1e3, "traffic": None}
+                "us_per_launch": syrk_ms * 1e3, "flops_per_launch": syrk_flops, "traffic": None}
     prof = os.path.join(ROOT, "profiles", "syrk_traffic.json")
     if os.path.exists(prof):
         try:

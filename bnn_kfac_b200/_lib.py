@@ -54,6 +54,13 @@ SIGNATURES = {
     "bk_philox_normal": (_i, [_ull, _u, _u, _i, _i, _i, _p, _ll, _ll, _p, _p, _ll, _ll, _p]),
     "bk_syrk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "bk_syrk_accum": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _f, _f, _f, _i, _p, _sz, _p]),
+    "bk_syrk_grouped_workspace_bytes": (_sz, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _i]),
+    "bk_syrk_accum_grouped": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_ll),
+                                   C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f),
+                                   C.POINTER(_f), C.POINTER(_f), _i, _i, _p, _sz, _p]),
+    "bk_syrk_accum_staged_grouped": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_p),
+                                          C.POINTER(_ll), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f),
+                                          C.POINTER(_f), _i, _i, _p]),
     "bk_syrk_accum_staged": (_i, [_p, _ll, _p, _p, _ll, _i, _i, _f, _f, _i, _p]),
     "bk_conv_a_accum": (_i, [_p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     "bk_conv_g_accum": (_i, [_p, _ll, _p, _i, _i, _i, _f, _f, _f, _p]),

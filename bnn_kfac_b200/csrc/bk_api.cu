@@ -185,6 +185,125 @@ int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ld
   return rc;
 }
 
+// Grouped factor update: every wide, TMA-addressable factor of the batch is staged and then
+// accumulated by ONE persistent tensor-core launch (bk::launch_umma_syrk_grouped); the rest (small,
+// fp32-precision or unaligned factors) go through bk_syrk_accum one by one.
+size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* has_bias, int count,
+                                       int precision) {
+  size_t total = 0;
+  for (int i = 0; i < count; ++i)
+    total += align_up(bk_syrk_workspace_bytes(ns[i], ds[i], has_bias[i], precision), 256);
+  return total;
+}
+
+int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const float* const* xs,
+                          const long long* ldxs, const int* ns, const int* ds, const int* has_bias,
+                          const float* in_scales, const float* alphas, const float* betas, int count,
+                          int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (count <= 0) return BK_OK;
+  if (states == nullptr || ld_states == nullptr || xs == nullptr || ldxs == nullptr ||
+      ns == nullptr || ds == nullptr || has_bias == nullptr || in_scales == nullptr ||
+      alphas == nullptr || betas == nullptr)
+    return BK_ERR_ARG;
+  if (bk_syrk_grouped_workspace_bytes(ns, ds, has_bias, count, precision) > workspace_bytes ||
+      (workspace == nullptr && workspace_bytes > 0) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return BK_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char* base = static_cast<char*>(workspace);
+  size_t off = 0;
+  bk::SyrkGroupItem items[64];
+  struct Border {
+    float* state;
+    long long ld;
+    int d;
+    const float* colsum;
+    float alpha, beta, n;
+  } borders[64];
+  int n_items = 0, n_borders = 0;
+  for (int i = 0; i < count; ++i) {
+    const size_t need = bk_syrk_workspace_bytes(ns[i], ds[i], has_bias[i], precision);
+    char* ws = base + off;
+    off += align_up(need, 256);
+    const int d = ds[i], n = ns[i], hb = has_bias[i] ? 1 : 0;
+    const int dp = d + hb;
+    const bool tensor = dp > BK_SMALL_D_MAX && precision != BK_PREC_FP32;
+    const bool aligned = (ld_states[i] % 4) == 0 && (reinterpret_cast<uintptr_t>(states[i]) & 15) == 0 &&
+                         (ldxs[i] % 4) == 0 && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0 &&
+                         (betas[i] == 0.f || betas[i] == 1.f) && d >= 192;
+    if (!tensor || !aligned || n_items >= 64) {
+      const int rc = bk_syrk_accum(states[i], ld_states[i], xs[i], ldxs[i], n, d, hb, in_scales[i],
+                                   alphas[i], betas[i], precision, ws, need, stream);
+      if (rc) return rc;
+      continue;
+    }
+    if (states[i] == nullptr || xs[i] == nullptr || n <= 0 || ld_states[i] < dp || ldxs[i] < d)
+      return BK_ERR_ARG;
+    const long long ldt = round8(n);
+    const size_t one = align_up(static_cast<size_t>(dp) * ldt * 2, 256);
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* lo =
+        precision == BK_PREC_BF16X3 ? reinterpret_cast<__nv_bfloat16*>(ws + one) : nullptr;
+    float* colsum =
+        hb ? reinterpret_cast<float*>(ws + (precision == BK_PREC_BF16X3 ? 2 : 1) * one) : nullptr;
+    if (colsum != nullptr &&
+        cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, st) != cudaSuccess)
+      return BK_ERR_CUDA;
+    const int rc = bk::launch_transpose_split(xs[i], ldxs[i], n, d, in_scales[i], 0, hi, lo, ldt, st,
+                                              colsum);
+    if (rc) return rc;
+    bk::SyrkGroupItem& it = items[n_items++];
+    it.X_hi = hi;
+    it.X_lo = lo;
+    it.ldx = ldt;
+    it.d = d;
+    it.n = n;
+    it.alpha = alphas[i];
+    it.beta = betas[i];
+    it.C = states[i];
+    it.ldc = ld_states[i];
+    if (hb) borders[n_borders++] = {states[i], ld_states[i], d, colsum, alphas[i], betas[i],
+                                    static_cast<float>(n)};
+  }
+  for (int g0 = 0; g0 < n_items; g0 += 8) {
+    const int gc = n_items - g0 < 8 ? n_items - g0 : 8;
+    const int rc = bk::launch_umma_syrk_grouped(items + g0, gc, precision, st);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < n_borders; ++b) {
+    const int rc = bk::launch_bias_border(borders[b].state, borders[b].ld, borders[b].d,
+                                          borders[b].colsum, borders[b].alpha, borders[b].beta,
+                                          borders[b].n, st);
+    if (rc) return rc;
+  }
+  return BK_OK;
+}
+
+int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_states,
+                                 const void* const* xt_his, const void* const* xt_los,
+                                 const long long* ldts, const int* ns, const int* ds,
+                                 const float* alphas, const float* betas, int count, int precision,
+                                 void* stream) {
+  if (count <= 0) return BK_OK;
+  if (count > 8 || states == nullptr || ld_states == nullptr || xt_his == nullptr ||
+      ldts == nullptr || ns == nullptr || ds == nullptr || alphas == nullptr || betas == nullptr)
+    return BK_ERR_ARG;
+  if (precision != BK_PREC_BF16 && precision != BK_PREC_BF16X3) return BK_ERR_ARG;
+  bk::SyrkGroupItem items[8];
+  for (int i = 0; i < count; ++i) {
+    items[i].X_hi = static_cast<const __nv_bfloat16*>(xt_his[i]);
+    items[i].X_lo = xt_los != nullptr ? static_cast<const __nv_bfloat16*>(xt_los[i]) : nullptr;
+    items[i].ldx = ldts[i];
+    items[i].d = ds[i];
+    items[i].n = ns[i];
+    items[i].alpha = alphas[i];
+    items[i].beta = betas[i];
+    items[i].C = states[i];
+    items[i].ldc = ld_states[i];
+  }
+  return bk::launch_umma_syrk_grouped(items, count, precision, as_stream(stream));
+}
+
 int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int c, int h, int w,
                     int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w, int has_bias,
                     float alpha, float beta, void* stream) {

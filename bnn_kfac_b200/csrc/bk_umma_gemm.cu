@@ -115,11 +115,85 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
   return r;
 }
 
-template <int CG, bool kTmaEpi>
-__global__ void __launch_bounds__(kThreads, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ CUtensorMap tmC, const KParams p) {
+// ---- grouped SYRK: several independent factor updates C_g += alpha_g X_g^T X_g in ONE persistent
+// launch (all layers of a KFAC.update): one tile list over all problems, so wave quantisation, the
+// pipeline prologue and the exposed last-tile epilogue are paid once per update instead of once per
+// factor.  CTA pairs, 256 x 256 lower-triangle tiles, TMA-reduce epilogue.
+constexpr int kMaxGroup = 8;
+struct GroupMaps {
+  CUtensorMap a0[kMaxGroup];  // X^T hi  (A and B operand: both are 128-row boxes for CTA pairs)
+  CUtensorMap a1[kMaxGroup];  // X^T lo  (bf16x3 only)
+  CUtensorMap c[kMaxGroup];   // fp32 state
+};
+struct GroupParams {
+  int count, nparts;
+  int tile_begin[kMaxGroup + 1];
+  int M[kMaxGroup], K[kMaxGroup];
+  float alpha[kMaxGroup];
+};
+
+__device__ __forceinline__ Tile decode_group_tile(const GroupParams& gp, int t, int& g) {
+  g = 0;
+  while (t >= gp.tile_begin[g + 1]) ++g;
+  int rem = t - gp.tile_begin[g];
+  int mi = 0;
+  while (rem >= mi + 1) {  // row mi of the 256-tile lower triangle holds mi + 1 tiles
+    rem -= mi + 1;
+    ++mi;
+  }
+  Tile r;
+  r.b = 0;
+  r.m0 = mi * 256;
+  r.n0 = rem * BN;
+  r.kb0 = 0;
+  r.nkb = (gp.K[g] + BK - 1) / BK;
+  return r;
+}
+
+// Per-tile view of "which problem": tensor maps, extents and scale.
+struct Work {
+  Tile tl;
+  const CUtensorMap *a0, *a1, *b0, *b1, *c;
+  int M, N;
+  float alpha;
+};
+
+template <int CG, bool kGrouped>
+__device__ __forceinline__ Work get_work(int t, const KParams& p, const CUtensorMap* tmA0,
+                                         const CUtensorMap* tmA1, const CUtensorMap* tmB0,
+                                         const CUtensorMap* tmB1, const CUtensorMap* tmC,
+                                         const GroupMaps* gm, const GroupParams* gp) {
+  Work w;
+  if (kGrouped) {
+    int g;
+    w.tl = decode_group_tile(*gp, t, g);
+    w.a0 = w.b0 = &gm->a0[g];
+    w.a1 = w.b1 = &gm->a1[g];
+    w.c = &gm->c[g];
+    w.M = w.N = gp->M[g];
+    w.alpha = gp->alpha[g];
+  } else {
+    w.tl = decode_tile<CG>(p, t);
+    w.a0 = tmA0;
+    w.a1 = tmA1;
+    w.b0 = tmB0;
+    w.b1 = tmB1;
+    w.c = tmC;
+    w.M = p.M;
+    w.N = p.N;
+    w.alpha = p.alpha;
+  }
+  return w;
+}
+
+template <int CG, bool kTmaEpi, bool kGrouped>
+__device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtensorMap* tmA1,
+                                          const CUtensorMap* tmB0, const CUtensorMap* tmB1,
+                                          const CUtensorMap* tmC, const KParams& p,
+                                          const GroupMaps* gm, const GroupParams* gp) {
+  const int num_tiles = kGrouped ? gp->tile_begin[gp->count] : p.num_tiles;
+  const int nparts = kGrouped ? gp->nparts : p.nparts;
+  const int flags = kGrouped ? (kSyrkLower | kMirror) : p.flags;
   constexpr int kStages = Cfg<CG>::kStages;
   constexpr uint32_t kStageBytes = Cfg<CG>::kStageBytes;
   constexpr int kTileM = Cfg<CG>::kTileM;
@@ -143,13 +217,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int first_tile = (CG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = (CG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmB0);
-    if (kTmaEpi) tma_prefetch_desc(&tmC);
-    if (p.nparts > 1) {
-      tma_prefetch_desc(&tmA1);
-      tma_prefetch_desc(&tmB1);
+  if (warp == 0 && lane == 0 && !kGrouped) {
+    tma_prefetch_desc(tmA0);
+    tma_prefetch_desc(tmB0);
+    if (kTmaEpi) tma_prefetch_desc(tmC);
+    if (nparts > 1) {
+      tma_prefetch_desc(tmA1);
+      tma_prefetch_desc(tmB1);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -178,9 +252,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = first_tile; t < p.num_tiles; t += tile_step) {
-        const Tile tl = decode_tile<CG>(p, t);
-        const int iters = tl.nkb * p.nparts;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        const Work wk = get_work<CG, kGrouped>(t, p, tmA0, tmA1, tmB0, tmB1, tmC, gm, gp);
+        const Tile tl = wk.tl;
+        const int iters = tl.nkb * nparts;
         // this CTA's slice of the cluster tile: its own 128 rows of A, its share of the B rows
         const int a_row = tl.m0 + static_cast<int>(cta_rank) * BM;
         const int b_row = tl.n0 + static_cast<int>(cta_rank) * kRowsB;
@@ -188,8 +263,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int part = it / tl.nkb;
           const int kb = tl.kb0 + it - part * tl.nkb;
           // part 0: hi*hi, part 1: hi*lo, part 2: lo*hi
-          const CUtensorMap* ma = (part == 2) ? &tmA1 : &tmA0;
-          const CUtensorMap* mb = (part == 1) ? &tmB1 : &tmB0;
+          const CUtensorMap* ma = (part == 2) ? wk.a1 : wk.a0;
+          const CUtensorMap* mb = (part == 1) ? wk.b1 : wk.b0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           if (CG == 2) {
@@ -218,9 +293,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = first_tile; t < p.num_tiles; t += tile_step) {
-        const Tile tl = decode_tile<CG>(p, t);
-        const int iters = tl.nkb * p.nparts;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        const Tile tl = get_work<CG, kGrouped>(t, p, tmA0, tmA1, tmB0, tmB1, tmC, gm, gp).tl;
+        const int iters = tl.nkb * nparts;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -261,15 +336,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // ------------------------------------------------------------------ epilogue
     const int q = warp - kEpiWarp0;  // TMEM lane quadrant == warp % 4
     float* stg = reinterpret_cast<float*>(smem_epi + q * kEpiStageBytes);
-    const bool syrk = (p.flags & kSyrkLower) != 0;
-    const bool mirror = (p.flags & kMirror) != 0;
-    const bool relu = (p.flags & kRelu) != 0;
+    const bool syrk = (flags & kSyrkLower) != 0;
+    const bool mirror = (flags & kMirror) != 0;
+    const bool relu = (flags & kRelu) != 0;
     const bool use_beta = p.beta != 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
-    for (int t = first_tile; t < p.num_tiles; t += tile_step) {
-      const Tile tl = decode_tile<CG>(p, t);
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const Work wk = get_work<CG, kGrouped>(t, p, tmA0, tmA1, tmB0, tmB1, tmC, gm, gp);
+      const Tile tl = wk.tl;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       // first row of this warp's 32-row band (the peer CTA of a pair holds rows 128..255)
@@ -297,10 +373,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
         // band entirely outside the matrix, or (SYRK) entirely above the diagonal: nothing to do
-        if (r0 >= p.M || c0 >= p.N) continue;
+        if (r0 >= wk.M || c0 >= wk.N) continue;
         if (syrk && c0 > r0 + 31) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+        for (int j = 0; j < 32; ++j) v[j] *= wk.alpha;
 
         if (kTmaEpi) {
           // ---- accumulate through the TMA: C[tile] += alpha*acc as an L2-side reduction.  The warp
@@ -335,8 +411,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_reduce_add_3d(&tmC, sd, c0, r0, tl.b * p.c_bmul);
-            if (do_mirror) tma_reduce_add_3d(&tmC, sm, r0, c0, tl.b * p.c_bmul);
+            tma_reduce_add_3d(wk.c, sd, c0, r0, tl.b * p.c_bmul);
+            if (do_mirror) tma_reduce_add_3d(wk.c, sm, r0, c0, tl.b * p.c_bmul);
             tma_store_commit();
           }
           continue;
@@ -432,6 +508,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+template <int CG, bool kTmaEpi>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmC, const KParams p) {
+  gemm_body<CG, kTmaEpi, false>(&tmA0, &tmA1, &tmB0, &tmB1, &tmC, p, nullptr, nullptr);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+umma_syrk_grouped_kernel(const __grid_constant__ GroupMaps maps,
+                         const __grid_constant__ GroupParams gp) {
+  KParams p{};  // batch / bias / bf16-output fields unused by the grouped accumulate path
+  gemm_body<2, true, true>(nullptr, nullptr, nullptr, nullptr, nullptr, p, &maps, &gp);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -605,6 +696,75 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts,
+                             cudaStream_t stream) {
+  if (count <= 0) return 0;
+  if (count > kMaxGroup || (nparts != 1 && nparts != 3)) return -2;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(umma_syrk_grouped_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(Cfg<2>::kSmemBytes));
+  });
+  if (attr_err != cudaSuccess) return -5;
+  GroupMaps maps;
+  GroupParams gp{};
+  gp.count = count;
+  gp.nparts = nparts;
+  int total = 0;
+  for (int g = 0; g < count; ++g) {
+    const SyrkGroupItem& it = items[g];
+    if (it.X_hi == nullptr || it.C == nullptr || it.d <= 0 || it.n <= 0) return -2;
+    if (nparts == 3 && it.X_lo == nullptr) return -2;
+    if ((it.ldc % 4) != 0 || (reinterpret_cast<uintptr_t>(it.C) & 15) != 0) return -2;
+    if (it.beta != 0.f && it.beta != 1.f) return -2;
+    int rc = make_operand_map(&maps.a0[g], it.X_hi, it.d, it.n, it.ldx, 0, 1, BM);
+    if (rc) return rc;
+    if (nparts == 3) {
+      rc = make_operand_map(&maps.a1[g], it.X_lo, it.d, it.n, it.ldx, 0, 1, BM);
+      if (rc) return rc;
+    } else {
+      maps.a1[g] = maps.a0[g];
+    }
+    rc = make_output_map(&maps.c[g], it.C, it.d, it.d, it.ldc, 0, 1);
+    if (rc) return rc;
+    if (it.beta == 0.f &&
+        cudaMemset2DAsync(it.C, static_cast<size_t>(it.ldc) * 4, 0, static_cast<size_t>(it.d) * 4,
+                          static_cast<size_t>(it.d), stream) != cudaSuccess)
+      return -5;
+    const int tm = (it.d + 255) / 256;
+    gp.tile_begin[g] = total;
+    total += tm * (tm + 1) / 2;
+    gp.M[g] = it.d;
+    gp.K[g] = it.n;
+    gp.alpha[g] = it.alpha;
+  }
+  for (int g = count; g <= kMaxGroup; ++g) gp.tile_begin[g] = total;
+  for (int g = count; g < kMaxGroup; ++g) {
+    maps.a0[g] = maps.a0[0];
+    maps.a1[g] = maps.a1[0];
+    maps.c[g] = maps.c[0];
+  }
+  const int clusters_max = sm_count() / 2;
+  const int clusters = total < clusters_max ? total : clusters_max;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, umma_syrk_grouped_kernel, maps, gp);
+  note_launch();
+  return (err == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -5;
+}
 
 // cta_group override for bring-up / A-B timing: 0 = automatic, 1 or 2 = forced; +16 disables the
 // TMA-reduce epilogue (register read-modify-write epilogue everywhere).

@@ -48,6 +48,20 @@ struct GemmArgs {
 
 // Returns 0 on success, negative on argument / CUDA error (see include/bk_kfac.h error codes).
 int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream);
+// One problem of a grouped factor update: C (+)= alpha * X^T X with X^T staged K-major bf16 [d, n]
+// (row pitch ldx), C fp32 [d, d] with a 16 B aligned base and pitch (ldc % 4 == 0), beta in {0, 1}.
+struct SyrkGroupItem {
+  const __nv_bfloat16* X_hi = nullptr;
+  const __nv_bfloat16* X_lo = nullptr;  // bf16x3 only
+  long long ldx = 0;
+  int d = 0, n = 0;
+  float alpha = 1.f, beta = 1.f;
+  float* C = nullptr;
+  long long ldc = 0;
+};
+// Up to 8 problems in one persistent CTA-pair launch (see bk_umma_gemm.cu).
+int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, cudaStream_t stream);
+
 // Tuning / bring-up knob: force the tcgen05 cta_group of the contraction core (1 or 2; 0 = automatic).
 void set_umma_cta_group(int cg);
 

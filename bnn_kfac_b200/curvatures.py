@@ -285,6 +285,7 @@ class KFAC(Curvature):
         super().__init__(model, layer_types, precision=precision, seed=seed)
         self.hooks = list()
         self.record = dict()
+        self._pending = []
         self._staged = dict()  # layer -> bf16 K-major copies of (L_A, L_G) for the tensor-core GEMMs
 
         for layer in model.modules():
@@ -307,19 +308,38 @@ class KFAC(Curvature):
     # ------------------------------------------------------------------ factor update
     def _syrk(self, state: Tensor, beta: float, x: Tensor, has_bias: bool, in_scale: float,
               alpha: float):
-        n, d = x.shape
+        """Queue state = beta*state + alpha*[in_scale*x ; 1]^T[...]; issued by _flush_syrks()."""
+        self._pending.append((state, beta, x, has_bias, in_scale, alpha))
+
+    def _flush_syrks(self):
+        """All queued factor updates of this update() in ONE grouped library call: the wide factors
+        share one persistent tensor-core launch (bk_syrk_accum_grouped)."""
+        items, self._pending = self._pending, []
+        n = len(items)
+        if n == 0:
+            return
         prec = _PRECISIONS[self.precision]
-        nbytes = self._lib.bk_syrk_workspace_bytes(n, d, int(has_bias), prec)
-        ws = self._ws.get(nbytes, x.device)
-        _lib.check(self._lib.bk_syrk_accum(state.data_ptr(), state.stride(0), x.data_ptr(),
-                                           x.stride(0), n, d, int(has_bias), in_scale, alpha, beta,
-                                           prec, ws.data_ptr(), nbytes, _lib.stream_ptr()),
-                   "bk_syrk_accum")
+        ns = (C.c_int * n)(*[it[2].shape[0] for it in items])
+        ds = (C.c_int * n)(*[it[2].shape[1] for it in items])
+        hb = (C.c_int * n)(*[int(it[3]) for it in items])
+        nbytes = self._lib.bk_syrk_grouped_workspace_bytes(ns, ds, hb, n, prec)
+        ws = self._ws.get(nbytes, items[0][2].device)
+        states = (C.c_void_p * n)(*[it[0].data_ptr() for it in items])
+        lds = (C.c_longlong * n)(*[it[0].stride(0) for it in items])
+        xs = (C.c_void_p * n)(*[it[2].data_ptr() for it in items])
+        ldx = (C.c_longlong * n)(*[it[2].stride(0) for it in items])
+        insc = (C.c_float * n)(*[it[4] for it in items])
+        alph = (C.c_float * n)(*[it[5] for it in items])
+        beta = (C.c_float * n)(*[it[1] for it in items])
+        _lib.check(self._lib.bk_syrk_accum_grouped(states, lds, xs, ldx, ns, ds, hb, insc, alph, beta, n, prec,
+                                                   ws.data_ptr(), nbytes, _lib.stream_ptr()),
+                   "bk_syrk_accum_grouped")
 
     def update(self, batch_size: int = None):
         """Accumulates A = [a;1][a;1]^T / cols and G = g g^T / cols per selected layer, with
         g = grad_output * N (curvatures.py:325-365).  `batch_size` is ignored, as in the reference."""
         del batch_size
+        self._pending = []
         for _, layer in self._selected_layers():
             module_class = layer.__class__.__name__
             forward, backward = self.record[layer]
@@ -352,6 +372,7 @@ class KFAC(Curvature):
                 g = backward.float().contiguous()
                 self._syrk(first, beta, x, has_bias, 1.0, 1.0 / x.shape[0])
                 self._syrk(second, beta, g, False, float(n_batch), 1.0 / g.shape[0])
+        self._flush_syrks()
 
     def _update_conv(self, layer, forward, backward, first, second, beta, has_bias, n_batch):
         st = _lib.stream_ptr()

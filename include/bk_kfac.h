@@ -102,6 +102,24 @@ size_t bk_syrk_workspace_bytes(int n, int d, int has_bias, int precision);
 int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
                   int has_bias, float in_scale, float alpha, float beta, int precision,
                   void* workspace, size_t workspace_bytes, void* stream);
+/* All factors of one KFAC.update in one call (host arrays of `count` entries, same meaning as the
+ * bk_syrk_accum arguments).  Wide factors with a 16 B aligned state (base and pitch) and input are
+ * staged and then accumulated by ONE persistent tensor-core launch over all of them, so wave
+ * quantisation and the pipeline fill / drain are paid once per update, not once per factor; the
+ * others take the bk_syrk_accum route one by one. */
+size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* has_bias, int count,
+                                       int precision);
+int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const float* const* xs,
+                          const long long* ldxs, const int* ns, const int* ds, const int* has_bias,
+                          const float* in_scales, const float* alphas, const float* betas, int count,
+                          int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* The grouped tensor-core launch alone, on operands already staged as K-major bf16 [d, n] (no bias
+ * row): up to 8 problems, states 16 B aligned with ld % 4 == 0, beta in {0, 1}. */
+int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_states,
+                                 const void* const* xt_his, const void* const* xt_los,
+                                 const long long* ldts, const int* ns, const int* ds,
+                                 const float* alphas, const float* betas, int count, int precision,
+                                 void* stream);
 /* Same, operand already staged as K-major bf16 [d+has_bias, n] (e.g. by bk_transpose_split). */
 int bk_syrk_accum_staged(float* state, long long ld_state, const void* xt_hi, const void* xt_lo,
                          long long ldt, int n, int dprime, float alpha, float beta, int precision,
