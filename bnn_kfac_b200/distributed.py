@@ -78,6 +78,17 @@ def _flat_views(tensors: Sequence[Tensor]) -> Tuple[Tensor, List[Tensor]]:
     return flat, views
 
 
+def _dense_view(t: Tensor) -> Tensor:
+    """Collectives need contiguous tensors.  Wide factors are [d, d] views of 16-byte pitched
+    [d, pitch] buffers (curvatures._alloc_factor): return the whole pitched buffer (the padding columns
+    are never read, so reducing them too is harmless)."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return torch.as_strided(t, (t.shape[0], t.stride(0)), (t.stride(0), 1))
+    raise ValueError("factor tensors must be row-major (optionally pitched) for the collectives")
+
+
 def allreduce_state(est, group=None, average: bool = True) -> None:
     """In-place all-reduce of an estimator's accumulated `state` (KFAC: [A, G] per layer; Diagonal:
     one tensor per layer).  average=True divides by the world size (global-batch mean, see module
@@ -90,6 +101,7 @@ def allreduce_state(est, group=None, average: bool = True) -> None:
         tensors += list(v) if isinstance(v, (list, tuple)) else [v]
     if not tensors:
         return
+    tensors = [_dense_view(t) for t in tensors]
     small = [t for t in tensors if t.numel() * t.element_size() < (1 << 20)]
     large = [t for t in tensors if t.numel() * t.element_size() >= (1 << 20)]
     works = []
@@ -168,7 +180,7 @@ def invert_sharded(est, add=0., multiply=1., group=None,
         reduced = factors
     else:
         # reduce into scratch copies so that the local partial `state` stays a valid accumulator
-        reduced = [f.clone() for f in factors]
+        reduced = [f.clone(memory_format=torch.contiguous_format) for f in factors]
         reduce_to_owners(reduced, owners, group)
     mine = [i for i, o in enumerate(owners) if o == me]
     outs: List[Optional[Tensor]] = [None] * len(factors)

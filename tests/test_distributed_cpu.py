@@ -71,8 +71,13 @@ def _worker(rank, world, port, tmp):
                     sum(_spd(b, 100 + 10 * i + r) for r in range(world)) / world]
                 for i, (l, (a, b)) in enumerate(zip(layers, dims))}
 
-        # 1) deferred all-reduce of the state == mean over ranks
+        # 1) deferred all-reduce of the state == mean over ranks (one factor is a 16-byte pitched view,
+        #    as curvatures._alloc_factor hands out for wide odd-sized factors)
         est = _FakeEst({l: [t.clone() for t in v] for l, v in part.items()})
+        pitched = torch.full((6, 8), float("nan"), dtype=torch.float64)[:, :6]
+        pitched.copy_(est.state[layers[0]][0])
+        est.state[layers[0]][0] = pitched
+        assert not pitched.is_contiguous()
         D.allreduce_state(est)
         for l in layers:
             for k in range(2):
