@@ -20,8 +20,9 @@ four Linear layers (A 4097^2 x4, G 4096^2 x3 + 10^2), accumulated into the runni
   cpu_baseline : oracle/ (CPU restatement of the reference's update) on a bounded sample, rank 0 only
 
 Multi-GPU: the batch axis shards (each rank owns its own 4096-sample batches, weak scaling); the
-factors are plain sums (curvatures.py:359-361), so the only exchange is ONE all-reduce of the factor
-states after the K accumulation steps (it is what `invert()` needs); it is inside the timed region.
+factors are plain sums (curvatures.py:359-361), so the only exchange is ONE reduction of the factor
+states after the K accumulation steps (what `distributed.invert_sharded` needs); it is inside the
+timed region.
 """
 from __future__ import annotations
 
@@ -208,7 +209,7 @@ def main():
 
     from bnn_kfac_b200 import _lib
     from bnn_kfac_b200.curvatures import KFAC
-    from bnn_kfac_b200.distributed import allreduce_state
+    from bnn_kfac_b200.distributed import reduce_state_copy
     from bnn_kfac_b200.wrapper import MLP
     L = _lib.load()
     _lib.require_device()
@@ -259,9 +260,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    reduce_after = (lambda: allreduce_state(est)) if world > 1 else None
+    # the exchange invert_sharded() performs: one all-reduce of (copies of) the accumulated factors
+    reduce_after = (lambda: reduce_state_copy(est)) if world > 1 else None
     for _ in range(args.warmup):
         step_device(resident)
+    if reduce_after is not None:
+        reduce_after()          # warm the NCCL channels: the timed region holds exactly one reduction
     with ClockSampler(local_rank) as clocks:
         ms_dev = timed(lambda: step_device(resident), args.steps, reduce_after)
     for _ in range(args.warmup):
@@ -332,6 +336,18 @@ def main():
         except Exception:
             pass
 
+    reduce_ms = None
+    if world > 1:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reduce_state_copy(est)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reduce_ms = t.item()
+
     line = {"metric": "kfac_factor_update_samples_per_s", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -344,6 +360,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": checksum_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": None, "roofline": roofline, "clocks": clocks.summary()}
+    if reduce_ms is not None:
+        state_bytes = sum(t.numel() * 4 for l in layers for t in est.state[l])
+        line["factor_allreduce"] = {
+            "ms": reduce_ms, "bytes": state_bytes, "algbw_GBps": state_bytes / (reduce_ms * 1e-3) / 1e9,
+            "note": "one per timed region (deferred: state is a plain sum of batch means); local copy + NCCL "
+                    "all-reduce of every factor"}
 
     # kernels launched by this library inside the device-timed region (counted by the library itself)
     c0 = L.bk_launch_count()
