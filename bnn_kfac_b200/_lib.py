@@ -75,6 +75,7 @@ SIGNATURES = {
     "bk_eigh_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
     "bk_eigh_batched": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
                              _i, _f, _i, _p, _sz, _p]),
+    "bk_ger_accum": (_i, [_p, _ll, _p, _i, _f, _f, _p]),
     "bk_kron": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "bk_dominance": (_i, [_p, _ll, _i, _f, _p, _p, _i, _p, _p]),
     "bk_chol_inv_workspace_bytes": (_sz, [C.POINTER(_i), _i]),

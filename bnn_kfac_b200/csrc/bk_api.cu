@@ -384,6 +384,12 @@ int bk_dominance(const float* h, long long ld, int p, float tau, const int* bloc
                               as_stream(stream));
 }
 
+int bk_ger_accum(float* state, long long ld, const float* g, int p, float alpha, float beta,
+                 void* stream) {
+  if (state == nullptr || g == nullptr || ld < p) return BK_ERR_ARG;
+  return bk::launch_ger_accum(state, ld, g, p, alpha, beta, as_stream(stream));
+}
+
 int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream) {
   if (a == nullptr || b == nullptr || out == nullptr) return BK_ERR_ARG;
   return bk::launch_kron(a, m, n, b, p, q, out, as_stream(stream));

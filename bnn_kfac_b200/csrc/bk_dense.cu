@@ -80,7 +80,31 @@ __global__ void kron_kernel(const float* __restrict__ a, int m, int n, const flo
   }
 }
 
+// state[i][j] = beta*state[i][j] + alpha*g[i]*g[j]   (BlockDiagonal.update: torch.ger(grads, grads) *
+// batch_size accumulated with +=, models/curvatures.py:228-232).  One pass, float4 rows when aligned.
+__global__ void __launch_bounds__(256)
+ger_accum_kernel(float* __restrict__ state, long long ld, const float* __restrict__ g, int P,
+                 float alpha, float beta) {
+  for (int i = blockIdx.x; i < P; i += gridDim.x) {
+    const float gi = alpha * g[i];
+    float* row = state + static_cast<long long>(i) * ld;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+      const float old = (beta == 0.f) ? 0.f : beta * row[j];
+      row[j] = fmaf(gi, g[j], old);
+    }
+  }
+}
+
 }  // namespace
+
+int launch_ger_accum(float* state, long long ld, const float* g, int P, float alpha, float beta,
+                     cudaStream_t stream) {
+  if (P <= 0) return 0;
+  const int grid = P < kNumSMsB200 * 8 ? P : kNumSMsB200 * 8;
+  ger_accum_kernel<<<grid, 256, 0, stream>>>(state, ld, g, P, alpha, beta);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
 
 int launch_kron(const float* a, int m, int n, const float* b, int p, int q, float* out,
                 cudaStream_t stream) {

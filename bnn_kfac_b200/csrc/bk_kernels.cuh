@@ -69,6 +69,8 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
 int launch_dominance(const float* H, long long ld, int P, float tau, const int* block_begin,
                      const int* block_end, int nblocks, double* out3, cudaStream_t stream);
 
+int launch_ger_accum(float* state, long long ld, const float* g, int P, float alpha, float beta,
+                     cudaStream_t stream);
 int launch_kron(const float* a, int m, int n, const float* b, int p, int q, float* out,
                 cudaStream_t stream);
 

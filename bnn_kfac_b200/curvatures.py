@@ -537,3 +537,225 @@ def invert_factors(factors: List[Tensor], adds: List[float], mults: List[float],
         raise RuntimeError(f"factor {rc - 1} (d={fs[rc - 1].shape[0]}) is not positive definite after "
                            f"damping (add={adds[rc - 1]}, multiply={mults[rc - 1]})")
     return outs
+
+
+# ---------------------------------------------------------------------------------------------------
+def _layer_grads(layer: Module) -> Tensor:
+    """[d_out, d_in(+1)]: weight.grad viewed [d_out, -1] with the bias gradient as last column."""
+    g = layer.weight.grad.contiguous().view(layer.weight.grad.shape[0], -1).float()
+    if layer.bias is not None:
+        g = torch.cat([g, layer.bias.grad.float().unsqueeze(1)], dim=1)
+    return g.contiguous()
+
+
+class BlockDiagonal(Curvature):
+    """Per-layer full Fisher.  Reference: models/curvatures.py:210-275.
+
+        update   state[layer] += ger(g, g) * batch_size,  g = [W.grad.view(-1), b.grad]      (:224-232)
+        invert   inv_state[layer] = pinverse(multiply * state + add * I)                      (:258-268)
+        sample   x = z @ inv_state[layer], reshaped to [d_out, d_in(+1)]                       (:270-275)
+
+    `multiply*state + add*I` is symmetric positive definite for add > 0, so the pseudo-inverse is the
+    inverse and comes from the batched Cholesky kernels (L L^T).  For add == 0 (rank-deficient sums of
+    outer products) the pseudo-inverse is built from the Jacobi eigendecomposition; singular values
+    below d * eps32 * max are dropped (torch.pinverse's rcond = 1e-15 presumes fp64 data)."""
+
+    def update(self, batch_size: int):
+        st = _lib.stream_ptr()
+        for _, layer in self._selected_layers():
+            g = layer.weight.grad.contiguous().view(-1).float()
+            if layer.bias is not None:
+                g = torch.cat([g, layer.bias.grad.float()])
+            g = g.contiguous()
+            P = g.numel()
+            if layer in self.state:
+                state, beta = self.state[layer], 1.0
+            else:
+                state, beta = _alloc_factor(P, g.device), 0.0
+                self.state[layer] = state
+            _lib.check(self._lib.bk_ger_accum(state.data_ptr(), state.stride(0), g.data_ptr(), P,
+                                              float(batch_size), beta, st), "bk_ger_accum")
+
+    def invert(self, add: Union[float, list, tuple] = 0., multiply: Union[float, list, tuple] = 1.):
+        from .predictive import inverse_from_chol
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        for index, (layer, value) in enumerate(self.state.items()):
+            if not isinstance(add, float) and not isinstance(multiply, float):
+                assert len(add) == len(multiply) == len(self.state)
+                n, s = add[index], multiply[index]
+            else:
+                n, s = add, multiply
+            if n > 0:
+                (Lc,) = invert_factors([value], [float(n) ** 2], [float(s) ** 2], self._ws)
+                self.inv_state[layer] = inverse_from_chol(Lc)
+            else:
+                self.inv_state[layer] = _pinv_eigh(value, float(s))
+        self._staged = dict()
+
+    def _staged_inverse(self, layer):
+        if not hasattr(self, "_staged"):
+            self._staged = dict()
+        if layer not in self._staged:
+            self._staged[layer] = stage_operand(self.inv_state[layer])
+        return self._staged[layer]
+
+    def sample_batch(self, layer: Module, n_samples: int, z: Optional[Tensor] = None,
+                     sample0: Optional[int] = None) -> Tensor:
+        """[S, d_out, d_in(+1)] samples x_s = z_s @ inv (one batched tensor-core GEMM; inv is symmetric)."""
+        inv = self.inv_state[layer]
+        P = inv.shape[0]
+        dev = inv.device
+        lib = self._lib
+        if sample0 is None:
+            sample0 = self._sample_counter
+            self._sample_counter += n_samples
+        if z is None:
+            layer_id = [l for _, l in self._selected_layers()].index(layer)
+            zf = torch.empty(n_samples, P, device=dev, dtype=torch.float32)
+            # sample s = row 0 of the [1, P] matrix of Philox subsequence sample0 + s (shard-invariant)
+            _lib.check(lib.bk_philox_normal(self.seed, sample0, layer_id, 1, P, n_samples, zf.data_ptr(), P, P,
+                                            0, 0, 0, 0, _lib.stream_ptr()), "bk_philox_normal")
+        else:
+            zf = z.to(dev, torch.float32).reshape(n_samples, P).contiguous()
+        z_hi, z_lo, ldz = stage_operand(zf)
+        i_hi, i_lo, ldi = self._staged_inverse(layer)
+        prec = gemm_precision(self.precision)
+        x3 = prec == _lib.BK_PREC_BF16X3
+        out = torch.empty(n_samples, P, device=dev, dtype=torch.float32)
+        _lib.check(lib.bk_gemm_nt(z_hi.data_ptr(), z_lo.data_ptr() if x3 else 0, ldz, 0,
+                                  i_hi.data_ptr(), i_lo.data_ptr() if x3 else 0, ldi, 0,
+                                  n_samples, P, P, 1, prec, 0, 1.0, 0.0, out.data_ptr(), P, 0, 0, 0, 0, 0, 0, 0,
+                                  _lib.stream_ptr()), "bk_gemm_nt(z inv)")
+        d_out = layer.weight.shape[0]
+        nw = layer.weight.numel()
+        w = out[:, :nw].reshape(n_samples, d_out, -1)
+        if layer.bias is None:
+            return w
+        return torch.cat([w, out[:, nw:].unsqueeze(2)], dim=2)
+
+    def sample(self, layer: Module, z: Optional[Tensor] = None) -> Tensor:
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        return self.sample_batch(layer, 1, z=None if z is None else z.reshape(1, -1))[0]
+
+
+def _pinv_eigh(value: Tensor, s: float) -> Tensor:
+    """pinverse(s * value) for a symmetric PSD matrix through the Jacobi eigensolver:
+    V diag(1 / w_i for w_i > 1e-15 * w_max) V^T (torch.pinverse's default rcond)."""
+    from .utilities import eigh_factors
+    lib = _lib.load()
+    (w,), (v,) = eigh_factors([value], sym_scale=0.5 * s)
+    # torch.pinverse's rcond is 1e-15, meaningful for the reference's fp64 runs; in fp32 arithmetic
+    # eigenvalues below d * eps32 * w_max are rounding noise of the (rank-deficient) sum of outer
+    # products and are dropped
+    cut = max(1e-15, value.shape[0] * 1.2e-7) * w.abs().max()
+    winv = torch.where(w.abs() > cut, 1.0 / w, torch.zeros_like(w))
+    # (V * winv) V^T as one contraction: A = V * winv (columns scaled), B = V
+    a = (v * winv.unsqueeze(0)).contiguous()
+    a_hi, a_lo, lda = stage_operand(a)
+    b_hi, b_lo, ldb = stage_operand(v)
+    d = v.shape[0]
+    out = torch.empty(d, d, device=v.device, dtype=torch.float32)
+    _lib.check(lib.bk_gemm_nt(a_hi.data_ptr(), a_lo.data_ptr(), lda, 0, b_hi.data_ptr(), b_lo.data_ptr(), ldb, 0,
+                              d, d, d, 1, _lib.BK_PREC_BF16X3, 0, 1.0, 0.0, out.data_ptr(), d, 0, 0, 0, 0, 0, 0, 0,
+                              _lib.stream_ptr()), "bk_gemm_nt(V w^-1 V^T)")
+    return out
+
+
+class EFB(Curvature):
+    """Eigenvalue-corrected Kronecker-factored Fisher.  Reference: models/curvatures.py:408-473 (which
+    no longer runs: get_eigenvectors calls the removed torch.symeig).
+
+        __init__  eigvecs[layer] = (U_A, U_G) = eigenvectors of (A + A^T, G + G^T)             (:423-424)
+        update    state[layer] += (U_G^T g U_A)^2 ;  diags[layer] += g^2 * batch_size          (:438-446)
+        invert    inv_state[layer] = 1 / sqrt(multiply * state + add)                           (:462-463)
+        sample    z ~ N(0,1)[d_in', d_out];  z *= inv_state^T;  (U_A z U_G^T)^T -> [d_out, d_in'] (:467-473)
+    """
+
+    def __init__(self, model, factors: Dict[Module, Any], layer_types=None, *, precision: str = "bf16x3",
+                 seed: int = 0):
+        from .utilities import get_eigenvectors
+        super().__init__(model, layer_types, precision=precision, seed=seed)
+        self.eigvecs = get_eigenvectors(factors)
+        self.diags: Dict[Any, Tensor] = dict()
+        self._staged = dict()
+
+    def _staged_eigvecs(self, layer):
+        """bf16 operands: U_A [d_in', d_in'] and U_G^T [d_out, d_out] (row-major, K contiguous)."""
+        if layer not in self._staged:
+            ua, ug = self.eigvecs[layer]
+            self._staged[layer] = {"UA": stage_operand(ua), "UAT": stage_operand(ua.t().contiguous()),
+                                   "UG": stage_operand(ug), "UGT": stage_operand(ug.t().contiguous())}
+        return self._staged[layer]
+
+    def _sandwich(self, left, mid: Tensor, right, rows: int, cols: int) -> Tensor:
+        """left[rows, rows] @ mid[rows, cols] @ right[cols, cols]^T with staged bf16x3 operands:
+        P^T = right mid^T (K = cols), out = left P (K = rows)."""
+        lib = self._lib
+        dev = mid.device
+        m_hi, m_lo, ldm = stage_operand(mid)                    # [rows, cols]
+        ldp = _round8(rows)
+        p_hi = torch.zeros(cols, ldp, dtype=torch.bfloat16, device=dev)
+        p_lo = torch.zeros_like(p_hi)
+        r_hi, r_lo, ldr = right
+        # P^T[j, o] = sum_i right[j, i] mid[o, i]
+        _lib.check(lib.bk_gemm_nt(r_hi.data_ptr(), r_lo.data_ptr(), ldr, 0, m_hi.data_ptr(), m_lo.data_ptr(), ldm, 0,
+                                  cols, rows, cols, 1, _lib.BK_PREC_BF16X3, 0, 1.0, 0.0, 0, 0, 0, 0, 0,
+                                  p_hi.data_ptr(), p_lo.data_ptr(), ldp, 0, _lib.stream_ptr()), "bk_gemm_nt(R M^T)")
+        l_hi, l_lo, ldl = left
+        out = torch.empty(rows, cols, device=dev, dtype=torch.float32)
+        # out[p, j] = sum_o left[p, o] P^T[j, o]
+        _lib.check(lib.bk_gemm_nt(l_hi.data_ptr(), l_lo.data_ptr(), ldl, 0, p_hi.data_ptr(), p_lo.data_ptr(), ldp, 0,
+                                  rows, cols, rows, 1, _lib.BK_PREC_BF16X3, 0, 1.0, 0.0, out.data_ptr(), cols, 0,
+                                  0, 0, 0, 0, 0, 0, _lib.stream_ptr()), "bk_gemm_nt(L P)")
+        return out
+
+    def update(self, batch_size: int):
+        st = _lib.stream_ptr()
+        for _, layer in self._selected_layers():
+            g = _layer_grads(layer)                               # [d_out, d_in']
+            d_out, d_inp = g.shape
+            ops = self._staged_eigvecs(layer)
+            # U_G^T g U_A = UGT @ g @ (UAT)^T
+            proj = self._sandwich(ops["UGT"], g, ops["UAT"], d_out, d_inp)
+            if layer in self.state:
+                state, diag, beta = self.state[layer], self.diags[layer], 1.0
+            else:
+                state = torch.empty(d_out, d_inp, device=g.device, dtype=torch.float32)
+                diag = torch.empty_like(state)
+                self.state[layer], self.diags[layer], beta = state, diag, 0.0
+            _lib.check(self._lib.bk_diag_accum(state.data_ptr(), proj.data_ptr(), 0, d_out, d_inp, 1.0, beta, st),
+                       "bk_diag_accum(lambdas)")
+            _lib.check(self._lib.bk_diag_accum(diag.data_ptr(), g.data_ptr(), 0, d_out, d_inp, float(batch_size),
+                                               beta, st), "bk_diag_accum(diags)")
+
+    def invert(self, add: Union[float, list, tuple] = 0., multiply: Union[float, list, tuple] = 1.):
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        st = _lib.stream_ptr()
+        for index, (layer, value) in enumerate(self.state.items()):
+            if not isinstance(add, float) and not isinstance(multiply, float):
+                assert len(add) == len(multiply) == len(self.state)
+                n, s = add[index], multiply[index]
+            else:
+                n, s = add, multiply
+            inv = torch.empty_like(value)
+            _lib.check(self._lib.bk_diag_invert(inv.data_ptr(), value.data_ptr(), value.numel(), float(n), float(s),
+                                                st), "bk_diag_invert")
+            self.inv_state[layer] = inv
+
+    def sample(self, layer: Module, z: Optional[Tensor] = None) -> Tensor:
+        """(U_A (z * inv_state^T) U_G^T)^T = U_G (z^T * inv_state) U_A^T -> [d_out, d_in'].
+        `z` ([d_in', d_out], the reference's orientation) replaces the Philox draw."""
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        inv = self.inv_state[layer]
+        d_out, d_inp = inv.shape
+        zt = None
+        if z is not None:
+            zt = z.to(inv.device, torch.float32).t().contiguous()
+            assert zt.shape == inv.shape
+        scaled = torch.empty_like(inv)
+        layer_id = [l for _, l in self._selected_layers()].index(layer)
+        _lib.check(self._lib.bk_diag_sample(scaled.data_ptr(), inv.data_ptr(), inv.numel(), 1, self.seed,
+                                            self._next_sample_id(), layer_id, _lib.ptr(zt), _lib.stream_ptr()),
+                   "bk_diag_sample")
+        ops = self._staged_eigvecs(layer)
+        return self._sandwich(ops["UG"], scaled, ops["UA"], d_out, d_inp)

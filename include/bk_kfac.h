@@ -187,6 +187,10 @@ int bk_eigh_batched(const float* const* factors_host, const long long* ld_host,
  */
 int bk_dominance(const float* h, long long ld, int p, float tau, const int* block_begin,
                  const int* block_end, int nblocks, double* out3, void* stream);
+/* Rank-1 accumulation state = beta*state + alpha * g g^T, state [p, p] fp32 (row pitch ld), g [p]:
+ * BlockDiagonal.update (models/curvatures.py:228-232, `torch.ger(grads, grads) * batch_size`, `+=`). */
+int bk_ger_accum(float* state, long long ld, const float* g, int p, float alpha, float beta,
+                 void* stream);
 /* Kronecker product out[m*p, n*q] = a[m, n] (x) b[p, q], all contiguous fp32
  * (models/utilities.py:387-409, sampling_free/utils.py:279-290). */
 int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream);

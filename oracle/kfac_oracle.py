@@ -469,3 +469,55 @@ def philox_normal(seed: int, sample: int, stream_id: int, count: int) -> np.ndar
         out[:, o] = rad * np.cos(2.0 * math.pi * u2)
         out[:, o + 1] = rad * np.sin(2.0 * math.pi * u2)
     return out.reshape(-1)[:count]
+
+
+# =============================================================================== BlockDiagonal / EFB
+def layer_grad_matrix(layer: torch.nn.Module) -> Tensor:
+    """[d_out, d_in(+1)]: weight.grad viewed [d_out, -1] with bias.grad as last column.
+    models/curvatures.py:436-438 (EFB.update)."""
+    g = layer.weight.grad.contiguous().view(layer.weight.grad.shape[0], -1)
+    if layer.bias is not None:
+        g = torch.cat([g, layer.bias.grad.unsqueeze(dim=1)], dim=1)
+    return g
+
+
+def blockdiag_update(state: Optional[Tensor], layer: torch.nn.Module, batch_size: int) -> Tensor:
+    """state (+)= ger(g, g) * batch_size with g = [W.grad.view(-1), b.grad].  models/curvatures.py:224-232."""
+    g = layer.weight.grad.contiguous().view(-1)
+    if layer.bias is not None:
+        g = torch.cat([g, layer.bias.grad])
+    upd = torch.outer(g, g) * batch_size
+    return upd if state is None else state + upd
+
+
+def blockdiag_invert(state: Tensor, add: float, multiply: float) -> Tensor:
+    """pinverse(multiply * state + add * I).  models/curvatures.py:266-268."""
+    reg = torch.diag(state.new_full((state.shape[0],), add))
+    return torch.pinverse(multiply * state + reg)
+
+
+def blockdiag_sample(inv: Tensor, layer: torch.nn.Module, z: Tensor) -> Tensor:
+    """x = z @ inv reshaped to [d_out, d_in(+1)].  models/curvatures.py:272-275."""
+    x = z @ inv
+    return torch.cat([x[:layer.weight.numel()].contiguous().view(*layer.weight.shape),
+                      torch.unsqueeze(x[layer.weight.numel():], dim=1)], dim=1)
+
+
+def efb_update(state: Optional[Tensor], diags: Optional[Tensor], layer: torch.nn.Module,
+               eigvecs: Tuple[Tensor, Tensor], batch_size: int) -> Tuple[Tensor, Tensor]:
+    """lambdas = (U_G^T g U_A)^2 accumulated; diags += g^2 * batch_size.  models/curvatures.py:436-446."""
+    g = layer_grad_matrix(layer)
+    lambdas = (eigvecs[1].t() @ g @ eigvecs[0]) ** 2
+    d = g ** 2 * batch_size
+    return (lambdas, d) if state is None else (state + lambdas, diags + d)
+
+
+def efb_invert(state: Tensor, add: float, multiply: float) -> Tensor:
+    """reciprocal(multiply * state + add).sqrt().  models/curvatures.py:462-463."""
+    return torch.reciprocal(multiply * state + add).sqrt()
+
+
+def efb_sample(eigvecs: Tuple[Tensor, Tensor], inv: Tensor, z: Tensor) -> Tensor:
+    """(U_A (z * inv^T) U_G^T)^T with z [d_in', d_out].  models/curvatures.py:467-473."""
+    first, second = eigvecs
+    return (first @ (z * inv.t()) @ second.t()).t()

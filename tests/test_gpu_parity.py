@@ -571,3 +571,74 @@ def test_mc_forward_implicit_equals_materialised(dev):
     assert relerr(a[1].cpu(), a[0].cpu()) > 1e-3          # samples really differ
     c = torch.cat([mc_logits(est, xt, 2, sample0=3, implicit=True), mc_logits(est, xt, 3, sample0=5, implicit=True)])
     assert torch.equal(a, c)                               # shard invariance of the implicit path
+
+
+# ------------------------------------------------------------------ "next" rows: f2, f1
+@pytest.fixture(scope="module")
+def golden_next():
+    from conftest import ROOT
+    return dict(np.load(ROOT / "tests" / "golden" / "reference_golden_next.npz"))
+
+
+def test_blockdiagonal_vs_reference_golden(golden, golden_next, dev):
+    """models/curvatures.py:210-275 against outputs of the reference's own BlockDiagonal."""
+    from bnn_kfac_b200.curvatures import BlockDiagonal
+    model = load_params(MLP(), golden, "mlp", torch.float32).to(dev)
+    est = BlockDiagonal(model)
+    for i in range(2):
+        x = torch.tensor(golden[f"mlp_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"mlp_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        est.update(batch_size=x.shape[0])
+    est.invert(0.5, 10.0)
+    for li, layer in enumerate(_layers(est)):
+        assert relerr(est.state[layer].cpu(), golden_next[f"bd_state_{li}"]) < 1e-5
+        assert relerr(est.inv_state[layer].cpu(), golden_next[f"bd_inv_a_{li}"]) < TOL
+        z = torch.tensor(golden_next[f"bd_z_{li}"]).float().to(dev)
+        smp = est.sample(layer, z=z)
+        assert smp.shape == golden_next[f"bd_sample_{li}"].shape
+        assert relerr(smp.cpu(), golden_next[f"bd_sample_{li}"]) < TOL
+        s1 = est.sample(layer)
+        assert s1.shape == smp.shape and torch.isfinite(s1).all()
+    est.sample_and_replace()
+    # add == 0: rank-deficient sum of outer products -> pseudo-inverse through the eigensolver
+    est.invert(0.0, 1.0)
+    for li, layer in enumerate(_layers(est)):
+        assert relerr(est.inv_state[layer].cpu(), golden_next[f"bd_inv_pinv_{li}"]) < 5e-3
+
+
+def test_efb_vs_reference_golden(golden, golden_next, dev):
+    """models/curvatures.py:408-473 against the reference's EFB (run with a torch.symeig shim).
+    lambdas are squares of projections on the factor eigenbases: invariant to eigenvector signs, but a
+    degenerate eigenvalue leaves its basis free, so they are compared through per-eigenspace sums
+    (here: the total); the sampling arithmetic is compared exactly with the reference's eigenvectors."""
+    from bnn_kfac_b200.curvatures import EFB
+    model, kf = _gpu_kfac_mlp(golden, dev)
+    est = EFB(model, kf.state)
+    for i in range(2):
+        x = torch.tensor(golden[f"mlp_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"mlp_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        est.update(batch_size=x.shape[0])
+    est.invert(0.04, 200.0)
+    for li, layer in enumerate(_layers(est)):
+        assert relerr(est.diags[layer].cpu(), golden_next[f"efb_diags_{li}"]) < 1e-5
+        assert abs(est.state[layer].double().sum().item() / golden_next[f"efb_state_{li}"].sum() - 1) < TOL
+        assert est.inv_state[layer].shape == golden_next[f"efb_inv_{li}"].shape
+    # same eigenvectors as the reference -> identical lambdas, inverse and sample
+    est2 = EFB(model, kf.state)
+    for li, layer in enumerate(_layers(est2)):
+        est2.eigvecs[layer] = (torch.tensor(golden_next[f"efb_UA_{li}"]).float().to(dev),
+                               torch.tensor(golden_next[f"efb_UG_{li}"]).float().to(dev))
+    for i in range(2):
+        x = torch.tensor(golden[f"mlp_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"mlp_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        est2.update(batch_size=x.shape[0])
+    est2.invert(0.04, 200.0)
+    for li, layer in enumerate(_layers(est2)):
+        assert relerr(est2.state[layer].cpu(), golden_next[f"efb_state_{li}"]) < TOL
+        assert relerr(est2.inv_state[layer].cpu(), golden_next[f"efb_inv_{li}"]) < TOL
+        z = torch.tensor(golden_next[f"efb_z_{li}"]).float().to(dev)
+        assert relerr(est2.sample(layer, z=z).cpu(), golden_next[f"efb_sample_{li}"]) < TOL
+    est2.sample_and_replace()

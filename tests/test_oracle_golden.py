@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import relerr
+from conftest import ROOT, relerr
 from models_for_tests import MLP, RegNet, load_params
 from oracle import kfac_oracle as O
 from bnn_kfac_b200.wrapper import BaseNet_750
@@ -174,3 +174,63 @@ def test_philox_known_answer():
     assert [hex(v) for v in out[0]] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
     z = O.philox_normal(1234, 0, 7, 200000)
     assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.02
+
+
+# ------------------------------------------------------------------ "next" rows: BlockDiagonal, EFB
+@pytest.fixture(scope="module")
+def golden_next():
+    return dict(np.load(ROOT / "tests" / "golden" / "reference_golden_next.npz"))
+
+
+def _mlp_with_grads(golden, i):
+    model = load_params(MLP(), golden, "mlp", torch.float64)
+    x = torch.tensor(golden[f"mlp_x_{i}"]).double()
+    y = torch.tensor(golden[f"mlp_y_{i}"])
+    loss = torch.nn.functional.cross_entropy(model(x), y)
+    model.zero_grad()
+    loss.backward()
+    return model, x.shape[0]
+
+
+def test_blockdiagonal_oracle_vs_reference(golden, golden_next):
+    states = [None, None]
+    for i in range(2):
+        model, bs = _mlp_with_grads(golden, i)
+        layers = O.selected_layers(model)
+        states = [O.blockdiag_update(states[li], l, bs) for li, l in enumerate(layers)]
+    for li, l in enumerate(layers):
+        np.testing.assert_allclose(states[li].numpy(), golden_next[f"bd_state_{li}"], rtol=1e-12, atol=1e-14)
+        inv = O.blockdiag_invert(states[li], 0.5, 10.0)
+        np.testing.assert_allclose(inv.numpy(), golden_next[f"bd_inv_a_{li}"], rtol=1e-9, atol=1e-12)
+        smp = O.blockdiag_sample(inv, l, torch.tensor(golden_next[f"bd_z_{li}"]))
+        np.testing.assert_allclose(smp.numpy(), golden_next[f"bd_sample_{li}"], rtol=1e-9, atol=1e-12)
+        pinv = O.blockdiag_invert(states[li], 0.0, 1.0)
+        assert relerr(pinv.numpy(), golden_next[f"bd_inv_pinv_{li}"]) < 1e-6
+
+
+def test_efb_oracle_vs_reference(golden, golden_next):
+    eig = [(torch.tensor(golden_next[f"efb_UA_{li}"]), torch.tensor(golden_next[f"efb_UG_{li}"])) for li in range(2)]
+    state, diags = [None, None], [None, None]
+    for i in range(2):
+        model, bs = _mlp_with_grads(golden, i)
+        layers = O.selected_layers(model)
+        for li, l in enumerate(layers):
+            state[li], diags[li] = O.efb_update(state[li], diags[li], l, eig[li], bs)
+    for li in range(2):
+        np.testing.assert_allclose(state[li].numpy(), golden_next[f"efb_state_{li}"], rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(diags[li].numpy(), golden_next[f"efb_diags_{li}"], rtol=1e-12, atol=1e-16)
+        inv = O.efb_invert(state[li], 0.04, 200.0)
+        np.testing.assert_allclose(inv.numpy(), golden_next[f"efb_inv_{li}"], rtol=1e-10)
+        smp = O.efb_sample(eig[li], inv, torch.tensor(golden_next[f"efb_z_{li}"]))
+        np.testing.assert_allclose(smp.numpy(), golden_next[f"efb_sample_{li}"], rtol=1e-9, atol=1e-12)
+    # the oracle's own eigenvectors (linalg.eigh of F + F^T) span the same eigenspaces: lambdas agree
+    A = torch.tensor(golden["mlp64_state_0_A"])
+    G = torch.tensor(golden["mlp64_state_0_G"])
+    _, va, _, vg = O.factor_eigenvectors(A, G)
+    model, bs = _mlp_with_grads(golden, 0)
+    l0 = O.selected_layers(model)[0]
+    lam_own, _ = O.efb_update(None, None, l0, (va, vg), bs)
+    lam_ref, _ = O.efb_update(None, None, l0, eig[0], bs)
+    # squares of projections are invariant to eigenvector signs; degenerate eigenvalues (rank-deficient
+    # factors) leave the basis of the null space free, so compare the sums over the free blocks: totals
+    assert abs(lam_own.sum().item() / lam_ref.sum().item() - 1) < 1e-9
