@@ -404,6 +404,20 @@ def extras(est, model, layers, dev, world, rank):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # second figure of SURVEY 8(d): the update INCLUDING the model's own forward / backward (torch fp32)
+    xb = torch.randn(BATCH, WIDTHS[0], device=dev)
+    yb = torch.randint(0, WIDTHS[-1], (BATCH,), device=dev)
+
+    def full_step():
+        loss = torch.nn.functional.cross_entropy(model(xb), yb)
+        model.zero_grad()
+        loss.backward()
+        est.update(BATCH)
+    for _ in range(2):
+        full_step()
+    ms_full = ev_ms(full_step, reps=5)
+    out["update_incl_model_fwd_bwd"] = {"ms_per_step": ms_full, "samples_per_s": BATCH * world / (ms_full * 1e-3),
+                                        "note": "torch fp32 forward + backward of the MLP, hooks, then KFAC.update"}
     est.invert(1.0, 200.0)      # warm-up (workspace allocation)
     out["invert_ms_all_layers"] = ev_ms(lambda: est.invert(1.0, 200.0))
     out["invert_config"] = "8 factors (4 x 4097^2, 3 x 4096^2, 10^2), add=1, multiply=200, one batched launch sequence"
