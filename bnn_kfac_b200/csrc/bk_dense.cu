@@ -20,6 +20,7 @@ dominance_kernel(const float* __restrict__ H, long long ld, int P, float tau,
                  double* __restrict__ out) {
   __shared__ double red[3][8];
   double s_diag = 0.0, s_all = 0.0, s_blk = 0.0;
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(H) & 15) == 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = blockIdx.x; i < P; i += gridDim.x) {
     // diagonal block that contains row i (blocks are disjoint, ascending): binary search
@@ -37,15 +38,50 @@ dominance_kernel(const float* __restrict__ H, long long ld, int P, float tau,
     }
     const float* row = H + static_cast<long long>(i) * ld;
     float a_all = 0.f, a_blk = 0.f;  // fp32 per-thread partials over <= P/256 addends, fp64 above
-    for (int j = threadIdx.x; j < P; j += blockDim.x) {
-      float v = row[j];
-      if (j == i) {
-        v += tau;
-        s_diag += fabs(static_cast<double>(v));
+    auto take = [&](float x, int jj) {
+      if (jj == i) {
+        x += tau;
+        s_diag += fabs(static_cast<double>(x));
       }
-      const float av = fabsf(v);
+      const float av = fabsf(x);
       a_all += av;
-      if (j >= b0 && j < b1) a_blk += av;
+      if (jj >= b0 && jj < b1) a_blk += av;
+    };
+    if (vec) {
+      const float4* row4 = reinterpret_cast<const float4*>(row);
+      const int n4 = P >> 2;
+      for (int j = threadIdx.x; j < n4; j += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = j + u * blockDim.x;
+          v[u] = (jj < n4) ? __ldcs(row4 + jj) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = j + u * blockDim.x;
+          if (jj >= n4) continue;
+          take(v[u].x, 4 * jj);
+          take(v[u].y, 4 * jj + 1);
+          take(v[u].z, 4 * jj + 2);
+          take(v[u].w, 4 * jj + 3);
+        }
+      }
+      for (int jj = (n4 << 2) + threadIdx.x; jj < P; jj += blockDim.x) take(row[jj], jj);
+    } else {
+      for (int j = threadIdx.x; j < P; j += 4 * blockDim.x) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = j + u * blockDim.x;
+          v[u] = (jj < P) ? __ldcs(row + jj) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = j + u * blockDim.x;
+          if (jj < P) take(v[u], jj);
+        }
+      }
     }
     s_all += a_all;
     s_blk += a_blk;
@@ -88,9 +124,19 @@ ger_accum_kernel(float* __restrict__ state, long long ld, const float* __restric
   for (int i = blockIdx.x; i < P; i += gridDim.x) {
     const float gi = alpha * g[i];
     float* row = state + static_cast<long long>(i) * ld;
-    for (int j = threadIdx.x; j < P; j += blockDim.x) {
-      const float old = (beta == 0.f) ? 0.f : beta * row[j];
-      row[j] = fmaf(gi, g[j], old);
+    for (int j = threadIdx.x; j < P; j += 4 * blockDim.x) {
+      float old[4], gj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + u * blockDim.x;
+        old[u] = (jj < P && beta != 0.f) ? row[jj] : 0.f;
+        gj[u] = (jj < P) ? __ldg(g + jj) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = j + u * blockDim.x;
+        if (jj < P) row[jj] = fmaf(gi, gj[u], beta * old[u]);
+      }
     }
   }
 }
@@ -100,7 +146,7 @@ ger_accum_kernel(float* __restrict__ state, long long ld, const float* __restric
 int launch_ger_accum(float* state, long long ld, const float* g, int P, float alpha, float beta,
                      cudaStream_t stream) {
   if (P <= 0) return 0;
-  const int grid = P < kNumSMsB200 * 8 ? P : kNumSMsB200 * 8;
+  const int grid = P < kNumSMsB200 * 16 ? P : kNumSMsB200 * 16;
   ger_accum_kernel<<<grid, 256, 0, stream>>>(state, ld, g, P, alpha, beta);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
@@ -121,7 +167,7 @@ int launch_dominance(const float* H, long long ld, int P, float tau, const int* 
                      const int* block_end, int nblocks, double* out3, cudaStream_t stream) {
   if (P <= 0) return 0;
   if (cudaMemsetAsync(out3, 0, 3 * sizeof(double), stream) != cudaSuccess) return -5;
-  int grid = P < kNumSMsB200 * 8 ? P : kNumSMsB200 * 8;
+  int grid = P < kNumSMsB200 * 16 ? P : kNumSMsB200 * 16;
   dominance_kernel<<<grid, 256, 0, stream>>>(H, ld, P, tau, block_begin, block_end, nblocks, out3);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;

@@ -151,14 +151,27 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
   }
 }
 
-__global__ void frob_dot_kernel(float* __restrict__ out, const float* __restrict__ X,
-                                long long stride_x, const float* __restrict__ Y, long long stride_y,
-                                long long count, int absolute, int accumulate) {
-  const float* x = X + blockIdx.x * stride_x;
-  const float* y = Y + blockIdx.x * stride_y;
+// out[b] (+)= <x_b, y_b> over this CTA's chunk: grid (chunks, batch), fp64 per-CTA partials combined
+// with one atomic per CTA; `absolute` is applied by frob_abs_kernel after all chunks landed.
+__global__ void __launch_bounds__(256)
+frob_dot_kernel(double* __restrict__ acc_out, const float* __restrict__ X, long long stride_x,
+                const float* __restrict__ Y, long long stride_y, long long count, long long chunk) {
+  const float* x = X + blockIdx.y * stride_x;
+  const float* y = Y + blockIdx.y * stride_y;
+  const long long j0 = blockIdx.x * chunk;
+  const long long j1 = (j0 + chunk < count) ? j0 + chunk : count;
   double acc = 0.0;
-  for (long long j = threadIdx.x; j < count; j += blockDim.x)
-    acc += static_cast<double>(x[j]) * static_cast<double>(y[j]);
+  for (long long j = j0 + threadIdx.x; j < j1; j += 4 * 256) {
+    float a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long jj = j + u * 256;
+      a[u] = (jj < j1) ? __ldcs(x + jj) : 0.f;
+      b[u] = (jj < j1) ? __ldcs(y + jj) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += static_cast<double>(a[u]) * static_cast<double>(b[u]);
+  }
   __shared__ double part[8];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
@@ -166,10 +179,17 @@ __global__ void frob_dot_kernel(float* __restrict__ out, const float* __restrict
   if (threadIdx.x < 32) {
     double v = (threadIdx.x < 8) ? part[threadIdx.x] : 0.0;
     v = warp_sum(v);
-    if (threadIdx.x == 0) {
-      float r = static_cast<float>(absolute ? fabs(v) : v);
-      out[blockIdx.x] = accumulate ? out[blockIdx.x] + r : r;
-    }
+    if (threadIdx.x == 0) atomicAdd(&acc_out[blockIdx.y], v);
+  }
+}
+
+__global__ void frob_finish_kernel(float* __restrict__ out, const double* __restrict__ acc, int batch,
+                                   int absolute, int accumulate) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < batch) {
+    double v = acc[b];
+    if (absolute) v = fabs(v);
+    out[b] = accumulate ? out[b] + static_cast<float>(v) : static_cast<float>(v);
   }
 }
 
@@ -228,10 +248,21 @@ int launch_frob_dot(float* out, const float* X, long long stride_x, const float*
                     long long stride_y, long long count, int batch, int absolute, int accumulate,
                     cudaStream_t stream) {
   if (batch <= 0) return 0;
-  frob_dot_kernel<<<batch, 256, 0, stream>>>(out, X, stride_x, Y, stride_y, count, absolute,
-                                             accumulate);
-  note_launch();
-  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+  // fp64 accumulators: a small stream-ordered scratch (batch doubles)
+  double* acc = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&acc), sizeof(double) * batch, stream) != cudaSuccess)
+    return -5;
+  if (cudaMemsetAsync(acc, 0, sizeof(double) * batch, stream) != cudaSuccess) return -5;
+  long long chunk = 16384;
+  const long long max_ctas = static_cast<long long>(kNumSMsB200) * 32;
+  while ((count + chunk - 1) / chunk * batch > max_ctas) chunk *= 2;
+  const dim3 grid(static_cast<unsigned>((count + chunk - 1) / chunk), batch);
+  frob_dot_kernel<<<grid, 256, 0, stream>>>(acc, X, stride_x, Y, stride_y, count, chunk);
+  frob_finish_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(out, acc, batch, absolute, accumulate);
+  note_launch(2);
+  const bool ok = cudaGetLastError() == cudaSuccess;
+  cudaFreeAsync(acc, stream);
+  return ok ? 0 : -5;
 }
 
 }  // namespace bk

@@ -57,65 +57,90 @@ __global__ void transpose_split_kernel(const float* __restrict__ X, long long ld
 // (sum_n scale * x[n, j], exact fp32) for the bias row of the first Kronecker factor: the caller then
 // runs the SYRK on the d x d block only and fills row/column d from these sums
 // (models/curvatures.py:346-349 without materialising the row of ones).
+template <int ST, int FT>  // samples x features per CTA tile
 __global__ void __launch_bounds__(256)
 transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
                          __nv_bfloat16* __restrict__ Thi, __nv_bfloat16* __restrict__ Tlo,
                          long long ldt, float* __restrict__ colsum) {
-  __shared__ float tile[64][65];  // [sample][feature]
-  const int c0 = blockIdx.x * 64;
-  const int r0 = blockIdx.y * 64;
+  __shared__ float tile[ST][FT + 1];  // [sample][feature]
+  const int c0 = blockIdx.x * FT;
+  const int r0 = blockIdx.y * ST;
   const int tid = threadIdx.x;
   {
-    const int f4 = (tid & 15) * 4;  // feature offset of this thread's float4
-    const int sr = tid >> 4;        // 16 sample rows per pass
+    constexpr int kF4 = FT / 4;           // float4 per row of the tile
+    constexpr int kRowsPerPass = 256 / kF4;
+    const int f4 = (tid % kF4) * 4;       // feature offset of this thread's float4
+    const int sr = tid / kF4;
+    float4 v[ST / kRowsPerPass];
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int s = sr + 16 * pass;
-      const int r = r0 + s, c = c0 + f4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pass = 0; pass < ST / kRowsPerPass; ++pass) {
+      const int r = r0 + sr + kRowsPerPass * pass, c = c0 + f4;
+      v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < rows) {
         const float* src = X + static_cast<long long>(r) * ldx + c;
         if (c + 3 < cols) {
-          v = __ldg(reinterpret_cast<const float4*>(src));
+          v[pass] = __ldcs(reinterpret_cast<const float4*>(src));
         } else {
-          if (c < cols) v.x = src[0];
-          if (c + 1 < cols) v.y = src[1];
-          if (c + 2 < cols) v.z = src[2];
+          if (c < cols) v[pass].x = src[0];
+          if (c + 1 < cols) v[pass].y = src[1];
+          if (c + 2 < cols) v[pass].z = src[2];
         }
       }
-      tile[s][f4 + 0] = v.x * scale;
-      tile[s][f4 + 1] = v.y * scale;
-      tile[s][f4 + 2] = v.z * scale;
-      tile[s][f4 + 3] = v.w * scale;
+    }
+#pragma unroll
+    for (int pass = 0; pass < ST / kRowsPerPass; ++pass) {
+      const int s = sr + kRowsPerPass * pass;
+      tile[s][f4 + 0] = v[pass].x * scale;
+      tile[s][f4 + 1] = v[pass].y * scale;
+      tile[s][f4 + 2] = v[pass].z * scale;
+      tile[s][f4 + 3] = v[pass].w * scale;
     }
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  const int oc = r0 + 2 * lane;  // sample pair written by this lane
+  constexpr int kPer = ST / 32;            // consecutive samples written by one lane (2 or 4)
+  const int oc = r0 + kPer * lane;
 #pragma unroll
-  for (int pass = 0; pass < 8; ++pass) {
+  for (int pass = 0; pass < FT / 8; ++pass) {
     const int f = warp + 8 * pass;
     const int orow = c0 + f;
     if (orow >= cols) continue;
-    const float a = tile[2 * lane][f], b = tile[2 * lane + 1][f];
-    __nv_bfloat16 ah, al, bh, bl;
-    split_bf16(a, ah, al);
-    split_bf16(b, bh, bl);
+    __nv_bfloat16 h[kPer], l[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) split_bf16(tile[kPer * lane + j][f], h[j], l[j]);
     __nv_bfloat16* dh = Thi + static_cast<long long>(orow) * ldt + oc;
-    if (oc + 1 < rows) {
-      *reinterpret_cast<__nv_bfloat162*>(dh) = __halves2bfloat162(ah, bh);
-      if (Tlo != nullptr)
-        *reinterpret_cast<__nv_bfloat162*>(Tlo + static_cast<long long>(orow) * ldt + oc) =
-            __halves2bfloat162(al, bl);
-    } else if (oc < rows) {
-      dh[0] = ah;
-      if (Tlo != nullptr) Tlo[static_cast<long long>(orow) * ldt + oc] = al;
+    __nv_bfloat16* dl = Tlo != nullptr ? Tlo + static_cast<long long>(orow) * ldt + oc : nullptr;
+    if (oc + kPer - 1 < rows) {
+      if (kPer == 2) {
+        *reinterpret_cast<__nv_bfloat162*>(dh) = __halves2bfloat162(h[0], h[1]);
+        if (dl != nullptr) *reinterpret_cast<__nv_bfloat162*>(dl) = __halves2bfloat162(l[0], l[1]);
+      } else {
+        uint2 ph, pl;
+        ph.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
+        ph.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[kPer - 1])) << 16) |
+               __bfloat16_as_ushort(h[kPer - 2]);
+        *reinterpret_cast<uint2*>(dh) = ph;
+        if (dl != nullptr) {
+          pl.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
+          pl.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[kPer - 1])) << 16) |
+                 __bfloat16_as_ushort(l[kPer - 2]);
+          *reinterpret_cast<uint2*>(dl) = pl;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        if (oc + j < rows) {
+          dh[j] = h[j];
+          if (dl != nullptr) dl[j] = l[j];
+        }
+      }
     }
   }
-  if (colsum != nullptr && tid < 64 && c0 + tid < cols) {
+  if (colsum != nullptr && tid < FT && c0 + tid < cols) {
     float sacc = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < 64; ++k) sacc += tile[k][tid];  // rows beyond `rows` hold zeros
+    for (int k = 0; k < ST; ++k) sacc += tile[k][tid];  // rows beyond `rows` hold zeros
     atomicAdd(&colsum[c0 + tid], sacc);
   }
 }
@@ -146,21 +171,76 @@ __global__ void bias_border_kernel(float* __restrict__ state, long long ld, int 
   }
 }
 
-__global__ void convert_split_kernel(const float* __restrict__ X, long long ldx, int rows, int cols,
-                                     float scale, int lower_only, __nv_bfloat16* __restrict__ Ohi,
-                                     __nv_bfloat16* __restrict__ Olo, long long ldo) {
-  const int r = blockIdx.y;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
-    float v = X[static_cast<long long>(r) * ldx + c] * scale;
-    if (lower_only && c > r) v = 0.f;
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    Ohi[static_cast<long long>(r) * ldo + c] = h;
-    if (Olo != nullptr) Olo[static_cast<long long>(r) * ldo + c] = l;
+// fp32 [rows, cols] -> bf16 hi[/lo] same orientation.  kVec: 4 columns per thread (float4 load,
+// 8-byte bf16x4 stores), 4 independent loads in flight per thread.
+template <bool kVec>
+__global__ void __launch_bounds__(256)
+convert_split_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
+                     int lower_only, __nv_bfloat16* __restrict__ Ohi,
+                     __nv_bfloat16* __restrict__ Olo, long long ldo) {
+  constexpr int kU = 4;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float* src = X + static_cast<long long>(r) * ldx;
+    __nv_bfloat16* dh = Ohi + static_cast<long long>(r) * ldo;
+    __nv_bfloat16* dl = Olo != nullptr ? Olo + static_cast<long long>(r) * ldo : nullptr;
+    if (kVec) {
+      const int n4 = cols >> 2;
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x * kU) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int ii = i + u * gridDim.x * blockDim.x;
+          if (ii < n4) v[u] = __ldcs(reinterpret_cast<const float4*>(src) + ii);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int ii = i + u * gridDim.x * blockDim.x;
+          if (ii >= n4) continue;
+          const int c = ii << 2;
+          float e[4] = {v[u].x * scale, v[u].y * scale, v[u].z * scale, v[u].w * scale};
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (lower_only && c + j > r) e[j] = 0.f;
+            split_bf16(e[j], h[j], l[j]);
+          }
+          uint2 ph;
+          ph.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
+          ph.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16) | __bfloat16_as_ushort(h[2]);
+          *reinterpret_cast<uint2*>(dh + c) = ph;
+          if (dl != nullptr) {
+            uint2 pl;
+            pl.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
+            pl.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[3])) << 16) | __bfloat16_as_ushort(l[2]);
+            *reinterpret_cast<uint2*>(dl + c) = pl;
+          }
+        }
+      }
+      for (int c = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; c < cols;
+           c += gridDim.x * blockDim.x) {
+        float v = src[c] * scale;
+        if (lower_only && c > r) v = 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        dh[c] = h;
+        if (dl != nullptr) dl[c] = l;
+      }
+    } else {
+      for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+        float v = src[c] * scale;
+        if (lower_only && c > r) v = 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        dh[c] = h;
+        if (dl != nullptr) dl[c] = l;
+      }
+    }
   }
 }
 
 }  // namespace
+
+int g_transpose_variant = 0;  // tile shape of the staging kernel (tuning knob, see bk_set_cta_group)
 
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
@@ -171,9 +251,21 @@ int launch_transpose_split(const float* X, long long ldx, int rows, int cols, fl
                     (Tlo == nullptr || reinterpret_cast<uintptr_t>(Tlo) % 4 == 0);
   if (colsum != nullptr && !fast) return -2;  // callers only request sums on the aligned path
   if (fast) {
-    dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-    transpose_split64_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo, ldt,
-                                                       colsum);
+    const bool wide = (ldt % 4 == 0) && (reinterpret_cast<uintptr_t>(Thi) % 8 == 0) &&
+                      (Tlo == nullptr || reinterpret_cast<uintptr_t>(Tlo) % 8 == 0);
+    if (g_transpose_variant == 1) {
+      dim3 grid((cols + 127) / 128, (rows + 63) / 64);
+      transpose_split64_kernel<64, 128><<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
+                                                                  ldt, colsum);
+    } else if (g_transpose_variant == 2 && wide) {
+      dim3 grid((cols + 63) / 64, (rows + 127) / 128);
+      transpose_split64_kernel<128, 64><<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
+                                                                  ldt, colsum);
+    } else {
+      dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+      transpose_split64_kernel<64, 64><<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
+                                                                 ldt, colsum);
+    }
     note_launch();
     if (ones_row) {  // generic operand with an explicit row of ones (bk_transpose_split ABI)
       fill_ones_row_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
@@ -201,11 +293,20 @@ int launch_convert_split(const float* X, long long ldx, int rows, int cols, floa
                          int lower_only, __nv_bfloat16* Ohi, __nv_bfloat16* Olo, long long ldo,
                          cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return 0;
-  int bx = (cols + 255) / 256;
+  const bool vec = (ldx % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(Ohi) % 8 == 0) &&
+                   (Olo == nullptr || reinterpret_cast<uintptr_t>(Olo) % 8 == 0);
+  // one block column covers 256 threads x 4 float4 x 4 columns = 4096 columns per sweep
+  int bx = vec ? (cols + 4095) / 4096 : (cols + 255) / 256;
   if (bx > 64) bx = 64;
-  dim3 grid(bx, rows), block(256);
-  convert_split_kernel<<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, lower_only, Ohi, Olo,
-                                                   ldo);
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, rows < 65535 ? rows : 65535), block(256);
+  if (vec)
+    convert_split_kernel<true><<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, lower_only, Ohi,
+                                                           Olo, ldo);
+  else
+    convert_split_kernel<false><<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, lower_only,
+                                                            Ohi, Olo, ldo);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
@@ -221,44 +322,57 @@ philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_
                      int cols, int nsamples, float* __restrict__ Zf, long long ldf,
                      long long stridef, __nv_bfloat16* __restrict__ Zhi,
                      __nv_bfloat16* __restrict__ Zlo, long long ldz, long long stridez) {
-  const int groups = (cols + 3) >> 2;  // column groups per row
+  const int groups = (cols + 3) >> 2;  // column groups (Philox blocks) per row
+  const int pairs = (groups + 1) >> 1; // each thread produces two adjacent groups = 8 columns
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-  const bool vec = (Zhi != nullptr) && ((ldz & 3) == 0) && ((stridez & 3) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(Zhi) & 7) == 0) &&
-                   (Zlo == nullptr || (reinterpret_cast<uintptr_t>(Zlo) & 7) == 0);
-  // grid: x -> column groups, y -> rows (grid-stride), z -> samples (grid-stride)
+  // 16-byte stores of 8 bf16 need 16 B aligned rows
+  const bool vec = (Zhi != nullptr) && ((ldz & 7) == 0) && ((stridez & 7) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(Zhi) & 15) == 0) &&
+                   (Zlo == nullptr || (reinterpret_cast<uintptr_t>(Zlo) & 15) == 0);
+  // grid: x -> column-group pairs, y -> rows (grid-stride), z -> samples (grid-stride)
   for (int s = blockIdx.z; s < nsamples; s += gridDim.z) {
     for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-      for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
-        uint32_t c[4] = {static_cast<uint32_t>(g), static_cast<uint32_t>(r), sample0 + s, stream_id};
-        philox4x32_10(c, k0, k1);
-        float z[4];
-        box_muller(c[0], c[1], z[0], z[1]);
-        box_muller(c[2], c[3], z[2], z[3]);
-        const int c0 = g << 2;
-        const int nv = min(4, cols - c0);
+      for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += gridDim.x * blockDim.x) {
+        // two independent Philox blocks per thread: the 10-round dependency chains interleave
+        uint32_t ca[4] = {static_cast<uint32_t>(2 * t), static_cast<uint32_t>(r), sample0 + s, stream_id};
+        uint32_t cb[4] = {static_cast<uint32_t>(2 * t + 1), static_cast<uint32_t>(r), sample0 + s,
+                          stream_id};
+        philox4x32_10(ca, k0, k1);
+        philox4x32_10(cb, k0, k1);
+        float z[8];
+        box_muller(ca[0], ca[1], z[0], z[1]);
+        box_muller(ca[2], ca[3], z[2], z[3]);
+        box_muller(cb[0], cb[1], z[4], z[5]);
+        box_muller(cb[2], cb[3], z[6], z[7]);
+        const int c0 = t << 3;
+        const int nv = min(8, cols - c0);
         if (Zf != nullptr) {
           float* dst = Zf + s * stridef + static_cast<long long>(r) * ldf + c0;
           for (int j = 0; j < nv; ++j) dst[j] = z[j];
         }
         if (Zhi != nullptr) {
-          __nv_bfloat16 h[4], l[4];
+          __nv_bfloat16 h[8], l[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split_bf16(z[j], h[j], l[j]);
+          for (int j = 0; j < 8; ++j) split_bf16(z[j], h[j], l[j]);
           const long long o = s * stridez + static_cast<long long>(r) * ldz + c0;
-          if (vec && c0 + 3 < ldz) {
+          if (vec && c0 + 7 < ldz) {
             // the padding columns [cols, ldz) of the operand are written as zeros
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
               if (j >= nv) h[j] = l[j] = __float2bfloat16_rn(0.f);
-            uint2 ph, pl;
+            uint4 ph;
             ph.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
             ph.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16) | __bfloat16_as_ushort(h[2]);
-            *reinterpret_cast<uint2*>(Zhi + o) = ph;
+            ph.z = (static_cast<uint32_t>(__bfloat16_as_ushort(h[5])) << 16) | __bfloat16_as_ushort(h[4]);
+            ph.w = (static_cast<uint32_t>(__bfloat16_as_ushort(h[7])) << 16) | __bfloat16_as_ushort(h[6]);
+            *reinterpret_cast<uint4*>(Zhi + o) = ph;
             if (Zlo != nullptr) {
+              uint4 pl;
               pl.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
               pl.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[3])) << 16) | __bfloat16_as_ushort(l[2]);
-              *reinterpret_cast<uint2*>(Zlo + o) = pl;
+              pl.z = (static_cast<uint32_t>(__bfloat16_as_ushort(l[5])) << 16) | __bfloat16_as_ushort(l[4]);
+              pl.w = (static_cast<uint32_t>(__bfloat16_as_ushort(l[7])) << 16) | __bfloat16_as_ushort(l[6]);
+              *reinterpret_cast<uint4*>(Zlo + o) = pl;
             }
           } else {
             for (int j = 0; j < nv; ++j) {
@@ -279,8 +393,8 @@ int launch_philox_normal(unsigned long long seed, unsigned sample0, unsigned str
                          __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, long long ldz, long long stridez,
                          cudaStream_t stream) {
   if (rows <= 0 || cols <= 0 || nsamples <= 0) return 0;
-  const int groups = (cols + 3) / 4;
-  dim3 grid((groups + 255) / 256, rows < 4096 ? rows : 4096, nsamples < 16 ? nsamples : 16);
+  const int pairs = ((cols + 3) / 4 + 1) / 2;
+  dim3 grid((pairs + 255) / 256, rows < 4096 ? rows : 4096, nsamples < 16 ? nsamples : 16);
   philox_normal_kernel<<<grid, 256, 0, stream>>>(seed, sample0, stream_id, rows, cols, nsamples, Zf,
                                                  ldf, stridef, Zhi, Zlo, ldz, stridez);
   note_launch();
