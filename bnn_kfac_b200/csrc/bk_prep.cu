@@ -57,24 +57,33 @@ __global__ void transpose_split_kernel(const float* __restrict__ X, long long ld
 // (sum_n scale * x[n, j], exact fp32) for the bias row of the first Kronecker factor: the caller then
 // runs the SYRK on the d x d block only and fills row/column d from these sums
 // (models/curvatures.py:346-349 without materialising the row of ones).
-template <int ST, int FT>  // samples x features per CTA tile
+// Shared-memory layout of the 64 x 64 tile: sample PAIRS are stored together,
+//   addr(s, f) = (s >> 1) * 129 + (s & 1) * 64 + f          (bank = (s >> 1) + f  mod 32),
+// which makes both phases conflict-free: the load phase writes, per warp instruction, eight 4-float
+// groups of the rows {s0, s0+2, s0+4, s0+6}; the transposed phase reads, for one feature f, the even
+// (then the odd) samples 2*lane (+1).
 __global__ void __launch_bounds__(256)
 transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
                          __nv_bfloat16* __restrict__ Thi, __nv_bfloat16* __restrict__ Tlo,
                          long long ldt, float* __restrict__ colsum) {
-  __shared__ float tile[ST][FT + 1];  // [sample][feature]
-  const int c0 = blockIdx.x * FT;
-  const int r0 = blockIdx.y * ST;
+  __shared__ float tile[32 * 129];
+  const int c0 = blockIdx.x * 64;
+  const int r0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   {
-    constexpr int kF4 = FT / 4;           // float4 per row of the tile
-    constexpr int kRowsPerPass = 256 / kF4;
-    const int f4 = (tid % kF4) * 4;       // feature offset of this thread's float4
-    const int sr = tid / kF4;
-    float4 v[ST / kRowsPerPass];
+    // unit u = pass * 8 + warp in [0, 32): (half of the 64 features, group of 8 rows, row parity)
+    float4 v[4];
+    int srow[4], fcol[4];
 #pragma unroll
-    for (int pass = 0; pass < ST / kRowsPerPass; ++pass) {
-      const int r = r0 + sr + kRowsPerPass * pass, c = c0 + f4;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int u = pass * 8 + warp;
+      const int half = u & 1, parity = (u >> 1) & 1, grp = u >> 2;  // grp in [0, 8)
+      const int s = grp * 8 + parity + 2 * (lane >> 3);             // rows s0, s0+2, s0+4, s0+6
+      const int f = half * 32 + 4 * (lane & 7);
+      srow[pass] = s;
+      fcol[pass] = f;
+      const int r = r0 + s, c = c0 + f;
       v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < rows) {
         const float* src = X + static_cast<long long>(r) * ldx + c;
@@ -88,59 +97,41 @@ transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, i
       }
     }
 #pragma unroll
-    for (int pass = 0; pass < ST / kRowsPerPass; ++pass) {
-      const int s = sr + kRowsPerPass * pass;
-      tile[s][f4 + 0] = v[pass].x * scale;
-      tile[s][f4 + 1] = v[pass].y * scale;
-      tile[s][f4 + 2] = v[pass].z * scale;
-      tile[s][f4 + 3] = v[pass].w * scale;
+    for (int pass = 0; pass < 4; ++pass) {
+      float* d = tile + (srow[pass] >> 1) * 129 + (srow[pass] & 1) * 64 + fcol[pass];
+      d[0] = v[pass].x * scale;
+      d[1] = v[pass].y * scale;
+      d[2] = v[pass].z * scale;
+      d[3] = v[pass].w * scale;
     }
   }
   __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int kPer = ST / 32;            // consecutive samples written by one lane (2 or 4)
-  const int oc = r0 + kPer * lane;
+  const int oc = r0 + 2 * lane;  // sample pair written by this lane
 #pragma unroll
-  for (int pass = 0; pass < FT / 8; ++pass) {
+  for (int pass = 0; pass < 8; ++pass) {
     const int f = warp + 8 * pass;
     const int orow = c0 + f;
     if (orow >= cols) continue;
-    __nv_bfloat16 h[kPer], l[kPer];
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) split_bf16(tile[kPer * lane + j][f], h[j], l[j]);
+    const float a = tile[lane * 129 + f], b = tile[lane * 129 + 64 + f];
+    __nv_bfloat16 ah, al, bh, bl;
+    split_bf16(a, ah, al);
+    split_bf16(b, bh, bl);
     __nv_bfloat16* dh = Thi + static_cast<long long>(orow) * ldt + oc;
-    __nv_bfloat16* dl = Tlo != nullptr ? Tlo + static_cast<long long>(orow) * ldt + oc : nullptr;
-    if (oc + kPer - 1 < rows) {
-      if (kPer == 2) {
-        *reinterpret_cast<__nv_bfloat162*>(dh) = __halves2bfloat162(h[0], h[1]);
-        if (dl != nullptr) *reinterpret_cast<__nv_bfloat162*>(dl) = __halves2bfloat162(l[0], l[1]);
-      } else {
-        uint2 ph, pl;
-        ph.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
-        ph.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[kPer - 1])) << 16) |
-               __bfloat16_as_ushort(h[kPer - 2]);
-        *reinterpret_cast<uint2*>(dh) = ph;
-        if (dl != nullptr) {
-          pl.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
-          pl.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[kPer - 1])) << 16) |
-                 __bfloat16_as_ushort(l[kPer - 2]);
-          *reinterpret_cast<uint2*>(dl) = pl;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        if (oc + j < rows) {
-          dh[j] = h[j];
-          if (dl != nullptr) dl[j] = l[j];
-        }
-      }
+    if (oc + 1 < rows) {
+      *reinterpret_cast<__nv_bfloat162*>(dh) = __halves2bfloat162(ah, bh);
+      if (Tlo != nullptr)
+        *reinterpret_cast<__nv_bfloat162*>(Tlo + static_cast<long long>(orow) * ldt + oc) =
+            __halves2bfloat162(al, bl);
+    } else if (oc < rows) {
+      dh[0] = ah;
+      if (Tlo != nullptr) Tlo[static_cast<long long>(orow) * ldt + oc] = al;
     }
   }
-  if (colsum != nullptr && tid < FT && c0 + tid < cols) {
+  if (colsum != nullptr && tid < 64 && c0 + tid < cols) {
     float sacc = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < ST; ++k) sacc += tile[k][tid];  // rows beyond `rows` hold zeros
+    for (int k = 0; k < 32; ++k)  // rows beyond `rows` hold zeros
+      sacc += tile[k * 129 + tid] + tile[k * 129 + 64 + tid];
     atomicAdd(&colsum[c0 + tid], sacc);
   }
 }
@@ -240,8 +231,6 @@ convert_split_kernel(const float* __restrict__ X, long long ldx, int rows, int c
 
 }  // namespace
 
-int g_transpose_variant = 0;  // tile shape of the staging kernel (tuning knob, see bk_set_cta_group)
-
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
                            cudaStream_t stream, float* colsum) {
@@ -251,21 +240,9 @@ int launch_transpose_split(const float* X, long long ldx, int rows, int cols, fl
                     (Tlo == nullptr || reinterpret_cast<uintptr_t>(Tlo) % 4 == 0);
   if (colsum != nullptr && !fast) return -2;  // callers only request sums on the aligned path
   if (fast) {
-    const bool wide = (ldt % 4 == 0) && (reinterpret_cast<uintptr_t>(Thi) % 8 == 0) &&
-                      (Tlo == nullptr || reinterpret_cast<uintptr_t>(Tlo) % 8 == 0);
-    if (g_transpose_variant == 1) {
-      dim3 grid((cols + 127) / 128, (rows + 63) / 64);
-      transpose_split64_kernel<64, 128><<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
-                                                                  ldt, colsum);
-    } else if (g_transpose_variant == 2 && wide) {
-      dim3 grid((cols + 63) / 64, (rows + 127) / 128);
-      transpose_split64_kernel<128, 64><<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
-                                                                  ldt, colsum);
-    } else {
-      dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-      transpose_split64_kernel<64, 64><<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
-                                                                 ldt, colsum);
-    }
+    dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+    transpose_split64_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo, ldt,
+                                                       colsum);
     note_launch();
     if (ones_row) {  // generic operand with an explicit row of ones (bk_transpose_split ABI)
       fill_ones_row_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(

@@ -769,9 +769,7 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts,
 // cta_group override for bring-up / A-B timing: 0 = automatic, 1 or 2 = forced; +16 disables the
 // TMA-reduce epilogue (register read-modify-write epilogue everywhere).
 static int g_force_cta_group = 0;
-extern int g_transpose_variant;
 void set_umma_cta_group(int cg) {
-  g_transpose_variant = (cg >> 8) & 3;  // bring-up: staging-kernel tile shape
   g_allow_tma_epilogue = (cg & 16) ? 0 : 1;
   cg &= 15;
   g_force_cta_group = (cg == 1 || cg == 2) ? cg : 0;
