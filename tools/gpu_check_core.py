@@ -177,6 +177,79 @@ def t_syrk():
         report(f"syrk n={n} d={d} symmetric", (st - st.T).abs().max().item() / st.abs().max().item(), 1e-6)
 
 
+def t_syrk_edges():
+    """Boundary / ragged shapes: SIMT <-> tensor-core switch at d' = 176 | 177, rows that are not 16 B
+    aligned (ones-row fallback), batch sizes that are not multiples of 8, a single sample, pitched
+    state, grouped launch with mixed shapes."""
+    import ctypes as C
+    g = torch.Generator(device="cpu").manual_seed(14)
+    for (n, d, hb) in [(37, 175, 1), (37, 176, 1), (37, 176, 0), (37, 177, 0), (1, 300, 1), (7, 193, 1),
+                       (130, 255, 1), (130, 257, 0), (129, 512, 1), (1000, 201, 1)]:
+        x = torch.randn(n, d, generator=g).to(dev)
+        ref = syrk_ref(x, hb, 1.5, 1.0 / n)
+        for prec, tol in [(0, 3e-6), (3, 3e-5)]:
+            st = syrk_call(x, hb, 1.5, 1.0 / n, 0.0, prec)
+            report(f"syrk edge n={n} d={d} bias={hb} prec={prec}", relerr(st, ref), tol)
+    # pitched state view (ld % 4 == 0 -> TMA-reduce epilogue) must equal the dense one
+    n, d = 96, 300
+    x = torch.randn(n, d, generator=g).to(dev)
+    buf = torch.full((d + 1, 304), float("nan"), device=dev)
+    st = buf[:, :d + 1]
+    wsb = L.bk_syrk_workspace_bytes(n, d, 1, 3)
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+    for beta in (0.0, 1.0):
+        _lib.check(L.bk_syrk_accum(st.data_ptr(), 304, x.data_ptr(), d, n, d, 1, 1.0, 1.0 / n, beta, 3,
+                                   ws.data_ptr(), wsb, _lib.stream_ptr()), "syrk pitched")
+    torch.cuda.synchronize()
+    report("syrk pitched state, beta 0 then 1 (TMA-reduce epilogue)", relerr(st, 2 * syrk_ref(x, 1, 1.0, 1.0 / n)), 3e-5)
+    report("syrk pitched state leaves the padding untouched", float(torch.isnan(buf[:, d + 1:]).all().item() == 0), 0.0)
+    # grouped call with mixed shapes (wide + small + unaligned)
+    shapes = [(64, 400, 1), (64, 256, 0), (64, 20, 1), (50, 301, 1), (64, 1024, 1)]
+    xs = [torch.randn(n_, d_, generator=g).to(dev) for n_, d_, _ in shapes]
+    sts = []
+    for (n_, d_, hb_) in shapes:
+        dp = d_ + hb_
+        pitch = (dp + 3) // 4 * 4 if dp > 176 else dp
+        sts.append(torch.zeros(dp, pitch, device=dev)[:, :dp])
+    cnt = len(shapes)
+    ns = (C.c_int * cnt)(*[s_[0] for s_ in shapes]); ds = (C.c_int * cnt)(*[s_[1] for s_ in shapes])
+    hbs = (C.c_int * cnt)(*[s_[2] for s_ in shapes])
+    nb = L.bk_syrk_grouped_workspace_bytes(ns, ds, hbs, cnt, 3)
+    ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
+    for beta in (0.0, 1.0):
+        rc = L.bk_syrk_accum_grouped((C.c_void_p * cnt)(*[t.data_ptr() for t in sts]),
+                                     (C.c_longlong * cnt)(*[t.stride(0) for t in sts]),
+                                     (C.c_void_p * cnt)(*[t.data_ptr() for t in xs]),
+                                     (C.c_longlong * cnt)(*[t.stride(0) for t in xs]), ns, ds, hbs,
+                                     (C.c_float * cnt)(*[1.0] * cnt), (C.c_float * cnt)(*[1.0 / s_[0] for s_ in shapes]),
+                                     (C.c_float * cnt)(*[beta] * cnt), cnt, 3, ws.data_ptr(), nb, _lib.stream_ptr())
+        _lib.check(rc, "bk_syrk_accum_grouped")
+    torch.cuda.synchronize()
+    for (n_, d_, hb_), x_, st_ in zip(shapes, xs, sts):
+        report(f"grouped syrk n={n_} d={d_} bias={hb_} (beta 0 then 1)", relerr(st_, 2 * syrk_ref(x_, hb_, 1.0, 1.0 / n_)), 3e-5)
+
+
+def t_chol_small():
+    g = torch.Generator(device="cpu").manual_seed(8)
+    fs = []
+    for d in (1, 5, 10, 26, 64, 65, 81, 126, 161, 300, 785, 1025):
+        x = torch.relu(torch.randn(256, d, generator=g)).to(dev)
+        F_ = (x.T @ x / 256)
+        F_ = F_ + 0.01 * torch.randn(d, d, generator=g).to(dev) * 1e-3  # slightly non-symmetric input
+        fs.append(F_.contiguous())
+    for (add, mult) in [(0.04, 200.0), (1.0, 200.0)]:
+        rc, outs = chol_inv(fs, [add] * len(fs), [mult] * len(fs))
+        report(f"chol_inv batched rc==0 add={add}", float(rc), 0.0)
+        for F_, Lo in zip(fs, outs):
+            Lref, R = chol_ref(F_, add, mult)
+            d = F_.shape[0]
+            report(f"chol_inv d={d} add={add} L vs reference", relerr(Lo, Lref), 1e-3)
+            report(f"chol_inv d={d} upper triangle zero", torch.triu(Lo, 1).abs().max().item() if d > 1 else 0.0, 0.0)
+    bad = torch.eye(70, device=dev); bad[40, 40] = -5.0
+    rc, _ = chol_inv([fs[3], bad], [0.0, 0.0], [1.0, 1.0])
+    report("chol_inv reports non-SPD factor index (expect 2)", abs(rc - 2), 0.0)
+
+
 def t_syrk_wide():
     g = torch.Generator(device="cpu").manual_seed(5)
     n, d = 4096, 4096
@@ -375,7 +448,7 @@ if __name__ == "__main__":
     print(L.bk_version().decode(), torch.cuda.get_device_name(0), flush=True)
     t0 = time.time()
     only = sys.argv[1:]
-    allfn = (t_diag, t_philox, t_conv, t_gemm_basic, t_gemm_epilogue, t_gemm_tri, t_syrk, t_syrk_wide, t_chol)
+    allfn = (t_diag, t_philox, t_conv, t_gemm_basic, t_gemm_epilogue, t_gemm_tri, t_syrk, t_syrk_edges, t_syrk_wide, t_chol_small, t_chol)
     for fn in [f for f in allfn if not only or f.__name__ in only]:
         print(f"--- {fn.__name__}", flush=True)
         case(fn)
