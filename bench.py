@@ -418,9 +418,19 @@ def extras(est, model, layers, dev, world, rank):
     ms_full = ev_ms(full_step, reps=5)
     out["update_incl_model_fwd_bwd"] = {"ms_per_step": ms_full, "samples_per_s": BATCH * world / (ms_full * 1e-3),
                                         "note": "torch fp32 forward + backward of the MLP, hooks, then KFAC.update"}
-    est.invert(1.0, 200.0)      # warm-up (workspace allocation)
-    out["invert_ms_all_layers"] = ev_ms(lambda: est.invert(1.0, 200.0))
-    out["invert_config"] = "8 factors (4 x 4097^2, 3 x 4096^2, 10^2), add=1, multiply=200, one batched launch sequence"
+    if world > 1:
+        from bnn_kfac_b200.distributed import invert_sharded
+        inv = lambda: invert_sharded(est, 1.0, 200.0)     # noqa: E731
+        cfg = f"8 factors sharded over {world} ranks: all-reduce, owner inverts, broadcast of L"
+    else:
+        inv = lambda: est.invert(1.0, 200.0)              # noqa: E731
+        cfg = "one batched launch sequence"
+    inv()      # warm-up (workspace allocation)
+    t_inv = torch.tensor([ev_ms(inv)], device=dev)
+    if world > 1:
+        dist.all_reduce(t_inv, op=dist.ReduceOp.MAX)
+    out["invert_ms_all_layers"] = t_inv.item()
+    out["invert_config"] = "8 factors (4 x 4097^2, 3 x 4096^2, 10^2), add=1, multiply=200; " + cfg
     # posterior predictive: S weight samples per rank (sample ids sharded over ranks), 1024 test inputs
     S, B = 16, 1024
     x = torch.randn(B, WIDTHS[0], device=dev)

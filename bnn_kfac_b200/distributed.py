@@ -160,21 +160,13 @@ def reduce_state_copy(est, group=None) -> List[Tensor]:
     factors: List[Tensor] = []
     for v in est.state.values():
         factors += list(v) if isinstance(v, (list, tuple)) else [v]
-    reduced = [f.clone(memory_format=torch.contiguous_format) for f in factors]
-    if w == 1:
-        return reduced
-    small = [t for t in reduced if t.numel() * t.element_size() < (1 << 20)]
-    works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
-             for t in reduced if t.numel() * t.element_size() >= (1 << 20)]
-    if small:
-        flat, views = _flat_views(small)
+    if not factors:
+        return []
+    # one flat buffer, one collective: the copies are the send buffer
+    flat, reduced = _flat_views(factors)
+    if w > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        for t, v in zip(small, views):
-            t.copy_(v)
-    for wk in works:
-        wk.wait()
-    for t in reduced:
-        t.mul_(1.0 / w)
+        flat.mul_(1.0 / w)
     return reduced
 
 
