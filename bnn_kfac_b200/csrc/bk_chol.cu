@@ -18,6 +18,9 @@
 // inverse is 1e-3, which rules out bf16 trailing updates.
 #include "bk_common.cuh"
 #include "bk_kernels.cuh"
+#include "bk_umma_gemm.cuh"
+
+#include <vector>
 
 namespace bk {
 
@@ -154,9 +157,12 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
 // ------------------------------------------------------------------ rank-64 update
 enum Mode : int { kPanel = 0, kTrail = 1, kRowScale = 2, kXUpdate = 3 };
 
-// C[m x n] = beta*C + alpha * A[m x 64] * (NT ? B[n x 64]^T : B[64 x n]);  one 128x128 tile / CTA
+// C[m x n] = beta*C + alpha * A[m x 64] * (NT ? B[n x 64]^T : B[64 x n]);  one 128x128 tile / CTA.
+// `limit` (two-level blocking, 0 = none): the rank-64 update only reaches up to row / column `limit`
+// of the matrix (the end of the current 256-wide outer block); everything beyond it receives the
+// whole outer block at once from the tensor-core GEMM (see chol_inv_batched).
 __global__ void __launch_bounds__(256)
-rank64_kernel(const CholProb* __restrict__ tab, int k, int mode) {
+rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
   const CholProb p = tab[blockIdx.y];
   if (k >= p.nb) return;
   const long long ld = p.dpad;
@@ -174,6 +180,7 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode) {
     alpha = 1.f; beta = 0.f;
   } else if (mode == kTrail) {
     m = n = p.dpad - k1;
+    if (limit > 0) n = min(limit, p.dpad) - k1;  // columns inside the outer block only
     C = p.R + k1 * ld + k1; A = p.R + k1 * ld + k0; lda = ld; B = A; ldb = ld; nt = true;
     lower = true; alpha = -1.f; beta = 1.f;
   } else if (mode == kRowScale) {
@@ -183,13 +190,19 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode) {
     alpha = 1.f; beta = 0.f;
   } else {
     m = p.dpad - k1; n = k1;
+    if (limit > 0) m = min(limit, p.dpad) - k1;  // rows inside the outer block only
     C = p.X + k1 * ld; A = p.R + k1 * ld + k0; lda = ld; B = p.X + k0 * ld; ldb = ld; nt = false;
     alpha = -1.f; beta = 1.f;
   }
   if (m <= 0 || n <= 0) return;
   const int tiles_m = (m + TM - 1) / TM, tiles_n = (n + TN - 1) / TN;
   int ti, tj;
-  if (lower) {
+  if (lower && limit > 0) {
+    // rectangular m x n region (n <= 192) of the lower triangle: plain enumeration + masking
+    ti = blockIdx.x / tiles_n;
+    tj = blockIdx.x - ti * tiles_n;
+    if (ti >= tiles_m || tj * TN > ti * TM + TM - 1) return;
+  } else if (lower) {
     const int t = blockIdx.x;
     ti = static_cast<int>((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
@@ -341,17 +354,87 @@ __global__ void flip_out_kernel(const CholProb* __restrict__ tab) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int pad_dim(int d) { return (d + NB - 1) / NB * NB; }
 
+constexpr int kOuter = 256;       // outer block width of the two-level algorithm (4 inner blocks)
+constexpr int kTwoLevelMin = 2048;  // padded size from which the tensor-core trailing updates pay off
+
+inline size_t staging_bytes(int max_pad) {
+  // two operands (L21 and the transposed X block), three bf16 parts each, [max_pad, kOuter]
+  return max_pad >= kTwoLevelMin ? 2 * 3 * align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) : 0;
+}
+
 }  // namespace
 
 size_t chol_inv_workspace_bytes(const int* dims, int count) {
   size_t bytes = align_up(sizeof(CholProb) * static_cast<size_t>(count), 256) +
                  align_up(sizeof(int) * static_cast<size_t>(count), 256);
+  int max_pad = 0;
   for (int f = 0; f < count; ++f) {
     const size_t dp = pad_dim(dims[f]);
     bytes += align_up(dp * dp * 4, 256) * 2 + align_up((dp / NB) * NB * NB * 4, 256);
+    if (static_cast<int>(dp) > max_pad) max_pad = static_cast<int>(dp);
   }
-  return bytes;
+  return bytes + staging_bytes(max_pad);
 }
+
+namespace {
+
+// One 256-wide outer block of factor p is final in `src` (R for phase 1, R again for phase 2): hand
+// its contribution to everything beyond the block to the tensor cores as an fp32-class bf16x6 GEMM
+// (hi/lo/lo2 splits carry 24 mantissa bits, six accumulating passes; a plain bf16 or bf16x3 update
+// would perturb the Schur complement by 1e-3 .. 1e-5 and the inverse by cond(R) times that).
+//   phase 1:  R[c1:, c1:]  -= L21 L21^T          (SYRK, lower tiles only)
+//   phase 2:  X[c1:, :c1]  -= L21 X[c0:c1, :c1]
+int outer_update(const CholProb& p, int c0, bool phase2, __nv_bfloat16* sa, __nv_bfloat16* sb,
+                 size_t part_stride, cudaStream_t stream) {
+  const int c1 = c0 + kOuter;
+  if (c1 >= p.dpad) return 0;
+  const int m2 = p.dpad - c1;
+  const long long ld = p.dpad;
+  __nv_bfloat16* a0 = sa;
+  __nv_bfloat16* a1 = sa + part_stride;
+  __nv_bfloat16* a2 = sa + 2 * part_stride;
+  int rc = launch_convert_split3(p.R + static_cast<long long>(c1) * ld + c0, ld, m2, kOuter, a0, a1, a2,
+                                 kOuter, stream);
+  if (rc) return rc;
+  GemmArgs g;
+  g.A_hi = a0;
+  g.A_lo = a1;
+  g.A_lo2 = a2;
+  g.lda = kOuter;
+  g.K = kOuter;
+  g.M = m2;
+  g.batch = 1;
+  g.nparts = 6;
+  g.alpha = -1.f;
+  g.beta = 1.f;
+  g.ldc = ld;
+  if (!phase2) {
+    g.B_hi = a0;
+    g.B_lo = a1;
+    g.B_lo2 = a2;
+    g.ldb = kOuter;
+    g.N = m2;
+    g.flags = kSyrkLower;
+    g.C = p.R + static_cast<long long>(c1) * ld + c1;
+  } else {
+    __nv_bfloat16* b0 = sb;
+    __nv_bfloat16* b1 = sb + part_stride;
+    __nv_bfloat16* b2 = sb + 2 * part_stride;
+    rc = launch_transpose_split3(p.X + static_cast<long long>(c0) * ld, ld, kOuter, c1, b0, b1, b2,
+                                 kOuter, stream);
+    if (rc) return rc;
+    g.B_hi = b0;
+    g.B_lo = b1;
+    g.B_lo2 = b2;
+    g.ldb = kOuter;
+    g.N = c1;
+    g.flags = 0;
+    g.C = p.X + static_cast<long long>(c1) * ld;
+  }
+  return launch_umma_gemm(g, stream);
+}
+
+}  // namespace
 
 int chol_inv_batched(const float* const* factors, float* const* outs, const int* dims,
                      const float* add, const float* multiply, int count, void* workspace,
@@ -402,6 +485,7 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
                                   stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_info, 0, sizeof(int) * count, stream);
   // the table copy is from pageable memory: it has been staged when the call returns
+  std::vector<CholProb> h_tab2(h_tab, h_tab + count);
   delete[] h_tab;
   if (e != cudaSuccess) return -5;
 
@@ -410,28 +494,63 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   const dim3 tg((max_pad + 31) / 32, (max_pad + 31) / 32, count);
   damp_flip_kernel<<<tg, tb, 0, stream>>>(d_tab);
   note_launch();
+  // Two-level blocking for wide factors: rank-64 SIMT updates stay inside the current 256-wide outer
+  // block; the update of everything beyond it is ONE fp32-class (bf16x6) tensor-core GEMM per factor.
+  const bool two_level = max_pad >= kTwoLevelMin;
+  const int inner_per_outer = kOuter / NB;
+  __nv_bfloat16* stage_a = reinterpret_cast<__nv_bfloat16*>(w);
+  const size_t part_stride = align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) / 2;
+  __nv_bfloat16* stage_b = stage_a + 3 * part_stride;
+  // ---- phase 1: right-looking Cholesky of the flipped damped matrix
   for (int k = 0; k < max_nb; ++k) {
+    const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
     potrf_diag_kernel<<<count, 256, 0, stream>>>(d_tab, k, d_info);
-  note_launch();
+    note_launch();
     const int m = max_pad - (k + 1) * NB;
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
-      rank64_kernel<<<dim3(tm, count), 256, smem, stream>>>(d_tab, k, kPanel);
-  note_launch();
-      rank64_kernel<<<dim3(tm * (tm + 1) / 2, count), 256, smem, stream>>>(d_tab, k, kTrail);
-  note_launch();
+      rank64_kernel<<<dim3(tm, count), 256, smem, stream>>>(d_tab, k, kPanel, 0);
+      note_launch();
+      if (!two_level) {
+        rank64_kernel<<<dim3(tm * (tm + 1) / 2, count), 256, smem, stream>>>(d_tab, k, kTrail, 0);
+        note_launch();
+      } else {
+        const int ncols = limit - (k + 1) * NB;  // columns of the outer block right of this step
+        if (ncols > 0) {
+          const int tn = (ncols + TN - 1) / TN;
+          rank64_kernel<<<dim3(tm * tn, count), 256, smem, stream>>>(d_tab, k, kTrail, limit);
+          note_launch();
+        }
+      }
+    }
+    if (two_level && (k + 1) % inner_per_outer == 0) {
+      const int c0 = (k + 1 - inner_per_outer) * NB;
+      for (int f = 0; f < count; ++f) {
+        const int rc = outer_update(h_tab2[f], c0, false, stage_a, stage_b, part_stride, stream);
+        if (rc) return rc;
+      }
     }
   }
+  // ---- phase 2: X = C^-1 by block forward substitution on the identity
   for (int k = 0; k < max_nb; ++k) {
+    const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
     const int n = (k + 1) * NB;
     const int tn = (n + TN - 1) / TN;
-    rank64_kernel<<<dim3(tn, count), 256, smem, stream>>>(d_tab, k, kRowScale);
-  note_launch();
-    const int m = max_pad - (k + 1) * NB;
+    rank64_kernel<<<dim3(tn, count), 256, smem, stream>>>(d_tab, k, kRowScale, 0);
+    note_launch();
+    int m = max_pad - (k + 1) * NB;
+    if (two_level) m = (limit < max_pad ? limit : max_pad) - (k + 1) * NB;
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
-      rank64_kernel<<<dim3(tm * tn, count), 256, smem, stream>>>(d_tab, k, kXUpdate);
-  note_launch();
+      rank64_kernel<<<dim3(tm * tn, count), 256, smem, stream>>>(d_tab, k, kXUpdate, limit);
+      note_launch();
+    }
+    if (two_level && (k + 1) % inner_per_outer == 0) {
+      const int c0 = (k + 1 - inner_per_outer) * NB;
+      for (int f = 0; f < count; ++f) {
+        const int rc = outer_update(h_tab2[f], c0, true, stage_a, stage_b, part_stride, stream);
+        if (rc) return rc;
+      }
     }
   }
   flip_out_kernel<<<tg, tb, 0, stream>>>(d_tab);

@@ -13,6 +13,12 @@ namespace bk {
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
                            cudaStream_t stream, float* colsum = nullptr);
+// Three-way bf16 splits (hi + lo + lo2: 24 mantissa bits) for the bf16x6 products of bk_chol.cu.
+int launch_convert_split3(const float* X, long long ldx, int rows, int cols, __nv_bfloat16* O0,
+                          __nv_bfloat16* O1, __nv_bfloat16* O2, long long ldo, cudaStream_t stream);
+int launch_transpose_split3(const float* X, long long ldx, int rows, int cols, __nv_bfloat16* T0,
+                            __nv_bfloat16* T1, __nv_bfloat16* T2, long long ldt,
+                            cudaStream_t stream);
 // Row / column d of a bias-augmented factor from the column sums (see bk_prep.cu).
 int launch_bias_border(float* state, long long ld, int d, const float* colsum, float alpha,
                        float beta, float n, cudaStream_t stream);

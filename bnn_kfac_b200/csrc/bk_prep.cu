@@ -229,7 +229,96 @@ convert_split_kernel(const float* __restrict__ X, long long ldx, int rows, int c
   }
 }
 
+// ---- three-way bf16 splits (hi + lo + lo2 = 24 mantissa bits) for the fp32-class bf16x6 products of
+// the blocked Cholesky trailing updates.
+__device__ __forceinline__ void split3_bf16(float x, __nv_bfloat16& h, __nv_bfloat16& m,
+                                            __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+
+// fp32 [rows, cols] (pitch ldx, 16 B aligned rows, cols % 4 == 0) -> three bf16 [rows, ldo] parts.
+__global__ void __launch_bounds__(256)
+convert_split3_kernel(const float* __restrict__ X, long long ldx, int rows, int cols,
+                      __nv_bfloat16* __restrict__ O0, __nv_bfloat16* __restrict__ O1,
+                      __nv_bfloat16* __restrict__ O2, long long ldo) {
+  const int n4 = cols >> 2;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const float4* src = reinterpret_cast<const float4*>(X + static_cast<long long>(r) * ldx);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const float4 v = __ldg(src + i);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 h[4], m[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split3_bf16(e[j], h[j], m[j], l[j]);
+      const long long o = static_cast<long long>(r) * ldo + (i << 2);
+      uint2 p;
+      p.x = (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16) | __bfloat16_as_ushort(h[0]);
+      p.y = (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16) | __bfloat16_as_ushort(h[2]);
+      *reinterpret_cast<uint2*>(O0 + o) = p;
+      p.x = (static_cast<uint32_t>(__bfloat16_as_ushort(m[1])) << 16) | __bfloat16_as_ushort(m[0]);
+      p.y = (static_cast<uint32_t>(__bfloat16_as_ushort(m[3])) << 16) | __bfloat16_as_ushort(m[2]);
+      *reinterpret_cast<uint2*>(O1 + o) = p;
+      p.x = (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16) | __bfloat16_as_ushort(l[0]);
+      p.y = (static_cast<uint32_t>(__bfloat16_as_ushort(l[3])) << 16) | __bfloat16_as_ushort(l[2]);
+      *reinterpret_cast<uint2*>(O2 + o) = p;
+    }
+  }
+}
+
+// fp32 [rows, cols] -> three bf16 [cols, ldt] parts (transposed).  32 x 32 tiles through shared memory.
+__global__ void transpose_split3_kernel(const float* __restrict__ X, long long ldx, int rows, int cols,
+                                        __nv_bfloat16* __restrict__ T0,
+                                        __nv_bfloat16* __restrict__ T1,
+                                        __nv_bfloat16* __restrict__ T2, long long ldt) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    tile[ty + 8 * k][tx] = (r < rows && c < cols) ? X[static_cast<long long>(r) * ldx + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int orow = c0 + ty + 8 * k, ocol = r0 + tx;
+    if (orow < cols && ocol < rows) {
+      __nv_bfloat16 h, m, l;
+      split3_bf16(tile[tx][ty + 8 * k], h, m, l);
+      const long long o = static_cast<long long>(orow) * ldt + ocol;
+      T0[o] = h;
+      T1[o] = m;
+      T2[o] = l;
+    }
+  }
+}
+
 }  // namespace
+
+int launch_convert_split3(const float* X, long long ldx, int rows, int cols, __nv_bfloat16* O0,
+                          __nv_bfloat16* O1, __nv_bfloat16* O2, long long ldo, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if ((cols & 3) || (ldx & 3) || (ldo & 3) || (reinterpret_cast<uintptr_t>(X) & 15)) return -2;
+  int bx = (cols / 4 + 255) / 256;
+  if (bx > 16) bx = 16;
+  dim3 grid(bx, rows < 65535 ? rows : 65535);
+  convert_split3_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, O0, O1, O2, ldo);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_transpose_split3(const float* X, long long ldx, int rows, int cols, __nv_bfloat16* T0,
+                            __nv_bfloat16* T1, __nv_bfloat16* T2, long long ldt,
+                            cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_split3_kernel<<<grid, block, 0, stream>>>(X, ldx, rows, cols, T0, T1, T2, ldt);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
 
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,

@@ -150,35 +150,51 @@ __device__ __forceinline__ Tile decode_group_tile(const GroupParams& gp, int t, 
   return r;
 }
 
+// Operand maps of a single problem: up to three bf16 parts per operand (hi, lo, lo2) + the fp32 output.
+struct OpMaps {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+  CUtensorMap c;
+};
+
+// Split-precision schedules: which (A part, B part) product each pass accumulates.
+//   1 pass  : hi*hi                                   (bf16)
+//   3 passes: + hi*lo, lo*hi                          (bf16x3, ~2^-17 per product)
+//   6 passes: + hi*lo2, lo2*hi, lo*lo                 (bf16x6, 24 mantissa bits: fp32-class)
+__device__ __forceinline__ void part_pair(int part, int& ia, int& ib) {
+  ia = (part == 2) ? 1 : (part == 4) ? 2 : (part == 5) ? 1 : 0;
+  ib = (part == 1) ? 1 : (part == 3) ? 2 : (part == 5) ? 1 : 0;
+}
+
 // Per-tile view of "which problem": tensor maps, extents and scale.
 struct Work {
   Tile tl;
-  const CUtensorMap *a0, *a1, *b0, *b1, *c;
+  const CUtensorMap *a[3], *b[3], *c;
   int M, N;
   float alpha;
 };
 
 template <int CG, bool kGrouped>
-__device__ __forceinline__ Work get_work(int t, const KParams& p, const CUtensorMap* tmA0,
-                                         const CUtensorMap* tmA1, const CUtensorMap* tmB0,
-                                         const CUtensorMap* tmB1, const CUtensorMap* tmC,
+__device__ __forceinline__ Work get_work(int t, const KParams& p, const OpMaps* om,
                                          const GroupMaps* gm, const GroupParams* gp) {
   Work w;
   if (kGrouped) {
     int g;
     w.tl = decode_group_tile(*gp, t, g);
-    w.a0 = w.b0 = &gm->a0[g];
-    w.a1 = w.b1 = &gm->a1[g];
+    w.a[0] = w.b[0] = &gm->a0[g];
+    w.a[1] = w.b[1] = &gm->a1[g];
+    w.a[2] = w.b[2] = &gm->a1[g];
     w.c = &gm->c[g];
     w.M = w.N = gp->M[g];
     w.alpha = gp->alpha[g];
   } else {
     w.tl = decode_tile<CG>(p, t);
-    w.a0 = tmA0;
-    w.a1 = tmA1;
-    w.b0 = tmB0;
-    w.b1 = tmB1;
-    w.c = tmC;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      w.a[i] = &om->a[i];
+      w.b[i] = &om->b[i];
+    }
+    w.c = &om->c;
     w.M = p.M;
     w.N = p.N;
     w.alpha = p.alpha;
@@ -187,10 +203,8 @@ __device__ __forceinline__ Work get_work(int t, const KParams& p, const CUtensor
 }
 
 template <int CG, bool kTmaEpi, bool kGrouped>
-__device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtensorMap* tmA1,
-                                          const CUtensorMap* tmB0, const CUtensorMap* tmB1,
-                                          const CUtensorMap* tmC, const KParams& p,
-                                          const GroupMaps* gm, const GroupParams* gp) {
+__device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, const GroupMaps* gm,
+                                          const GroupParams* gp) {
   const int num_tiles = kGrouped ? gp->tile_begin[gp->count] : p.num_tiles;
   const int nparts = kGrouped ? gp->nparts : p.nparts;
   const int flags = kGrouped ? (kSyrkLower | kMirror) : p.flags;
@@ -218,12 +232,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtenso
   const int tile_step = (CG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0 && !kGrouped) {
-    tma_prefetch_desc(tmA0);
-    tma_prefetch_desc(tmB0);
-    if (kTmaEpi) tma_prefetch_desc(tmC);
+    tma_prefetch_desc(&om->a[0]);
+    tma_prefetch_desc(&om->b[0]);
+    if (kTmaEpi) tma_prefetch_desc(&om->c);
     if (nparts > 1) {
-      tma_prefetch_desc(tmA1);
-      tma_prefetch_desc(tmB1);
+      tma_prefetch_desc(&om->a[1]);
+      tma_prefetch_desc(&om->b[1]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -253,7 +267,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtenso
       int stage = 0;
       uint32_t phase = 0;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
-        const Work wk = get_work<CG, kGrouped>(t, p, tmA0, tmA1, tmB0, tmB1, tmC, gm, gp);
+        const Work wk = get_work<CG, kGrouped>(t, p, om, gm, gp);
         const Tile tl = wk.tl;
         const int iters = tl.nkb * nparts;
         // this CTA's slice of the cluster tile: its own 128 rows of A, its share of the B rows
@@ -262,9 +276,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtenso
         for (int it = 0; it < iters; ++it) {
           const int part = it / tl.nkb;
           const int kb = tl.kb0 + it - part * tl.nkb;
-          // part 0: hi*hi, part 1: hi*lo, part 2: lo*hi
-          const CUtensorMap* ma = (part == 2) ? wk.a1 : wk.a0;
-          const CUtensorMap* mb = (part == 1) ? wk.b1 : wk.b0;
+          int ia, ib;
+          part_pair(part, ia, ib);
+          const CUtensorMap* ma = wk.a[ia];
+          const CUtensorMap* mb = wk.b[ib];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           if (CG == 2) {
@@ -294,7 +309,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtenso
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
-        const Tile tl = get_work<CG, kGrouped>(t, p, tmA0, tmA1, tmB0, tmB1, tmC, gm, gp).tl;
+        const Tile tl = get_work<CG, kGrouped>(t, p, om, gm, gp).tl;
         const int iters = tl.nkb * nparts;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -344,7 +359,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtenso
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
-      const Work wk = get_work<CG, kGrouped>(t, p, tmA0, tmA1, tmB0, tmB1, tmC, gm, gp);
+      const Work wk = get_work<CG, kGrouped>(t, p, om, gm, gp);
       const Tile tl = wk.tl;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -512,17 +527,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA0, const CUtenso
 
 template <int CG, bool kTmaEpi>
 __global__ void __launch_bounds__(kThreads, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                 const __grid_constant__ CUtensorMap tmC, const KParams p) {
-  gemm_body<CG, kTmaEpi, false>(&tmA0, &tmA1, &tmB0, &tmB1, &tmC, p, nullptr, nullptr);
+umma_gemm_kernel(const __grid_constant__ OpMaps om, const KParams p) {
+  gemm_body<CG, kTmaEpi, false>(&om, p, nullptr, nullptr);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 umma_syrk_grouped_kernel(const __grid_constant__ GroupMaps maps,
                          const __grid_constant__ GroupParams gp) {
   KParams p{};  // batch / bias / bf16-output fields unused by the grouped accumulate path
-  gemm_body<2, true, true>(nullptr, nullptr, nullptr, nullptr, nullptr, p, &maps, &gp);
+  gemm_body<2, true, true>(nullptr, p, &maps, &gp);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -648,24 +661,22 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.strideO = a.strideO;
 
   // Each CTA loads boxes of its own 128 A rows and of its share (256 / CG) of the B rows.
-  CUtensorMap mA0, mA1, mB0, mB1;
-  int rc = make_operand_map(&mA0, a.A_hi, a.M, a.K, a.lda, a.strideA, a.batch, BM);
-  if (rc) return rc;
-  rc = make_operand_map(&mB0, a.B_hi, a.N, a.K, a.ldb, a.strideB, a.batch, Cfg<CG>::kRowsB);
-  if (rc) return rc;
-  if (a.nparts == 3) {
-    rc = make_operand_map(&mA1, a.A_lo, a.M, a.K, a.lda, a.strideA, a.batch, BM);
+  OpMaps om;
+  const __nv_bfloat16* ap[3] = {a.A_hi, a.A_lo, a.A_lo2};
+  const __nv_bfloat16* bp[3] = {a.B_hi, a.B_lo, a.B_lo2};
+  const int nsplit = a.nparts == 6 ? 3 : (a.nparts == 3 ? 2 : 1);
+  int rc = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int src = i < nsplit ? i : 0;
+    rc = make_operand_map(&om.a[i], ap[src], a.M, a.K, a.lda, a.strideA, a.batch, BM);
     if (rc) return rc;
-    rc = make_operand_map(&mB1, a.B_lo, a.N, a.K, a.ldb, a.strideB, a.batch, Cfg<CG>::kRowsB);
+    rc = make_operand_map(&om.b[i], bp[src], a.N, a.K, a.ldb, a.strideB, a.batch, Cfg<CG>::kRowsB);
     if (rc) return rc;
-  } else {
-    mA1 = mA0;
-    mB1 = mB0;
   }
+  om.c = om.a[0];
   // beta == 0 with the accumulating epilogue: zero-fill C first.
-  CUtensorMap mC = mA0;
   if (kTmaEpi) {
-    rc = make_output_map(&mC, a.C, a.M, a.N, a.ldc, a.strideC, a.batch);
+    rc = make_output_map(&om.c, a.C, a.M, a.N, a.ldc, a.strideC, a.batch);
     if (rc) return rc;
     if (a.beta == 0.f) {
       for (int b = 0; b < a.batch; ++b)
@@ -689,8 +700,7 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  const cudaError_t err = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<CG, kTmaEpi>, mA0, mA1, mB0, mB1,
-                                             mC, p);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<CG, kTmaEpi>, om, p);
   note_launch();
   return (err == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -5;
 }
@@ -779,8 +789,9 @@ int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return 0;
   if (a.K <= 0) return -2;
   if (a.A_hi == nullptr || a.B_hi == nullptr) return -2;
-  if (a.nparts != 1 && a.nparts != 3) return -2;
-  if (a.nparts == 3 && (a.A_lo == nullptr || a.B_lo == nullptr)) return -2;
+  if (a.nparts != 1 && a.nparts != 3 && a.nparts != 6) return -2;
+  if (a.nparts >= 3 && (a.A_lo == nullptr || a.B_lo == nullptr)) return -2;
+  if (a.nparts == 6 && (a.A_lo2 == nullptr || a.B_lo2 == nullptr)) return -2;
   if ((a.flags & kSyrkLower) && a.M != a.N) return -2;
   // CTA pairs (256-row tiles) pay off once the 256-row quantisation wastes little: at least one
   // full pair tile of rows and a full 256-column tile.
@@ -791,8 +802,7 @@ int launch_umma_gemm(const GemmArgs& a, cudaStream_t stream) {
   const bool tma_epi =
       g_allow_tma_epilogue && a.C != nullptr && a.bias == nullptr && a.O_hi == nullptr &&
       !(a.flags & kRelu) && (a.beta == 1.f || a.beta == 0.f) && (a.ldc % 4) == 0 &&
-      (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.batch == 1 || (a.strideC % 4) == 0) &&
-      (!(a.flags & kSyrkLower) || (a.flags & kMirror));
+      (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.batch == 1 || (a.strideC % 4) == 0);
   if (cg == 2)
     return tma_epi ? launch_cg<2, true>(a, stream) : launch_cg<2, false>(a, stream);
   return tma_epi ? launch_cg<1, true>(a, stream) : launch_cg<1, false>(a, stream);

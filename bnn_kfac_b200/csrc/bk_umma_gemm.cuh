@@ -28,10 +28,12 @@ struct GemmArgs {
   const __nv_bfloat16* A_lo = nullptr;
   const __nv_bfloat16* B_hi = nullptr;
   const __nv_bfloat16* B_lo = nullptr;
+  const __nv_bfloat16* A_lo2 = nullptr;  // third split (nparts == 6: hi + lo + lo2 carries 24 mantissa bits)
+  const __nv_bfloat16* B_lo2 = nullptr;
   long long lda = 0, ldb = 0;
   long long strideA = 0, strideB = 0;  // per-batch element strides; 0 = operand shared by all batches
   int M = 0, N = 0, K = 0, batch = 1;
-  int nparts = 1;
+  int nparts = 1;  // 1 (bf16), 3 (bf16x3), 6 (bf16x6, fp32-class products)
   int flags = 0;
   int tri_koff = 0;  // with kTriB: B[n][k] == 0 for k > tri_koff + n (dense columns [0, tri_koff))
   // epilogue:  v = alpha * acc + beta * C + bias[n];  optional relu;  outputs: C (fp32) and/or
