@@ -79,74 +79,96 @@ __global__ void damp_flip_kernel(const CholProb* __restrict__ tab) {
 
 // ------------------------------------------------------------------ diagonal block: potrf + inverse
 // One CTA factorises the 64 x 64 diagonal block AND inverts the factor, both in REGISTERS and in the
-// same sweep: thread (c, rq) owns column c, rows rq + 4r (r = 0..15) of the block A and of X (X = I
+// same sweep.  Thread (c, rq) owns column c, rows 16 rq .. 16 rq + 15 of the block A and of X (X = I
 // initially).  Step j: the owners of column j of A and of row j of X publish them through
-// double-buffered shared vectors, ONE barrier, then every thread does 16 + 16 independent FMAs:
-//     A[i][c] -= L[i][j] L[c][j]   (i > j, c > j)         right-looking Cholesky
-//     X[j][c]  = X[j][c] / L[j][j];  X[i][c] -= L[i][j] X[j][c]  (i > j)   forward substitution on I
-// so that X ends as L^-1.  (Earlier versions kept the block in shared memory - two barriers and a
-// dependent load-modify-store chain per step - and inverted it afterwards with one thread per
-// column: ~75 us per block, 35 % of a 4097-wide inversion, all of it serial latency.)
+// double-buffered shared vectors, ONE barrier, then
+//     c > j :  A[i][c] -= L[i][j] L[c][j]              (i > j)    right-looking Cholesky
+//     c <= j:  X[i][c] -= L[i][j] X[j][c]              (i > j)    forward substitution on I
+// (X[j][c] is zero for c > j and columns c < j of A are final, so a thread does ONE of the two), with
+// L[i][j] L[c][j] = colj[i] colj[c] / piv.  Rows are blocked, not cyclic: warps whose 16 rows are all
+// <= j have nothing left to do and fall through to the barrier, so the work shrinks with j, and the
+// published column is read with 128-bit loads.
+// (Earlier versions: block in shared memory, two barriers and a dependent load-modify-store chain per
+// step, inverse afterwards by one thread per column: ~64-75 us per block, a third of a 4097-wide
+// inversion, all of it serial latency.)
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ info) {
   const CholProb p = tab[blockIdx.x];
   if (k >= p.nb) return;
-  __shared__ float colj[2][NB];
+  __shared__ __align__(16) float colj[2][NB];
   __shared__ float xrow[2][NB];
   __shared__ int bad;
   const int tid = threadIdx.x;
   float* blk = p.R + static_cast<long long>(k) * NB * p.dpad + k * NB;
   if (tid == 0) bad = 0;
-  const int c = tid % NB, rq = tid / NB;  // column, row phase (0..3)
+  const int c = tid % NB, rq = tid / NB;  // column, row block (0..3)
   constexpr int R = NB / 4;
+  const int i0 = R * rq;
   float a[R], x[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    a[r] = blk[static_cast<long long>(rq + 4 * r) * p.dpad + c];
-    x[r] = (rq + 4 * r == c) ? 1.f : 0.f;
+    a[r] = blk[static_cast<long long>(i0 + r) * p.dpad + c];
+    x[r] = (i0 + r == c) ? 1.f : 0.f;
   }
 #pragma unroll 1
   for (int j = 0; j < NB; ++j) {
     float* cj = colj[j & 1];
     float* xj = xrow[j & 1];
-    const int rj = j >> 2;
-    if (c == j) {
+    const bool row_owner = (j >> 4) == rq;  // this thread holds row j (warp-uniform)
+    if (c == j && i0 + R - 1 >= j) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) cj[rq + 4 * r] = a[r];
+      for (int r = 0; r < R; r += 4)
+        *reinterpret_cast<float4*>(&cj[i0 + r]) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
     }
-    if (rq == (j & 3)) {
+    if (row_owner) {
       float xv = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) xv = (r == rj) ? x[r] : xv;
+      for (int r = 0; r < R; ++r) xv = (r == (j & 15)) ? x[r] : xv;
       xj[c] = xv;  // X[j][c] before the division by L[j][j]
     }
     __syncthreads();
+    if (i0 + R - 1 < j) continue;  // all rows of this warp are final (warp-uniform)
     float piv = cj[j];
     if (!(piv > 0.f)) {  // not positive definite (or NaN)
-      if (tid == 0) bad = 1;
+      if (tid == 0 || c == j) bad = 1;
       piv = 1.f;
     }
     const float rs = rsqrtf(piv);  // 1 / L[j][j]
-    const float xjc = xj[c] * rs;  // final X[j][c]
-    const float lcj = (c > j) ? cj[c] * rs : 0.f;
+    const float ipiv = rs * rs;
+    const float4 q0 = *reinterpret_cast<const float4*>(&cj[i0]);
+    const float4 q1 = *reinterpret_cast<const float4*>(&cj[i0 + 4]);
+    const float4 q2 = *reinterpret_cast<const float4*>(&cj[i0 + 8]);
+    const float4 q3 = *reinterpret_cast<const float4*>(&cj[i0 + 12]);
+    const float cv[R] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                         q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+    if (c > j) {
+      const float lc = cj[c] * ipiv;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = rq + 4 * r;
-      const float lij = cj[i] * rs;  // L[i][j] (meaningful for i > j)
-      if (i > j) {
-        x[r] = fmaf(-lij, xjc, x[r]);
-        if (c > j) a[r] = fmaf(-lij, lcj, a[r]);
-        else if (c == j) a[r] = lij;
-      } else if (i == j) {
-        x[r] = xjc;
-        if (c == j) a[r] = piv * rs;
+      for (int r = 0; r < R; ++r)
+        if (i0 + r > j) a[r] = fmaf(-cv[r], lc, a[r]);
+    } else {
+      const float xc = xj[c] * ipiv;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (i0 + r > j) x[r] = fmaf(-cv[r], xc, x[r]);
+      if (c == j) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (i0 + r > j) a[r] = cv[r] * rs;
+          else if (i0 + r == j) a[r] = piv * rs;
+        }
       }
+    }
+    if (row_owner) {
+      const float xf = xj[c] * rs;  // final X[j][c]
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[r] = (r == (j & 15)) ? xf : x[r];
     }
   }
   float* di = p.Dinv + static_cast<long long>(k) * NB * NB;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int i = rq + 4 * r;
+    const int i = i0 + r;
     if (c <= i) blk[static_cast<long long>(i) * p.dpad + c] = a[r];
     di[i * NB + c] = (c <= i) ? x[r] : 0.f;
   }
