@@ -8,14 +8,19 @@
 //     L[i][j] = Cinv[d-1-j][d-1-i].
 // Same unique factor as the reference (positive diagonal), 2/3 d^3 flops instead of 7/3 d^3.
 //
-// Blocked fp32 algorithm, NB = 64, every step one launch for ALL factors of the batch (device-side
+// Blocked algorithm, NB = 64, every step one launch for ALL factors of the batch (device-side
 // problem table; CTAs of factors that are already finished exit immediately):
 //   phase 1 (right-looking Cholesky)   potrf_diag -> panel (A21 L11^-T) -> trailing A22 -= L21 L21^T
 //   phase 2 (triangular inverse, X = C^-1 built by block eliminations from X = I)
 //                                       rowscale X_k = L_kk^-1 X_k -> X_below -= L_below,k X_k
-// The O(d^3) work is in the rank-64 update kernel (128x128 register-tiled fp32 SIMT GEMM).  fp32 is
-// required here: cond(R) reaches 1e4 at the reference's damping values and the tolerance on the
-// inverse is 1e-3, which rules out bf16 trailing updates.
+// Two-level blocking for wide factors (padded size >= 2048): the rank-64 fp32 SIMT updates
+// (128x128 register-tiled) only reach to the end of the current 256-wide outer block; everything
+// beyond it receives the whole outer block at once from the tcgen05 contraction core
+// (bk_umma_gemm.cu) with K = 256 and the TMA reduce-add epilogue.  Precision: cond(R) reaches 1e4-1e6
+// at the reference's damping values and the tolerance on the inverse is 1e-3, which rules out bf16
+// (1e-3 per product) and bf16x3 (1e-5) trailing updates; the operands are therefore split THREE ways
+// (hi + lo + lo2 = 24 mantissa bits) and accumulated in six tensor-core passes (bf16x6), which is
+// fp32-class and still ~4x the SIMT fp32 rate.
 #include "bk_common.cuh"
 #include "bk_kernels.cuh"
 #include "bk_umma_gemm.cuh"
