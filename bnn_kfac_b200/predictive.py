@@ -258,7 +258,7 @@ def _prefetch_noise(lib, est: KFAC, prog, layer_index, B, S, sample0, x3, implic
         dinp, dout = LA.shape[0], LG.shape[0]
         use = implicit
         if use is None:
-            use = 2 * B < min(dinp, dout) and min(dinp - 1, dout) >= 64
+            use = 2 * B <= min(dinp, dout) and min(dinp - 1, dout) >= 700
         if not use:
             continue
         li = layer_index[op.layer]
@@ -306,7 +306,7 @@ def _mc_logits_chunk(est: KFAC, x: Tensor, S: int, sample0: int, prog, noise, im
         last = all(o.kind == "flatten" for o in prog[oi + 1:])
         use_implicit = implicit
         if use_implicit is None:   # forming W_s costs ~2 d^3 per sample, the implicit form ~6 B d^2
-            use_implicit = 2 * B < min(d_in + 1, d_out) and min(d_in, d_out) >= 64
+            use_implicit = 2 * B <= min(d_in + 1, d_out) and min(d_in, d_out) >= 700   # measured crossover
         if op.kind == "linear" and use_implicit and has_bias:
             kx = _round8(d_in + 1)
             if cat is None:
