@@ -78,6 +78,12 @@ SIGNATURES = {
     "bk_ger_accum": (_i, [_p, _ll, _p, _i, _f, _f, _p]),
     "bk_kron": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "bk_dominance": (_i, [_p, _ll, _i, _f, _p, _p, _i, _p, _p]),
+    "bk_inf_regularise": (_i, [_p, _ll, _p, _ll, _f, _f, _p, _p, _p]),
+    "bk_inf_presample_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "bk_inf_presample": (_i, [_p, _ll, _i, _i, _p, _ll, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "bk_inf_combine": (_i, [_p, _p, _p, _p, _ll, _p]),
+    "bk_calibration_rows": (_i, [_p, _ll, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "bk_binned_stats": (_i, [_p, _p, _p, _ll, _p, _i, _i, _p, _p]),
     "bk_chol_inv_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
     "bk_damp_chol_inv_batched": (_i, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
                                       C.POINTER(_f), C.POINTER(_f), _i, _p, _sz, _p]),

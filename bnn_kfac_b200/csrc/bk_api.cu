@@ -395,6 +395,53 @@ int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* o
   return bk::launch_kron(a, m, n, b, p, q, out, as_stream(stream));
 }
 
+// ----------------------------------------------------------------------- INF curvature
+int bk_inf_regularise(float* correction, long long nm, const float* lambda, long long r, float add,
+                      float multiply, float* reg_inv_correction, float* reg_lambda, void* stream) {
+  if (nm < 0 || r < 0) return BK_ERR_ARG;
+  if (nm > 0 && (correction == nullptr || reg_inv_correction == nullptr)) return BK_ERR_ARG;
+  if (r > 0 && (lambda == nullptr || reg_lambda == nullptr)) return BK_ERR_ARG;
+  return bk::launch_inf_regularise(correction, nm, lambda, r, add, multiply, reg_inv_correction,
+                                   reg_lambda, as_stream(stream));
+}
+
+size_t bk_inf_presample_workspace_bytes(int n, int a, int m, int b) {
+  return bk::inf_presample_workspace_bytes(n, a, m, b);
+}
+
+int bk_inf_presample(const float* ua, long long lda, int n, int a, const float* ug, long long ldg, int m,
+                     int b, const float* reg_inv_correction, const float* reg_lambda, float* p_out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (ua == nullptr || ug == nullptr || reg_inv_correction == nullptr || reg_lambda == nullptr ||
+      p_out == nullptr || workspace == nullptr || lda < a || ldg < b)
+    return BK_ERR_ARG;
+  return bk::inf_presample(ua, lda, n, a, ug, ldg, m, b, reg_inv_correction, reg_lambda, p_out, workspace,
+                           workspace_bytes, as_stream(stream));
+}
+
+int bk_inf_combine(float* out, const float* y_l, const float* reg_inv_correction, const float* x_ps_t,
+                   long long count, void* stream) {
+  if (count > 0 && (out == nullptr || y_l == nullptr || reg_inv_correction == nullptr || x_ps_t == nullptr))
+    return BK_ERR_ARG;
+  return bk::launch_inf_combine(out, y_l, reg_inv_correction, x_ps_t, count, as_stream(stream));
+}
+
+// ----------------------------------------------------------------------- calibration metrics
+int bk_calibration_rows(const float* probs, long long ld, const long long* labels, int n, int classes,
+                        float* conf, float* correct, float* nll, float* entropy, int* pred, double* totals4,
+                        void* stream) {
+  if (n < 0 || classes <= 0 || ld < classes || totals4 == nullptr || (n > 0 && probs == nullptr))
+    return BK_ERR_ARG;
+  return bk::launch_calibration_rows(probs, ld, labels, n, classes, conf, correct, nll, entropy, pred,
+                                     totals4, as_stream(stream));
+}
+
+int bk_binned_stats(const float* x, const float* w1, const float* w2, long long n, const double* edges,
+                    int nbins, int mode, double* out3, void* stream) {
+  if (n < 0 || edges == nullptr || out3 == nullptr || (n > 0 && x == nullptr)) return BK_ERR_ARG;
+  return bk::launch_binned_stats(x, w1, w2, n, edges, nbins, mode, out3, as_stream(stream));
+}
+
 // ----------------------------------------------------------------------- predictive glue
 int bk_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b, int d_out,
                          int d_in, int has_bias, int nsamples, float* w_f32, void* w_hi, void* w_lo,

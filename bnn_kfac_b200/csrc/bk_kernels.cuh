@@ -80,6 +80,25 @@ int launch_ger_accum(float* state, long long ld, const float* g, int P, float al
 int launch_kron(const float* a, int m, int n, const float* b, int p, int q, float* out,
                 cudaStream_t stream);
 
+// ---- bk_inf.cu  (INF curvature: regularisation, fp64 pre-sampler chain, sampler tail)
+int launch_inf_regularise(float* corr, long long nm, const float* lam, long long r, float add, float mult,
+                          float* ric, float* rl, cudaStream_t stream);
+int launch_inf_combine(float* out, const float* yl, const float* c, const float* xt, long long count,
+                       cudaStream_t stream);
+size_t inf_presample_workspace_bytes(int n, int a, int m, int b);
+// Returns 0, 1 (vtv not positive definite), 2 (vtv + I not positive definite) or a negative error.
+// Synchronises `stream`.
+int inf_presample(const float* ua, long long lda, int n, int a, const float* ug, long long ldg, int m, int b,
+                  const float* ric, const float* rl, float* p_out, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+
+// ---- bk_metrics.cu  (calibration metrics)
+int launch_calibration_rows(const float* probs, long long ld, const long long* labels, int n, int classes,
+                            float* conf, float* correct, float* nll, float* ent, int* pred, double* totals,
+                            cudaStream_t stream);
+int launch_binned_stats(const float* x, const float* w1, const float* w2, long long n, const double* edges,
+                        int nbins, int mode, double* out, cudaStream_t stream);
+
 // ---- bk_forward.cu
 int launch_sample_to_weights(const float* samples, const float* mean_w, const float* mean_b,
                              int d_out, int d_in, int has_bias, int nsamples, float* w_f32,

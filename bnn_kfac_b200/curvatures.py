@@ -188,6 +188,30 @@ class Curvature(ABC):
         self._invalidate_caches()
         print('Loading %s complete!\n' % filename)
 
+    def load_by_name(self, filename):
+        """Restores `state` / `inv_state` from the name-keyed copies of a file written by save() onto
+        the CURRENT model's modules (same `named_modules()` names), keeping `self.model`: the checkpoint
+        then survives re-instantiating the network, which the reference's module-object keys do not."""
+        blob = torch.load(filename, weights_only=False)
+        modules = dict(self.model.named_modules())
+        dev = next(self.model.parameters()).device
+
+        def to_dev(v):
+            if isinstance(v, Tensor):
+                return v.to(dev)
+            if isinstance(v, (list, tuple)):
+                return type(v)(to_dev(u) for u in v)
+            return v
+
+        for attr in ("state", "inv_state"):
+            named = blob[attr + "_by_name"]
+            missing = [k for k in named if k not in modules]
+            if missing:
+                raise KeyError(f"checkpoint layers {missing} do not exist in the current model")
+            setattr(self, attr, {modules[k]: to_dev(v) for k, v in named.items()})
+        self._invalidate_caches()
+        print('Loading %s complete!\n' % filename)
+
     def _invalidate_caches(self):
         pass
 
@@ -759,3 +783,192 @@ class EFB(Curvature):
                    "bk_diag_sample")
         ops = self._staged_eigvecs(layer)
         return self._sandwich(ops["UG"], scaled, ops["UA"], d_out, d_inp)
+
+
+# ---------------------------------------------------------------------------------------------------
+def stage_operand_t(x: Tensor):
+    """fp32 [rows, cols] -> staged bf16 (hi, lo, ld) of x^T [cols, rows] (bk_transpose_split)."""
+    lib = _lib.load()
+    rows, cols = x.shape
+    ld = _round8(rows)
+    hi = torch.zeros(cols, ld, dtype=torch.bfloat16, device=x.device)
+    lo = torch.zeros_like(hi)
+    xc = x.float()
+    if xc.stride(1) != 1:
+        xc = xc.contiguous()
+    _lib.check(lib.bk_transpose_split(xc.data_ptr(), xc.stride(0), rows, cols, 1.0, 0, hi.data_ptr(),
+                                      lo.data_ptr(), ld, _lib.stream_ptr()), "bk_transpose_split")
+    return hi, lo, ld
+
+
+def mm_nt_staged(a, b, m: int, n: int, k: int, alpha: float = 1.0, beta: float = 0.0,
+                 out: Optional[Tensor] = None) -> Tensor:
+    """out[m, n] = alpha * A B^T + beta * out for staged K-major operands A [m, k], B [n, k]
+    (split-bf16, three tensor-core passes: fp32-class accuracy)."""
+    lib = _lib.load()
+    a_hi, a_lo, lda = a
+    b_hi, b_lo, ldb = b
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty(m, n, device=a_hi.device, dtype=torch.float32)
+    _lib.check(lib.bk_gemm_nt(a_hi.data_ptr(), a_lo.data_ptr(), lda, 0, b_hi.data_ptr(), b_lo.data_ptr(), ldb, 0,
+                              m, n, k, 1, _lib.BK_PREC_BF16X3, 0, alpha, beta, out.data_ptr(), out.stride(0), 0,
+                              0, 0, 0, 0, 0, 0, _lib.stream_ptr()), "bk_gemm_nt")
+    return out
+
+
+def mm_nt(x: Tensor, y: Tensor, x_t: bool = False, y_t: bool = False, alpha: float = 1.0, beta: float = 0.0,
+          out: Optional[Tensor] = None) -> Tensor:
+    """op(x) @ op(y)^T on the tensor cores; op transposes first when the flag is set
+    (x [K, M] / y [K, N] are then staged transposed)."""
+    a = stage_operand_t(x) if x_t else stage_operand(x)
+    b = stage_operand_t(y) if y_t else stage_operand(y)
+    m, k = (x.shape[1], x.shape[0]) if x_t else x.shape
+    n, k2 = (y.shape[1], y.shape[0]) if y_t else y.shape
+    assert k == k2
+    return mm_nt_staged(a, b, m, n, k, alpha, beta, out)
+
+
+def _square(x: Tensor) -> Tensor:
+    """Elementwise x^2 (the squaring form of the diagonal accumulate kernel)."""
+    lib = _lib.load()
+    xc = x.float().contiguous()
+    out = torch.empty_like(xc)
+    _lib.check(lib.bk_diag_accum(out.data_ptr(), xc.data_ptr(), 0, xc.shape[0], xc.shape[1], 1.0, 0.0,
+                                 _lib.stream_ptr()), "bk_diag_accum(square)")
+    return out
+
+
+class INF(Curvature):
+    """Information-form low-rank approximation with diagonal correction.  Reference:
+    models/curvatures.py:476-682 (paths relative to /root/reference).
+
+        __init__  eigvecs = get_eigenvectors(factors); lambdas (EFB.state), diags (Diagonal.state)   (:494-498)
+        update    per layer: keep the eigen-directions of the `rank` largest |lambda| (index sets
+                  idx_left x idx_right, _dim_reduction :615-658), correction = diag - sif_diag with
+                  sif_diag[i*m + p] = sum_{q,x} U_A[i,q]^2 U_G[p,x]^2 lambda[q,x] (_diagonal_accumulator
+                  :660-682, there an O(n) Python loop over Kronecker rows)                              (:500-520)
+        invert    clamp the correction at 0, regularise, pre_sampler -> P_c                           (:522-542)
+        sample    sampler :587-613, reshaped [n, m] and transposed -> [d_out, d_in']                  (:544-548)
+
+    The dense products run on the tensor cores (split-bf16), the r x r pre-sampler chain in fp64
+    (bk_inf_presample, see bk_inf.cu for why), element-wise stages in bk_inf_regularise / bk_inf_combine.
+    Index selection (top-k, unique, gathers) is tensor bookkeeping in torch."""
+
+    def __init__(self, model, diags: Dict[Module, Tensor], factors: Dict[Module, Any],
+                 lambdas: Dict[Module, Tensor], layer_types=None, *, precision: str = "bf16x3", seed: int = 0):
+        from .utilities import get_eigenvectors
+        super().__init__(model, layer_types, precision=precision, seed=seed)
+        assert diags.keys() == factors.keys() == lambdas.keys()
+        self.eigvecs = get_eigenvectors(factors)
+        self.lambdas = lambdas
+        self.diags = diags
+        self._staged = dict()
+
+    # --------------------------------------------------------------------------- update
+    @staticmethod
+    def _dim_reduction(frst_eigvecs: Tensor, scnd_eigvecs: Tensor, lambda_vec: Tensor, rank: int):
+        """Rows / columns of the (d_in' x d_out) lambda grid touched by the `rank` largest |lambda|;
+        returns (U_A[:, rows], U_G[:, cols], lambda[rows x cols] flattened row-major)."""
+        if rank >= lambda_vec.shape[0]:
+            return frst_eigvecs, scnd_eigvecs, lambda_vec
+        m = scnd_eigvecs.shape[1]
+        top = torch.topk(lambda_vec.abs(), rank).indices
+        idx_left = torch.unique(torch.div(top, m, rounding_mode="floor"))
+        idx_right = torch.unique(top - torch.div(top, m, rounding_mode="floor") * m)
+        grid = (idx_left.unsqueeze(1) * m + idx_right.unsqueeze(0)).reshape(-1)
+        return (frst_eigvecs.index_select(1, idx_left).contiguous(),
+                scnd_eigvecs.index_select(1, idx_right).contiguous(),
+                lambda_vec.index_select(0, grid).contiguous())
+
+    @staticmethod
+    def _corrected_diagonal(xxt_eigvecs: Tensor, ggt_eigvecs: Tensor, lambda_vec: Tensor, diag_vec: Tensor):
+        """diag_vec - sif_diag with sif_diag = (U_A^2 Lambda U_G^2^T) flattened [n, m] row-major: two
+        contractions, the subtraction in the epilogue of the second (alpha = -1, beta = 1)."""
+        n, a = xxt_eigvecs.shape
+        m, b = ggt_eigvecs.shape
+        lam_t = lambda_vec.view(a, b).t()                              # [b, a]
+        t = mm_nt(_square(xxt_eigvecs), lam_t.contiguous())            # [n, b] = U_A^2 Lambda
+        out = diag_vec.clone().view(n, m)
+        mm_nt(t, _square(ggt_eigvecs), alpha=-1.0, beta=1.0, out=out)  # diag - T U_G^2^T
+        return out.view(-1)
+
+    def update(self, rank: int = 100):
+        for layer in list(self.diags.keys()):
+            xxt_eigvecs, ggt_eigvecs = self.eigvecs[layer]
+            lambda_vec = self.lambdas[layer].float().t().contiguous().view(-1)
+            diag_vec = self.diags[layer].float().t().contiguous().view(-1)
+            lr_a, lr_g, lr_lambda = self._dim_reduction(xxt_eigvecs, ggt_eigvecs, lambda_vec, rank)
+            correction = self._corrected_diagonal(lr_a, lr_g, lr_lambda, diag_vec)
+            self.state[layer] = (lr_a, lr_g, lr_lambda, correction)
+
+    # --------------------------------------------------------------------------- invert
+    def invert(self, add: Union[float, list, tuple] = 0., multiply: Union[float, list, tuple] = 1.):
+        assert self.state, "State dict is empty. Did you call 'update' prior to this?"
+        st = _lib.stream_ptr()
+        lib = self._lib
+        for index, (layer, value) in enumerate(self.state.items()):
+            if not isinstance(add, float) and not isinstance(multiply, float):
+                assert len(add) == len(multiply) == len(self.state)
+                n_, s_ = add[index], multiply[index]
+            else:
+                n_, s_ = add, multiply
+            lr_a, lr_g, lr_lambda, correction = value
+            lr_a, lr_g = lr_a.contiguous(), lr_g.contiguous()
+            n, a = lr_a.shape
+            m, b = lr_g.shape
+            r = a * b
+            reg_inv_correction = torch.empty_like(correction)
+            reg_lambda = torch.empty_like(lr_lambda)
+            _lib.check(lib.bk_inf_regularise(correction.data_ptr(), correction.numel(), lr_lambda.data_ptr(), r,
+                                             float(n_), float(s_), reg_inv_correction.data_ptr(),
+                                             reg_lambda.data_ptr(), st), "bk_inf_regularise")
+            pre_sample = torch.empty(r, r, device=lr_a.device, dtype=torch.float32)
+            nbytes = lib.bk_inf_presample_workspace_bytes(n, a, m, b)
+            ws = self._ws.get(nbytes, lr_a.device)
+            rc = _lib.check(lib.bk_inf_presample(lr_a.data_ptr(), lr_a.stride(0), n, a, lr_g.data_ptr(),
+                                                 lr_g.stride(0), m, b, reg_inv_correction.data_ptr(),
+                                                 reg_lambda.data_ptr(), pre_sample.data_ptr(), ws.data_ptr(),
+                                                 nbytes, st), "bk_inf_presample")
+            if rc > 0:
+                raise RuntimeError(f"INF.invert: V^T V{' + I' if rc == 2 else ''} of layer {index} (rank {r}) is "
+                                   f"not positive definite (the reference's cholesky() raises here too)")
+            self.inv_state[layer] = (lr_a, lr_g, reg_inv_correction, pre_sample)
+        self._staged = dict()
+
+    # --------------------------------------------------------------------------- sample
+    def _staged_inv(self, layer):
+        if layer not in self._staged:
+            a_, b_, _, p = self.inv_state[layer]
+            self._staged[layer] = {"A": stage_operand(a_), "AT": stage_operand_t(a_), "G": stage_operand(b_),
+                                   "GT": stage_operand_t(b_), "P": stage_operand(p)}
+        return self._staged[layer]
+
+    def sample(self, layer: Module, z: Optional[Tensor] = None) -> Tensor:
+        """One INF posterior sample [d_out, d_in'].  `z` (flat [d_in' * d_out], the reference's X)
+        replaces the Philox draw."""
+        assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
+        a_, b_, c, p = self.inv_state[layer]
+        n, a = a_.shape
+        m, b = b_.shape
+        r = a * b
+        ops = self._staged_inv(layer)
+        if z is not None:
+            z = z.to(c.device, torch.float32).contiguous().view(-1)
+            assert z.numel() == n * m
+        y_l = torch.empty(n * m, device=c.device, dtype=torch.float32)
+        layer_id = list(self.inv_state.keys()).index(layer)
+        _lib.check(self._lib.bk_diag_sample(y_l.data_ptr(), c.data_ptr(), n * m, 1, self.seed,
+                                            self._next_sample_id(), layer_id, _lib.ptr(z), _lib.stream_ptr()),
+                   "bk_diag_sample")
+        unvec = y_l.view(m, n)                                              # the reference's reshape (:604)
+        t1 = mm_nt_staged(ops["GT"], stage_operand_t(unvec), b, n, m)       # U_G^T unvec          [b, n]
+        xq_t = mm_nt_staged(ops["AT"], stage_operand(t1), a, b, n)          # (U_G^T unvec U_A)^T  [a, b]
+        qx = mm_nt_staged(stage_operand(xq_t.view(1, r)), ops["P"], 1, r, r)  # (P vec)^T          [1, r]
+        wq = qx.view(b, a)                                                  # the reference's reshape (:608)
+        t2 = mm_nt_staged(ops["A"], stage_operand(wq), n, b, a)             # U_A wq^T             [n, b]
+        xps_t = mm_nt_staged(stage_operand(t2), ops["G"], n, m, b)          # (U_G wq U_A^T)^T     [n, m]
+        out = torch.empty_like(y_l)
+        _lib.check(self._lib.bk_inf_combine(out.data_ptr(), y_l.data_ptr(), c.data_ptr(), xps_t.data_ptr(),
+                                            n * m, _lib.stream_ptr()), "bk_inf_combine")
+        return out.view(n, m).t()

@@ -5,14 +5,22 @@
     get_eigenvectors(factors)       models/utilities.py:144-159 (symeig of F + F^T per factor)
     get_eigenvalues(factors)        models/utilities.py:120-141 (ger of the factors' eigenvalues)
 
+    accuracy, confidence, negative_log_likelihood, predictive_entropy,
+    expected_calibration_error, calibration_curve, binned_kl_distance
+                                    models/utilities.py:178-366 (calibration metrics)
+
 `torch.symeig` no longer exists, so the reference versions crash on a current torch; these run the
-batched one-sided Jacobi eigensolver of libbk_kfac.so (bk_eigh_batched).  Metrics / plotting / argparse
-helpers of that file are out of scope."""
+batched one-sided Jacobi eigensolver of libbk_kfac.so (bk_eigh_batched).  The metrics take the class
+probabilities as a device tensor (or numpy array) and reduce them on the GPU in one pass
+(bk_calibration_rows + bk_binned_stats); only the per-bin tail (<= 256 numbers) is combined on the host.
+They return what the reference returns (Python floats / numpy arrays).  Plotting / argparse helpers of
+that file are out of scope."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple, Union
 
+import numpy as np
 import torch
 from torch import Tensor
 from torch.nn import Module
@@ -88,3 +96,142 @@ def get_eigenvalues(factors: List[Sequence[Tensor]], verbose: bool = False) -> T
         else:
             out.append(f.contiguous().view(-1))
     return torch.cat(out) if out else torch.Tensor()
+
+
+# ------------------------------------------------------------------------------- calibration metrics
+def _device_probs(probabilities) -> Tensor:
+    p = torch.as_tensor(probabilities)
+    if not p.is_cuda:
+        p = p.cuda()
+    p = p.float()
+    if p.dim() != 2:
+        raise ValueError("probabilities must be [n, classes]")
+    return p if p.stride(1) == 1 else p.contiguous()
+
+
+def calibration_rows(probabilities, labels=None) -> Dict[str, Tensor]:
+    """One pass over probs [n, classes]: per-row confidence (max p), correctness of the arg-max (0/1),
+    -log(p[label] + 1e-12), entropy of the row, arg-max — device tensors — plus `totals` = their four
+    sums over rows (fp64, host).  Everything below is derived from this."""
+    lib = _lib.load()
+    _lib.require_device()
+    p = _device_probs(probabilities)
+    n, classes = p.shape
+    lab = None
+    if labels is not None:
+        lab = torch.as_tensor(labels).to(p.device, torch.int64).contiguous()
+        assert lab.shape == (n,)
+    out = {k: torch.empty(n, device=p.device, dtype=torch.float32) for k in ("conf", "correct", "nll", "entropy")}
+    out["pred"] = torch.empty(n, device=p.device, dtype=torch.int32)
+    totals = torch.empty(4, device=p.device, dtype=torch.float64)
+    _lib.check(lib.bk_calibration_rows(p.data_ptr(), p.stride(0), _lib.ptr(lab), n, classes,
+                                       out["conf"].data_ptr(), out["correct"].data_ptr(), out["nll"].data_ptr(),
+                                       out["entropy"].data_ptr(), out["pred"].data_ptr(), totals.data_ptr(),
+                                       _lib.stream_ptr()), "bk_calibration_rows")
+    out["totals"] = totals.cpu()
+    out["n"] = n
+    return out
+
+
+def _binned(x: Tensor, w1: Optional[Tensor], w2: Optional[Tensor], edges: Tensor, mode: int) -> np.ndarray:
+    """[3, nbins] fp64: count, sum w1, sum w2 per bin (bk_binned_stats; edges fp64 on the device)."""
+    lib = _lib.load()
+    nbins = edges.numel() - 1
+    out = torch.empty(3, nbins, device=x.device, dtype=torch.float64)
+    _lib.check(lib.bk_binned_stats(x.data_ptr(), _lib.ptr(w1), _lib.ptr(w2), x.numel(), edges.data_ptr(), nbins,
+                                   mode, out.data_ptr(), _lib.stream_ptr()), "bk_binned_stats")
+    return out.cpu().numpy()
+
+
+def accuracy(probabilities, labels) -> float:
+    """Top-1 accuracy in percent (models/utilities.py:178-189)."""
+    rows = calibration_rows(probabilities, labels)
+    return 100.0 * float(rows["totals"][0]) / rows["n"]
+
+
+def confidence(probabilities, mean: bool = True) -> Union[float, np.ndarray]:
+    """Maximum predicted class probability (models/utilities.py:220-233)."""
+    rows = calibration_rows(probabilities)
+    if mean:
+        return float(rows["totals"][1]) / rows["n"]
+    return rows["conf"].cpu().numpy()
+
+
+def negative_log_likelihood(probabilities, labels) -> float:
+    """-mean(log(p[label] + 1e-12)) (models/utilities.py:236-247)."""
+    rows = calibration_rows(probabilities, labels)
+    return float(rows["totals"][2]) / rows["n"]
+
+
+def predictive_entropy(probabilities, mean: bool = False) -> Union[np.ndarray, float]:
+    """H(y) = -sum_c y_c ln y_c per prediction, rows normalised as scipy.stats.entropy does
+    (models/utilities.py:335-353)."""
+    rows = calibration_rows(probabilities)
+    if mean:
+        return float(rows["totals"][3]) / rows["n"]
+    return rows["entropy"].cpu().numpy()
+
+
+def expected_calibration_error(probabilities, labels, bins: int = 10):
+    """ECE over `bins` equally spaced confidence bins (lo, hi] (models/utilities.py:300-332): returns
+    (ece, per-bin conf - acc, per-bin accuracy, per-bin confidence); empty bins report 0."""
+    rows = calibration_rows(probabilities, labels)
+    edges = torch.linspace(0, 1, bins + 1, dtype=torch.float64).to(rows["conf"].device)
+    cnt, s_ok, s_conf = _binned(rows["conf"], rows["correct"], rows["conf"], edges, 0)
+    n = rows["n"]
+    bin_ace, bin_accuracy, bin_confidence = [], [], []
+    ece = 0
+    for i in range(bins):
+        if cnt[i] > 0:
+            acc, conf = s_ok[i] / cnt[i], s_conf[i] / cnt[i]
+            ece += cnt[i] / n * abs(conf - acc)
+            bin_ace.append(conf - acc)
+            bin_accuracy.append(acc)
+            bin_confidence.append(conf)
+        else:
+            bin_ace.append(0)
+            bin_accuracy.append(0)
+            bin_confidence.append(0)
+    return ece, np.array(bin_ace), np.array(bin_accuracy), np.array(bin_confidence)
+
+
+def calibration_curve(probabilities, labels, bins: int = 20):
+    """ECE over equal-mass bins whose edges are every `step`-th sorted confidence, intervals open on
+    both sides (models/utilities.py:250-297): (ece, mean confidence, accuracy, proportion) of the
+    non-empty bins."""
+    rows = calibration_rows(probabilities, labels)
+    conf = rows["conf"]
+    n = rows["n"]
+    step = (n + bins - 1) // bins
+    srt = torch.sort(conf).values
+    edges = srt[::step]
+    if n % step != 1:
+        edges = torch.cat([edges, srt[-1:]])
+    cnt, s_ok, s_conf = _binned(conf, rows["correct"], conf, edges.double().contiguous(), 1)
+    ece = 0.0
+    xs, ys, zs = [], [], []
+    for i in range(cnt.shape[0]):
+        if cnt[i] > 0:
+            prop, acc, avg = cnt[i] / n, s_ok[i] / cnt[i], s_conf[i] / cnt[i]
+            ece += abs(avg - acc) * prop
+            xs.append(avg)
+            ys.append(acc)
+            zs.append(prop)
+    return ece, np.array(xs), np.array(ys), np.array(zs)
+
+
+def binned_kl_distance(dist1, dist2, smooth: float = 1e-7, bins=None) -> float:
+    """Symmetrised discrete KL divergence between two sample sets, histogrammed over `bins`
+    (default logspace(-7, 1, 200)) with additive smoothing (models/utilities.py:192-217)."""
+    _lib.require_device()
+    if bins is None:
+        bins = np.logspace(-7, 1, num=200)
+    edges = torch.as_tensor(np.asarray(bins, dtype=np.float64)).cuda()
+    pdfs = []
+    for d in (dist1, dist2):
+        x = torch.as_tensor(d)
+        x = (x if x.is_cuda else x.cuda()).float().contiguous().view(-1)
+        h = _binned(x, None, None, edges, 2)[0] + smooth
+        pdfs.append(h / h.sum())
+    p, q = pdfs
+    return float(np.sum(p * np.log(p / q)) + np.sum(q * np.log(q / p)))

@@ -196,6 +196,43 @@ int bk_ger_accum(float* state, long long ld, const float* g, int p, float alpha,
 int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * INF curvature: low-rank eigenbasis + diagonal correction (models/curvatures.py:476-682).
+ */
+/* INF.invert :537-539.  correction[correction < 0] = 0 IN PLACE (nm values);
+ * reg_inv_correction = 1/sqrt(multiply*correction + add) (nm); reg_lambda = sqrt(multiply*lambda) (r). */
+int bk_inf_regularise(float* correction, long long nm, const float* lambda, long long r, float add,
+                      float multiply, float* reg_inv_correction, float* reg_lambda, void* stream);
+/* INF.pre_sampler :565-585.  ua [n, a] / ug [m, b]: low-rank eigenvector columns (row pitches lda / ldg);
+ * reg_inv_correction [n*m] (index i*m + p); reg_lambda [a*b] (index q*b + x); p_out [a*b, a*b] fp32 =
+ * diag(s) (C^-1 + V^T V)^-1 diag(s) with V = c (.) kron(ua, ug) diag(s), never materialised; the r x r
+ * Cholesky / triangular-inverse chain runs in fp64 (see bk_inf.cu).  Returns 0, 1 if V^T V is not
+ * positive definite, 2 if V^T V + I is not, < 0 on error.  Synchronises the stream. */
+size_t bk_inf_presample_workspace_bytes(int n, int a, int m, int b);
+int bk_inf_presample(const float* ua, long long lda, int n, int a, const float* ug, long long ldg, int m,
+                     int b, const float* reg_inv_correction, const float* reg_lambda, float* p_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* INF.sampler :611.  out = y_l - reg_inv_correction^2 * x_ps_t (all [count] fp32). */
+int bk_inf_combine(float* out, const float* y_l, const float* reg_inv_correction, const float* x_ps_t,
+                   long long count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Calibration metrics of class probabilities (models/utilities.py:178-366).
+ */
+/* One pass over probs [n, classes] (row pitch ld), labels int64 [n] (nullable).  Per-row outputs (each
+ * nullable): conf = max p, correct = (argmax == label) as 0/1, nll = -log(p[label] + 1e-12), entropy of
+ * the row normalised to sum 1, pred = argmax (first maximum).  totals4 (device, fp64) receives
+ * { sum correct, sum conf, sum nll, sum entropy }. */
+int bk_calibration_rows(const float* probs, long long ld, const long long* labels, int n, int classes,
+                        float* conf, float* correct, float* nll, float* entropy, int* pred, double* totals4,
+                        void* stream);
+/* out3 (device, fp64 [3, nbins]) = per bin { count, sum w1, sum w2 } of the values x[i] (w1 / w2 nullable)
+ * for fp64 bin edges [nbins + 1] (device; nbins <= 256).  mode 0: (lo, hi] (expected_calibration_error
+ * :322); mode 1: (lo, hi) (calibration_curve :287; edges may repeat); mode 2: [lo, hi) with the last bin
+ * closed (np.histogram, binned_kl_distance :207-208). */
+int bk_binned_stats(const float* x, const float* w1, const float* w2, long long n, const double* edges,
+                    int nbins, int mode, double* out3, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Predictive glue (the dense contractions of these stages are bk_gemm_nt calls).
  */
 /* Curvature._replace for a batch of samples (models/curvatures.py:67-82):

@@ -521,3 +521,153 @@ def efb_sample(eigvecs: Tuple[Tensor, Tensor], inv: Tensor, z: Tensor) -> Tensor
     """(U_A (z * inv^T) U_G^T)^T with z [d_in', d_out].  models/curvatures.py:467-473."""
     first, second = eigvecs
     return (first @ (z * inv.t()) @ second.t()).t()
+
+
+# =============================================================================== INF (SURVEY §8f, f4)
+def inf_dim_reduction(frst_eigvecs: Tensor, scnd_eigvecs: Tensor, lambda_vec: Tensor, rank: int
+                      ) -> Tuple[Tensor, Tensor, Tensor]:
+    """models/curvatures.py:615-658.  The `rank` largest |lambda| of the flat (d_in' x d_out) grid pick a
+    set of grid rows (-> columns of U_A) and grid columns (-> columns of U_G); the low-rank lambda is the
+    full rows x cols sub-grid, rows-major.  (The reference's list-of-0-dim-tensor indexing no longer runs;
+    this follows its arithmetic: 1-based idx, i = int((idx - 1)/m + 1), j = idx - m (i - 1).)"""
+    if rank >= lambda_vec.shape[0]:
+        return frst_eigvecs, scnd_eigvecs, lambda_vec
+    m = scnd_eigvecs.shape[1]
+    order = np.argsort(-np.abs(lambda_vec.numpy()), kind="stable")[:rank]
+    rows = np.unique(order // m)
+    cols = np.unique(order % m)
+    grid = (rows[:, None] * m + cols[None, :]).reshape(-1)
+    return frst_eigvecs[:, rows], scnd_eigvecs[:, cols], lambda_vec[grid]
+
+
+def inf_diagonal_accumulator(xxt_eigvecs: Tensor, ggt_eigvecs: Tensor, lambda_vec: Tensor) -> Tensor:
+    """models/curvatures.py:660-682: diag_vec[i*m + p] = sum_{q,x} (U_A[i,q] U_G[p,x])^2 lambda[q*b + x]
+    (the reference builds one Kronecker row block per i).  The reference accumulates into
+    `torch.zeros(n * m)` (:675), a FLOAT32 buffer whatever the dtype of the factors, so its result is
+    rounded to fp32; reproduced here."""
+    a, b = xxt_eigvecs.shape[1], ggt_eigvecs.shape[1]
+    lam = lambda_vec.view(a, b)
+    return torch.einsum("iq,qx,px->ip", xxt_eigvecs ** 2, lam, ggt_eigvecs ** 2).reshape(-1).float()
+
+
+def inf_update(eigvecs: Tuple[Tensor, Tensor], lambdas: Tensor, diags: Tensor, rank: int
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """INF.update, models/curvatures.py:500-520: (lr U_A, lr U_G, lr lambda, diag - sif_diag)."""
+    xxt, ggt = eigvecs
+    lambda_vec = lambdas.t().contiguous().view(-1)
+    diag_vec = diags.t().contiguous().view(-1)
+    lr_a, lr_g, lr_lambda = inf_dim_reduction(xxt, ggt, lambda_vec, rank)
+    return lr_a, lr_g, lr_lambda, diag_vec - inf_diagonal_accumulator(lr_a, lr_g, lr_lambda)
+
+
+def inf_pre_sampler(frst: Tensor, scnd: Tensor, reg_lambda: Tensor, reg_inv_correction: Tensor) -> Tensor:
+    """INF.pre_sampler, models/curvatures.py:565-585, statement by statement (explicit Kronecker matrix,
+    Cholesky factors, LU inverses)."""
+    scale_sqrt = torch.diag(reg_lambda)
+    v_s = reg_inv_correction.contiguous().view(-1, 1) * kron(frst, scnd) @ scale_sqrt
+    vtv = v_s.t() @ v_s
+    vtv = (vtv + vtv.t()) / 2.
+    eye = torch.eye(scale_sqrt.shape[0], dtype=vtv.dtype)
+    a_c_inv = torch.linalg.inv(torch.linalg.cholesky(vtv))
+    b_c = torch.linalg.cholesky(vtv + eye)
+    c = a_c_inv.t() @ (b_c - eye) @ a_c_inv
+    l_c = torch.linalg.inv(torch.linalg.inv(c) + vtv)
+    return scale_sqrt @ l_c @ scale_sqrt
+
+
+def inf_invert(value: Tuple[Tensor, Tensor, Tensor, Tensor], add: float, multiply: float
+               ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """INF.invert, models/curvatures.py:535-542 (returns a clamped copy; the reference clamps in place)."""
+    lr_a, lr_g, lr_lambda, correction = value
+    correction = correction.clamp(min=0)
+    reg_lr_lambda = (multiply * lr_lambda).sqrt()
+    reg_inv_correction = torch.reciprocal(multiply * correction + add).sqrt()
+    return lr_a, lr_g, reg_inv_correction, inf_pre_sampler(lr_a, lr_g, reg_lr_lambda, reg_inv_correction)
+
+
+def inf_sample(inv_value: Tuple[Tensor, Tensor, Tensor, Tensor], x: Tensor) -> Tensor:
+    """INF.sampler + INF.sample, models/curvatures.py:544-548, 587-613, with the noise X given.
+    Note the reference's two plain reshapes of flat vectors ((m, n) and (b, a)), kept as they are."""
+    frst, scnd, c, pre = inv_value
+    n, m = frst.shape[0], scnd.shape[0]
+    y_l = c * x
+    unvec_y_l = y_l.reshape(m, n)
+    xq = scnd.t() @ unvec_y_l @ frst
+    qx = pre @ xq.t().contiguous().view(-1)
+    unvec_qx = qx.reshape(scnd.shape[1], frst.shape[1])
+    x_p_s = scnd @ unvec_qx @ frst.t()
+    y_r = c ** 2 * x_p_s.t().contiguous().view(-1)
+    return (y_l - y_r).reshape(n, m).t()
+
+
+# =============================================================================== calibration metrics (f3)
+def metric_rows(probs: np.ndarray, labels: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+    """Per-row quantities every metric of models/utilities.py:178-366 is built from."""
+    p = np.asarray(probs)
+    out = {"conf": p.max(axis=1), "pred": p.argmax(axis=1)}
+    pn = p.astype(np.float64) / p.astype(np.float64).sum(axis=1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["entropy"] = -np.where(pn > 0, pn * np.log(pn), 0.0).sum(axis=1)     # scipy.stats.entropy
+    if labels is not None:
+        out["correct"] = out["pred"] == labels
+        out["nll"] = -np.log(p[np.arange(p.shape[0]), labels] + 1e-12)
+    return out
+
+
+def metric_accuracy(probs, labels) -> float:
+    """models/utilities.py:178-189."""
+    return 100.0 * float(np.mean(metric_rows(probs, labels)["correct"]))
+
+
+def metric_nll(probs, labels) -> float:
+    """models/utilities.py:236-247."""
+    return float(np.mean(metric_rows(probs, labels)["nll"]))
+
+
+def metric_ece(probs, labels, bins: int = 10):
+    """models/utilities.py:300-332: equally spaced bins (lo, hi]; empty bins report zeros."""
+    rows = metric_rows(probs, labels)
+    conf, ok = rows["conf"], rows["correct"]
+    edges = np.linspace(0, 1, bins + 1)
+    which = np.full(conf.shape, -1)
+    for i in range(bins):
+        which[(conf > edges[i]) & (conf <= edges[i + 1])] = i
+    ace, acc, cf = np.zeros(bins), np.zeros(bins), np.zeros(bins)
+    ece = 0.0
+    for i in range(bins):
+        sel = which == i
+        if sel.any():
+            acc[i], cf[i] = ok[sel].mean(), conf[sel].mean()
+            ace[i] = cf[i] - acc[i]
+            ece += sel.mean() * abs(ace[i])
+    return ece, ace, acc, cf
+
+
+def metric_calibration_curve(probs, labels, bins: int = 20):
+    """models/utilities.py:250-297: edges = every step-th sorted confidence (+ the maximum unless
+    n % step == 1), intervals open on both sides, only non-empty bins reported."""
+    rows = metric_rows(probs, labels)
+    conf, ok = rows["conf"], rows["correct"]
+    n = conf.shape[0]
+    step = (n + bins - 1) // bins
+    edges = np.sort(conf)[::step]
+    if n % step != 1:
+        edges = np.concatenate((edges, [conf.max()]))
+    ece, xs, ys, zs = 0.0, [], [], []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        sel = (conf > lo) & (conf < hi)
+        if sel.mean() > 0:
+            xs.append(conf[sel].mean())
+            ys.append(ok[sel].mean())
+            zs.append(sel.mean())
+            ece += abs(xs[-1] - ys[-1]) * zs[-1]
+    return ece, np.array(xs), np.array(ys), np.array(zs)
+
+
+def metric_binned_kl(dist1, dist2, smooth: float = 1e-7, bins=None) -> float:
+    """models/utilities.py:192-217: np.histogram both sample sets, smooth, normalise, KL both ways."""
+    bins = np.logspace(-7, 1, num=200) if bins is None else bins
+    p = np.histogram(dist1, bins)[0] + smooth
+    q = np.histogram(dist2, bins)[0] + smooth
+    p, q = p / p.sum(), q / q.sum()
+    return float(np.sum(p * np.log(p / q)) + np.sum(q * np.log(q / p)))

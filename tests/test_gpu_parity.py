@@ -642,3 +642,171 @@ def test_efb_vs_reference_golden(golden, golden_next, dev):
         z = torch.tensor(golden_next[f"efb_z_{li}"]).float().to(dev)
         assert relerr(est2.sample(layer, z=z).cpu(), golden_next[f"efb_sample_{li}"]) < TOL
     est2.sample_and_replace()
+
+
+# ------------------------------------------------------------------ "next" rows: f4 INF, f3
+@pytest.fixture(scope="module")
+def golden_inf():
+    from conftest import ROOT
+    return dict(np.load(ROOT / "tests" / "golden" / "reference_golden_inf.npz"))
+
+
+def _inf_with_reference_inputs(golden, golden_inf, dev):
+    """INF fed the reference's eigenvectors, EFB lambdas and Diagonal state (fp32 copies): a degenerate
+    eigenvalue leaves its eigenbasis free, so parity of everything downstream needs the same basis."""
+    from bnn_kfac_b200.curvatures import INF
+    model, kf = _gpu_kfac_mlp(golden, dev)
+    layers = _layers(kf)
+    lambdas = {l: torch.tensor(golden_inf[f"inf_lambdas_{li}"]).float().to(dev) for li, l in enumerate(layers)}
+    diags = {l: torch.tensor(golden_inf[f"inf_diags_{li}"]).float().to(dev) for li, l in enumerate(layers)}
+    est = INF(model, diags, kf.state, lambdas)
+    for li, l in enumerate(layers):
+        est.eigvecs[l] = (torch.tensor(golden_inf[f"inf_UA_{li}"]).float().to(dev),
+                          torch.tensor(golden_inf[f"inf_UG_{li}"]).float().to(dev))
+    return model, kf, est, layers
+
+
+@pytest.mark.parametrize("rank", [10, 30])
+def test_inf_vs_reference_golden(golden, golden_inf, dev, rank):
+    """models/curvatures.py:476-682 against the reference's own INF (fp64 CPU run, see make_golden_inf.py)."""
+    g = golden_inf
+    model, kf, est, layers = _inf_with_reference_inputs(golden, golden_inf, dev)
+    est.update(rank=rank)
+    for li, l in enumerate(layers):
+        lr_a, lr_g, lr_lam, corr = est.state[l]
+        assert lr_a.shape == g[f"inf_r{rank}_lrA_{li}"].shape and lr_g.shape == g[f"inf_r{rank}_lrG_{li}"].shape
+        assert relerr(lr_a.cpu(), g[f"inf_r{rank}_lrA_{li}"]) < 1e-6      # same index sets selected
+        assert relerr(lr_g.cpu(), g[f"inf_r{rank}_lrG_{li}"]) < 1e-6
+        assert relerr(lr_lam.cpu(), g[f"inf_r{rank}_lrlam_{li}"]) < 1e-6
+        assert relerr(corr.cpu(), g[f"inf_r{rank}_corr_{li}"]) < 1e-4
+    est.invert(0.04, 200.0)
+    for li, l in enumerate(layers):
+        a_, b_, ric, p = est.inv_state[l]
+        assert float(est.state[l][3].min()) >= 0.0                        # clamped in place, as the reference
+        assert relerr(ric.cpu(), g[f"inf_r{rank}_ric_{li}"]) < TOL
+        assert relerr(p.cpu(), g[f"inf_r{rank}_P_{li}"]) < TOL
+        z = torch.tensor(g[f"inf_r{rank}_z_{li}"]).float().to(dev)
+        smp = est.sample(l, z=z)
+        assert smp.shape == g[f"inf_r{rank}_sample_{li}"].shape
+        assert relerr(smp.cpu(), g[f"inf_r{rank}_sample_{li}"]) < TOL
+        s1 = est.sample(l)
+        assert s1.shape == smp.shape and torch.isfinite(s1).all()
+    est.sample_and_replace()
+
+
+def test_inf_own_eigenvectors_end_to_end(golden, dev):
+    """Diagonal + KFAC + EFB + INF entirely on the device (own Jacobi eigenvectors)."""
+    from bnn_kfac_b200.curvatures import EFB, INF, Diagonal
+    model, kf = _gpu_kfac_mlp(golden, dev)
+    dg, efb = Diagonal(model), EFB(model, kf.state)
+    for i in range(2):
+        x = torch.tensor(golden[f"mlp_x_{i}"]).to(dev)
+        y = torch.tensor(golden[f"mlp_y_{i}"]).to(dev)
+        _fisher_step(model, x, y)
+        dg.update(batch_size=x.shape[0])
+        efb.update(batch_size=x.shape[0])
+    est = INF(model, dg.state, kf.state, efb.state)
+    est.update(rank=10)
+    est.invert(0.04, 200.0)
+    for l in _layers(kf):
+        a_, b_, ric, p = est.inv_state[l]
+        assert p.shape == (a_.shape[1] * b_.shape[1],) * 2 and torch.isfinite(p).all()
+        s = est.sample(l)
+        assert s.shape == (l.weight.shape[0], l.weight.shape[1] + 1) and torch.isfinite(s).all()
+    est.sample_and_replace()
+    with pytest.raises(AssertionError):
+        INF(model, dg.state, kf.state, efb.state).invert(0.04, 200.0)      # empty state
+
+
+@pytest.mark.parametrize("shape", [(40, 12, 30, 12), (70, 20, 12, 10), (33, 1, 5, 3), (300, 40, 64, 25)])
+def test_inf_presampler_fp64_chain_vs_oracle(dev, shape):
+    """bk_inf_presample (Kronecker-free V^T V, blocked fp64 Cholesky, triangular inverses, products) against
+    the oracle's statement-by-statement pre_sampler with the materialised Kronecker matrix; r = a*b from 3
+    to 1000 crosses the 32-wide Cholesky block boundaries (ragged last block, single block)."""
+    from bnn_kfac_b200 import _lib
+    n, a, m, b = shape
+    g = torch.Generator().manual_seed(n * 1000 + a)
+    ua = torch.linalg.qr(torch.randn(n, n, generator=g, dtype=torch.float64))[0][:, :a].float()
+    ug = torch.linalg.qr(torch.randn(m, m, generator=g, dtype=torch.float64))[0][:, :b].float()
+    c = (0.5 + torch.rand(n * m, generator=g)).float()
+    s = (0.3 + torch.rand(a * b, generator=g)).float()
+    want = O.inf_pre_sampler(ua.double(), ug.double(), s.double(), c.double())
+    lib = _lib.load()
+    r = a * b
+    ua_d, ug_d, c_d, s_d = (t.to(dev).contiguous() for t in (ua, ug, c, s))
+    out = torch.empty(r, r, device=dev)
+    nbytes = lib.bk_inf_presample_workspace_bytes(n, a, m, b)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = lib.bk_inf_presample(ua_d.data_ptr(), a, n, a, ug_d.data_ptr(), b, m, b, c_d.data_ptr(), s_d.data_ptr(),
+                              out.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr())
+    assert rc == 0
+    assert relerr(out.cpu(), want) < 1e-5
+    # a rank-deficient V^T V (more directions than rows: r > n*m is impossible here, so zero a scale) -> 1
+    s_bad = s_d.clone()
+    s_bad[0] = 0.0
+    rc = lib.bk_inf_presample(ua_d.data_ptr(), a, n, a, ug_d.data_ptr(), b, m, b, c_d.data_ptr(), s_bad.data_ptr(),
+                              out.data_ptr(), ws.data_ptr(), nbytes, _lib.stream_ptr())
+    assert rc == 1
+
+
+def test_calibration_metrics_vs_reference_golden(golden_inf, dev):
+    """models/utilities.py:178-366 against the reference's own numpy functions on the same probabilities."""
+    from bnn_kfac_b200 import utilities as U
+    g = golden_inf
+    p = torch.tensor(g["met_probs"]).to(dev)
+    lab = torch.tensor(g["met_labels"]).to(dev)
+    assert abs(U.accuracy(p, lab) - g["met_accuracy"]) < 1e-9
+    assert abs(U.confidence(p) - g["met_confidence"]) < 1e-6
+    np.testing.assert_array_equal(U.confidence(p, mean=False), g["met_confidence_rows"])
+    assert abs(U.negative_log_likelihood(p, lab) - g["met_nll"]) < 1e-5
+    np.testing.assert_allclose(U.predictive_entropy(p), g["met_entropy_rows"], rtol=1e-4, atol=1e-6)
+    assert abs(U.predictive_entropy(p, mean=True) - g["met_entropy_mean"]) < 1e-5
+    for bins in (10, 15):
+        ece, ace, acc, conf = U.expected_calibration_error(p, lab, bins=bins)
+        assert abs(ece - g[f"met_ece{bins}"]) < 1e-6
+        np.testing.assert_allclose(ace, g[f"met_ece{bins}_ace"], atol=1e-6)
+        np.testing.assert_allclose(acc, g[f"met_ece{bins}_acc"], atol=1e-6)
+        np.testing.assert_allclose(conf, g[f"met_ece{bins}_conf"], atol=1e-6)
+    for bins in (20, 7):
+        ece, xs, ys, zs = U.calibration_curve(p, lab, bins=bins)
+        assert abs(ece - g[f"met_curve{bins}"]) < 1e-6
+        assert xs.shape == g[f"met_curve{bins}_x"].shape
+        np.testing.assert_allclose(xs, g[f"met_curve{bins}_x"], atol=1e-6)
+        np.testing.assert_allclose(ys, g[f"met_curve{bins}_y"], atol=1e-6)
+        np.testing.assert_allclose(zs, g[f"met_curve{bins}_z"], atol=1e-12)
+    assert abs(U.binned_kl_distance(g["met_kl_d1"], g["met_kl_d2"]) - g["met_kl"]) < 1e-6 * max(1.0, g["met_kl"])
+    # numpy inputs (what the reference's callers hold) are accepted as they are
+    assert abs(U.accuracy(g["met_probs"], g["met_labels"]) - g["met_accuracy"]) < 1e-9
+    # size-independent properties at a large size: 2^20 rows x 10 classes against the oracle's numpy
+    gen = torch.Generator().manual_seed(3)
+    big = torch.softmax(3 * torch.randn(1 << 20, 10, generator=gen), 1)
+    labs = torch.randint(0, 10, (1 << 20,), generator=gen)
+    rows = O.metric_rows(big.numpy(), labs.numpy())
+    assert abs(U.accuracy(big, labs) - 100.0 * rows["correct"].mean()) < 1e-9
+    assert abs(U.negative_log_likelihood(big, labs) - rows["nll"].astype(np.float64).mean()) < 1e-5
+    ece, _, _, _ = U.expected_calibration_error(big, labs, bins=10)
+    assert abs(ece - O.metric_ece(big.numpy(), labs.numpy(), 10)[0]) < 1e-6
+
+
+def test_load_by_name_survives_new_model_instance(dev, tmp_path):
+    from bnn_kfac_b200.curvatures import KFAC
+    model = MLP().to(dev)
+    est = KFAC(model)
+    x = torch.rand(8, 20, device=dev)
+    _fisher_step(model, x, torch.randint(0, 5, (8,), device=dev))
+    est.update(8)
+    est.invert(0.04, 200.0)
+    fn = str(tmp_path / "kfac_named.dat")
+    est.save(fn)
+    model2 = MLP().to(dev)
+    est2 = KFAC(model2)
+    est2.load_by_name(fn)
+    assert est2.model is model2 and list(est2.state.keys()) == [model2.fc1, model2.fc2]
+    for l1, l2 in zip((model.fc1, model.fc2), (model2.fc1, model2.fc2)):
+        assert torch.equal(est.state[l1][0], est2.state[l2][0])
+        assert torch.equal(est.inv_state[l1][1], est2.inv_state[l2][1])
+    z = torch.randn(21, 16, device=dev)
+    assert torch.equal(est.sample(model.fc1, z=z), est2.sample(model2.fc1, z=z))
+    est2.sample_and_replace()
+    with pytest.raises(KeyError):
+        KFAC(torch.nn.Sequential(torch.nn.Linear(20, 5)).to(dev)).load_by_name(fn)

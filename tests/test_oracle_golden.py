@@ -234,3 +234,72 @@ def test_efb_oracle_vs_reference(golden, golden_next):
     # squares of projections are invariant to eigenvector signs; degenerate eigenvalues (rank-deficient
     # factors) leave the basis of the null space free, so compare the sums over the free blocks: totals
     assert abs(lam_own.sum().item() / lam_ref.sum().item() - 1) < 1e-9
+
+
+# ------------------------------------------------------------------ "next" rows: INF (f4), metrics (f3)
+@pytest.fixture(scope="module")
+def golden_inf():
+    return dict(np.load(ROOT / "tests" / "golden" / "reference_golden_inf.npz"))
+
+
+@pytest.mark.parametrize("rank", [10, 30])
+def test_inf_oracle_vs_reference(golden_inf, rank):
+    g = golden_inf
+    for li in range(2):
+        eig = (torch.tensor(g[f"inf_UA_{li}"]), torch.tensor(g[f"inf_UG_{li}"]))
+        state = O.inf_update(eig, torch.tensor(g[f"inf_lambdas_{li}"]), torch.tensor(g[f"inf_diags_{li}"]), rank)
+        for name, t in zip(("lrA", "lrG", "lrlam", "corr"), state):
+            # the reference accumulates sif_diag in a float32 buffer (torch.zeros(n*m), curvatures.py:675)
+            # whatever the factors' dtype: its correction carries that rounding (~1e-10 absolute here)
+            atol = 1e-9 if name == "corr" else 1e-14   # one fp32 ulp of sif_diag
+            np.testing.assert_allclose(t.numpy(), g[f"inf_r{rank}_{name}_{li}"], rtol=1e-9, atol=atol)
+        # stage-wise from here: feed the reference's own correction so that a flipped fp32 rounding of
+        # sif_diag is not amplified by the (ill-conditioned) pre-sampler
+        state = state[:3] + (torch.tensor(g[f"inf_r{rank}_corr_{li}"]),)
+        inv = O.inf_invert(state, 0.04, 200.0)
+        np.testing.assert_allclose(inv[2].numpy(), g[f"inf_r{rank}_ric_{li}"], rtol=1e-10)
+        assert relerr(inv[3].numpy(), g[f"inf_r{rank}_P_{li}"]) < 1e-7      # five LAPACK inverses, cond 1e5..1e7
+        ref_inv = (inv[0], inv[1], inv[2], torch.tensor(g[f"inf_r{rank}_P_{li}"]))
+        smp = O.inf_sample(ref_inv, torch.tensor(g[f"inf_r{rank}_z_{li}"]))
+        np.testing.assert_allclose(smp.numpy(), g[f"inf_r{rank}_sample_{li}"], rtol=1e-9, atol=1e-11)
+
+
+def test_inf_presampler_closed_form(golden_inf):
+    """The identity the CUDA path uses: L_c = A^-T (I - B^-1) A^-1 with A = chol(vtv), B = chol(vtv + I)
+    equals the reference's (C^-1 + vtv)^-1 (see bk_inf.cu)."""
+    g = golden_inf
+    li, rank = 1, 10
+    a, b = torch.tensor(g[f"inf_r{rank}_lrA_{li}"]), torch.tensor(g[f"inf_r{rank}_lrG_{li}"])
+    c = torch.tensor(g[f"inf_r{rank}_ric_{li}"])
+    s = (200.0 * torch.tensor(g[f"inf_r{rank}_lrlam_{li}"])).sqrt()
+    v = c.view(-1, 1) * O.kron(a, b) @ torch.diag(s)
+    vtv = v.t() @ v
+    eye = torch.eye(vtv.shape[0], dtype=vtv.dtype)
+    ainv = torch.linalg.inv(torch.linalg.cholesky(vtv))
+    binv = torch.linalg.inv(torch.linalg.cholesky(vtv + eye))
+    p = torch.diag(s) @ ainv.t() @ (eye - binv) @ ainv @ torch.diag(s)
+    assert relerr(p.numpy(), g[f"inf_r{rank}_P_{li}"]) < 1e-8
+
+
+def test_metrics_oracle_vs_reference(golden_inf):
+    g = golden_inf
+    p, lab = g["met_probs"], g["met_labels"]
+    rows = O.metric_rows(p, lab)
+    assert abs(O.metric_accuracy(p, lab) - g["met_accuracy"]) < 1e-12
+    assert abs(float(rows["conf"].mean()) - g["met_confidence"]) < 1e-7
+    np.testing.assert_array_equal(rows["conf"], g["met_confidence_rows"])
+    assert abs(O.metric_nll(p, lab) - g["met_nll"]) < 1e-6
+    np.testing.assert_allclose(rows["entropy"], g["met_entropy_rows"], rtol=1e-5, atol=1e-7)
+    for bins in (10, 15):
+        ece, ace, acc, cf = O.metric_ece(p, lab, bins)
+        assert abs(ece - g[f"met_ece{bins}"]) < 1e-7
+        np.testing.assert_allclose(ace, g[f"met_ece{bins}_ace"], atol=1e-6)
+        np.testing.assert_allclose(acc, g[f"met_ece{bins}_acc"], atol=1e-6)
+        np.testing.assert_allclose(cf, g[f"met_ece{bins}_conf"], atol=1e-6)
+    for bins in (20, 7):
+        ece, xs, ys, zs = O.metric_calibration_curve(p, lab, bins)
+        assert abs(ece - g[f"met_curve{bins}"]) < 1e-7
+        np.testing.assert_allclose(xs, g[f"met_curve{bins}_x"], atol=1e-6)
+        np.testing.assert_allclose(ys, g[f"met_curve{bins}_y"], atol=1e-6)
+        np.testing.assert_allclose(zs, g[f"met_curve{bins}_z"], atol=1e-12)
+    assert abs(O.metric_binned_kl(g["met_kl_d1"], g["met_kl_d2"]) - g["met_kl"]) < 1e-9
