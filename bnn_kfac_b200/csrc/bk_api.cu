@@ -39,6 +39,10 @@ int bk_device_check(void) {
 
 void bk_set_cta_group(int cta_group) { bk::set_umma_cta_group(cta_group); }
 
+void bk_set_eigh_mode(int mode) { bk::set_eigh_mode(mode); }
+
+void bk_set_eigh_pair_width(int width) { bk::set_eigh_pair_width(width); }
+
 int bk_gemm_nt(const void* a_hi, const void* a_lo, long long lda, long long stride_a,
                const void* b_hi, const void* b_lo, long long ldb, long long stride_b, int m, int n,
                int k, int batch, int precision, int flags, float alpha, float beta, float* c,

@@ -82,7 +82,7 @@ eigh_small_kernel(const EighProb* __restrict__ tab, int max_sweeps) {
   extern __shared__ float sm[];
   const EighProb P = tab[blockIdx.x];
   const int d = P.d;
-  if (d > kSmallMax) return;
+  if (d <= 0 || d > kSmallMax) return;
   const int ld = d + 1;
   float* U = sm;
   float* V = sm + d * ld;
@@ -342,16 +342,29 @@ __global__ void eigh_sort_kernel(const EighProb* __restrict__ tab) {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+// 0: wide factors by the tensor-core block Jacobi (bk_eigh_blocked.cu); 1: streamed element-wise Jacobi;
+// 2 (bring-up): block Jacobi for every size
+int g_eigh_mode = 0;
+inline bool use_blocked(int d) { return g_eigh_mode == 2 || (g_eigh_mode == 0 && d > kSmallMax); }
+
 }  // namespace
+
+void set_eigh_mode(int mode) { g_eigh_mode = (mode == 1 || mode == 2) ? mode : 0; }
 
 size_t eigh_workspace_bytes(const int* dims, int count) {
   size_t total = align256(sizeof(EighProb) * static_cast<size_t>(count)) + 2 * align256(4 * count);
+  size_t blocked = 0;
   for (int i = 0; i < count; ++i) {
     const size_t d = static_cast<size_t>(dims[i]);
     total += align256(d * 4);  // lam
-    if (dims[i] > kSmallMax) total += 2 * align256(d * d * 4);
+    if (use_blocked(dims[i])) {
+      const size_t b = eigh_blocked_workspace_bytes(dims[i]);  // wide factors run one after another
+      if (b > blocked) blocked = b;
+    } else if (dims[i] > kSmallMax) {
+      total += 2 * align256(d * d * 4);
+    }
   }
-  return total;
+  return total + blocked;
 }
 
 // Returns 0, or the 1-based index of the first factor that did not converge in max_sweeps, or < 0.
@@ -373,7 +386,7 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
   if (cudaMemsetAsync(d_scale2, 0, 4 * count, stream) != cudaSuccess) return -5;
   EighProb h_tab[64];
   if (count > 64) return -2;
-  int max_small = 0, max_large = 0, n_large = 0;
+  int max_small = 0, max_large = 0, n_large = 0, n_blocked = 0;
   for (int i = 0; i < count; ++i) {
     EighProb& P = h_tab[i];
     const size_t d = static_cast<size_t>(dims[i]);
@@ -392,7 +405,10 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
     P.lam = reinterpret_cast<float*>(base + off);
     off += align256(d * 4);
     P.U = P.V = nullptr;
-    if (dims[i] > kSmallMax) {
+    if (use_blocked(dims[i])) {
+      ++n_blocked;
+      P.d = 0;  // the element-wise kernels skip this entry
+    } else if (dims[i] > kSmallMax) {
       P.U = reinterpret_cast<float*>(base + off);
       off += align256(d * d * 4);
       P.V = reinterpret_cast<float*>(base + off);
@@ -418,6 +434,19 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
     }
     eigh_small_kernel<<<count, 512, smem, stream>>>(d_tab, max_sweeps);
     note_launch();
+  }
+  if (n_blocked > 0) {
+    // wide factors: tensor-core block Jacobi, one factor after another on the shared scratch region
+    void* scratch = base + off;
+    const size_t scratch_bytes = workspace_bytes - off;
+    for (int i = 0; i < count; ++i) {
+      if (!use_blocked(dims[i])) continue;
+      const int rc = eigh_blocked(factors[i], ldf[i], dims[i], sym_scale, h_tab[i].tol, max_sweeps, evals[i],
+                                  evecs != nullptr ? evecs[i] : nullptr, d_scale2 + i, scratch, scratch_bytes,
+                                  stream);
+      if (rc < 0) return rc;
+      if (rc > 0 && status == 0) status = i + 1;
+    }
   }
   if (n_large > 0) {
     const dim3 tb(32, 8);

@@ -1,0 +1,509 @@
+// bk_eigh_blocked.cu — symmetric eigendecomposition of WIDE Kronecker factors (d > 164) by a two-sided
+// BLOCK Jacobi method whose O(d^3) work runs on the tensor cores.
+//
+// Reference: models/utilities.py:144-159 / :120-141 (torch.symeig of F + F^T / of F; LAPACK syevd on the
+// CPU, cuSOLVER on CUDA).  The element-wise one-sided Jacobi of bk_eigh.cu streams the whole matrix once
+// per round of d/2 rotations (d - 1 launches per sweep): L2/latency-bound, 283 ms at d = 2049.  Here the
+// rotations are aggregated into 128 x 128 orthogonal blocks and applied as GEMMs:
+//
+//   S (d_pad x d_pad, symmetric) is cut into nb blocks of b = 64 rows / columns (d padded to a multiple of
+//   128; the pad carries a diagonal M > |lambda|_max that never couples, see init).  One ROUND pairs
+//   adjacent blocks — (0,1)(2,3).. in even rounds, (1,2)(3,4).. in odd rounds, the two blocks of a pair
+//   SWAPPING places afterwards (odd-even transposition ordering: after nb rounds every pair of blocks has
+//   met exactly once = one sweep).  Because partners are always adjacent, every pair is a contiguous
+//   128-wide slab at a uniform stride and a whole round is three BATCHED GEMMs:
+//     inner   per pair: two-sided Jacobi sweep(s) on the 128 x 128 diagonal block G = S[pair, pair] in
+//             shared memory (rotation angles straight from G: no dot products), accumulating Q^T
+//     step 1  T[pair rows, :]  = Q^T S[pair rows, :]     (B operand = S[:, pair cols] by symmetry)
+//     step 2  S[:, pair cols]  = T[:, pair cols] Q
+//     step 3  V[:, pair cols]  = V[:, pair cols] Q       (eigenvector accumulation, columns = vectors)
+//   All three are K-major "NT" contractions of the tcgen05 core; operands live as three-way bf16 splits
+//   (hi + lo + lo2 = 24 mantissa bits, six MMA passes = fp32-class products) that the GEMM epilogue emits
+//   directly, so no separate staging pass exists.  Per round the matrix is read and written a constant
+//   number of times (HBM-bound, ~0.5 GB at d = 4097) instead of once per 2-column rotation.
+// Convergence: a round-robin pass of the inner kernel applies a rotation only where
+// |g_pq| > tol sqrt(|g_pp g_qq|) and |g_pq| > 5e-7 |S|_F (null space of rank-deficient factors); a sweep
+// without any rotation ends the iteration.
+#include "bk_common.cuh"
+#include "bk_kernels.cuh"
+#include "bk_umma_gemm.cuh"
+
+#include <string.h>
+
+namespace bk {
+
+namespace {
+
+struct Parts {
+  __nv_bfloat16* p[3];
+};
+
+// ------------------------------------------------------------------------------ init
+// S_pad = [[sym_scale (F + F^T), 0], [0, 0]] (pad diagonal set by pad_diag_kernel); V_pad = I and
+// fro2 += |S|_F^2 when V / fro2 are given (the final Rayleigh pass re-creates S only).
+__global__ void blk_init_kernel(const float* __restrict__ F, long long ldf, int d, int dp, float sym_scale,
+                                float* __restrict__ S, float* __restrict__ V, float* __restrict__ fro2) {
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  __shared__ float tr[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = j0 + ty + 8 * k, i = i0 + tx;  // F[j][i], i fastest
+    tr[ty + 8 * k][tx] = (i < d && j < d) ? F[static_cast<long long>(j) * ldf + i] : 0.f;
+  }
+  __syncthreads();
+  float fro = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + ty + 8 * k, j = j0 + tx;
+    if (i < dp && j < dp) {
+      float v = 0.f;
+      if (i < d && j < d) v = sym_scale * (F[static_cast<long long>(i) * ldf + j] + tr[tx][ty + 8 * k]);
+      S[static_cast<long long>(i) * dp + j] = v;
+      if (V != nullptr) V[static_cast<long long>(i) * dp + j] = (i == j) ? 1.f : 0.f;
+      fro = fmaf(v, v, fro);
+    }
+  }
+  if (fro2 != nullptr) {
+    fro = warp_sum(fro);
+    if (tx == 0 && fro != 0.f) atomicAdd(fro2, fro);
+  }
+}
+
+// pad diagonal M = 2 |S|_F (1 if S == 0): larger than every |lambda|, so the pad eigenpairs sort last;
+// S[real, pad] is exactly 0 and every product with it stays exactly 0, so the pad never mixes in.
+__global__ void blk_pad_diag_kernel(float* __restrict__ S, int d, int dp, const float* __restrict__ fro2) {
+  const int i = d + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dp) return;
+  const float f = sqrtf(*fro2);
+  S[static_cast<long long>(i) * dp + i] = f > 0.f ? 2.f * f : 1.f;
+}
+
+__global__ void blk_identity_kernel(int b, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    __nv_bfloat16* __restrict__ lo2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= b * b) return;
+  hi[idx] = __float2bfloat16_rn((idx / b == idx % b) ? 1.f : 0.f);
+  lo[idx] = __float2bfloat16_rn(0.f);
+  lo2[idx] = __float2bfloat16_rn(0.f);
+}
+
+// ------------------------------------------------------------------------------ inner two-sided Jacobi
+template <int P>
+__device__ __forceinline__ void rr_pair_p(int r, int k, int& p, int& q) {
+  // round-robin tournament on P players, round r in [0, P - 1), slot k in [0, P / 2)
+  if (k == 0) {
+    p = P - 1;
+    q = r;
+  } else {
+    p = (r + k) % (P - 1);
+    q = (r - k + (P - 1)) % (P - 1);
+  }
+  if (p > q) {
+    const int t = p;
+    p = q;
+    q = t;
+  }
+}
+
+// One CTA per pair of blocks (P = pair width = 2 b).  G = sym(S[o:o+P, o:o+P]) rebuilt exactly from the
+// three bf16 splits of S, Q^T = I; `sweeps` cyclic two-sided Jacobi sweeps; writes Q^T with its two halves
+// exchanged (the blocks of the pair swap places) as bf16 splits.  stats[0] |= 1 if any rotation was
+// applied, stats[1] = max |sin| of the applied rotations (as float bits).
+template <int P>
+__global__ void __launch_bounds__(P * 8, 1)
+blk_inner_kernel(Parts ss, int dp, int off, float tol, const float* __restrict__ fro2, int sweeps, Parts qt,
+                 int* __restrict__ stats) {
+  constexpr int kLd = P + 1, kHalf = P / 2, kThreads = P * 8;
+  constexpr int kShift = P == 128 ? 7 : 6;
+  static_assert(P == 128 || P == 64, "pair width");
+  extern __shared__ float sm[];
+  float* G = sm;
+  float* Q = sm + P * kLd;
+  __shared__ float cs_c[kHalf], cs_s[kHalf];
+  __shared__ int cs_p[kHalf], cs_q[kHalf];
+  __shared__ int s_any, s_round;
+  __shared__ float s_max;
+  const int tid = threadIdx.x;
+  const int o = off + blockIdx.x * P;
+  const long long sb = static_cast<long long>(o) * dp + o;
+  for (int idx = tid; idx < P * P; idx += kThreads) {
+    const int i = idx >> kShift, j = idx & (P - 1);
+    const long long a = sb + static_cast<long long>(i) * dp + j;
+    G[i * kLd + j] = __bfloat162float(ss.p[0][a]) + __bfloat162float(ss.p[1][a]) + __bfloat162float(ss.p[2][a]);
+    Q[i * kLd + j] = (i == j) ? 1.f : 0.f;
+  }
+  if (tid == 0) {
+    s_any = 0;
+    s_max = 0.f;
+  }
+  __syncthreads();
+  // symmetrise (S is symmetric up to the rounding of two different summation orders)
+  for (int idx = tid; idx < P * P; idx += kThreads) {
+    const int i = idx >> kShift, j = idx & (P - 1);
+    if (j < i) {
+      const float v = 0.5f * (G[i * kLd + j] + G[j * kLd + i]);
+      G[i * kLd + j] = v;
+      G[j * kLd + i] = v;
+    }
+  }
+  __syncthreads();
+  const float abs_floor = 5e-7f * sqrtf(*fro2);
+  for (int sw = 0; sw < sweeps; ++sw) {
+    for (int r = 0; r < P - 1; ++r) {
+      if (tid == 0) s_round = 0;
+      __syncthreads();
+      if (tid < kHalf) {
+        int p, q;
+        rr_pair_p<P>(r, tid, p, q);
+        const float gpp = G[p * kLd + p], gqq = G[q * kLd + q], gpq = G[p * kLd + q];
+        float c = 1.f, s = 0.f;
+        const float a = fabsf(gpq);
+        if (a > tol * sqrtf(fabsf(gpp * gqq)) && a > abs_floor) {
+          const float zeta = (gqq - gpp) / (2.f * gpq);
+          const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+          c = 1.f / sqrtf(1.f + t * t);
+          s = c * t;
+          s_round = 1;
+          atomicMax(reinterpret_cast<int*>(&s_max), __float_as_int(fabsf(s)));
+        }
+        cs_c[tid] = c;
+        cs_s[tid] = s;
+        cs_p[tid] = p;
+        cs_q[tid] = q;
+      }
+      __syncthreads();
+      if (s_round == 0) continue;  // nothing to rotate in this round (block-uniform)
+      if (tid == 0) s_any = 1;
+      // rows: G <- J^T G, Q^T <- J^T Q^T   (row_p' = c row_p - s row_q, row_q' = s row_p + c row_q)
+      for (int idx = tid; idx < kHalf * P; idx += kThreads) {
+        const int k = idx >> kShift, j = idx & (P - 1);
+        const float s = cs_s[k];
+        if (s == 0.f) continue;
+        const float c = cs_c[k];
+        const int p = cs_p[k], q = cs_q[k];
+        const float gp = G[p * kLd + j], gq = G[q * kLd + j];
+        G[p * kLd + j] = c * gp - s * gq;
+        G[q * kLd + j] = s * gp + c * gq;
+        const float qp = Q[p * kLd + j], qq = Q[q * kLd + j];
+        Q[p * kLd + j] = c * qp - s * qq;
+        Q[q * kLd + j] = s * qp + c * qq;
+      }
+      __syncthreads();
+      // columns: G <- G J
+      for (int idx = tid; idx < kHalf * P; idx += kThreads) {
+        const int k = idx >> kShift, i = idx & (P - 1);
+        const float s = cs_s[k];
+        if (s == 0.f) continue;
+        const float c = cs_c[k];
+        const int p = cs_p[k], q = cs_q[k];
+        const float gp = G[i * kLd + p], gq = G[i * kLd + q];
+        G[i * kLd + p] = c * gp - s * gq;
+        G[i * kLd + q] = s * gp + c * gq;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && s_any) {
+    atomicOr(&stats[0], 1);
+    atomicMax(&stats[1], __float_as_int(s_max));
+  }
+  // Q^T out, halves exchanged: output row i = Q^T row (i + P/2) mod P
+  const long long base = static_cast<long long>(blockIdx.x) * P * P;
+  for (int idx = tid; idx < P * P; idx += kThreads) {
+    const int i = idx >> kShift, j = idx & (P - 1);
+    const float v = Q[((i + kHalf) & (P - 1)) * kLd + j];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+    qt.p[0][base + idx] = h;
+    qt.p[1][base + idx] = l;
+    qt.p[2][base + idx] = __float2bfloat16_rn(r1 - __bfloat162float(l));
+  }
+}
+
+// ------------------------------------------------------------------------------ output
+// num[c] += sum over this block's rows of P[i][c] * V[i][c], den[c] += sum V[i][c]^2
+// (Rayleigh quotients v_c^T S v_c / v_c^T v_c with P = S V)
+__global__ void blk_coldot_kernel(const float* __restrict__ Pm, const float* __restrict__ V, int dp,
+                                  int rows_per_block, float* __restrict__ num, float* __restrict__ den) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= dp) return;
+  const int i0 = blockIdx.y * rows_per_block;
+  const int i1 = min(dp, i0 + rows_per_block);
+  float acc = 0.f, nrm = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float v = V[static_cast<long long>(i) * dp + c];
+    acc = fmaf(Pm[static_cast<long long>(i) * dp + c], v, acc);
+    nrm = fmaf(v, v, nrm);
+  }
+  atomicAdd(&num[c], acc);
+  atomicAdd(&den[c], nrm);
+}
+
+__global__ void blk_rank_kernel(const float* __restrict__ num, const float* __restrict__ den, int d, int dp,
+                                float* __restrict__ evals, int* __restrict__ ranks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= dp) return;
+  const float lc = num[c] / den[c];
+  int rank = 0;
+  for (int j = 0; j < dp; ++j) {
+    const float lj = num[j] / den[j];
+    rank += (lj < lc) || (lj == lc && j < c);
+  }
+  ranks[c] = rank;
+  if (rank < d) evals[rank] = lc;
+}
+
+// evecs[j][rank[c]] = V[j][c]
+__global__ void blk_gather_kernel(const float* __restrict__ V, int d, int dp, const int* __restrict__ ranks,
+                                  float* __restrict__ evecs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rank = c < dp ? ranks[c] : d;
+  for (int j = blockIdx.y; j < d; j += gridDim.y)
+    if (rank < d) evecs[static_cast<long long>(j) * d + rank] = V[static_cast<long long>(j) * dp + c];
+}
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// pair width: 64-column blocks (128-wide pairs) halve the number of rounds and matrix passes, 32-column
+// blocks make the shared-memory Jacobi of a pair 8x cheaper and double the pairs in flight.  Measured on
+// B200 (tools/gpu_eigh_blocked.py): see DESIGN.md.
+int g_pair = 0;  // 0 = automatic
+inline int pair_width(int d) {
+  if (g_pair == 64 || g_pair == 128) return g_pair;
+  return d > 1500 ? 128 : 64;
+}
+inline int pad_dim(int d, int P) { return (d + P - 1) / P * P; }
+
+// One batched contraction of a round: out[:, blocks] (op) with operands at `off` and stride `bstride`.
+int gemm6(const Parts& A, long long a_off, long long lda, long long strideA, const Parts& B, long long b_off,
+          long long ldb, long long strideB, int M, int N, int K, int batch, float* C, long long c_off,
+          long long ldc, long long strideC, const Parts* O, long long o_off, long long ldo, long long strideO,
+          cudaStream_t stream) {
+  GemmArgs g;
+  g.A_hi = A.p[0] + a_off;
+  g.A_lo = A.p[1] + a_off;
+  g.A_lo2 = A.p[2] + a_off;
+  g.lda = lda;
+  g.strideA = strideA;
+  g.B_hi = B.p[0] + b_off;
+  g.B_lo = B.p[1] + b_off;
+  g.B_lo2 = B.p[2] + b_off;
+  g.ldb = ldb;
+  g.strideB = strideB;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.batch = batch;
+  g.nparts = 6;
+  g.alpha = 1.f;
+  g.beta = 0.f;
+  if (C != nullptr) {
+    g.C = C + c_off;
+    g.ldc = ldc;
+    g.strideC = strideC;
+  }
+  if (O != nullptr) {
+    g.O_hi = O->p[0] + o_off;
+    g.O_lo = O->p[1] + o_off;
+    g.O_lo2 = O->p[2] + o_off;
+    g.ldo = ldo;
+    g.strideO = strideO;
+  }
+  return launch_umma_gemm(g, stream);
+}
+
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t q_ready[2] = {nullptr, nullptr}, v_done[2] = {nullptr, nullptr};
+  bool ok = false;
+  SideStream() {
+    ok = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&q_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&v_done[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+};
+
+template <int P>
+int launch_inner(int npairs, const Parts& Ss, int dp, int off, float tol, const float* fro2, int sweeps,
+                 const Parts& Qs, int* stats, cudaStream_t stream) {
+  constexpr size_t smem = 2ull * P * (P + 1) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(blk_inner_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return -5;
+    attr_done = true;
+  }
+  blk_inner_kernel<P><<<npairs, P * 8, smem, stream>>>(Ss, dp, off, tol, fro2, sweeps, Qs, stats);
+  note_launch();
+  return 0;
+}
+
+}  // namespace
+
+void set_eigh_pair_width(int p) { g_pair = p; }
+
+size_t eigh_blocked_workspace_bytes(int d) {
+  const int P = pair_width(d);
+  const size_t dp = static_cast<size_t>(pad_dim(d, P));
+  const size_t f32 = align256(dp * dp * 4), b16 = align256(dp * dp * 2);
+  const size_t npairs = dp / P;
+  // P_f32 (Rayleigh products), V_f32, 3 x (S, T, V0, V1) splits, 2 x Q^T splits, identity splits, lam, ranks, stats
+  return 2 * f32 + 12 * b16 + 6 * align256(npairs * P * P * 2) + 3 * align256(static_cast<size_t>(P / 2) * (P / 2) * 2) +
+         3 * align256(dp * 4) + 256;
+}
+
+// Returns 0, 1 if not converged after max_sweeps, < 0 on error.  Synchronises `stream` once per sweep.
+int eigh_blocked(const float* F, long long ldf, int d, float sym_scale, float tol, int max_sweeps,
+                 float* evals, float* evecs, float* fro2, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+  if (d <= 0 || F == nullptr || evals == nullptr) return -2;
+  if (workspace_bytes < eigh_blocked_workspace_bytes(d) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return -6;
+  static SideStream side;
+  if (!side.ok) return -5;
+  const int kP = pair_width(d), kB = kP / 2;
+  const int dp = pad_dim(d, kP);
+  const int nb = dp / kB;  // even
+  const size_t f32 = align256(static_cast<size_t>(dp) * dp * 4), b16 = align256(static_cast<size_t>(dp) * dp * 2);
+  char* w = static_cast<char*>(workspace);
+  float* Pm = reinterpret_cast<float*>(w);  // fp32 scratch: S at init, S V in the final Rayleigh pass
+  w += f32;
+  float* V = reinterpret_cast<float*>(w);
+  w += f32;
+  Parts Ss, Ts, Vs[2], Qs[2], Is;
+  auto carve = [&](Parts& X, size_t bytes) {
+    for (int i = 0; i < 3; ++i) {
+      X.p[i] = reinterpret_cast<__nv_bfloat16*>(w);
+      w += bytes;
+    }
+  };
+  carve(Ss, b16);
+  carve(Ts, b16);
+  carve(Vs[0], b16);
+  carve(Vs[1], b16);
+  carve(Qs[0], align256(static_cast<size_t>(dp / kP) * kP * kP * 2));
+  carve(Qs[1], align256(static_cast<size_t>(dp / kP) * kP * kP * 2));
+  carve(Is, align256(static_cast<size_t>(kB) * kB * 2));
+  float* lam = reinterpret_cast<float*>(w);  // [2][dp]: Rayleigh numerators, squared norms
+  w += 2 * align256(static_cast<size_t>(dp) * 4);
+  float* den = lam + align256(static_cast<size_t>(dp) * 4) / 4;
+  int* ranks = reinterpret_cast<int*>(w);
+  w += align256(static_cast<size_t>(dp) * 4);
+  int* stats = reinterpret_cast<int*>(w);
+
+  if (cudaMemsetAsync(fro2, 0, 4, stream) != cudaSuccess) return -5;
+  const int t32 = (dp + 31) / 32;
+  blk_init_kernel<<<dim3(t32, t32), dim3(32, 8), 0, stream>>>(F, ldf, d, dp, sym_scale, Pm, V, fro2);
+  if (dp > d) blk_pad_diag_kernel<<<(dp - d + 127) / 128, 128, 0, stream>>>(Pm, d, dp, fro2);
+  blk_identity_kernel<<<(kB * kB + 255) / 256, 256, 0, stream>>>(kB, Is.p[0], Is.p[1], Is.p[2]);
+  note_launch(dp > d ? 3 : 2);
+  int rc = launch_convert_split3(Pm, dp, dp, dp, Ss.p[0], Ss.p[1], Ss.p[2], dp, stream);
+  if (rc) return rc;
+  rc = launch_convert_split3(V, dp, dp, dp, Vs[0].p[0], Vs[0].p[1], Vs[0].p[2], dp, stream);
+  if (rc) return rc;
+
+  const long long ld = dp;
+  const long long qstride = static_cast<long long>(kP) * kP;
+  const long long bs = static_cast<long long>(nb - 1) * kB;  // blocks 0 and nb-1 sit odd rounds out: carried
+                                                             // through unchanged (identity Q)
+  int cur = 0;  // V split buffer holding the current eigenvector estimates
+  long long round = 0;
+  bool converged = false;
+  for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+    if (cudaMemsetAsync(stats, 0, 8, stream) != cudaSuccess) return -5;
+    const int inner_sweeps = sweep == 0 ? 2 : 1;
+    for (int t = 0; t < nb; ++t, ++round) {
+      const int odd = t & 1;
+      const int off = odd ? kB : 0;
+      const int npairs = odd ? nb / 2 - 1 : nb / 2;
+      const int slot = static_cast<int>(round & 1);
+      const Parts& Q = Qs[slot];
+      const Parts& Vin = Vs[cur];
+      const Parts& Vout = Vs[cur ^ 1];
+      // Q^T slot `slot` was last read by the eigenvector update of round - 2 (side stream)
+      if (round >= 2 && cudaStreamWaitEvent(stream, side.v_done[slot], 0) != cudaSuccess) return -5;
+      if (npairs > 0) {
+        rc = kP == 128 ? launch_inner<128>(npairs, Ss, dp, off, tol, fro2, inner_sweeps, Q, stats, stream)
+                       : launch_inner<64>(npairs, Ss, dp, off, tol, fro2, inner_sweeps, Q, stats, stream);
+        if (rc) return rc;
+      }
+      if (cudaEventRecord(side.q_ready[slot], stream) != cudaSuccess) return -5;
+      // step 3 on the side stream (overlaps the S path of this round and the next inner solve):
+      // V[:, cols] = V[:, cols] Q
+      if (cudaStreamWaitEvent(side.stream, side.q_ready[slot], 0) != cudaSuccess) return -5;
+      if (npairs > 0) {
+        rc = gemm6(Vin, off, ld, kP, Q, 0, kP, qstride, dp, kP, kP, npairs, V, off, ld, kP, &Vout, off, ld, kP,
+                   side.stream);
+        if (rc) return rc;
+      }
+      if (odd) {
+        rc = gemm6(Vin, 0, ld, bs, Is, 0, kB, 0, dp, kB, kB, 2, V, 0, ld, bs, &Vout, 0, ld, bs, side.stream);
+        if (rc) return rc;
+      }
+      if (cudaEventRecord(side.v_done[slot], side.stream) != cudaSuccess) return -5;
+      // step 1 (all rows of T before any column slab of it is read): T[rows, :] = Q^T S[rows, :]
+      if (npairs > 0) {
+        rc = gemm6(Q, 0, kP, qstride, Ss, off, ld, kP, kP, dp, kP, npairs, nullptr, 0, 0, 0, &Ts,
+                   static_cast<long long>(off) * ld, ld, static_cast<long long>(kP) * ld, stream);
+        if (rc) return rc;
+      }
+      if (odd) {
+        rc = gemm6(Is, 0, kB, 0, Ss, 0, ld, bs, kB, dp, kB, 2, nullptr, 0, 0, 0, &Ts, 0, ld, bs * ld, stream);
+        if (rc) return rc;
+      }
+      // step 2: S[:, cols] = T[:, cols] Q
+      if (npairs > 0) {
+        rc = gemm6(Ts, off, ld, kP, Q, 0, kP, qstride, dp, kP, kP, npairs, nullptr, 0, 0, 0, &Ss, off, ld, kP,
+                   stream);
+        if (rc) return rc;
+      }
+      if (odd) {
+        rc = gemm6(Ts, 0, ld, bs, Is, 0, kB, 0, dp, kB, kB, 2, nullptr, 0, 0, 0, &Ss, 0, ld, bs, stream);
+        if (rc) return rc;
+      }
+      cur ^= 1;
+    }
+    int h[2] = {0, 0};
+    if (cudaMemcpyAsync(h, stats, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+      return -5;
+    float smax;
+    memcpy(&smax, &h[1], 4);
+    // quadratic convergence: after a sweep whose largest rotation had |sin| = s, the remaining relative
+    // off-diagonals are O(s^2); 3e-4 squared is the fp32 rounding level
+    converged = (h[0] == 0) || (smax < 3e-4f);
+  }
+  // the last eigenvector updates run on the side stream
+  if (round >= 1 && cudaStreamWaitEvent(stream, side.v_done[(round - 1) & 1], 0) != cudaSuccess) return -5;
+  if (round >= 2 && cudaStreamWaitEvent(stream, side.v_done[round & 1], 0) != cudaSuccess) return -5;
+  // eigenvalues as Rayleigh quotients with the ORIGINAL matrix: lambda_c = v_c^T S v_c (second-order accurate
+  // in the eigenvector error, free of the rounding drift of the iterated S): P = S V, lam = colsum(P . V)
+  blk_init_kernel<<<dim3(t32, t32), dim3(32, 8), 0, stream>>>(F, ldf, d, dp, sym_scale, Pm, nullptr, nullptr);
+  if (dp > d) blk_pad_diag_kernel<<<(dp - d + 127) / 128, 128, 0, stream>>>(Pm, d, dp, fro2);
+  note_launch(dp > d ? 2 : 1);
+  rc = launch_convert_split3(Pm, dp, dp, dp, Ss.p[0], Ss.p[1], Ss.p[2], dp, stream);
+  if (rc) return rc;
+  rc = launch_transpose_split3(V, dp, dp, dp, Ts.p[0], Ts.p[1], Ts.p[2], dp, stream);
+  if (rc) return rc;
+  rc = gemm6(Ss, 0, ld, 0, Ts, 0, ld, 0, dp, dp, dp, 1, Pm, 0, ld, 0, nullptr, 0, 0, 0, stream);
+  if (rc) return rc;
+  if (cudaMemsetAsync(lam, 0, 2 * align256(static_cast<size_t>(dp) * 4), stream) != cudaSuccess) return -5;
+  const int rows_per_block = 64;
+  blk_coldot_kernel<<<dim3((dp + 127) / 128, (dp + rows_per_block - 1) / rows_per_block), 128, 0, stream>>>(
+      Pm, V, dp, rows_per_block, lam, den);
+  blk_rank_kernel<<<(dp + 127) / 128, 128, 0, stream>>>(lam, den, d, dp, evals, ranks);
+  note_launch(2);
+  if (evecs != nullptr) {
+    const int gy = d < 1024 ? d : 1024;
+    blk_gather_kernel<<<dim3((dp + 127) / 128, gy), 128, 0, stream>>>(V, d, dp, ranks, evecs);
+    note_launch();
+  }
+  if (cudaGetLastError() != cudaSuccess) return -5;
+  return converged ? 0 : 1;
+}
+
+}  // namespace bk

@@ -71,6 +71,15 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
                  float* const* evecs, const int* dims, int count, float sym_scale, int max_sweeps,
                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// ---- bk_eigh_blocked.cu  (tensor-core block Jacobi for factors wider than the shared-memory path)
+size_t eigh_blocked_workspace_bytes(int d);
+// Returns 0, 1 if not converged after max_sweeps, < 0 on error.  fro2: device scalar scratch.
+int eigh_blocked(const float* F, long long ldf, int d, float sym_scale, float tol, int max_sweeps,
+                 float* evals, float* evecs, float* fro2, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
+void set_eigh_mode(int mode);
+void set_eigh_pair_width(int p);  // 0 = automatic, 64 or 128
+
 // ---- bk_dense.cu
 int launch_dominance(const float* H, long long ld, int P, float tau, const int* block_begin,
                      const int* block_end, int nblocks, double* out3, cudaStream_t stream);

@@ -70,6 +70,7 @@ struct KParams {
   long long strideBias;
   __nv_bfloat16* Ohi;
   __nv_bfloat16* Olo;
+  __nv_bfloat16* Olo2;
   long long ldo, strideO;
 };
 
@@ -370,6 +371,7 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
       const float* biasb = p.bias ? p.bias + static_cast<long long>(tl.b) * p.strideBias : nullptr;
       __nv_bfloat16* Ohb = p.Ohi ? p.Ohi + static_cast<long long>(tl.b) * p.strideO : nullptr;
       __nv_bfloat16* Olb = p.Olo ? p.Olo + static_cast<long long>(tl.b) * p.strideO : nullptr;
+      __nv_bfloat16* Ol2b = p.Olo2 ? p.Olo2 + static_cast<long long>(tl.b) * p.strideO : nullptr;
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
@@ -495,14 +497,20 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
         if (Ohb != nullptr) {
           __nv_bfloat16* o0 = Ohb + static_cast<long long>(r0) * p.ldo + gc;
           __nv_bfloat16* l0 = Olb != nullptr ? Olb + static_cast<long long>(r0) * p.ldo + gc : nullptr;
+          __nv_bfloat16* m0 = (Ol2b != nullptr && l0 != nullptr)
+                                  ? Ol2b + static_cast<long long>(r0) * p.ldo + gc : nullptr;
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             if (rr >= rlo && rr < rhi) {
               const __nv_bfloat16 h = __float2bfloat16_rn(x[rr]);
               o0[static_cast<long long>(rr) * p.ldo] = h;
-              if (l0 != nullptr)
-                l0[static_cast<long long>(rr) * p.ldo] =
-                    __float2bfloat16_rn(x[rr] - __bfloat162float(h));
+              if (l0 != nullptr) {
+                const float r1 = x[rr] - __bfloat162float(h);
+                const __nv_bfloat16 l = __float2bfloat16_rn(r1);
+                l0[static_cast<long long>(rr) * p.ldo] = l;
+                if (m0 != nullptr)
+                  m0[static_cast<long long>(rr) * p.ldo] = __float2bfloat16_rn(r1 - __bfloat162float(l));
+              }
             }
           }
         }
@@ -657,6 +665,7 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.strideBias = a.strideBias;
   p.Ohi = a.O_hi;
   p.Olo = a.O_lo;
+  p.Olo2 = a.O_lo2;
   p.ldo = a.ldo;
   p.strideO = a.strideO;
 

@@ -45,6 +45,7 @@ struct GemmArgs {
   long long strideBias = 0;
   __nv_bfloat16* O_hi = nullptr;
   __nv_bfloat16* O_lo = nullptr;
+  __nv_bfloat16* O_lo2 = nullptr;  // third split of the output (with O_lo): hi + lo + lo2 = 24 mantissa bits
   long long ldo = 0, strideO = 0;
 };
 

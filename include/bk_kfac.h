@@ -172,6 +172,12 @@ int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* out
  * Returns 0, > 0 = 1-based index of the first factor not converged after max_sweeps (<= 0: 30),
  * < 0 error.  Host arrays of device pointers / leading dimensions / dims (count <= 64).
  */
+/* Tuning knob (process-wide) for factors wider than the shared-memory path (d > 164): 0 (default) = two-sided
+ * block Jacobi whose rotations are applied as batched tensor-core GEMMs; 1 = element-wise one-sided
+ * Jacobi streamed from L2 (one launch per round).  Set it before querying the workspace size. */
+void bk_set_eigh_mode(int mode);
+/* Width of a block pair of the block Jacobi (64 or 128 columns; 0 = automatic by size). */
+void bk_set_eigh_pair_width(int width);
 size_t bk_eigh_workspace_bytes(const int* dims_host, int count);
 int bk_eigh_batched(const float* const* factors_host, const long long* ld_host,
                     float* const* evals_host, float* const* evecs_host, const int* dims_host,

@@ -443,12 +443,13 @@ def _psd(d, n, g, dev):
 def test_eigh_jacobi_vs_linalg(dev):
     """bk_eigh_batched (one-sided Jacobi) against torch.linalg.eigh in fp64: eigenvalues, the
     reconstruction V diag(w) V^T and orthogonality - never raw eigenvectors (sign / basis ambiguity).
-    Sizes cover the shared-memory path (<= 164), the streamed path, odd sizes, rank deficiency
-    (n < d) and an indefinite matrix."""
+    Sizes cover the shared-memory path (<= 164), the tensor-core block-Jacobi path with both pair widths
+    (64 up to d = 1500, 128 above), odd sizes / padding, rank deficiency (n < d) and an indefinite matrix;
+    the element-wise streamed path (bk_set_eigh_mode(1)) is checked on two sizes."""
     from bnn_kfac_b200.utilities import eigh_factors
     g = torch.Generator().manual_seed(11)
     mats = [_psd(d, n, g, dev) for d, n in [(1, 4), (5, 64), (30, 64), (126, 512), (161, 64), (165, 400),
-                                           (300, 512), (785, 256)]]
+                                           (300, 512), (785, 256), (1153, 2400), (1700, 500)]]
     ind = torch.randn(97, 97, generator=g).to(dev)
     mats.append(ind + ind.t())
     vals, vecs = eigh_factors(mats, sym_scale=0.5)
@@ -462,6 +463,31 @@ def test_eigh_jacobi_vs_linalg(dev):
         vd = v.double().cpu()
         assert relerr(vd @ torch.diag(w.double().cpu()) @ vd.t(), S) < TOL, d
         assert relerr(vd.t() @ vd, torch.eye(d, dtype=torch.float64)) < 5e-4, d
+
+
+def test_eigh_streamed_path_and_forced_pair_widths(dev):
+    """The tuning knobs of the wide-factor eigensolver give the same decomposition."""
+    from bnn_kfac_b200 import _lib
+    from bnn_kfac_b200.utilities import eigh_factors
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(12)
+    mats = [_psd(200, 512, g, dev), _psd(385, 100, g, dev)]
+    refs = [torch.linalg.eigvalsh((0.5 * (m + m.t())).double().cpu()) for m in mats]
+    try:
+        for mode, pair in [(1, 0), (0, 64), (0, 128), (2, 64)]:
+            lib.bk_set_eigh_mode(mode)
+            lib.bk_set_eigh_pair_width(pair)
+            vals, vecs = eigh_factors(mats, sym_scale=0.5)
+            for m, w, v, wref in zip(mats, vals, vecs, refs):
+                d = m.shape[0]
+                assert (w.double().cpu() - wref).abs().max().item() < TOL * wref.abs().max().item(), (mode, pair, d)
+                vd = v.double().cpu()
+                S = (0.5 * (m + m.t())).double().cpu()
+                assert relerr(vd @ torch.diag(w.double().cpu()) @ vd.t(), S) < TOL, (mode, pair, d)
+                assert relerr(vd.t() @ vd, torch.eye(d, dtype=torch.float64)) < 5e-4, (mode, pair, d)
+    finally:
+        lib.bk_set_eigh_mode(0)
+        lib.bk_set_eigh_pair_width(0)
 
 
 def test_get_eigenvectors_eigenvalues_kron_api(golden, dev):

@@ -8,7 +8,7 @@ g = torch.Generator().manual_seed(3)
 def psd(d, n):
     x = torch.relu(torch.randn(n, d, generator=g))
     return (x.t() @ x / n).to(dev)
-for dims in ([26, 126, 161, 81, 5, 10, 80, 10], [785, 1025, 1025, 1024, 1024, 10], [2049]):
+for dims in ([26, 126, 161, 81, 5, 10, 80, 10], [785, 1025, 1025, 1024, 1024, 10], [2049], [4097]):
     mats = [psd(d, 512) for d in dims]
     eigh_factors(mats)
     torch.cuda.synchronize()
