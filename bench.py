@@ -365,10 +365,12 @@ def main():
             "gpu_launches": None, "roofline": roofline, "clocks": clocks.summary()}
     if reduce_ms is not None:
         state_bytes = sum(t.numel() * 4 for l in layers for t in est.state[l])
+        wire_bytes = sum(t.shape[0] * (t.shape[0] + 1) // 2 * 4 for l in layers for t in est.state[l])
         line["factor_allreduce"] = {
-            "ms": reduce_ms, "bytes": state_bytes, "algbw_GBps": state_bytes / (reduce_ms * 1e-3) / 1e9,
-            "note": "one per timed region (deferred: state is a plain sum of batch means); local copy + NCCL "
-                    "all-reduce of every factor"}
+            "ms": reduce_ms, "state_bytes": state_bytes, "wire_bytes": wire_bytes,
+            "algbw_GBps": wire_bytes / (reduce_ms * 1e-3) / 1e9,
+            "note": "one per timed region (deferred: state is a plain sum of batch means); bk_tri_pack -> ONE NCCL "
+                    "all-reduce of the packed lower triangles -> bk_tri_unpack (mirror, 1/world)"}
 
     # kernels launched by this library inside the device-timed region (counted by the library itself)
     c0 = L.bk_launch_count()

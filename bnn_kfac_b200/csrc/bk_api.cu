@@ -399,6 +399,23 @@ int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* o
   return bk::launch_kron(a, m, n, b, p, q, out, as_stream(stream));
 }
 
+// ----------------------------------------------------------------------- multi-GPU exchange packing
+int bk_tri_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
+                float* packed, void* stream) {
+  if (count < 0 || (count > 0 && (factors_host == nullptr || ld_host == nullptr || dims_host == nullptr ||
+                                  packed == nullptr)))
+    return BK_ERR_ARG;
+  return bk::launch_tri_pack(factors_host, ld_host, dims_host, count, packed, as_stream(stream));
+}
+
+int bk_tri_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
+                  const float* packed, float scale, void* stream) {
+  if (count < 0 || (count > 0 && (outs_host == nullptr || ld_host == nullptr || dims_host == nullptr ||
+                                  packed == nullptr)))
+    return BK_ERR_ARG;
+  return bk::launch_tri_unpack(outs_host, ld_host, dims_host, count, packed, scale, as_stream(stream));
+}
+
 // ----------------------------------------------------------------------- INF curvature
 int bk_inf_regularise(float* correction, long long nm, const float* lambda, long long r, float add,
                       float multiply, float* reg_inv_correction, float* reg_lambda, void* stream) {

@@ -89,6 +89,12 @@ int launch_ger_accum(float* state, long long ld, const float* g, int P, float al
 int launch_kron(const float* a, int m, int n, const float* b, int p, int q, float* out,
                 cudaStream_t stream);
 
+// ---- bk_tri.cu  (lower-triangle packing of symmetric factors for the multi-GPU exchange)
+int launch_tri_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
+                    cudaStream_t stream);
+int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims, int count, const float* packed,
+                      float scale, cudaStream_t stream);
+
 // ---- bk_inf.cu  (INF curvature: regularisation, fp64 pre-sampler chain, sampler tail)
 int launch_inf_regularise(float* corr, long long nm, const float* lam, long long r, float add, float mult,
                           float* ric, float* rl, cudaStream_t stream);

@@ -202,6 +202,18 @@ int bk_ger_accum(float* state, long long ld, const float* g, int p, float alpha,
 int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU factor exchange (no counterpart in the single-device reference).  The accumulated
+ * factors are symmetric, so ranks exchange packed lower triangles: factor after factor in one flat fp32
+ * buffer, row i of a factor = its i + 1 values at offset i (i + 1) / 2 (sum over factors of d (d + 1) / 2
+ * values in total).  Host arrays of device pointers / row pitches / dims.
+ */
+int bk_tri_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
+                float* packed, void* stream);
+/* Expands the packed buffer into full symmetric [d, ld] matrices, every value multiplied by `scale`. */
+int bk_tri_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
+                  const float* packed, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * INF curvature: low-rank eigenbasis + diagonal correction (models/curvatures.py:476-682).
  */
 /* INF.invert :537-539.  correction[correction < 0] = 0 IN PLACE (nm values);

@@ -836,3 +836,46 @@ def test_load_by_name_survives_new_model_instance(dev, tmp_path):
     est2.sample_and_replace()
     with pytest.raises(KeyError):
         KFAC(torch.nn.Sequential(torch.nn.Linear(20, 5)).to(dev)).load_by_name(fn)
+
+
+def test_packed_triangle_exchange_roundtrip(golden, dev):
+    """bk_tri_pack / bk_tri_unpack (the payload of the multi-GPU factor exchange): lossless for symmetric
+    factors of ragged sizes, pitched storage included; reduce_state_copy at world size 1 returns the state."""
+    import ctypes as C
+    from bnn_kfac_b200 import _lib
+    from bnn_kfac_b200.curvatures import _alloc_factor
+    from bnn_kfac_b200.distributed import reduce_state_copy
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    dims = [1, 5, 32, 33, 177, 1025, 10]
+    mats = []
+    for d in dims:
+        x = torch.randn(d, d, generator=g)
+        f = _alloc_factor(d, dev)          # d = 177, 1025: [d, d] views of 16-byte pitched buffers
+        f.copy_((x + x.t()).to(dev))
+        mats.append(f)
+    n = len(mats)
+    total = sum(d * (d + 1) // 2 for d in dims)
+    packed = torch.full((total + 8,), 7.0, device=dev)
+    cd = (C.c_int * n)(*dims)
+    src = (C.c_void_p * n)(*[m.data_ptr() for m in mats])
+    lds = (C.c_longlong * n)(*[m.stride(0) for m in mats])
+    assert lib.bk_tri_pack(src, lds, cd, n, packed.data_ptr(), _lib.stream_ptr()) == 0
+    assert torch.all(packed[total:] == 7.0)                      # nothing written past the packed length
+    off = 0
+    for d, m in zip(dims, mats):
+        rows, cols = torch.tril_indices(d, d)
+        assert torch.equal(packed[off:off + d * (d + 1) // 2], m[rows.to(dev), cols.to(dev)])
+        off += d * (d + 1) // 2
+    outs = [torch.full((d, d), -1.0, device=dev) for d in dims]
+    dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    ldo = (C.c_longlong * n)(*[o.stride(0) for o in outs])
+    assert lib.bk_tri_unpack(dst, ldo, cd, n, packed.data_ptr(), 0.5, _lib.stream_ptr()) == 0
+    for m, o in zip(mats, outs):
+        assert torch.equal(o, 0.5 * m)
+    model, est = _gpu_kfac_mlp(golden, dev)
+    red = reduce_state_copy(est)
+    flat = [f for v in est.state.values() for f in v]
+    for f, r in zip(flat, red):
+        assert r.data_ptr() != f.data_ptr()
+        assert relerr(r.cpu(), f.cpu()) < 1e-7                   # lower triangle mirrored: exact up to symmetry
