@@ -11,7 +11,8 @@
 //                        mode 2  [lo, hi), last bin [lo, hi]   np.histogram (binned_kl_distance :207-208)
 //                      Edges are fp64 and values are compared in fp64, as numpy does when it compares a
 //                      float32 confidence with a linspace edge.  Edges may repeat (calibration_curve takes
-//                      them from the sorted confidences), so every element tests every bin.
+//                      them from the sorted confidences): binary search for the number of edges below the
+//                      value, then the interval rule; warp-aggregated shared-memory accumulation.
 // HBM-bound single passes; the per-bin tail (<= 256 numbers) is combined on the host.
 #include "bk_common.cuh"
 #include "bk_kernels.cuh"
@@ -20,70 +21,153 @@ namespace bk {
 
 namespace {
 
-// one warp per row
-__global__ void __launch_bounds__(256)
-calibration_rows_kernel(const float* __restrict__ probs, long long ld, const long long* __restrict__ labels,
-                        int n, int classes, float* __restrict__ conf, float* __restrict__ correct,
-                        float* __restrict__ nll, float* __restrict__ ent, int* __restrict__ pred,
-                        double* __restrict__ totals) {
+// Per-row reduction shared by both layouts.  acc: running (best, arg, sum, sum p log p); fp32 logf per
+// element and per row (1 ulp: absolute error < 4e-6 on an NLL term, far below the statistical error of a mean over
+// rows); the sums over rows are carried in fp64.
+struct RowAcc {
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  // per-thread partial sums in fp32 (<= 64 addends per thread on either path), fp64 across threads / rows
+  float sum = 0.f, plogp = 0.f;
+  __device__ __forceinline__ void take(float v, int c) {
+    if (v > best || (v == best && c < arg)) {
+      best = v;
+      arg = c;
+    }
+    sum += v;
+    if (v > 0.f) plogp = fmaf(v, logf(v), plogp);
+  }
+};
+
+struct RowOut {
+  float* conf;
+  float* correct;
+  float* nll;
+  float* ent;
+  int* pred;
+};
+
+__device__ __forceinline__ void finish_row(float best, int arg, double sum, double plogp, int row, const float* p,
+                                           const long long* labels, int classes, const RowOut& o,
+                                           double (&t)[4]) {
+  struct {
+    float best;
+    int arg;
+    double sum, plogp;
+  } a{best, arg, sum, plogp};
+  const long long lab = labels != nullptr ? labels[row] : -1;
+  const float ok = (lab == a.arg) ? 1.f : 0.f;
+  float nl = 0.f;
+  if (lab >= 0 && lab < classes) nl = -logf(static_cast<float>(static_cast<double>(p[lab]) + 1e-12));
+  // entropy of p / S:  -(1/S) sum p log p + log S
+  const float e = a.sum > 0.0 ? static_cast<float>(-a.plogp / a.sum) + logf(static_cast<float>(a.sum)) : 0.f;
+  if (o.conf != nullptr) o.conf[row] = a.best;
+  if (o.correct != nullptr) o.correct[row] = ok;
+  if (o.nll != nullptr) o.nll[row] = nl;
+  if (o.ent != nullptr) o.ent[row] = e;
+  if (o.pred != nullptr) o.pred[row] = a.arg;
+  t[0] += ok;
+  t[1] += a.best;
+  t[2] += nl;
+  t[3] += e;
+}
+
+__device__ __forceinline__ void block_totals(double (&t)[4], double* __restrict__ totals) {
   __shared__ double red[4][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double t_correct = 0.0, t_conf = 0.0, t_nll = 0.0, t_ent = 0.0;
-  for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
-    const float* p = probs + static_cast<long long>(row) * ld;
-    float best = -INFINITY;
-    int arg = 0x7fffffff;
-    double sum = 0.0, plogp = 0.0;
-    for (int c = lane; c < classes; c += 32) {
-      const float v = p[c];
-      if (v > best || (v == best && c < arg)) {
-        best = v;
-        arg = c;
-      }
-      sum += v;
-      if (v > 0.f) plogp += static_cast<double>(v) * log(static_cast<double>(v));
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ob > best || (ob == best && oa < arg)) {
-        best = ob;
-        arg = oa;
-      }
-    }
-    sum = warp_sum(sum);
-    plogp = warp_sum(plogp);
-    if (lane == 0) {
-      const long long lab = labels != nullptr ? labels[row] : -1;
-      const float ok = (lab == arg) ? 1.f : 0.f;
-      float nl = 0.f;
-      if (lab >= 0 && lab < classes) nl = static_cast<float>(-log(static_cast<double>(p[lab]) + 1e-12));
-      // entropy of p / sum:  -(1/S) sum p log p + log S
-      const float e = sum > 0.0 ? static_cast<float>(-plogp / sum + log(sum)) : 0.f;
-      if (conf != nullptr) conf[row] = best;
-      if (correct != nullptr) correct[row] = ok;
-      if (nll != nullptr) nll[row] = nl;
-      if (ent != nullptr) ent[row] = e;
-      if (pred != nullptr) pred[row] = arg;
-      t_correct += ok;
-      t_conf += best;
-      t_nll += nl;
-      t_ent += e;
-    }
-  }
-  if (lane == 0) {
-    red[0][warp] = t_correct;
-    red[1][warp] = t_conf;
-    red[2][warp] = t_nll;
-    red[3][warp] = t_ent;
+  for (int k = 0; k < 4; ++k) {
+    const double v = warp_sum(t[k]);
+    if (lane == 0) red[k][warp] = v;
   }
   __syncthreads();
   if (threadIdx.x < 4) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
-    atomicAdd(&totals[threadIdx.x], t);
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s != 0.0) atomicAdd(&totals[threadIdx.x], s);
   }
+}
+
+// few classes (<= 64, the reference's 10-class nets): a block stages 256 rows with coalesced loads into shared
+// memory (pitch classes + 1: conflict-free), then one thread per row.
+constexpr int kNarrowMax = 64;
+__global__ void __launch_bounds__(256)
+calibration_rows_narrow_kernel(const float* __restrict__ probs, long long ld, const long long* __restrict__ labels,
+                               int n, int classes, RowOut o, double* __restrict__ totals) {
+  extern __shared__ float tile[];  // [256][classes + 1]
+  const int pitch = classes + 1;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool dense = ld == classes;
+  for (int row0 = blockIdx.x * 256; row0 < n; row0 += gridDim.x * 256) {
+    const int rows = min(256, n - row0);
+    // (r, c) of element idx = threadIdx.x + 256 k advanced incrementally: one division per tile, not per element
+    int r = threadIdx.x / classes, c = threadIdx.x - r * classes;
+    const int dr = 256 / classes, dc = 256 - dr * classes;
+    const float* src = probs + static_cast<long long>(row0) * ld;
+    const int total = rows * classes;
+    for (int idx = threadIdx.x; idx < total; idx += 4 * 256) {
+      float v[4];
+      int rr[4], cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        rr[u] = r;
+        cc[u] = c;
+        v[u] = (idx + u * 256 < total) ? __ldcs(dense ? src + idx + u * 256 : src + static_cast<long long>(r) * ld + c)
+                                       : 0.f;
+        r += dr;
+        c += dc;
+        if (c >= classes) {
+          c -= classes;
+          ++r;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (idx + u * 256 < total) tile[rr[u] * pitch + cc[u]] = v[u];
+    }
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < rows) {
+      RowAcc a;
+      const float* p = tile + threadIdx.x * pitch;
+      for (int c = 0; c < classes; ++c) a.take(p[c], c);
+      finish_row(a.best, a.arg, a.sum, a.plogp, row0 + threadIdx.x, p, labels, classes, o, t);
+    }
+    __syncthreads();
+  }
+  block_totals(t, totals);
+}
+
+// many classes: one warp per row, lanes stride the classes
+__global__ void __launch_bounds__(256)
+calibration_rows_kernel(const float* __restrict__ probs, long long ld, const long long* __restrict__ labels,
+                        int n, int classes, RowOut o, double* __restrict__ totals) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int row = blockIdx.x * 8 + warp; row < n; row += gridDim.x * 8) {
+    const float* p = probs + static_cast<long long>(row) * ld;
+    RowAcc a;
+    for (int c = lane; c < classes; c += 4 * 32) {  // four independent loads in flight per lane
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (c + 32 * u < classes) ? __ldcs(p + c + 32 * u) : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + 32 * u < classes) a.take(v[u], c + 32 * u);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, a.best, off);
+      const int oa = __shfl_xor_sync(0xffffffffu, a.arg, off);
+      if (ob > a.best || (ob == a.best && oa < a.arg)) {
+        a.best = ob;
+        a.arg = oa;
+      }
+    }
+    const double sum = warp_sum(static_cast<double>(a.sum));
+    const double plogp = warp_sum(static_cast<double>(a.plogp));
+    if (lane == 0) finish_row(a.best, a.arg, sum, plogp, row, p, labels, classes, o, t);
+  }
+  block_totals(t, totals);
 }
 
 constexpr int kMaxBins = 256;
@@ -98,20 +182,56 @@ binned_stats_kernel(const float* __restrict__ x, const float* __restrict__ w1, c
   for (int t = threadIdx.x; t < 3 * kMaxBins; t += blockDim.x) (&acc[0][0])[t] = 0.0;
   __syncthreads();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
-    const double v = static_cast<double>(x[i]);
-    for (int bn = 0; bn < nbins; ++bn) {
-      const double lo = se[bn], hi = se[bn + 1];
-      bool in;
-      if (mode == 0) in = v > lo && v <= hi;
-      else if (mode == 1) in = v > lo && v < hi;
-      else in = v >= lo && (v < hi || (bn == nbins - 1 && v == hi));
-      if (in) {
-        atomicAdd(&acc[0][bn], 1.0);
-        if (w1 != nullptr) atomicAdd(&acc[1][bn], static_cast<double>(w1[i]));
-        if (w2 != nullptr) atomicAdd(&acc[2][bn], static_cast<double>(w2[i]));
-        if (mode != 1) break;  // modes 0 / 2 have ascending, disjoint bins
+  const long long tid0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long n_up = (n + 31) / 32 * 32;  // whole warps stay in the loop (shuffles below)
+  for (long long i = tid0; i < n_up; i += stride) {
+    int bin = -1;
+    float a1 = 0.f, a2 = 0.f;
+    if (i < n) {
+      const double v = static_cast<double>(x[i]);
+      // edges ascending (repeats allowed): k = number of edges below v (modes 0 / 1) or not above v (mode 2)
+      int lo = 0, hi = nbins + 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const bool below = mode == 2 ? se[mid] <= v : se[mid] < v;
+        if (below) lo = mid + 1;
+        else hi = mid;
       }
+      const int k = lo;  // edges[k - 1] < (<=) v, edges[k] >= (>) v
+      if (mode == 0) {
+        if (k >= 1 && k <= nbins) bin = k - 1;                       // (lo, hi]: edges[k] >= v
+      } else if (mode == 1) {
+        if (k >= 1 && k <= nbins && se[k] > v) bin = k - 1;          // (lo, hi): an edge value is in no bin
+      } else {
+        if (k >= 1 && k <= nbins) bin = k - 1;                       // [lo, hi)
+        else if (k == nbins + 1 && v == se[nbins]) bin = nbins - 1;  // last bin closed on the right
+      }
+      if (bin >= 0) {
+        if (w1 != nullptr) a1 = w1[i];
+        if (w2 != nullptr) a2 = w2[i];
+      }
+    }
+    // one shared-memory atomic per (warp, distinct bin) instead of one per element: calibrated nets put most
+    // confidences into one or two bins
+    unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int b = __shfl_sync(0xffffffffu, bin, leader);
+      const bool mine = bin == b;
+      const unsigned peers = __ballot_sync(0xffffffffu, mine);
+      float s1 = mine ? a1 : 0.f, s2 = mine ? a2 : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == leader) {
+        atomicAdd(&acc[0][b], static_cast<double>(__popc(peers)));
+        if (w1 != nullptr) atomicAdd(&acc[1][b], static_cast<double>(s1));
+        if (w2 != nullptr) atomicAdd(&acc[2][b], static_cast<double>(s2));
+      }
+      todo &= ~peers;
     }
   }
   __syncthreads();
@@ -129,10 +249,24 @@ int launch_calibration_rows(const float* probs, long long ld, const long long* l
                             cudaStream_t stream) {
   if (cudaMemsetAsync(totals, 0, 4 * sizeof(double), stream) != cudaSuccess) return -5;
   if (n <= 0) return 0;
-  int grid = (n + 7) / 8;
-  if (grid > kNumSMsB200 * 8) grid = kNumSMsB200 * 8;
-  calibration_rows_kernel<<<grid, 256, 0, stream>>>(probs, ld, labels, n, classes, conf, correct, nll, ent,
-                                                    pred, totals);
+  const RowOut o{conf, correct, nll, ent, pred};
+  if (classes <= kNarrowMax) {
+    int grid = (n + 255) / 256;
+    if (grid > kNumSMsB200 * 8) grid = kNumSMsB200 * 8;
+    const size_t smem = 256ull * (classes + 1) * 4;  // <= 66.6 KB
+    static bool attr_done = false;
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(calibration_rows_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               256 * (kNarrowMax + 1) * 4) != cudaSuccess)
+        return -5;
+      attr_done = true;
+    }
+    calibration_rows_narrow_kernel<<<grid, 256, smem, stream>>>(probs, ld, labels, n, classes, o, totals);
+  } else {
+    int grid = (n + 7) / 8;
+    if (grid > kNumSMsB200 * 16) grid = kNumSMsB200 * 16;
+    calibration_rows_kernel<<<grid, 256, 0, stream>>>(probs, ld, labels, n, classes, o, totals);
+  }
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
