@@ -358,8 +358,7 @@ size_t eigh_workspace_bytes(const int* dims, int count) {
     const size_t d = static_cast<size_t>(dims[i]);
     total += align256(d * 4);  // lam
     if (use_blocked(dims[i])) {
-      const size_t b = eigh_blocked_workspace_bytes(dims[i]);  // wide factors run one after another
-      if (b > blocked) blocked = b;
+      blocked += eigh_blocked_workspace_bytes(dims[i]);  // wide factors are solved concurrently
     } else if (dims[i] > kSmallMax) {
       total += 2 * align256(d * d * 4);
     }
@@ -436,17 +435,30 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
     note_launch();
   }
   if (n_blocked > 0) {
-    // wide factors: tensor-core block Jacobi, one factor after another on the shared scratch region
-    void* scratch = base + off;
-    const size_t scratch_bytes = workspace_bytes - off;
+    // wide factors: tensor-core block Jacobi, all of them concurrently on their own streams
+    const float* bf[64];
+    long long bld[64];
+    int bd[64], bidx[64], bstat[64];
+    float btol[64];
+    float* bw[64];
+    float* bv[64];
+    int nbk = 0;
     for (int i = 0; i < count; ++i) {
       if (!use_blocked(dims[i])) continue;
-      const int rc = eigh_blocked(factors[i], ldf[i], dims[i], sym_scale, h_tab[i].tol, max_sweeps, evals[i],
-                                  evecs != nullptr ? evecs[i] : nullptr, d_scale2 + i, scratch, scratch_bytes,
-                                  stream);
-      if (rc < 0) return rc;
-      if (rc > 0 && status == 0) status = i + 1;
+      bf[nbk] = factors[i];
+      bld[nbk] = ldf[i];
+      bd[nbk] = dims[i];
+      btol[nbk] = h_tab[i].tol;
+      bw[nbk] = evals[i];
+      bv[nbk] = evecs != nullptr ? evecs[i] : nullptr;
+      bidx[nbk] = i;
+      ++nbk;
     }
+    const int rc = eigh_blocked_batch(bf, bld, bd, nbk, sym_scale, btol, max_sweeps, bw, bv, d_scale2, bstat,
+                                      base + off, workspace_bytes - off, stream);
+    if (rc < 0) return rc;
+    for (int k = 0; k < nbk && status == 0; ++k)
+      if (bstat[k] != 0) status = bidx[k] + 1;
   }
   if (n_large > 0) {
     const dim3 tb(32, 8);

@@ -30,6 +30,8 @@
 
 #include <string.h>
 
+#include <vector>
+
 namespace bk {
 
 namespace {
@@ -314,17 +316,30 @@ int gemm6(const Parts& A, long long a_off, long long lda, long long strideA, con
   return launch_umma_gemm(g, stream);
 }
 
-struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t q_ready[2] = {nullptr, nullptr}, v_done[2] = {nullptr, nullptr};
+// Streams of one factor's solve: `main` carries the S path, `side` the eigenvector updates.  Pooled (grow-only,
+// per process): a batch of wide factors advances concurrently, each factor on its own pair of streams.
+struct Lane {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t q_ready[2] = {nullptr, nullptr}, v_done[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
+  int* h_stats = nullptr;  // pinned: the per-sweep read-back must not block the host (other lanes are being fed)
   bool ok = false;
-  SideStream() {
-    ok = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess;
+  Lane() {
+    ok = cudaMallocHost(reinterpret_cast<void**>(&h_stats), 8) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
       ok = cudaEventCreateWithFlags(&q_ready[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&v_done[i], cudaEventDisableTiming) == cudaSuccess;
   }
 };
+
+Lane* get_lane(int i) {
+  static std::vector<Lane*> pool;
+  while (static_cast<int>(pool.size()) <= i) pool.push_back(new Lane());
+  return pool[i]->ok ? pool[i] : nullptr;
+}
 
 template <int P>
 int launch_inner(int npairs, const Parts& Ss, int dp, int off, float tol, const float* fro2, int sweeps,
@@ -356,66 +371,80 @@ size_t eigh_blocked_workspace_bytes(int d) {
          3 * align256(dp * 4) + 256;
 }
 
-// Returns 0, 1 if not converged after max_sweeps, < 0 on error.  Synchronises `stream` once per sweep.
-int eigh_blocked(const float* F, long long ldf, int d, float sym_scale, float tol, int max_sweeps,
-                 float* evals, float* evecs, float* fro2, void* workspace, size_t workspace_bytes,
-                 cudaStream_t stream) {
-  if (d <= 0 || F == nullptr || evals == nullptr) return -2;
-  if (workspace_bytes < eigh_blocked_workspace_bytes(d) || (reinterpret_cast<uintptr_t>(workspace) & 255))
-    return -6;
-  static SideStream side;
-  if (!side.ok) return -5;
-  const int kP = pair_width(d), kB = kP / 2;
-  const int dp = pad_dim(d, kP);
-  const int nb = dp / kB;  // even
-  const size_t f32 = align256(static_cast<size_t>(dp) * dp * 4), b16 = align256(static_cast<size_t>(dp) * dp * 2);
-  char* w = static_cast<char*>(workspace);
-  float* Pm = reinterpret_cast<float*>(w);  // fp32 scratch: S at init, S V in the final Rayleigh pass
-  w += f32;
-  float* V = reinterpret_cast<float*>(w);
-  w += f32;
+namespace {
+
+// One wide factor: buffers carved from its slice of the workspace, work enqueued sweep by sweep on its lane.
+struct BlockedSolve {
+  const float* F;
+  long long ldf;
+  int d, kP, kB, dp, nb;
+  float sym_scale, tol;
+  float *evals, *evecs, *fro2;
+  float *Pm, *V, *lam, *den;
   Parts Ss, Ts, Vs[2], Qs[2], Is;
-  auto carve = [&](Parts& X, size_t bytes) {
-    for (int i = 0; i < 3; ++i) {
-      X.p[i] = reinterpret_cast<__nv_bfloat16*>(w);
-      w += bytes;
-    }
-  };
-  carve(Ss, b16);
-  carve(Ts, b16);
-  carve(Vs[0], b16);
-  carve(Vs[1], b16);
-  carve(Qs[0], align256(static_cast<size_t>(dp / kP) * kP * kP * 2));
-  carve(Qs[1], align256(static_cast<size_t>(dp / kP) * kP * kP * 2));
-  carve(Is, align256(static_cast<size_t>(kB) * kB * 2));
-  float* lam = reinterpret_cast<float*>(w);  // [2][dp]: Rayleigh numerators, squared norms
-  w += 2 * align256(static_cast<size_t>(dp) * 4);
-  float* den = lam + align256(static_cast<size_t>(dp) * 4) / 4;
-  int* ranks = reinterpret_cast<int*>(w);
-  w += align256(static_cast<size_t>(dp) * 4);
-  int* stats = reinterpret_cast<int*>(w);
-
-  if (cudaMemsetAsync(fro2, 0, 4, stream) != cudaSuccess) return -5;
-  const int t32 = (dp + 31) / 32;
-  blk_init_kernel<<<dim3(t32, t32), dim3(32, 8), 0, stream>>>(F, ldf, d, dp, sym_scale, Pm, V, fro2);
-  if (dp > d) blk_pad_diag_kernel<<<(dp - d + 127) / 128, 128, 0, stream>>>(Pm, d, dp, fro2);
-  blk_identity_kernel<<<(kB * kB + 255) / 256, 256, 0, stream>>>(kB, Is.p[0], Is.p[1], Is.p[2]);
-  note_launch(dp > d ? 3 : 2);
-  int rc = launch_convert_split3(Pm, dp, dp, dp, Ss.p[0], Ss.p[1], Ss.p[2], dp, stream);
-  if (rc) return rc;
-  rc = launch_convert_split3(V, dp, dp, dp, Vs[0].p[0], Vs[0].p[1], Vs[0].p[2], dp, stream);
-  if (rc) return rc;
-
-  const long long ld = dp;
-  const long long qstride = static_cast<long long>(kP) * kP;
-  const long long bs = static_cast<long long>(nb - 1) * kB;  // blocks 0 and nb-1 sit odd rounds out: carried
-                                                             // through unchanged (identity Q)
-  int cur = 0;  // V split buffer holding the current eigenvector estimates
+  int *ranks, *stats;
+  Lane* lane;
+  int cur = 0;
   long long round = 0;
+  int sweeps_done = 0;
   bool converged = false;
-  for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+
+  int setup(void* workspace) {
+    kP = pair_width(d);
+    kB = kP / 2;
+    dp = pad_dim(d, kP);
+    nb = dp / kB;  // even
+    const size_t f32 = align256(static_cast<size_t>(dp) * dp * 4), b16 = align256(static_cast<size_t>(dp) * dp * 2);
+    char* w = static_cast<char*>(workspace);
+    Pm = reinterpret_cast<float*>(w);  // fp32 scratch: S at init, S V in the final Rayleigh pass
+    w += f32;
+    V = reinterpret_cast<float*>(w);
+    w += f32;
+    auto carve = [&](Parts& X, size_t bytes) {
+      for (int i = 0; i < 3; ++i) {
+        X.p[i] = reinterpret_cast<__nv_bfloat16*>(w);
+        w += bytes;
+      }
+    };
+    carve(Ss, b16);
+    carve(Ts, b16);
+    carve(Vs[0], b16);
+    carve(Vs[1], b16);
+    carve(Qs[0], align256(static_cast<size_t>(dp / kP) * kP * kP * 2));
+    carve(Qs[1], align256(static_cast<size_t>(dp / kP) * kP * kP * 2));
+    carve(Is, align256(static_cast<size_t>(kB) * kB * 2));
+    lam = reinterpret_cast<float*>(w);  // [2][dp]: Rayleigh numerators, squared norms
+    w += 2 * align256(static_cast<size_t>(dp) * 4);
+    den = lam + align256(static_cast<size_t>(dp) * 4) / 4;
+    ranks = reinterpret_cast<int*>(w);
+    w += align256(static_cast<size_t>(dp) * 4);
+    stats = reinterpret_cast<int*>(w);
+    return 0;
+  }
+
+  int begin() {
+    cudaStream_t stream = lane->main;
+    if (cudaMemsetAsync(fro2, 0, 4, stream) != cudaSuccess) return -5;
+    const int t32 = (dp + 31) / 32;
+    blk_init_kernel<<<dim3(t32, t32), dim3(32, 8), 0, stream>>>(F, ldf, d, dp, sym_scale, Pm, V, fro2);
+    if (dp > d) blk_pad_diag_kernel<<<(dp - d + 127) / 128, 128, 0, stream>>>(Pm, d, dp, fro2);
+    blk_identity_kernel<<<(kB * kB + 255) / 256, 256, 0, stream>>>(kB, Is.p[0], Is.p[1], Is.p[2]);
+    note_launch(dp > d ? 3 : 2);
+    int rc = launch_convert_split3(Pm, dp, dp, dp, Ss.p[0], Ss.p[1], Ss.p[2], dp, stream);
+    if (rc) return rc;
+    return launch_convert_split3(V, dp, dp, dp, Vs[0].p[0], Vs[0].p[1], Vs[0].p[2], dp, stream);
+  }
+
+  // one sweep = nb rounds; ends with an asynchronous read-back of the sweep's statistics
+  int enqueue_sweep() {
+    cudaStream_t stream = lane->main;
+    const long long ld = dp;
+    const long long qstride = static_cast<long long>(kP) * kP;
+    const long long bs = static_cast<long long>(nb - 1) * kB;  // blocks 0 and nb-1 sit odd rounds out: carried
+                                                               // through unchanged (identity Q)
+    int rc = 0;
     if (cudaMemsetAsync(stats, 0, 8, stream) != cudaSuccess) return -5;
-    const int inner_sweeps = sweep == 0 ? 2 : 1;
+    const int inner_sweeps = sweeps_done == 0 ? 2 : 1;
     for (int t = 0; t < nb; ++t, ++round) {
       const int odd = t & 1;
       const int off = odd ? kB : 0;
@@ -425,26 +454,26 @@ int eigh_blocked(const float* F, long long ldf, int d, float sym_scale, float to
       const Parts& Vin = Vs[cur];
       const Parts& Vout = Vs[cur ^ 1];
       // Q^T slot `slot` was last read by the eigenvector update of round - 2 (side stream)
-      if (round >= 2 && cudaStreamWaitEvent(stream, side.v_done[slot], 0) != cudaSuccess) return -5;
+      if (round >= 2 && cudaStreamWaitEvent(stream, lane->v_done[slot], 0) != cudaSuccess) return -5;
       if (npairs > 0) {
         rc = kP == 128 ? launch_inner<128>(npairs, Ss, dp, off, tol, fro2, inner_sweeps, Q, stats, stream)
                        : launch_inner<64>(npairs, Ss, dp, off, tol, fro2, inner_sweeps, Q, stats, stream);
         if (rc) return rc;
       }
-      if (cudaEventRecord(side.q_ready[slot], stream) != cudaSuccess) return -5;
-      // step 3 on the side stream (overlaps the S path of this round and the next inner solve):
+      if (cudaEventRecord(lane->q_ready[slot], stream) != cudaSuccess) return -5;
+      // step 3 on the side stream (overlaps the S path of this round and the next pair solves):
       // V[:, cols] = V[:, cols] Q
-      if (cudaStreamWaitEvent(side.stream, side.q_ready[slot], 0) != cudaSuccess) return -5;
+      if (cudaStreamWaitEvent(lane->side, lane->q_ready[slot], 0) != cudaSuccess) return -5;
       if (npairs > 0) {
         rc = gemm6(Vin, off, ld, kP, Q, 0, kP, qstride, dp, kP, kP, npairs, V, off, ld, kP, &Vout, off, ld, kP,
-                   side.stream);
+                   lane->side);
         if (rc) return rc;
       }
       if (odd) {
-        rc = gemm6(Vin, 0, ld, bs, Is, 0, kB, 0, dp, kB, kB, 2, V, 0, ld, bs, &Vout, 0, ld, bs, side.stream);
+        rc = gemm6(Vin, 0, ld, bs, Is, 0, kB, 0, dp, kB, kB, 2, V, 0, ld, bs, &Vout, 0, ld, bs, lane->side);
         if (rc) return rc;
       }
-      if (cudaEventRecord(side.v_done[slot], side.stream) != cudaSuccess) return -5;
+      if (cudaEventRecord(lane->v_done[slot], lane->side) != cudaSuccess) return -5;
       // step 1 (all rows of T before any column slab of it is read): T[rows, :] = Q^T S[rows, :]
       if (npairs > 0) {
         rc = gemm6(Q, 0, kP, qstride, Ss, off, ld, kP, kP, dp, kP, npairs, nullptr, 0, 0, 0, &Ts,
@@ -467,43 +496,117 @@ int eigh_blocked(const float* F, long long ldf, int d, float sym_scale, float to
       }
       cur ^= 1;
     }
-    int h[2] = {0, 0};
-    if (cudaMemcpyAsync(h, stats, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-        cudaStreamSynchronize(stream) != cudaSuccess)
-      return -5;
+    ++sweeps_done;
+    return cudaMemcpyAsync(lane->h_stats, stats, 8, cudaMemcpyDeviceToHost, stream) == cudaSuccess ? 0 : -5;
+  }
+
+  // after the lane's main stream has been synchronised
+  void check() {
     float smax;
-    memcpy(&smax, &h[1], 4);
+    memcpy(&smax, &lane->h_stats[1], 4);
     // quadratic convergence: after a sweep whose largest rotation had |sin| = s, the remaining relative
     // off-diagonals are O(s^2); 3e-4 squared is the fp32 rounding level
-    converged = (h[0] == 0) || (smax < 3e-4f);
+    converged = (lane->h_stats[0] == 0) || (smax < 3e-4f);
   }
-  // the last eigenvector updates run on the side stream
-  if (round >= 1 && cudaStreamWaitEvent(stream, side.v_done[(round - 1) & 1], 0) != cudaSuccess) return -5;
-  if (round >= 2 && cudaStreamWaitEvent(stream, side.v_done[round & 1], 0) != cudaSuccess) return -5;
-  // eigenvalues as Rayleigh quotients with the ORIGINAL matrix: lambda_c = v_c^T S v_c (second-order accurate
-  // in the eigenvector error, free of the rounding drift of the iterated S): P = S V, lam = colsum(P . V)
-  blk_init_kernel<<<dim3(t32, t32), dim3(32, 8), 0, stream>>>(F, ldf, d, dp, sym_scale, Pm, nullptr, nullptr);
-  if (dp > d) blk_pad_diag_kernel<<<(dp - d + 127) / 128, 128, 0, stream>>>(Pm, d, dp, fro2);
-  note_launch(dp > d ? 2 : 1);
-  rc = launch_convert_split3(Pm, dp, dp, dp, Ss.p[0], Ss.p[1], Ss.p[2], dp, stream);
-  if (rc) return rc;
-  rc = launch_transpose_split3(V, dp, dp, dp, Ts.p[0], Ts.p[1], Ts.p[2], dp, stream);
-  if (rc) return rc;
-  rc = gemm6(Ss, 0, ld, 0, Ts, 0, ld, 0, dp, dp, dp, 1, Pm, 0, ld, 0, nullptr, 0, 0, 0, stream);
-  if (rc) return rc;
-  if (cudaMemsetAsync(lam, 0, 2 * align256(static_cast<size_t>(dp) * 4), stream) != cudaSuccess) return -5;
-  const int rows_per_block = 64;
-  blk_coldot_kernel<<<dim3((dp + 127) / 128, (dp + rows_per_block - 1) / rows_per_block), 128, 0, stream>>>(
-      Pm, V, dp, rows_per_block, lam, den);
-  blk_rank_kernel<<<(dp + 127) / 128, 128, 0, stream>>>(lam, den, d, dp, evals, ranks);
-  note_launch(2);
-  if (evecs != nullptr) {
-    const int gy = d < 1024 ? d : 1024;
-    blk_gather_kernel<<<dim3((dp + 127) / 128, gy), 128, 0, stream>>>(V, d, dp, ranks, evecs);
-    note_launch();
+
+  int finish() {
+    cudaStream_t stream = lane->main;
+    const long long ld = dp;
+    // the last eigenvector updates run on the side stream
+    if (round >= 1 && cudaStreamWaitEvent(stream, lane->v_done[(round - 1) & 1], 0) != cudaSuccess) return -5;
+    if (round >= 2 && cudaStreamWaitEvent(stream, lane->v_done[round & 1], 0) != cudaSuccess) return -5;
+    // eigenvalues as Rayleigh quotients with the ORIGINAL matrix: lambda_c = v_c^T S v_c / v_c^T v_c (second-order
+    // accurate in the eigenvector error, free of the rounding drift of the iterated S): P = S V
+    const int t32 = (dp + 31) / 32;
+    blk_init_kernel<<<dim3(t32, t32), dim3(32, 8), 0, stream>>>(F, ldf, d, dp, sym_scale, Pm, nullptr, nullptr);
+    if (dp > d) blk_pad_diag_kernel<<<(dp - d + 127) / 128, 128, 0, stream>>>(Pm, d, dp, fro2);
+    note_launch(dp > d ? 2 : 1);
+    int rc = launch_convert_split3(Pm, dp, dp, dp, Ss.p[0], Ss.p[1], Ss.p[2], dp, stream);
+    if (rc) return rc;
+    rc = launch_transpose_split3(V, dp, dp, dp, Ts.p[0], Ts.p[1], Ts.p[2], dp, stream);
+    if (rc) return rc;
+    rc = gemm6(Ss, 0, ld, 0, Ts, 0, ld, 0, dp, dp, dp, 1, Pm, 0, ld, 0, nullptr, 0, 0, 0, stream);
+    if (rc) return rc;
+    if (cudaMemsetAsync(lam, 0, 2 * align256(static_cast<size_t>(dp) * 4), stream) != cudaSuccess) return -5;
+    const int rows_per_block = 64;
+    blk_coldot_kernel<<<dim3((dp + 127) / 128, (dp + rows_per_block - 1) / rows_per_block), 128, 0, stream>>>(
+        Pm, V, dp, rows_per_block, lam, den);
+    blk_rank_kernel<<<(dp + 127) / 128, 128, 0, stream>>>(lam, den, d, dp, evals, ranks);
+    note_launch(2);
+    if (evecs != nullptr) {
+      const int gy = d < 1024 ? d : 1024;
+      blk_gather_kernel<<<dim3((dp + 127) / 128, gy), 128, 0, stream>>>(V, d, dp, ranks, evecs);
+      note_launch();
+    }
+    return 0;
   }
-  if (cudaGetLastError() != cudaSuccess) return -5;
-  return converged ? 0 : 1;
+};
+
+}  // namespace
+
+// Batch of wide factors, all advancing concurrently (one lane = two streams per factor; the pair solves of
+// a single factor occupy only d / pair_width SMs and its slab GEMMs are latency-bound, so several factors
+// fit side by side).  status[i] = 0 / 1 (not converged after max_sweeps).  Returns 0 or a negative error.
+// The caller's stream is forked into the lanes and joined again; the host blocks once per sweep.
+int eigh_blocked_batch(const float* const* F, const long long* ldf, const int* dims, int count, float sym_scale,
+                       const float* tols, int max_sweeps, float* const* evals, float* const* evecs,
+                       float* fro2, int* status, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return -6;
+  std::vector<BlockedSolve> solves(count);
+  size_t off = 0;
+  for (int i = 0; i < count; ++i) {
+    BlockedSolve& s = solves[i];
+    if (dims[i] <= 0 || F[i] == nullptr || evals[i] == nullptr) return -2;
+    s.F = F[i];
+    s.ldf = ldf[i];
+    s.d = dims[i];
+    s.sym_scale = sym_scale;
+    s.tol = tols[i];
+    s.evals = evals[i];
+    s.evecs = evecs != nullptr ? evecs[i] : nullptr;
+    s.fro2 = fro2 + i;
+    s.lane = get_lane(i);
+    if (s.lane == nullptr) return -5;
+    const size_t need = eigh_blocked_workspace_bytes(dims[i]);
+    if (off + need > workspace_bytes) return -6;
+    s.setup(static_cast<char*>(workspace) + off);
+    off += need;
+  }
+  // fork: every lane starts after the work already queued on the caller's stream
+  Lane* l0 = solves[0].lane;
+  if (cudaEventRecord(l0->fork, stream) != cudaSuccess) return -5;
+  for (auto& s : solves) {
+    if (cudaStreamWaitEvent(s.lane->main, l0->fork, 0) != cudaSuccess) return -5;
+    if (cudaStreamWaitEvent(s.lane->side, l0->fork, 0) != cudaSuccess) return -5;
+    const int rc = s.begin();
+    if (rc) return rc;
+  }
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    bool any = false;
+    for (auto& s : solves) {
+      if (s.converged) continue;
+      const int rc = s.enqueue_sweep();
+      if (rc) return rc;
+      any = true;
+    }
+    if (!any) break;
+    for (auto& s : solves) {
+      if (s.converged || s.sweeps_done != sweep + 1) continue;
+      if (cudaStreamSynchronize(s.lane->main) != cudaSuccess) return -5;
+      s.check();
+    }
+  }
+  for (int i = 0; i < count; ++i) {
+    BlockedSolve& s = solves[i];
+    const int rc = s.finish();
+    if (rc) return rc;
+    status[i] = s.converged ? 0 : 1;
+    // join: the caller's stream continues after this factor's outputs are complete
+    if (cudaEventRecord(s.lane->join, s.lane->main) != cudaSuccess) return -5;
+    if (cudaStreamWaitEvent(stream, s.lane->join, 0) != cudaSuccess) return -5;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
 }  // namespace bk

@@ -73,10 +73,12 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
 
 // ---- bk_eigh_blocked.cu  (tensor-core block Jacobi for factors wider than the shared-memory path)
 size_t eigh_blocked_workspace_bytes(int d);
-// Returns 0, 1 if not converged after max_sweeps, < 0 on error.  fro2: device scalar scratch.
-int eigh_blocked(const float* F, long long ldf, int d, float sym_scale, float tol, int max_sweeps,
-                 float* evals, float* evecs, float* fro2, void* workspace, size_t workspace_bytes,
-                 cudaStream_t stream);
+// All wide factors of a batch concurrently (one pair of streams per factor, forked from / joined into `stream`).
+// workspace: sum of eigh_blocked_workspace_bytes(d_i); fro2: `count` device floats of scratch;
+// status[i] = 0 / 1 (not converged after max_sweeps).  Returns 0 or a negative error.
+int eigh_blocked_batch(const float* const* F, const long long* ldf, const int* dims, int count, float sym_scale,
+                       const float* tols, int max_sweeps, float* const* evals, float* const* evecs,
+                       float* fro2, int* status, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 void set_eigh_mode(int mode);
 void set_eigh_pair_width(int p);  // 0 = automatic, 64 or 128
 
