@@ -182,6 +182,36 @@ def cpu_baseline_leg(max_seconds=20.0):
             "sample": f"{n} steps of {REF_SAMPLE_ROWS} of {BATCH} rows, all 4 layers, fp32 torch CPU"}
 
 
+def cpu_predictive_leg(n_inputs=256):
+    """Oracle port of ONE posterior weight sample of every layer (curvatures.py:400-405: z, L_A z L_G^T, transpose;
+    :67-82 _replace) + one forward pass (wrapper.py:35-44) at cfg5 on the host cores.  The Cholesky factors are
+    random lower-triangular matrices: the arithmetic (two d^3 products per layer and sample) does not depend on
+    their values, and inverting 4097-wide factors on the CPU first would take longer than the whole bench."""
+    from oracle import kfac_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(4321)
+    dims = list(zip(WIDTHS[:-1], WIDTHS[1:]))
+    chol = [(torch.tril(torch.randn(i + 1, i + 1, generator=gen)) * 1e-2,
+             torch.tril(torch.randn(o, o, generator=gen)) * 1e-2) for i, o in dims]
+    weights = [(torch.randn(o, i, generator=gen) / i ** 0.5, torch.zeros(o)) for i, o in dims]
+    x = torch.randn(n_inputs, WIDTHS[0], generator=gen)
+    t0 = time.perf_counter()
+    h = x
+    for li, ((la, lg), (w, b)) in enumerate(zip(chol, weights)):
+        z = torch.randn(la.shape[0], lg.shape[0], generator=gen)
+        w_s, b_s = O.replace(O.kfac_sample(la, lg, z), w, b)
+        h = torch.nn.functional.linear(h, w_s, b_s)
+        if li + 1 < len(chol):
+            h = torch.relu(h)
+    torch.softmax(h, 1)
+    dt = time.perf_counter() - t0
+    return {"value": n_inputs / dt, "unit": "(weight samples x test inputs)/s", "weight_samples_per_s": 1.0 / dt,
+            "cores": cores, "kind": "port",
+            "sample": f"1 weight sample of all 4 layers + forward of {n_inputs} inputs, fp32 torch CPU "
+                      f"(per-sample cost is independent of the input count up to the forward GEMMs)"}
+
+
 # ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -382,6 +412,8 @@ def main():
         line["extras"] = extras(est, model, layers, dev, world, rank)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
+        if "extras" in line and "posterior_predictive" in line["extras"]:
+            line["extras"]["posterior_predictive"]["cpu_baseline"] = cpu_predictive_leg()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -438,7 +470,7 @@ def extras(est, model, layers, dev, world, rank):
     x = torch.randn(B, WIDTHS[0], device=dev)
     for _ in range(2):
         mc_moments(est, x, S, sample0=rank * S)
-    ms = ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=3)
+    ms = ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=8)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
