@@ -432,25 +432,36 @@ def mc_predict(est: KFAC, x: Tensor, n_samples: int = 30, mode: str = "classific
 
 # ------------------------------------------------------------------------------------------------
 def kron_quadform(V: Tensor, Q: Tensor, H: Tensor, *, precision: int = _lib.BK_PREC_BF16X3,
-                  triangular: bool = False, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+                  triangular: bool = False, out: Optional[Tensor] = None, accumulate: bool = False,
+                  staged=None) -> Tensor:
     """|<V_b, Q V_b H^T>| for a batch of V_b [d_in', d_out]  ==  |J_b (Q (x) H) J_b^T| with
     V_b = J_b.view(d_in', d_out) — the Kronecker product is never formed.
     `triangular=True`: Q and H are lower-triangular (Cholesky factors, reference quirk Q1) and the
-    zero k-blocks are skipped."""
+    zero k-blocks are skipped.  `staged` = ((q_hi, q_lo, ldq), (h_hi, h_lo, ldh)): bf16 operands of Q and H
+    staged once by the caller (they are constants of an inverted estimator)."""
     lib = _lib.load()
     st = _lib.stream_ptr()
     x3 = precision == _lib.BK_PREC_BF16X3
     Bn, dinp, dout = V.shape
     dev = V.device
     V = V.float().contiguous()
-    q_hi, q_lo, ldq = stage_operand(Q, lower_only=triangular)
-    h_hi, h_lo, ldh = stage_operand(H, lower_only=triangular)
+    if staged is None:
+        staged = (stage_operand(Q, lower_only=triangular), stage_operand(H, lower_only=triangular))
+    (q_hi, q_lo, ldq), (h_hi, h_lo, ldh) = staged
     ldv = _round8(dinp)
-    vt_hi = torch.zeros(Bn, dout, ldv, dtype=torch.bfloat16, device=dev)
-    vt_lo = torch.zeros_like(vt_hi)
-    for b in range(Bn):
-        _lib.check(lib.bk_transpose_split(V[b].data_ptr(), dout, dinp, dout, 1.0, 0, vt_hi[b].data_ptr(),
-                                          vt_lo[b].data_ptr(), ldv, st), "bk_transpose_split")
+    # all V_b^T in ONE launch: rows padded to ldv, [Bn * ldv, dout] -> [dout, Bn * ldv] = Bn adjacent column slabs,
+    # i.e. a [dout, Bn, ldv] buffer, permuted to the batched K-major operand [Bn, dout, ldv] by a strided copy
+    if ldv != dinp:
+        Vp = torch.zeros(Bn, ldv, dout, device=dev, dtype=torch.float32)
+        Vp[:, :dinp].copy_(V)
+    else:
+        Vp = V
+    t_hi = torch.empty(dout, Bn * ldv, dtype=torch.bfloat16, device=dev)
+    t_lo = torch.empty_like(t_hi)
+    _lib.check(lib.bk_transpose_split(Vp.data_ptr(), dout, Bn * ldv, dout, 1.0, 0, t_hi.data_ptr(),
+                                      t_lo.data_ptr(), Bn * ldv, st), "bk_transpose_split")
+    vt_hi = t_hi.view(dout, Bn, ldv).permute(1, 0, 2).contiguous()
+    vt_lo = t_lo.view(dout, Bn, ldv).permute(1, 0, 2).contiguous()
     ldu = _round8(dout)
     u_hi = torch.zeros(Bn, dinp, ldu, dtype=torch.bfloat16, device=dev)
     u_lo = torch.zeros_like(u_hi)
@@ -482,6 +493,40 @@ def _layer_jacobian(out: Tensor, layer: Module, grad_outputs: Optional[Tensor]) 
     return torch.cat(g, dim=0)
 
 
+def _layers_jacobians(out: Tensor, layers, grad_outputs: Optional[Tensor]) -> list:
+    """The J_i of several layers from ONE backward pass (the reference runs one `autograd.grad` per parameter,
+    classification_ll_block.py:128-130: same values, 2 x len(layers) backward passes)."""
+    params = [p for l in layers for p in l.parameters()]
+    grads = torch.autograd.grad(out, params, grad_outputs=grad_outputs, retain_graph=True, allow_unused=True)
+    res, k = [], 0
+    for l in layers:
+        n = len(list(l.parameters()))
+        res.append(torch.cat([torch.flatten(g) for g in grads[k:k + n]], dim=0).detach())
+        k += n
+    return res
+
+
+def _layers_jacobians_per_output(preds: Tensor, layers) -> list:
+    """Per-test-point Jacobians J[j] = d preds[j] / d params of every layer, [P, n_params_of_layer] each:
+    one batched backward (`is_grads_batched`) instead of the script's P x 2 x len(layers) backward passes
+    (regression_ll_block.py:131-134); falls back to the per-point loop where autograd cannot batch."""
+    P = preds.shape[0]
+    params = [p for l in layers for p in l.parameters()]
+    try:
+        eye = torch.eye(P, device=preds.device, dtype=preds.dtype).reshape((P,) + tuple(preds.shape))
+        grads = torch.autograd.grad(preds, params, grad_outputs=eye, retain_graph=True, allow_unused=True,
+                                    is_grads_batched=True)
+        res, k = [], 0
+        for l in layers:
+            n = len(list(l.parameters()))
+            res.append(torch.cat([g.reshape(P, -1) for g in grads[k:k + n]], dim=1).detach())
+            k += n
+        return res
+    except RuntimeError:
+        return [torch.stack([_layer_jacobian(preds[j], l, torch.ones_like(preds[j])).detach() for j in range(P)])
+                for l in layers]
+
+
 def argmax_grad_outputs(pred_mean: Tensor) -> Tensor:
     """grad_outputs[:, idx] = 1 with a vector idx (reference quirk Q3, classification_ll_block.py:119-121)."""
     idx = torch.argmax(pred_mean.detach(), dim=1)
@@ -498,12 +543,12 @@ def linearised_kfac_classification(est: KFAC, x: Tensor) -> Tuple[Tensor, float,
     go = argmax_grad_outputs(pred_mean)
     total = torch.zeros(1, device=x.device, dtype=torch.float32)
     prec = gemm_precision(est.precision)
-    for layer in list(est.model.modules())[1:]:
-        if layer in est.state:
-            Q_i, H_i = est.inv_state[layer]
-            J_i = _layer_jacobian(pred_mean, layer, go).detach()
-            V = J_i.reshape(1, Q_i.shape[0], H_i.shape[0])
-            kron_quadform(V, Q_i, H_i, precision=prec, triangular=True, out=total, accumulate=True)
+    layers = [layer for layer in list(est.model.modules())[1:] if layer in est.state]
+    for layer, J_i in zip(layers, _layers_jacobians(pred_mean, layers, go)):
+        Q_i, H_i = est.inv_state[layer]
+        V = J_i.reshape(1, Q_i.shape[0], H_i.shape[0])
+        kron_quadform(V, Q_i, H_i, precision=prec, triangular=True, out=total, accumulate=True,
+                      staged=est._staged_factors(layer))
     pred_std = float(total.item())
     entropy = 0.5 * np.log2(2 * np.e * np.pi * pred_std)
     return pred_mean.detach(), pred_std, float(entropy)
@@ -528,12 +573,9 @@ def linearised_kfac_regression(est: KFAC, x_test: Tensor, tau: float, N: float, 
     P = preds.shape[0]
     total = torch.zeros(P, device=x_test.device, dtype=torch.float32)
     prec = gemm_precision(est.precision)
-    for i, l in enumerate(layers):
+    for i, (l, J) in enumerate(zip(layers, _layers_jacobians_per_output(preds, layers))):
         q_inv, h_inv = invs[2 * i], invs[2 * i + 1]
-        Js = []
-        for j in range(P):
-            Js.append(_layer_jacobian(preds[j], l, torch.ones_like(preds[j])).detach())
-        V = torch.stack(Js).reshape(P, q_inv.shape[0], h_inv.shape[0])
+        V = J.reshape(P, q_inv.shape[0], h_inv.shape[0])
         kron_quadform(V, q_inv, h_inv, precision=prec, out=total, accumulate=True)
     return total.sqrt() + sigma
 

@@ -46,3 +46,21 @@ for name, ctor, shape in [("cfg1 MLP 784-1024-1024-10", lambda: MLP([784, 1024, 
     if "cfg4" in name:
         t_lin = ev(lambda: linearised_kfac_classification(est, x), reps=5, warm=1)
         print(f"   linearised KFAC predictive (batch 256): {t_lin[1]:.2f} ms", flush=True)
+
+# cfg2: sampling-free linearised predictive of the 1-D regression net (regression_ll_block.py:84-140)
+from bnn_kfac_b200.predictive import linearised_kfac_regression
+class RegNet(torch.nn.Module):
+    def __init__(self, n_hid=50):
+        super().__init__()
+        self.fc1 = torch.nn.Linear(1, n_hid); self.fc2 = torch.nn.Linear(n_hid, n_hid); self.fc3 = torch.nn.Linear(n_hid, 1)
+    def forward(self, x):
+        return self.fc3(torch.relu(self.fc2(torch.relu(self.fc1(x)))))
+torch.manual_seed(2)
+net = RegNet().to(dev)
+est = KFAC(net)
+xs = torch.sort(torch.rand(30, 1, device=dev) * 8 - 4, 0).values
+ys = xs ** 3 + 3 * torch.rand(30, 1, device=dev)
+loss = torch.nn.functional.mse_loss(net(xs), ys); net.zero_grad(); loss.backward(); est.update(30)
+xt = torch.linspace(-6, 6, 100, device=dev).reshape(-1, 1)
+t_reg = ev(lambda: linearised_kfac_regression(est, xt, 0.01, 30, 3.0), reps=5, warm=1)
+print(f"cfg2 Net(1,1,50): linearised KFAC regression predictive, 100 test points: {t_reg[1]:.2f} ms", flush=True)
