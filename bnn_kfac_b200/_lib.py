@@ -81,7 +81,7 @@ SIGNATURES = {
     "bk_kron": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "bk_dominance": (_i, [_p, _ll, _i, _f, _p, _p, _i, _p, _p]),
     "bk_tri_pack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _p]),
-    "bk_tri_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _f, _p]),
+    "bk_tri_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _f, _i, _p]),
     "bk_inf_regularise": (_i, [_p, _ll, _p, _ll, _f, _f, _p, _p, _p]),
     "bk_inf_presample_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "bk_inf_presample": (_i, [_p, _ll, _i, _i, _p, _ll, _i, _i, _p, _p, _p, _p, _sz, _p]),

@@ -409,11 +409,12 @@ int bk_tri_pack(const float* const* factors_host, const long long* ld_host, cons
 }
 
 int bk_tri_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
-                  const float* packed, float scale, void* stream) {
+                  const float* packed, float scale, int mirror, void* stream) {
   if (count < 0 || (count > 0 && (outs_host == nullptr || ld_host == nullptr || dims_host == nullptr ||
                                   packed == nullptr)))
     return BK_ERR_ARG;
-  return bk::launch_tri_unpack(outs_host, ld_host, dims_host, count, packed, scale, as_stream(stream));
+  return bk::launch_tri_unpack(outs_host, ld_host, dims_host, count, packed, scale, mirror ? 1 : 0,
+                               as_stream(stream));
 }
 
 // ----------------------------------------------------------------------- INF curvature

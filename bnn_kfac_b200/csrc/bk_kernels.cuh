@@ -95,7 +95,7 @@ int launch_kron(const float* a, int m, int n, const float* b, int p, int q, floa
 int launch_tri_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
                     cudaStream_t stream);
 int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims, int count, const float* packed,
-                      float scale, cudaStream_t stream);
+                      float scale, int mirror, cudaStream_t stream);
 
 // ---- bk_inf.cu  (INF curvature: regularisation, fp64 pre-sampler chain, sampler tail)
 int launch_inf_regularise(float* corr, long long nm, const float* lam, long long r, float add, float mult,

@@ -3,7 +3,8 @@
 // all-reduce of the accumulated state needs d(d+1)/2 values per factor, not d^2: the NVLink / NVSwitch
 // payload of the cfg5 exchange drops from 470 MB to 235 MB.
 //   tri_pack    factors [d, ld] fp32 -> one flat buffer, factor after factor, row i = i + 1 values at i(i+1)/2
-//   tri_unpack  flat buffer -> full symmetric [d, ld] matrices, scaled (1 / world size)
+//   tri_unpack  flat buffer -> full [d, ld] matrices, scaled (1 / world size): mirrored (symmetric factors) or
+//               with a zero upper triangle (the Cholesky factors the owners send back)
 // HBM-bound; 32 x 32 tiles, the mirrored half is written through a shared-memory transpose so that both
 // the direct and the mirrored stores are coalesced.  Up to 16 factors per launch (table in the kernel
 // parameters, grid.z = factor).
@@ -41,7 +42,7 @@ tri_pack_kernel(const __grid_constant__ TriTable t, float* __restrict__ packed) 
 }
 
 __global__ void __launch_bounds__(256)
-tri_unpack_kernel(const __grid_constant__ TriTable t, const float* __restrict__ packed, float scale) {
+tri_unpack_kernel(const __grid_constant__ TriTable t, const float* __restrict__ packed, float scale, int mirror) {
   __shared__ float tile[32][33];
   const int f = blockIdx.z;
   const int d = t.d[f];
@@ -69,12 +70,12 @@ tri_unpack_kernel(const __grid_constant__ TriTable t, const float* __restrict__ 
     const int r = threadIdx.y + 8 * k;      // row inside the mirrored tile = column index j
     const int jj = tj * 32 + r;
     const int ii = ti * 32 + threadIdx.x;   // column inside the mirrored tile = row index i
-    if (ii < d && jj < ii) m[static_cast<long long>(jj) * ld + ii] = tile[threadIdx.x][r];
+    if (ii < d && jj < ii) m[static_cast<long long>(jj) * ld + ii] = mirror ? tile[threadIdx.x][r] : 0.f;
   }
 }
 
 int run(bool pack, float* const* mats, const long long* lds, const int* dims, int count, float* packed,
-        float scale, cudaStream_t stream) {
+        float scale, int mirror, cudaStream_t stream) {
   long long off = 0;
   for (int base = 0; base < count; base += kMaxTri) {
     TriTable t{};
@@ -93,7 +94,7 @@ int run(bool pack, float* const* mats, const long long* lds, const int* dims, in
     const int tiles = (dmax + 31) / 32;
     const dim3 grid(tiles, tiles, n), block(32, 8);
     if (pack) tri_pack_kernel<<<grid, block, 0, stream>>>(t, packed);
-    else tri_unpack_kernel<<<grid, block, 0, stream>>>(t, packed, scale);
+    else tri_unpack_kernel<<<grid, block, 0, stream>>>(t, packed, scale, mirror);
     note_launch();
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
@@ -103,12 +104,12 @@ int run(bool pack, float* const* mats, const long long* lds, const int* dims, in
 
 int launch_tri_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
                     cudaStream_t stream) {
-  return run(true, const_cast<float* const*>(mats), lds, dims, count, packed, 1.f, stream);
+  return run(true, const_cast<float* const*>(mats), lds, dims, count, packed, 1.f, 1, stream);
 }
 
 int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims, int count, const float* packed,
-                      float scale, cudaStream_t stream) {
-  return run(false, mats, lds, dims, count, const_cast<float*>(packed), scale, stream);
+                      float scale, int mirror, cudaStream_t stream) {
+  return run(false, mats, lds, dims, count, const_cast<float*>(packed), scale, mirror, stream);
 }
 
 }  // namespace bk

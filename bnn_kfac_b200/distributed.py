@@ -190,7 +190,47 @@ def reduce_state_copy(est, group=None) -> List[Tensor]:
     outs = [torch.empty(f.shape[0], f.shape[0], dtype=torch.float32, device=f.device) for f in factors]
     dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
     ldo = (C.c_longlong * n)(*[o.stride(0) for o in outs])
-    _lib.check(lib.bk_tri_unpack(dst, ldo, dims, n, packed.data_ptr(), 1.0 / w, st), "bk_tri_unpack")
+    _lib.check(lib.bk_tri_unpack(dst, ldo, dims, n, packed.data_ptr(), 1.0 / w, 1, st), "bk_tri_unpack")
+    return outs
+
+
+def allgather_cholesky(owned: Dict[int, Tensor], dims: Sequence[int], owners: Sequence[int], device,
+                       group=None) -> List[Tensor]:
+    """Every rank ends up with all Cholesky factors: rank r packs the lower triangles of the factors it owns
+    (index order) into its segment, ONE NCCL all-gather moves the segments, and each segment is expanded again
+    with a zero upper triangle (the reference's `inv_state` layout).  Replaces one `broadcast` per factor —
+    serialised on the NCCL stream, 9 ms for the 8 cfg5 factors on 8 GPUs — and halves the bytes."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    w, me = world_size(group), rank(group)
+    tri = [d * (d + 1) // 2 for d in dims]
+    seg = [sum(tri[i] for i in range(len(dims)) if owners[i] == r) for r in range(w)]
+    maxlen = max(max(seg), 1)
+    st = _lib.stream_ptr()
+    mine = [i for i in range(len(dims)) if owners[i] == me]
+    send = torch.zeros(maxlen, dtype=torch.float32, device=device)
+    if mine:
+        n = len(mine)
+        src = (C.c_void_p * n)(*[owned[i].data_ptr() for i in mine])
+        lds = (C.c_longlong * n)(*[owned[i].stride(0) for i in mine])
+        dm = (C.c_int * n)(*[dims[i] for i in mine])
+        _lib.check(lib.bk_tri_pack(src, lds, dm, n, send.data_ptr(), st), "bk_tri_pack")
+    recv = torch.empty(w * maxlen, dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    outs: List[Optional[Tensor]] = [None] * len(dims)
+    for r in range(w):
+        idx = [i for i in range(len(dims)) if owners[i] == r]
+        if not idx:
+            continue
+        n = len(idx)
+        for i in idx:
+            outs[i] = torch.empty(dims[i], dims[i], dtype=torch.float32, device=device)
+        dst = (C.c_void_p * n)(*[outs[i].data_ptr() for i in idx])
+        ldo = (C.c_longlong * n)(*[outs[i].stride(0) for i in idx])
+        dm = (C.c_int * n)(*[dims[i] for i in idx])
+        _lib.check(lib.bk_tri_unpack(dst, ldo, dm, n, recv.data_ptr() + 4 * r * maxlen, 1.0, 0, st),
+                   "bk_tri_unpack")
     return outs
 
 
@@ -231,10 +271,15 @@ def invert_sharded(est, add=0., multiply=1., group=None,
         res = inverter([reduced[i] for i in mine], [adds[i] for i in mine], [mults[i] for i in mine])
         for i, r in zip(mine, res):
             outs[i] = r.contiguous()    # collectives ship the storage: it must be dense row-major
-    for i, f in enumerate(factors):
-        if outs[i] is None:
-            outs[i] = torch.empty_like(f)
-    broadcast_from_owners(outs, owners, group)
+    if w > 1 and factors[0].is_cuda:
+        # one all-gather of packed lower triangles instead of one broadcast per factor
+        outs = allgather_cholesky({i: outs[i] for i in mine}, [f.shape[0] for f in factors], owners,
+                                  factors[0].device, group)
+    else:
+        for i, f in enumerate(factors):
+            if outs[i] is None:
+                outs[i] = torch.empty_like(f)
+        broadcast_from_owners(outs, owners, group)
     for li, layer in enumerate(layers):
         est.inv_state[layer] = (outs[2 * li], outs[2 * li + 1])
     if hasattr(est, "_invalidate_caches"):

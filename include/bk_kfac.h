@@ -209,9 +209,11 @@ int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* o
  */
 int bk_tri_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
                 float* packed, void* stream);
-/* Expands the packed buffer into full symmetric [d, ld] matrices, every value multiplied by `scale`. */
+/* Expands the packed buffer into full [d, ld] matrices, every value multiplied by `scale`: mirror != 0 writes
+ * the symmetric matrix (accumulated factors), mirror == 0 a zero upper triangle (the lower-triangular Cholesky
+ * factors the owning ranks send back, models/curvatures.py:391-392). */
 int bk_tri_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
-                  const float* packed, float scale, void* stream);
+                  const float* packed, float scale, int mirror, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * INF curvature: low-rank eigenbasis + diagonal correction (models/curvatures.py:476-682).

@@ -870,9 +870,12 @@ def test_packed_triangle_exchange_roundtrip(golden, dev):
     outs = [torch.full((d, d), -1.0, device=dev) for d in dims]
     dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
     ldo = (C.c_longlong * n)(*[o.stride(0) for o in outs])
-    assert lib.bk_tri_unpack(dst, ldo, cd, n, packed.data_ptr(), 0.5, _lib.stream_ptr()) == 0
+    assert lib.bk_tri_unpack(dst, ldo, cd, n, packed.data_ptr(), 0.5, 1, _lib.stream_ptr()) == 0
     for m, o in zip(mats, outs):
         assert torch.equal(o, 0.5 * m)
+    assert lib.bk_tri_unpack(dst, ldo, cd, n, packed.data_ptr(), 1.0, 0, _lib.stream_ptr()) == 0
+    for m, o in zip(mats, outs):
+        assert torch.equal(o, torch.tril(m))                     # mirror = 0: zero upper triangle
     model, est = _gpu_kfac_mlp(golden, dev)
     red = reduce_state_copy(est)
     flat = [f for v in est.state.values() for f in v]
