@@ -918,6 +918,9 @@ class INF(Curvature):
             n, a = lr_a.shape
             m, b = lr_g.shape
             r = a * b
+            if r > 16384:
+                raise ValueError(f"INF.invert: layer {index} keeps a {a} x {b} grid of eigen-directions (r = {r}); the "
+                                 f"pre-sampler works on r x r matrices - choose a smaller `rank` in update()")
             reg_inv_correction = torch.empty_like(correction)
             reg_lambda = torch.empty_like(lr_lambda)
             _lib.check(lib.bk_inf_regularise(correction.data_ptr(), correction.numel(), lr_lambda.data_ptr(), r,

@@ -166,11 +166,16 @@ int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* out
 
 /* ---------------------------------------------------------------------------------------------
  * Symmetric eigendecomposition, batched over factors (models/utilities.py:144-159 get_eigenvectors:
- * symeig of F + F^T; :120-141 get_eigenvalues: symeig of F): S = sym_scale * (F + F^T), one-sided
- * Jacobi with warp-shuffle rotations.  evals[i]: [d] ascending; evecs[i]: [d, d] row-major with the
+ * symeig of F + F^T; :120-141 get_eigenvalues: symeig of F): S = sym_scale * (F + F^T).  d <= 164: one-sided
+ * Jacobi with warp-shuffle rotations, the whole problem in the shared memory of one CTA, all such factors
+ * in one launch.  Wider factors: two-sided block Jacobi (pair solves in shared memory, rotations applied as
+ * batched tensor-core GEMMs), all wide factors of the batch concurrently on internal streams that are
+ * forked from / joined into `stream`; accuracy: eigenvalues to ~1e-5 |lambda|_max, V diag(w) V^T = S to
+ * 1e-4 .. 1e-3 |S|_F (d = 300 .. 4097).  evals[i]: [d] ascending; evecs[i]: [d, d] row-major with the
  * eigenvectors as COLUMNS (symeig / linalg.eigh layout), may be null (host array or entries).
  * Returns 0, > 0 = 1-based index of the first factor not converged after max_sweeps (<= 0: 30),
- * < 0 error.  Host arrays of device pointers / leading dimensions / dims (count <= 64).
+ * < 0 error.  Host arrays of device pointers / leading dimensions / dims (count <= 64).  Blocks the host
+ * (one stream synchronisation per sweep).
  */
 /* Tuning knob (process-wide) for factors wider than the shared-memory path (d > 164): 0 (default) = two-sided
  * block Jacobi whose rotations are applied as batched tensor-core GEMMs; 1 = element-wise one-sided
