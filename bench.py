@@ -484,6 +484,8 @@ def extras(est, model, layers, dev, world, rank):
         inv = lambda: est.invert(1.0, 200.0)              # noqa: E731
         cfg = "one batched launch sequence"
     inv()      # warm-up (workspace allocation)
+    if world > 1:
+        dist.barrier()     # all ranks enter the collective phase together: the figure is not rank skew
     t_inv = torch.tensor([ev_ms(inv)], device=dev)
     if world > 1:
         dist.all_reduce(t_inv, op=dist.ReduceOp.MAX)

@@ -271,7 +271,8 @@ def invert_sharded(est, add=0., multiply=1., group=None,
         res = inverter([reduced[i] for i in mine], [adds[i] for i in mine], [mults[i] for i in mine])
         for i, r in zip(mine, res):
             outs[i] = r.contiguous()    # collectives ship the storage: it must be dense row-major
-    if w > 1 and factors[0].is_cuda:
+    import os
+    if w > 1 and factors[0].is_cuda and not os.environ.get("BK_SHARDED_BCAST"):
         # one all-gather of packed lower triangles instead of one broadcast per factor
         outs = allgather_cholesky({i: outs[i] for i in mine}, [f.shape[0] for f in factors], owners,
                                   factors[0].device, group)
