@@ -303,3 +303,21 @@ def test_metrics_oracle_vs_reference(golden_inf):
         np.testing.assert_allclose(ys, g[f"met_curve{bins}_y"], atol=1e-6)
         np.testing.assert_allclose(zs, g[f"met_curve{bins}_z"], atol=1e-12)
     assert abs(O.metric_binned_kl(g["met_kl_d1"], g["met_kl_d2"]) - g["met_kl"]) < 1e-9
+
+
+@pytest.mark.parametrize("rank", [10, 30, 1000])
+def test_inf_dim_reduction_product_host_logic(golden_inf, rank):
+    """The product's index bookkeeping (top-k / unique / gather in torch, `INF._dim_reduction`) selects the same
+    eigen-directions as the reference (fixtures) and the oracle; it is plain torch and runs on CPU tensors."""
+    from bnn_kfac_b200.curvatures import INF
+    g = golden_inf
+    for li in range(2):
+        ua, ug = torch.tensor(g[f"inf_UA_{li}"]), torch.tensor(g[f"inf_UG_{li}"])
+        lam = torch.tensor(g[f"inf_lambdas_{li}"]).t().contiguous().view(-1)
+        got = INF._dim_reduction(ua, ug, lam, rank)
+        want = O.inf_dim_reduction(ua, ug, lam, rank)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and torch.equal(a, b)
+        if rank < lam.numel():
+            np.testing.assert_array_equal(got[0].numpy(), g[f"inf_r{rank}_lrA_{li}"])
+            np.testing.assert_array_equal(got[2].numpy(), g[f"inf_r{rank}_lrlam_{li}"])
