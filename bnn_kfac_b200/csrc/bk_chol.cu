@@ -385,9 +385,32 @@ constexpr int kOuter = 256;       // outer block width of the two-level algorith
 constexpr int kTwoLevelMin = 2048;  // padded size from which the tensor-core trailing updates pay off
 
 inline size_t staging_bytes(int max_pad) {
-  // two operands (L21 and the transposed X block), three bf16 parts each, [max_pad, kOuter]
-  return max_pad >= kTwoLevelMin ? 2 * 3 * align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) : 0;
+  // three operands (L21 for the Cholesky phase; L21 again and the transposed X block for the inverse phase,
+  // which runs concurrently on its own stream), three bf16 parts each, [max_pad, kOuter]
+  return max_pad >= kTwoLevelMin ? 3 * 3 * align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) : 0;
 }
+
+// The triangular-inverse phase runs one step behind the Cholesky phase on a second stream: its step k needs
+// block column k of C (final after the panel of Cholesky step k) and its own step k - 1, nothing else.
+struct Pipeline {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  std::vector<cudaEvent_t> panel_done;
+  bool ok = false;
+  Pipeline() {
+    ok = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+  }
+  bool reserve(int n) {
+    while (ok && static_cast<int>(panel_done.size()) < n) {
+      cudaEvent_t e;
+      ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+      if (ok) panel_done.push_back(e);
+    }
+    return ok;
+  }
+};
 
 }  // namespace
 
@@ -528,7 +551,41 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   __nv_bfloat16* stage_a = reinterpret_cast<__nv_bfloat16*>(w);
   const size_t part_stride = align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) / 2;
   __nv_bfloat16* stage_b = stage_a + 3 * part_stride;
-  // ---- phase 1: right-looking Cholesky of the flipped damped matrix
+  __nv_bfloat16* stage_a2 = stage_a + 6 * part_stride;  // L21 staging of the inverse phase
+  // Wide problems: the inverse phase (X = C^-1 by block forward substitution on the identity) is pipelined one
+  // step behind the Cholesky phase on a side stream; both are chains of latency-bound steps that leave most
+  // of the GPU idle on their own.
+  static Pipeline pipe;
+  const bool pipelined = max_nb >= 4 && pipe.ok && pipe.reserve(max_nb);
+  cudaStream_t s2 = pipelined ? pipe.side : stream;
+  if (pipelined) {
+    if (cudaEventRecord(pipe.fork, stream) != cudaSuccess || cudaStreamWaitEvent(s2, pipe.fork, 0) != cudaSuccess)
+      return -5;
+  }
+  // one step of the inverse phase (enqueued on s2)
+  auto inverse_step = [&](int k) -> int {
+    const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
+    const int n = (k + 1) * NB;
+    const int tn = (n + TN - 1) / TN;
+    rank64_kernel<<<dim3(tn, count), 256, smem, s2>>>(d_tab, k, kRowScale, 0);
+    note_launch();
+    int m = max_pad - (k + 1) * NB;
+    if (two_level) m = (limit < max_pad ? limit : max_pad) - (k + 1) * NB;
+    if (m > 0) {
+      const int tm = (m + TM - 1) / TM;
+      rank64_kernel<<<dim3(tm * tn, count), 256, smem, s2>>>(d_tab, k, kXUpdate, limit);
+      note_launch();
+    }
+    if (two_level && (k + 1) % inner_per_outer == 0) {
+      const int c0 = (k + 1 - inner_per_outer) * NB;
+      for (int f = 0; f < count; ++f) {
+        const int rc = outer_update(h_tab2[f], c0, true, stage_a2, stage_b, part_stride, s2);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  };
+  // ---- phase 1: right-looking Cholesky of the flipped damped matrix (+ the pipelined inverse steps)
   for (int k = 0; k < max_nb; ++k) {
     const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
     potrf_diag_kernel<<<count, 256, 0, stream>>>(d_tab, k, d_info);
@@ -538,6 +595,17 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
       const int tm = (m + TM - 1) / TM;
       rank64_kernel<<<dim3(tm, count), 256, smem, stream>>>(d_tab, k, kPanel, 0);
       note_launch();
+    }
+    if (pipelined) {
+      // block column k of C and Dinv[k] are final: inverse step k may run
+      if (cudaEventRecord(pipe.panel_done[k], stream) != cudaSuccess ||
+          cudaStreamWaitEvent(s2, pipe.panel_done[k], 0) != cudaSuccess)
+        return -5;
+      const int rc = inverse_step(k);
+      if (rc) return rc;
+    }
+    if (m > 0) {
+      const int tm = (m + TM - 1) / TM;
       if (!two_level) {
         rank64_kernel<<<dim3(tm * (tm + 1) / 2, count), 256, smem, stream>>>(d_tab, k, kTrail, 0);
         note_launch();
@@ -558,27 +626,15 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
       }
     }
   }
-  // ---- phase 2: X = C^-1 by block forward substitution on the identity
-  for (int k = 0; k < max_nb; ++k) {
-    const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
-    const int n = (k + 1) * NB;
-    const int tn = (n + TN - 1) / TN;
-    rank64_kernel<<<dim3(tn, count), 256, smem, stream>>>(d_tab, k, kRowScale, 0);
-    note_launch();
-    int m = max_pad - (k + 1) * NB;
-    if (two_level) m = (limit < max_pad ? limit : max_pad) - (k + 1) * NB;
-    if (m > 0) {
-      const int tm = (m + TM - 1) / TM;
-      rank64_kernel<<<dim3(tm * tn, count), 256, smem, stream>>>(d_tab, k, kXUpdate, limit);
-      note_launch();
+  // ---- phase 2 (not pipelined: small problems): X = C^-1 by block forward substitution on the identity
+  if (!pipelined) {
+    for (int k = 0; k < max_nb; ++k) {
+      const int rc = inverse_step(k);
+      if (rc) return rc;
     }
-    if (two_level && (k + 1) % inner_per_outer == 0) {
-      const int c0 = (k + 1 - inner_per_outer) * NB;
-      for (int f = 0; f < count; ++f) {
-        const int rc = outer_update(h_tab2[f], c0, true, stage_a, stage_b, part_stride, stream);
-        if (rc) return rc;
-      }
-    }
+  } else {
+    if (cudaEventRecord(pipe.join, s2) != cudaSuccess || cudaStreamWaitEvent(stream, pipe.join, 0) != cudaSuccess)
+      return -5;
   }
   flip_out_kernel<<<tg, tb, 0, stream>>>(d_tab);
   note_launch();
