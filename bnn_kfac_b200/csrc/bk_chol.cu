@@ -115,22 +115,24 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
     a[r] = blk[static_cast<long long>(i0 + r) * p.dpad + c];
     x[r] = (i0 + r == c) ? 1.f : 0.f;
   }
+  // The column loop is unrolled by the 16 rows a thread owns: row j of X is then the STATICALLY indexed register
+  // x[jj] of its owners.  (With a rolled loop the compiler turned the select chain that picked x[j & 15] into a
+  // dynamic load from a local-memory copy of x[] — 64 bytes of stack, an STL per update and an LDL on the
+  // critical path in front of every barrier; ncu source view, round 1.)
 #pragma unroll 1
-  for (int j = 0; j < NB; ++j) {
-    float* cj = colj[j & 1];
-    float* xj = xrow[j & 1];
-    const bool row_owner = (j >> 4) == rq;  // this thread holds row j (warp-uniform)
+  for (int jb = 0; jb < NB / R; ++jb) {
+    const bool row_owner = jb == rq;  // this thread holds rows 16 jb .. 16 jb + 15 (warp-uniform)
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    const int j = jb * R + jj;
+    float* cj = colj[jj & 1];
+    float* xj = xrow[jj & 1];
     if (c == j && i0 + R - 1 >= j) {
 #pragma unroll
       for (int r = 0; r < R; r += 4)
         *reinterpret_cast<float4*>(&cj[i0 + r]) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
     }
-    if (row_owner) {
-      float xv = 0.f;
-#pragma unroll
-      for (int r = 0; r < R; ++r) xv = (r == (j & 15)) ? x[r] : xv;
-      xj[c] = xv;  // X[j][c] before the division by L[j][j]
-    }
+    if (row_owner) xj[c] = x[jj];  // X[j][c] before the division by L[j][j]
     __syncthreads();
     if (i0 + R - 1 < j) continue;  // all rows of this warp are final (warp-uniform)
     float piv = cj[j];
@@ -164,11 +166,8 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
         }
       }
     }
-    if (row_owner) {
-      const float xf = xj[c] * rs;  // final X[j][c]
-#pragma unroll
-      for (int r = 0; r < R; ++r) x[r] = (r == (j & 15)) ? xf : x[r];
-    }
+    if (row_owner) x[jj] = xj[c] * rs;  // final X[j][c]
+  }
   }
   float* di = p.Dinv + static_cast<long long>(k) * NB * NB;
 #pragma unroll
