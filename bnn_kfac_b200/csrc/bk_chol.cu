@@ -122,19 +122,22 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
 #pragma unroll 1
   for (int jb = 0; jb < NB / R; ++jb) {
     const bool row_owner = jb == rq;  // this thread holds rows 16 jb .. 16 jb + 15 (warp-uniform)
+    // row i0 + r lies below row j = 16 jb + jj  <=>  rq > jb (warp-uniform) or, for the owners of block jb,
+    // r > jj — a compile-time fact in the unrolled body: no per-element compare
+    const bool below = rq > jb;
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) {
     const int j = jb * R + jj;
     float* cj = colj[jj & 1];
     float* xj = xrow[jj & 1];
-    if (c == j && i0 + R - 1 >= j) {
+    if (c == j && rq >= jb) {
 #pragma unroll
       for (int r = 0; r < R; r += 4)
         *reinterpret_cast<float4*>(&cj[i0 + r]) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
     }
     if (row_owner) xj[c] = x[jj];  // X[j][c] before the division by L[j][j]
     __syncthreads();
-    if (i0 + R - 1 < j) continue;  // all rows of this warp are final (warp-uniform)
+    if (rq < jb) continue;  // all rows of this warp are final (warp-uniform)
     float piv = cj[j];
     if (!(piv > 0.f)) {  // not positive definite (or NaN)
       if (tid == 0 || c == j) bad = 1;
@@ -152,17 +155,17 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
       const float lc = cj[c] * ipiv;
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (i0 + r > j) a[r] = fmaf(-cv[r], lc, a[r]);
+        if (below || r > jj) a[r] = fmaf(-cv[r], lc, a[r]);
     } else {
       const float xc = xj[c] * ipiv;
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (i0 + r > j) x[r] = fmaf(-cv[r], xc, x[r]);
+        if (below || r > jj) x[r] = fmaf(-cv[r], xc, x[r]);
       if (c == j) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (i0 + r > j) a[r] = cv[r] * rs;
-          else if (i0 + r == j) a[r] = piv * rs;
+          if (below || r > jj) a[r] = cv[r] * rs;
+          else if (row_owner && r == jj) a[r] = piv * rs;
         }
       }
     }
