@@ -45,6 +45,32 @@ struct CholProb {
   float sqrt_s, sqrt_n;
 };
 
+// Programmatic dependent launch: the steps of both phases are chains of small dependent kernels, and the
+// launch latency between two of them (~2-3 us) is comparable to the kernels themselves.  Every chain kernel
+// first waits for the grids it depends on (complete and flushed) and then lets its own dependents be
+// scheduled; launched with cudaLaunchAttributeProgrammaticStreamSerialization the next kernel's CTAs are
+// resident and parked in their wait when this grid finishes.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... Args>
+inline void launch_chained(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                           Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ------------------------------------------------------------------ damping + flip + padding
 // R[i][j] = sqrt_s * (F[fi][fj] + F[fj][fi]) / 2 + sqrt_n * (i == j),  fi = d-1-i, fj = d-1-j;
 // identity on the padding; X = I.
@@ -98,6 +124,7 @@ __global__ void damp_flip_kernel(const CholProb* __restrict__ tab) {
 // inversion, all of it serial latency.)
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ info) {
+  pdl_wait_then_trigger();
   const CholProb p = tab[blockIdx.x];
   if (k >= p.nb) return;
   __shared__ __align__(16) float colj[2][NB];
@@ -192,6 +219,7 @@ enum Mode : int { kPanel = 0, kTrail = 1, kRowScale = 2, kXUpdate = 3 };
 // whole outer block at once from the tensor-core GEMM (see chol_inv_batched).
 __global__ void __launch_bounds__(256)
 rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
+  pdl_wait_then_trigger();
   const CholProb p = tab[blockIdx.y];
   if (k >= p.nb) return;
   const long long ld = p.dpad;
@@ -542,6 +570,7 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   if (e != cudaSuccess) return -5;
 
   const int max_nb = max_pad / NB;
+  const CholProb* cd_tab = d_tab;
   const dim3 tb(32, 8);
   const dim3 tg((max_pad + 31) / 32, (max_pad + 31) / 32, count);
   damp_flip_kernel<<<tg, tb, 0, stream>>>(d_tab);
@@ -569,13 +598,13 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
     const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
     const int n = (k + 1) * NB;
     const int tn = (n + TN - 1) / TN;
-    rank64_kernel<<<dim3(tn, count), 256, smem, s2>>>(d_tab, k, kRowScale, 0);
+    launch_chained(rank64_kernel, dim3(tn, count), dim3(256), smem, s2, cd_tab, k, static_cast<int>(kRowScale), 0);
     note_launch();
     int m = max_pad - (k + 1) * NB;
     if (two_level) m = (limit < max_pad ? limit : max_pad) - (k + 1) * NB;
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
-      rank64_kernel<<<dim3(tm * tn, count), 256, smem, s2>>>(d_tab, k, kXUpdate, limit);
+      launch_chained(rank64_kernel, dim3(tm * tn, count), dim3(256), smem, s2, cd_tab, k, static_cast<int>(kXUpdate), limit);
       note_launch();
     }
     if (two_level && (k + 1) % inner_per_outer == 0) {
@@ -590,12 +619,12 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   // ---- phase 1: right-looking Cholesky of the flipped damped matrix (+ the pipelined inverse steps)
   for (int k = 0; k < max_nb; ++k) {
     const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
-    potrf_diag_kernel<<<count, 256, 0, stream>>>(d_tab, k, d_info);
+    launch_chained(potrf_diag_kernel, dim3(count), dim3(256), 0, stream, cd_tab, k, d_info);
     note_launch();
     const int m = max_pad - (k + 1) * NB;
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
-      rank64_kernel<<<dim3(tm, count), 256, smem, stream>>>(d_tab, k, kPanel, 0);
+      launch_chained(rank64_kernel, dim3(tm, count), dim3(256), smem, stream, cd_tab, k, static_cast<int>(kPanel), 0);
       note_launch();
     }
     if (pipelined) {
@@ -609,13 +638,13 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
     if (m > 0) {
       const int tm = (m + TM - 1) / TM;
       if (!two_level) {
-        rank64_kernel<<<dim3(tm * (tm + 1) / 2, count), 256, smem, stream>>>(d_tab, k, kTrail, 0);
+        launch_chained(rank64_kernel, dim3(tm * (tm + 1) / 2, count), dim3(256), smem, stream, cd_tab, k, static_cast<int>(kTrail), 0);
         note_launch();
       } else {
         const int ncols = limit - (k + 1) * NB;  // columns of the outer block right of this step
         if (ncols > 0) {
           const int tn = (ncols + TN - 1) / TN;
-          rank64_kernel<<<dim3(tm * tn, count), 256, smem, stream>>>(d_tab, k, kTrail, limit);
+          launch_chained(rank64_kernel, dim3(tm * tn, count), dim3(256), smem, stream, cd_tab, k, static_cast<int>(kTrail), limit);
           note_launch();
         }
       }
