@@ -486,17 +486,20 @@ def extras(est, model, layers, dev, world, rank):
     inv()      # warm-up (workspace allocation)
     if world > 1:
         dist.barrier()     # all ranks enter the collective phase together: the figure is not rank skew
-    t_inv = torch.tensor([ev_ms(inv)], device=dev)
+    # ~2000 dependent launches in ~10 ms: this phase is as fast as the host thread can issue them, and the box is
+    # shared (another tenant's CPU leg shows up as a 2-8x slower sample) -> best of 3
+    t_inv = torch.tensor([min(ev_ms(inv) for _ in range(3))], device=dev)
     if world > 1:
         dist.all_reduce(t_inv, op=dist.ReduceOp.MAX)
     out["invert_ms_all_layers"] = t_inv.item()
-    out["invert_config"] = "8 factors (4 x 4097^2, 3 x 4096^2, 10^2), add=1, multiply=200; " + cfg
+    out["invert_config"] = "8 factors (4 x 4097^2, 3 x 4096^2, 10^2), add=1, multiply=200; best of 3; " + cfg
     # posterior predictive: S weight samples per rank (sample ids sharded over ranks), 1024 test inputs
     S, B = 16, 1024
     x = torch.randn(B, WIDTHS[0], device=dev)
     for _ in range(2):
         mc_moments(est, x, S, sample0=rank * S)
-    ms = ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=8)
+    # best of 3 x (4 repetitions): launch-heavy as well, see the inversion above
+    ms = min(ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=4) for _ in range(3))
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
