@@ -114,10 +114,15 @@ def load(build_if_missing: bool = True, strict: bool = True) -> C.CDLL:
         if _lib is not None:
             return _lib
         path = lib_path()
-        if not path.exists():
-            if not build_if_missing:
-                raise BkError(f"{path} is missing: run `python -m bnn_kfac_b200._build`")
+        if build_if_missing:
+            # no-op when the source digest matches the stamp; rebuilds after any edit of csrc/ or the header,
+            # so a stale library can never be loaded silently against newer Python glue
             _build.build()
+        elif not path.exists():
+            raise BkError(f"{path} is missing: run `python -m bnn_kfac_b200._build`")
+        elif not _build.is_current():
+            raise BkError(f"{path} is stale (csrc/ or include/bk_kfac.h changed since it was built): run "
+                          f"`python -m bnn_kfac_b200._build`")
         lib = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name, None)

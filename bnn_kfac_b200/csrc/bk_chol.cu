@@ -427,6 +427,7 @@ struct Pipeline {
   cudaEvent_t fork = nullptr, join = nullptr;
   std::vector<cudaEvent_t> panel_done;
   bool ok = false;
+  explicit Pipeline(bool) {}  // inert instance (no device)
   Pipeline() {
     ok = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -441,6 +442,18 @@ struct Pipeline {
     return ok;
   }
 };
+
+// one side stream + event set per device (created on first use with that device current)
+Pipeline& device_pipeline() {
+  static std::mutex mu;
+  static Pipeline* pipes[kMaxDevices] = {};
+  static Pipeline none{false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
+  std::lock_guard<std::mutex> g(mu);
+  if (pipes[dev] == nullptr) pipes[dev] = new Pipeline();
+  return *pipes[dev];
+}
 
 }  // namespace
 
@@ -523,14 +536,13 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   if (workspace == nullptr || workspace_bytes < chol_inv_workspace_bytes(dims, count) ||
       (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return -6;
-  static bool attr_done = false;
+  static DeviceOnce attr_once;
   const int smem = sizeof(float) * NB * ((TM + kPad) + (TN + kPad));
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(rank64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess)
-      return -5;
-    attr_done = true;
-  }
+  if (!attr_once([&] {
+        return cudaFuncSetAttribute(rank64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ==
+               cudaSuccess;
+      }))
+    return -5;
   char* w = static_cast<char*>(workspace);
   CholProb* d_tab = reinterpret_cast<CholProb*>(w);
   w += align_up(sizeof(CholProb) * static_cast<size_t>(count), 256);
@@ -586,7 +598,7 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   // Wide problems: the inverse phase (X = C^-1 by block forward substitution on the identity) is pipelined one
   // step behind the Cholesky phase on a side stream; both are chains of latency-bound steps that leave most
   // of the GPU idle on their own.
-  static Pipeline pipe;
+  Pipeline& pipe = device_pipeline();
   const bool pipelined = max_nb >= 4 && pipe.ok && pipe.reserve(max_nb);
   cudaStream_t s2 = pipelined ? pipe.side : stream;
   if (pipelined) {

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #ifndef BK_SPIN_LIMIT
 // A wait that spins this many times is a protocol bug: trap (the launch then fails with an error
 // code through the C ABI) instead of hanging the GPU box.
@@ -18,6 +20,23 @@
 namespace bk {
 
 constexpr int kNumSMsB200 = 148;
+
+// Host side: one-time initialisation PER DEVICE (cudaFuncSetAttribute opt-ins, side streams, pool settings are
+// properties of one device's context).  `once(f)` runs f() the first time it is called with a given device
+// current and remembers whether it succeeded; thread-safe.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+  std::mutex mu;
+  signed char state[kMaxDevices] = {};  // 0 = not run, 1 = ok, -1 = failed
+  template <class F>
+  bool operator()(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    std::lock_guard<std::mutex> g(mu);
+    if (state[dev] == 0) state[dev] = f() ? 1 : -1;
+    return state[dev] == 1;
+  }
+};
 
 // Host side: every kernel launch of this library is counted (bk_launch_count in the C ABI reports
 // the total, which is how bench.py states how many of OUR kernels ran inside a timed region).

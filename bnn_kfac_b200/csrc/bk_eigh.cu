@@ -424,13 +424,12 @@ int eigh_batched(const float* const* factors, const long long* ldf, float* const
   int status = 0;
   if (max_small > 0) {
     const size_t smem = 2ull * max_small * (max_small + 1) * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-      if (cudaFuncSetAttribute(eigh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               2 * kSmallMax * (kSmallMax + 1) * 4) != cudaSuccess)
-        return -5;
-      attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    if (!attr_once([] {
+          return cudaFuncSetAttribute(eigh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      2 * kSmallMax * (kSmallMax + 1) * 4) == cudaSuccess;
+        }))
+      return -5;
     eigh_small_kernel<<<count, 512, smem, stream>>>(d_tab, max_sweeps);
     note_launch();
   }

@@ -425,13 +425,12 @@ template <int P>
 int launch_inner(int npairs, const Parts& Ss, int dp, int off, float tol, float floor_rel, const float* fro2,
                  int sweeps, const Parts& Qs, int* stats, cudaStream_t stream) {
   constexpr size_t smem = 3ull * P * (P + 1) * 4;  // two G buffers + Q^T
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(blk_inner_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem)) != cudaSuccess)
-      return -5;
-    attr_done = true;
-  }
+  static DeviceOnce attr_once;
+  if (!attr_once([] {
+        return cudaFuncSetAttribute(blk_inner_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)) == cudaSuccess;
+      }))
+    return -5;
   blk_inner_kernel<P><<<npairs, P * 8, smem, stream>>>(Ss, dp, off, tol, floor_rel, fro2, sweeps, Qs, stats);
   note_launch();
   return 0;

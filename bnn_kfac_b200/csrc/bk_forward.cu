@@ -109,6 +109,43 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
   float m1[kMaxPerLane], m2[kMaxPerLane];
 #pragma unroll
   for (int k = 0; k < kMaxPerLane; ++k) m1[k] = m2[k] = 0.f;
+  if (mode == 2) {
+    // regression, CENTRED second moment (numpy std with ddof = 0, regression_sampling.py:86-88): pass 1
+    // the mean, pass 2 sum (y - mean)^2.  E[y^2] - E[y]^2 in fp32 loses variances below ~1e-7 * mean^2
+    // (|mean| reaches 200 on the reference's y = x^3 task); the [S, B, C] outputs are tiny, so the second
+    // read is free.
+    for (int s = 0; s < S; ++s) {
+      const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (k < per && c < Cn) m1[k] += row[c];
+      }
+    }
+    const float invS = 1.0f / static_cast<float>(S);
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) m1[k] *= invS;
+    for (int s = 0; s < S; ++s) {
+      const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
+#pragma unroll
+      for (int k = 0; k < kMaxPerLane; ++k) {
+        const int c = lane + 32 * k;
+        if (k < per && c < Cn) {
+          const float dv = row[c] - m1[k];
+          m2[k] = fmaf(dv, dv, m2[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      if (k < per && c < Cn) {
+        mean[static_cast<long long>(warp) * Cn + c] = m1[k];
+        if (meansq != nullptr) meansq[static_cast<long long>(warp) * Cn + c] = m2[k] * invS;
+      }
+    }
+    return;
+  }
   for (int s = 0; s < S; ++s) {
     const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
     float v[kMaxPerLane];
@@ -218,13 +255,12 @@ int launch_conv2d_relu_pool(const float* in, long long in_sample_stride, const f
   const size_t smem = sizeof(float) * (static_cast<size_t>(O) * C * KH * KW + O +
                                        static_cast<size_t>(C) * H * W);
   if (smem > 200 * 1024) return -2;
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && smem > attr_set) {
-    if (cudaFuncSetAttribute(conv2d_relu_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem)) != cudaSuccess)
-      return -5;
-    attr_set = smem;
-  }
+  static DeviceOnce attr_once;  // opt in to the kernel's maximum (200 KB) once per device
+  if (smem > 48 * 1024 && !attr_once([] {
+        return cudaFuncSetAttribute(conv2d_relu_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    200 * 1024) == cudaSuccess;
+      }))
+    return -5;
   conv2d_relu_pool_kernel<<<dim3(N, S), 256, smem, stream>>>(in, in_sample_stride, w, b, out, N, C, H,
                                                              W, O, KH, KW, SH, SW, PH, PW, relu,
                                                              pool);
@@ -250,20 +286,25 @@ int launch_frob_dot(float* out, const float* X, long long stride_x, const float*
   if (batch <= 0) return 0;
   // fp64 accumulators: a small stream-ordered scratch (batch doubles).  The default pool hands its memory back
   // to the OS at every synchronisation unless told otherwise (0.5 ms per call measured): keep it.
-  static bool pool_done = false;
-  if (!pool_done) {
+  // (The one allocation this library makes, and the one device-wide setting it touches: the release threshold
+  // of the device's DEFAULT stream-ordered pool is raised to 64 MB, once per device; see include/bk_kfac.h.)
+  static DeviceOnce pool_once;
+  pool_once([] {
     int dev = 0;
     cudaMemPool_t pool;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long keep = 64ull << 20;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    pool_done = true;
-  }
+    return true;
+  });
   double* acc = nullptr;
   if (cudaMallocAsync(reinterpret_cast<void**>(&acc), sizeof(double) * batch, stream) != cudaSuccess)
     return -5;
-  if (cudaMemsetAsync(acc, 0, sizeof(double) * batch, stream) != cudaSuccess) return -5;
+  if (cudaMemsetAsync(acc, 0, sizeof(double) * batch, stream) != cudaSuccess) {
+    cudaFreeAsync(acc, stream);
+    return -5;
+  }
   long long chunk = 16384;
   const long long max_ctas = static_cast<long long>(kNumSMsB200) * 32;
   while ((count + chunk - 1) / chunk * batch > max_ctas) chunk *= 2;

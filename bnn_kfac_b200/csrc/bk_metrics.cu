@@ -254,13 +254,12 @@ int launch_calibration_rows(const float* probs, long long ld, const long long* l
     int grid = (n + 255) / 256;
     if (grid > kNumSMsB200 * 8) grid = kNumSMsB200 * 8;
     const size_t smem = 256ull * (classes + 1) * 4;  // <= 66.6 KB
-    static bool attr_done = false;
-    if (!attr_done) {
-      if (cudaFuncSetAttribute(calibration_rows_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               256 * (kNarrowMax + 1) * 4) != cudaSuccess)
-        return -5;
-      attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    if (!attr_once([] {
+          return cudaFuncSetAttribute(calibration_rows_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      256 * (kNarrowMax + 1) * 4) == cudaSuccess;
+        }))
+      return -5;
     calibration_rows_narrow_kernel<<<grid, 256, smem, stream>>>(probs, ld, labels, n, classes, o, totals);
   } else {
     int grid = (n + 7) / 8;

@@ -612,27 +612,29 @@ int make_output_map(CUtensorMap* map, float* base, int rows, int cols, long long
 int g_allow_tma_epilogue = 1;
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static std::mutex mu;
+  static int cached[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return kNumSMsB200;
+  std::lock_guard<std::mutex> g(mu);
+  if (cached[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = kNumSMsB200;
+    cached[dev] = n > 0 ? n : kNumSMsB200;
   }
-  return n;
+  return cached[dev];
 }
 
 // kTmaEpi: epilogue = TMA reduce-add of alpha*acc into C (see tma_epilogue_ok()).
 template <int CG, bool kTmaEpi>
 int launch_cg(const GemmArgs& a, cudaStream_t stream) {
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(umma_gemm_kernel<CG, kTmaEpi>,
+  static DeviceOnce attr_once;
+  if (!attr_once([] {
+        return cudaFuncSetAttribute(umma_gemm_kernel<CG, kTmaEpi>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(Cfg<CG>::kSmemBytes));
-  });
-  if (attr_err != cudaSuccess) return -5;
+                                    static_cast<int>(Cfg<CG>::kSmemBytes)) == cudaSuccess;
+      }))
+    return -5;
 
   constexpr int kTileM = Cfg<CG>::kTileM;
   KParams p{};
@@ -720,14 +722,13 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts,
                              cudaStream_t stream) {
   if (count <= 0) return 0;
   if (count > kMaxGroup || (nparts != 1 && nparts != 3)) return -2;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(umma_syrk_grouped_kernel,
+  static DeviceOnce attr_once;
+  if (!attr_once([] {
+        return cudaFuncSetAttribute(umma_syrk_grouped_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(Cfg<2>::kSmemBytes));
-  });
-  if (attr_err != cudaSuccess) return -5;
+                                    static_cast<int>(Cfg<2>::kSmemBytes)) == cudaSuccess;
+      }))
+    return -5;
   GroupMaps maps;
   GroupParams gp{};
   gp.count = count;

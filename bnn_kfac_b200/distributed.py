@@ -301,15 +301,38 @@ def mc_predict_sharded(est, x: Tensor, n_samples: int, mode: str = "classificati
     if n_samples < w:  # same decision on every rank, before any collective
         raise ValueError(f"n_samples ({n_samples}) must be >= the number of ranks ({w})")
     s0, s1 = sample_slice(n_samples, w, me)
-    mean, meansq = moments_fn(est, x, s1 - s0, sample0=s0, mode=mode, program=program)
-    acc = torch.stack([mean * (s1 - s0), meansq * (s1 - s0)])
-    if w > 1:
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-    mean, meansq = acc[0] / n_samples, acc[1] / n_samples
     if mode == "classification":
-        return mean
-    var = (meansq - mean * mean).clamp_min(0.0)
-    return mean.squeeze(1), var.sqrt().squeeze(1)
+        mean, meansq = moments_fn(est, x, s1 - s0, sample0=s0, mode=mode, program=program)
+        acc = torch.stack([mean * (s1 - s0), meansq * (s1 - s0)])
+        if w > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        return acc[0] / n_samples
+    # regression: per-rank (count, mean, centred second moment) combined with Chan's parallel formula —
+    # E[y^2] - E[y]^2 would cancel in fp32 when |mean| >> std (y = x^3 reaches 200)
+    mean, m2 = moments_fn(est, x, s1 - s0, sample0=s0, mode="regression_centred", program=program)
+    return combine_centred_moments(mean, m2, s1 - s0, n_samples, group)
+
+
+def combine_centred_moments(mean: Tensor, var: Tensor, n_local: int, n_total: int, group=None):
+    """(mean, std) over all ranks' samples from per-rank (n_r, mean_r, var_r):
+        mean = sum n_r mean_r / n;   var = sum n_r (var_r + (mean_r - mean)^2) / n      (Chan et al.)
+    One all-gather of the stacked [2, B, C] moments; every rank evaluates the same fp64 combination, so the
+    result is identical on all ranks."""
+    w = world_size(group)
+    local = torch.stack([mean, var]).double()
+    if w > 1:
+        parts = [torch.empty_like(local) for _ in range(w)]
+        dist.all_gather(parts, local, group=group)
+        counts = [b - a for a, b in (sample_slice(n_total, w, r) for r in range(w))]
+    else:
+        parts, counts = [local], [n_local]
+    tot_mean = sum(c * p[0] for c, p in zip(counts, parts)) / n_total
+    tot_var = sum(c * (p[1] + (p[0] - tot_mean) ** 2) for c, p in zip(counts, parts)) / n_total
+    return tot_mean.float().squeeze(1), tot_var.clamp_min(0.0).sqrt().float().squeeze(1)
+
+
+# NOTE: the moments_fn contract: moments_fn(est, x, n, sample0=, mode=, program=) -> (mean, second) with
+# second = E[p^2] for mode "classification" and the centred E[(y - mean)^2] for "regression_centred".
 
 
 def gather_rows(local: Tensor, n_rows: int, group=None) -> Tensor:

@@ -318,6 +318,11 @@ def _mc_logits_chunk(est: KFAC, x: Tensor, S: int, sample0: int, prog, noise, im
                     cat[0][:, :, :d_in].copy_(s_hi.view(rows, B, s_ld)[:, :, :d_in].expand(S, B, d_in))
                     if x3:
                         cat[1][:, :, :d_in].copy_(s_lo.view(rows, B, s_ld)[:, :, :d_in].expand(S, B, d_in))
+                    # ones column (hi = 1, lo = 0) and the zero padding up to kx: all inside the K range
+                    # of the Y1 and output GEMMs (_new_cat only clears the columns beyond kx + d_out)
+                    cat[0][:, :, d_in:kx].zero_()
+                    if x3:
+                        cat[1][:, :, d_in:kx].zero_()
                     cat[0][:, :, d_in] = 1.0
                     shared = shared and rows == 1
                 else:
@@ -408,13 +413,16 @@ def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
 def mc_moments(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0, mode: str = "classification",
                program=None, noise=None) -> Tuple[Tensor, Tensor]:
     """(E_s[p], E_s[p^2]) over `n_samples` samples starting at global sample id `sample0`;
-    p = softmax(logits) (classification) or the raw output (regression)."""
+    p = softmax(logits) (classification) or the raw output (regression).  mode "regression_centred"
+    returns (E_s[y], E_s[(y - E_s[y])^2]): the variance directly, from a two-pass kernel (E[y^2] - E[y]^2
+    in fp32 cancels catastrophically when |mean| >> std, as on the reference's y = x^3 task)."""
     lib = _lib.load()
     logits = mc_logits(est, x, n_samples, sample0, program, noise).contiguous()
     S, B, Cn = logits.shape
     mean = torch.empty(B, Cn, device=x.device, dtype=torch.float32)
     meansq = torch.empty_like(mean)
-    _lib.check(lib.bk_predictive_moments(logits.data_ptr(), S, B, Cn, 0 if mode == "classification" else 1,
+    kmode = {"classification": 0, "regression": 1, "regression_centred": 2}[mode]
+    _lib.check(lib.bk_predictive_moments(logits.data_ptr(), S, B, Cn, kmode,
                                          mean.data_ptr(), meansq.data_ptr(), _lib.stream_ptr()),
                "bk_predictive_moments")
     return mean, meansq
@@ -423,10 +431,9 @@ def mc_moments(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0, mode: str
 def mc_predict(est: KFAC, x: Tensor, n_samples: int = 30, mode: str = "classification", program=None,
                noise=None, sample0: int = 0):
     """classification: mean softmax [B, C].  regression: (mean [B], std [B]) with ddof = 0."""
-    mean, meansq = mc_moments(est, x, n_samples, sample0, mode, program, noise)
     if mode == "classification":
-        return mean
-    var = (meansq - mean * mean).clamp_min(0.0)
+        return mc_moments(est, x, n_samples, sample0, mode, program, noise)[0]
+    mean, var = mc_moments(est, x, n_samples, sample0, "regression_centred", program, noise)
     return mean.squeeze(1), var.sqrt().squeeze(1)
 
 

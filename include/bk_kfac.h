@@ -275,7 +275,9 @@ int bk_conv2d_relu_pool(const float* in, long long in_sample_stride, const float
                         int sh, int sw, int ph, int pw, int relu, int pool, void* stream);
 /* Moments over posterior samples of logits [nsamples, batch, classes] (classes <= 1024):
  * mode 0: p = softmax (sampling/classification_sampling.py:74-79); mode 1: p = raw output
- * (sampling/regression_sampling.py:86-88).  mean = E_s[p]; meansq = E_s[p^2] (nullable). */
+ * (sampling/regression_sampling.py:86-88).  mean = E_s[p]; meansq = E_s[p^2] (nullable).
+ * mode 2: raw output with the CENTRED second moment, meansq = E_s[(p - mean)^2] (numpy std^2, ddof 0),
+ * computed in two passes so that small variances survive |mean| >> std. */
 int bk_predictive_moments(const float* logits, int nsamples, int batch, int classes, int mode,
                           float* mean, float* meansq, void* stream);
 /* out[b] (+)= <x_b, y_b> (optionally absolute value): the last step of the kron-free
