@@ -42,7 +42,6 @@ sys.path.insert(0, ROOT)
 
 WIDTHS = [4096, 4096, 4096, 4096, 10]
 BATCH = 4096
-REF_SAMPLE_ROWS = 1024
 
 
 def load_peaks():
@@ -120,19 +119,46 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_reference(args):
-    """The reference's own update arithmetic (oracle port, torch CPU fp32, all host threads)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    from oracle import kfac_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+class _HostMLP(torch.nn.Module):
+    """The cfg5 MLP as plain torch (Linear + ReLU), the model the reference estimator is attached to."""
+
+    def __init__(self, widths):
+        super().__init__()
+        self.layers = torch.nn.ModuleList(torch.nn.Linear(a, b) for a, b in zip(widths[:-1], widths[1:]))
+
+    def forward(self, x):
+        for i, l in enumerate(self.layers):
+            x = l(x)
+            if i + 1 < len(self.layers):
+                x = torch.relu(x)
+        return x
+
+
+def reference_stepper(rows):
+    """One step of the REFERENCE's own factor update on the host cores: the unmodified `KFAC.update`
+    (models/curvatures.py:325-365, staged under oracle/_ref by oracle/make_ref.py) fed the same (a, g) the GPU arm
+    gets — `record[layer] = [a, g * N]` is exactly what its hooks store (:319-323).  Falls back to the oracle port
+    (same arithmetic, restated) only if oracle/_ref was not staged.  Returns (step_fn, kind, description)."""
+    from oracle import make_ref
     gen = torch.Generator().manual_seed(1234)
-    data = synth_batch(gen, REF_SAMPLE_ROWS, WIDTHS)
+    data = synth_batch(gen, rows, WIDTHS)
+    if make_ref.available():
+        ref = make_ref.load()
+        torch.manual_seed(0)
+        model = _HostMLP(WIDTHS)
+        est = ref.KFAC(model)
+        layers = list(model.layers)
+        recs = [[a, g * a.shape[0]] for a, g in data]
+
+        def step():
+            for layer, rec in zip(layers, recs):
+                est.record[layer] = rec
+            est.update(rows)
+        return step, "reference", "unmodified reference KFAC.update (oracle/_ref/models/curvatures.py), fp32 torch CPU"
+    from oracle import kfac_oracle as O
     state = [None] * len(data)
 
-    def step():
+    def step_port():
         for i, (a, g) in enumerate(data):
             f1, f2 = O.kfac_linear_factors(a, g * a.shape[0], True)
             if state[i] is None:
@@ -140,21 +166,43 @@ def run_reference(args):
             else:  # models/curvatures.py:359-361
                 state[i][0] += f1
                 state[i][1] += f2
+    return step_port, "port", "oracle port of KFAC.update (oracle/_ref not staged), fp32 torch CPU"
 
-    for _ in range(args.warmup):
+
+def bench_config(world):
+    """The `config` object shared by both arms (the driver compares them key by key)."""
+    return {"workload": "cfg5_wide_mlp", "widths": WIDTHS, "batch_per_gpu": BATCH,
+            "parallelism": f"batch-sharded x{world}, one factor exchange per timed region",
+            "l2": "inputs_larger_than_l2 (0.47 GB of activations + 0.4 GB of factor state per step)"}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation at the FULL batch (same config as the GPU arm),
+    all host threads, median of the timed steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, kind, what = reference_stepper(BATCH)
+    for _ in range(max(args.warmup, 1)):
         step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    times = []
+    for _ in range(max(args.steps, 1)):
+        t0 = time.perf_counter()
         step()
-    dt = time.perf_counter() - t0
-    value = REF_SAMPLE_ROWS * args.steps / dt
-    sample = f"{REF_SAMPLE_ROWS} of {BATCH} rows per step, all 4 layers, fp32 torch CPU"
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    value = BATCH / med
+    sample = f"{len(times)} steps of the full {BATCH}-row batch, all 4 layers; median step; {what}"
     line = {"impl": "reference", "metric": "kfac_factor_update_samples_per_s", "value": value,
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": med * 1e3, "ms_per_step_min_max": [times[0] * 1e3, times[-1] * 1e3],
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg5_wide_mlp", "widths": WIDTHS, "batch_per_gpu": BATCH},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+            "config": bench_config(max(args.gpus, 1)),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -162,26 +210,21 @@ def run_reference(args):
 
 
 def cpu_baseline_leg(max_seconds=20.0):
-    from oracle import kfac_oracle as O
+    """Reported beside the GPU line (rank 0, N = 1): the same reference arm on a bounded number of full-batch
+    steps (1 warm-up + up to 5 timed within ~20 s)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    gen = torch.Generator().manual_seed(1234)
-    data = synth_batch(gen, REF_SAMPLE_ROWS, WIDTHS)
-
-    def step():
-        for a, g in data:
-            O.kfac_linear_factors(a, g * a.shape[0], True)
-
+    step, kind, what = reference_stepper(BATCH)
     step()
-    n, t0 = 0, time.perf_counter()
-    while True:
+    times, t_start = [], time.perf_counter()
+    while len(times) < 5 and (not times or time.perf_counter() - t_start < max_seconds):
+        t0 = time.perf_counter()
         step()
-        n += 1
-        if time.perf_counter() - t0 > max_seconds or n >= 8:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": REF_SAMPLE_ROWS * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{n} steps of {REF_SAMPLE_ROWS} of {BATCH} rows, all 4 layers, fp32 torch CPU"}
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": BATCH / med, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": f"{len(times)} steps of the full {BATCH}-row batch, all 4 layers; median step; {what}"}
 
 
 def cpu_predictive_leg(n_inputs=256):
@@ -410,9 +453,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "cfg5_wide_mlp", "widths": WIDTHS, "batch_per_gpu": BATCH,
-                       "parallelism": f"batch-sharded x{world}, one factor all-reduce per timed region",
-                       "l2": "inputs_larger_than_l2 (0.47 GB of activations + 0.4 GB of factor state per step)"},
+            "config": bench_config(world),
             "algorithmic_tflops": value * algorithmic_flops_per_sample(WIDTHS) / 1e12,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": checksum_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},

@@ -15,6 +15,9 @@ BK_PREC_FP32 = 0
 BK_PREC_BF16 = 1
 BK_PREC_BF16X3 = 3
 BK_SMALL_D_MAX = 176
+BK_SMALL64_MAX_DIM = 112
+BK_SMALL64_MAX_ELEMS = 12544
+BK_SMALL64_MAX_BATCH = 16
 
 GEMM_SYRK_LOWER = 1
 GEMM_MIRROR = 2
@@ -74,6 +77,9 @@ SIGNATURES = {
     "bk_conv2d_relu_pool": (_i, [_p, _ll, _p, _p, _p] + [_i] * 14 + [_p]),
     "bk_predictive_moments": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "bk_frob_dot": (_i, [_p, _p, _ll, _p, _ll, _ll, _i, _i, _i, _p]),
+    "bk_spd_inverse_f64": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), C.POINTER(_p), _i, _p, _p]),
+    "bk_kron_quadform_f64": (_i, [_p, _ll, _i, _i, _i, _p, _p, _p, _i, _p]),
     "bk_eigh_workspace_bytes": (_sz, [C.POINTER(_i), _i]),
     "bk_eigh_batched": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i),
                              _i, _f, _i, _p, _sz, _p]),

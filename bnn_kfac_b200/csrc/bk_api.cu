@@ -499,5 +499,22 @@ int bk_frob_dot(float* out, const float* x, long long stride_x, const float* y, 
                              as_stream(stream));
 }
 
+int bk_spd_inverse_f64(const float* const* factors_host, const long long* ld_host, const int* dims_host,
+                       const double* add_host, const double* multiply_host, double* const* outs_host,
+                       int count, int* status, void* stream) {
+  if (count < 0 || (count > 0 && (factors_host == nullptr || ld_host == nullptr || dims_host == nullptr ||
+                                  add_host == nullptr || multiply_host == nullptr || outs_host == nullptr)))
+    return BK_ERR_ARG;
+  return bk::launch_spd_inverse_f64(factors_host, ld_host, dims_host, add_host, multiply_host, outs_host,
+                                    count, status, as_stream(stream));
+}
+
+int bk_kron_quadform_f64(const float* v, long long stride_v, int batch, int d_in_p, int d_out,
+                         const double* q, const double* h, float* out, int accumulate, void* stream) {
+  if (batch > 0 && (v == nullptr || q == nullptr || h == nullptr || out == nullptr)) return BK_ERR_ARG;
+  return bk::launch_kron_quadform_f64(v, stride_v, batch, d_in_p, d_out, q, h, out, accumulate,
+                                      as_stream(stream));
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

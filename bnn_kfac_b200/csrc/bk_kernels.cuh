@@ -131,4 +131,15 @@ int launch_frob_dot(float* out, const float* X, long long stride_x, const float*
                     long long stride_y, long long count, int batch, int absolute, int accumulate,
                     cudaStream_t stream);
 
+// ---- bk_small64.cu  (fp64 small-matrix path of the linearised predictive)
+constexpr int kSmall64MaxDim = 112;       // two [d][d+1] fp64 buffers in one CTA's shared memory
+constexpr int kSmall64MaxElems = 12544;   // d_in' * d_out of one layer (two fp64 copies in shared memory)
+constexpr int kSmall64MaxBatch = 16;      // factors per launch
+int launch_spd_inverse_f64(const float* const* factors, const long long* lds, const int* dims,
+                           const double* add, const double* mult, double* const* outs, int count,
+                           int* status, cudaStream_t stream);
+int launch_kron_quadform_f64(const float* V, long long stride_v, int batch, int dinp, int dout,
+                             const double* Q, const double* H, float* out, int accumulate,
+                             cudaStream_t stream);
+
 }  // namespace bk

@@ -569,6 +569,23 @@ def linearised_kfac_regression(est: KFAC, x_test: Tensor, tau: float, N: float, 
     pseudo-inverse of the script is the inverse)."""
     lib = _lib.load()
     layers = [l for l in list(est.model.modules())[1:] if l in est.state]
+    dims = [(est.state[l][0].shape[0], est.state[l][1].shape[0]) for l in layers]
+    preds = est.model(x_test)
+    P = preds.shape[0]
+    total = torch.zeros(P, device=x_test.device, dtype=torch.float32)
+    jacs = _layers_jacobians_per_output(preds, layers)
+    if all(max(a, b) <= _lib.BK_SMALL64_MAX_DIM and a * b <= _lib.BK_SMALL64_MAX_ELEMS for a, b in dims):
+        # every factor fits one CTA: fp64 inverse + fp64 quadratic form (bk_small64.cu).  cond(N (F + tau I))
+        # reaches 1e5..5e6 on this problem; fp32 products resolve the result to ~1e-2 only.
+        invs = spd_inverse_f64([f for l in layers for f in est.state[l]], float(N) * tau, float(N))
+        st = _lib.stream_ptr()
+        for i, (l, J) in enumerate(zip(layers, jacs)):
+            dinp, dout = dims[i]
+            V = J.float().contiguous()
+            _lib.check(lib.bk_kron_quadform_f64(V.data_ptr(), dinp * dout, P, dinp, dout, invs[2 * i].data_ptr(),
+                                                invs[2 * i + 1].data_ptr(), total.data_ptr(), 1, st),
+                       "bk_kron_quadform_f64")
+        return total.sqrt() + sigma
     factors, adds, mults = [], [], []
     for l in layers:
         factors += list(est.state[l])
@@ -576,15 +593,39 @@ def linearised_kfac_regression(est: KFAC, x_test: Tensor, tau: float, N: float, 
         mults += [float(N) ** 2] * 2
     chol = invert_factors(factors, adds, mults, est._ws)
     invs = [inverse_from_chol(Lc) for Lc in chol]
-    preds = est.model(x_test)
-    P = preds.shape[0]
-    total = torch.zeros(P, device=x_test.device, dtype=torch.float32)
     prec = gemm_precision(est.precision)
-    for i, (l, J) in enumerate(zip(layers, _layers_jacobians_per_output(preds, layers))):
+    for i, (l, J) in enumerate(zip(layers, jacs)):
         q_inv, h_inv = invs[2 * i], invs[2 * i + 1]
         V = J.reshape(P, q_inv.shape[0], h_inv.shape[0])
         kron_quadform(V, q_inv, h_inv, precision=prec, out=total, accumulate=True)
     return total.sqrt() + sigma
+
+
+def spd_inverse_f64(factors: Sequence[Tensor], add: float, multiply: float) -> List[Tensor]:
+    """(multiply * sym(F) + add * I)^-1 in fp64 for small fp32 factors (d <= BK_SMALL64_MAX_DIM), one CTA each.
+    Raises RuntimeError naming the first factor that is not positive definite."""
+    import ctypes as C
+    lib = _lib.load()
+    outs: List[Tensor] = []
+    st = _lib.stream_ptr()
+    fs = [f.float() if f.stride(-1) == 1 else f.float().contiguous() for f in factors]
+    status = torch.zeros(1, dtype=torch.int32, device=fs[0].device)
+    for g0 in range(0, len(fs), _lib.BK_SMALL64_MAX_BATCH):
+        grp = fs[g0:g0 + _lib.BK_SMALL64_MAX_BATCH]
+        n = len(grp)
+        res = [torch.empty(f.shape[0], f.shape[0], dtype=torch.float64, device=f.device) for f in grp]
+        _lib.check(lib.bk_spd_inverse_f64((C.c_void_p * n)(*[f.data_ptr() for f in grp]),
+                                          (C.c_longlong * n)(*[f.stride(0) for f in grp]),
+                                          (C.c_int * n)(*[f.shape[0] for f in grp]),
+                                          (C.c_double * n)(*[add] * n), (C.c_double * n)(*[multiply] * n),
+                                          (C.c_void_p * n)(*[r.data_ptr() for r in res]), n,
+                                          status.data_ptr(), st), "bk_spd_inverse_f64")
+        code = int(status.item())
+        if code:
+            raise RuntimeError(f"factor {g0 + code // 65536} is not positive definite after damping "
+                               f"(add={add}, multiply={multiply})")
+        outs += res
+    return outs
 
 
 def inverse_from_chol(Lc: Tensor, precision: int = _lib.BK_PREC_BF16X3) -> Tensor:

@@ -285,6 +285,26 @@ int bk_predictive_moments(const float* logits, int nsamples, int batch, int clas
 int bk_frob_dot(float* out, const float* x, long long stride_x, const float* y, long long stride_y,
                 long long count, int batch, int absolute, int accumulate, void* stream);
 
+/* fp64 small-matrix path of the sampling-free regression predictive
+ * (sampling_free/regression/regression_ll_block.py:126-138: q_inv = pinverse(N (q_i + tau I)), ...,
+ * |J_i kron(q_inv, h_inv) J_i^T|).  The damped factors of that problem reach cond 1e5..5e6, where fp32
+ * arithmetic resolves the quadratic form to ~1e-2 only; factors that fit one CTA are therefore inverted and
+ * contracted in fp64.
+ * bk_spd_inverse_f64: outs[i] (device fp64 [d, d], dense) = (multiply[i] * sym(F_i) + add[i] * I)^-1 for up to
+ * BK_SMALL64_MAX_BATCH fp32 factors with d <= BK_SMALL64_MAX_DIM (host arrays of device pointers, as in
+ * bk_damp_chol_inv_batched).  `status` (device int, nullable) receives 0 or 65536 * i + (1-based pivot) of the
+ * first factor that is not positive definite.
+ * bk_kron_quadform_f64: out[b] (+)= |<V_b, Q V_b H^T>|, V_b fp32 [d_in', d_out] at v + b * stride_v,
+ * Q fp64 [d_in', d_in'], H fp64 [d_out, d_out], d_in' * d_out <= BK_SMALL64_MAX_ELEMS. */
+#define BK_SMALL64_MAX_DIM 112
+#define BK_SMALL64_MAX_ELEMS 12544
+#define BK_SMALL64_MAX_BATCH 16
+int bk_spd_inverse_f64(const float* const* factors_host, const long long* ld_host, const int* dims_host,
+                       const double* add_host, const double* multiply_host, double* const* outs_host,
+                       int count, int* status, void* stream);
+int bk_kron_quadform_f64(const float* v, long long stride_v, int batch, int d_in_p, int d_out,
+                         const double* q, const double* h, float* out, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

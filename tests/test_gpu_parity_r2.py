@@ -1,0 +1,345 @@
+"""GPU parity tests added in round 2 (the holes VERDICT.md round 1 lists), all through the public Python API ->
+C ABI -> sm_100a kernels, against the reference's own outputs (tests/golden/) or the CPU oracle on identical
+seeded inputs.  Tolerances are BASELINE.json's (1e-3) unless a test states and justifies another one."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, relerr
+from models_for_tests import RegNet, load_params
+from oracle import kfac_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from bnn_kfac_b200 import _lib
+    _lib.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def golden_cfg2():
+    return dict(np.load(ROOT / "tests" / "golden" / "reference_golden_cfg2.npz"))
+
+
+def _layers(est):
+    return [l for _, l in est._selected_layers()]
+
+
+def _fisher_step(model, x, y):
+    loss = torch.nn.functional.cross_entropy(model(x), y)
+    model.zero_grad()
+    loss.backward()
+
+
+def _pair(model_ctor, dev, lim, precision="bf16x3", seed=0):
+    """(cpu fp64 model, gpu fp32 model with the same parameters, oracle estimator, GPU estimator)."""
+    from bnn_kfac_b200.curvatures import KFAC
+    torch.manual_seed(seed)
+    cm = model_ctor().double()
+    cm.weight_init_uniform(lim)
+    gm = model_ctor()
+    gm.load_state_dict({k: v.float() for k, v in cm.state_dict().items()})
+    gm = gm.to(dev)
+    return cm, gm, O.OracleKFAC(cm), KFAC(gm, precision=precision)
+
+
+# ------------------------------------------------------------------------------------------ (a) config 2
+@pytest.mark.parametrize("n_hid", [30, 50])
+def test_cfg2_regression_linearised_fp64_golden(golden_cfg2, dev, n_hid):
+    """BASELINE config 2 at BASELINE.json's 1e-3: sampling-free predictive std of the toy regression MLP
+    (n_hid 30 = the script, 50 = BASELINE.json) against the REFERENCE's own fp64 run of
+    regression_ll_block.py:120-140.  The accumulated factors are the reference's (rounded to the fp32 `state`
+    the engine keeps; cond(N (F + tau I)) is 6.6e5 / 4.6e6 here); inverse and quadratic form run in fp64
+    (bk_small64.cu)."""
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.predictive import linearised_kfac_regression
+    g, p = golden_cfg2, f"reg{n_hid}"
+    model = load_params(RegNet(n_hid), g, p, torch.float32).to(dev)
+    est = KFAC(model)
+    for i, l in enumerate(_layers(est)):
+        est.state[l] = [torch.tensor(g[f"{p}_state_{i}_A"]).float().to(dev),
+                        torch.tensor(g[f"{p}_state_{i}_G"]).float().to(dev)]
+    xt = torch.tensor(g[f"{p}_xtest"]).float().to(dev)
+    std = linearised_kfac_regression(est, xt, tau=0.01, N=30, sigma=3)
+    got, ref = std.cpu().numpy() - 3, g[f"{p}_pred_std"] - 3
+    assert np.abs(got / ref - 1).max() < TOL, np.abs(got / ref - 1).max()
+    assert relerr(model(xt).detach().squeeze(1).cpu(), g[f"{p}_pred_mean"]) < 1e-5
+    # the factor stage on this net: one update at the final parameters vs the reference's
+    est2 = KFAC(model)
+    x, y = torch.tensor(g[f"{p}_x"]).float().to(dev), torch.tensor(g[f"{p}_y"]).float().to(dev)
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    model.zero_grad()
+    loss.backward()
+    est2.update(1)
+    for i, l in enumerate(_layers(est2)):
+        assert relerr(est2.state[l][0].cpu(), g[f"{p}_step_{i}_A"]) < 1e-5
+        assert relerr(est2.state[l][1].cpu(), g[f"{p}_step_{i}_G"]) < 1e-5
+
+
+def test_spd_inverse_f64_and_quadform_vs_numpy(dev):
+    """bk_spd_inverse_f64 / bk_kron_quadform_f64 against fp64 numpy at their size limits and on an
+    ill-conditioned factor; a non-SPD factor is reported."""
+    from bnn_kfac_b200 import _lib
+    from bnn_kfac_b200.predictive import spd_inverse_f64
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    fs = []
+    for d in (1, 2, 31, 51, 112):
+        x = torch.randn(max(d // 2, 1), d, generator=g, dtype=torch.float64)        # rank-deficient
+        fs.append((x.t() @ x / x.shape[0]).float())
+    invs = spd_inverse_f64([f.to(dev) for f in fs], add=0.3, multiply=30.0)
+    for f, inv in zip(fs, invs):
+        R = 30.0 * (f.double() + f.double().t()) / 2 + 0.3 * torch.eye(f.shape[0], dtype=torch.float64)
+        assert relerr(inv.cpu(), torch.linalg.inv(R)) < 1e-10
+    with pytest.raises(RuntimeError):
+        spd_inverse_f64([-torch.eye(5, device=dev)], add=0.1, multiply=1.0)
+    dinp, dout, B = 112, 112, 9
+    V = torch.randn(B, dinp, dout, generator=g)
+    Q = torch.randn(dinp, dinp, generator=g, dtype=torch.float64)
+    H = torch.randn(dout, dout, generator=g, dtype=torch.float64)
+    out = torch.full((B,), 2.0, device=dev)
+    Vd = V.to(dev)
+    _lib.check(lib.bk_kron_quadform_f64(Vd.data_ptr(), dinp * dout, B, dinp, dout, Q.to(dev).data_ptr(),
+                                        H.to(dev).data_ptr(), out.data_ptr(), 1, _lib.stream_ptr()), "quadform")
+    ref = 2.0 + torch.einsum("bik,ij,bjl,kl->b", V.double(), Q, V.double(), H).abs()
+    assert relerr(out.cpu(), ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ (b) config 4
+def _cfg4(model_ctor, dev, batch, S, n_test, lim=0.2):
+    from bnn_kfac_b200.predictive import mc_predict
+    cm, gm, oest, gest = _pair(model_ctor, dev, lim)
+    gen = torch.Generator().manual_seed(1234)
+    for _ in range(2):
+        xb = torch.rand(batch, 1, 28, 28, generator=gen)
+        labels = O.fisher_backward(cm, xb.double(), generator=gen)
+        oest.update()
+        _fisher_step(gm, xb.to(dev), labels.to(dev))
+        gest.update(batch)
+    oest.invert(0.04, 200.0)
+    gest.invert(0.04, 200.0)
+    errs = {}
+    for li, (ol, gl) in enumerate(zip(oest.layers, _layers(gest))):
+        for k in range(2):
+            errs[f"factor{li}{'AG'[k]}"] = relerr(gest.state[gl][k].cpu(), oest.state[ol][k])
+            R = 200.0 ** 0.5 * oest.state[ol][k] + 0.04 ** 0.5 * torch.eye(oest.state[ol][k].shape[0],
+                                                                         dtype=torch.float64)
+            tol = max(TOL, 3e-9 * torch.linalg.cond((R + R.t()) / 2).item())
+            e = relerr(gest.inv_state[gl][k].cpu(), oest.inv_state[ol][k])
+            assert e < tol, (li, k, e, tol)
+    assert max(errs.values()) < TOL, errs
+    zs = [[torch.randn(oest.inv_state[l][0].shape[0], oest.inv_state[l][1].shape[0], generator=gen,
+                       dtype=torch.float64) for l in oest.layers] for _ in range(S)]
+    xt = torch.rand(n_test, 1, 28, 28, generator=gen)
+    ref = O.mc_predict_classification(cm, oest, xt.double(), zs)
+    noise = [torch.stack([zs[s][li] for s in range(S)]).float().to(dev) for li in range(len(oest.layers))]
+    got = mc_predict(gest, xt.to(dev), S, noise=noise)
+    assert relerr(got.cpu(), ref) < TOL
+    return gest
+
+
+def test_cfg4_lenet5_batch256_s100_vs_oracle(dev):
+    """BASELINE config 4 on true LeNet-5 shapes at the stated sizes: batch 256, S = 100 shared-noise posterior
+    samples.  Its 401-wide fc1 factor crosses the SIMT -> tcgen05 switch on a conv net."""
+    from bnn_kfac_b200.wrapper import LeNet5
+    gest = _cfg4(LeNet5, dev, batch=256, S=100, n_test=32)
+    shapes = [(tuple(v[0].shape), tuple(v[1].shape)) for v in gest.state.values()]
+    assert shapes == [((26, 26), (6, 6)), ((151, 151), (16, 16)), ((401, 401), (120, 120)),
+                      ((121, 121), (84, 84)), ((85, 85), (10, 10))]
+
+
+def test_cfg4_basenet15k_batch256_s100_vs_oracle(dev):
+    from bnn_kfac_b200.wrapper import BaseNet_15k
+    _cfg4(BaseNet_15k, dev, batch=256, S=100, n_test=32)
+
+
+# ------------------------------------------------------------------------------------------ (c) config 5
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 2e-2)])
+def test_cfg5_size_sample_and_implicit_mc_forward_vs_oracle(dev, precision, tol):
+    """One cfg5-sized layer (4096 -> 4096, then a 10-wide head), 256 test inputs: `sample(z=...)` and the MC
+    forward the bench times — the IMPLICIT path (CTA pairs, triangular k-block skipping, K-concatenated
+    [x | Y2][M | L_G]^T) followed by a materialised layer — against the CPU oracle in fp64, consuming the same
+    z and the same Cholesky factors (stage-wise: the factor and inversion stages of this size are checked in
+    test_cfg5_wide_factor_properties).  precision="bf16x3" is the parity mode (1e-3); "bf16" is the
+    single-pass throughput mode the bench runs, whose products carry bf16 rounding (2^-9 per operand):
+    2e-2 on logits, stated here rather than hidden."""
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.predictive import mc_logits
+    from bnn_kfac_b200.wrapper import MLP as WMLP
+    torch.manual_seed(0)
+    gm = WMLP([4096, 4096, 10]).to(dev)
+    est = KFAC(gm, precision=precision)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(512, 4096, generator=gen).to(dev)
+    _fisher_step(gm, x, torch.randint(0, 10, (512,), generator=gen).to(dev))
+    est.update(512)
+    est.invert(1e4, 1e6)
+    l0, l1 = _layers(est)
+    LA, LG = (t.double().cpu() for t in est.inv_state[l0])
+    z0 = torch.randn(4097, 4096, generator=gen)
+    smp = est.sample(l0, z=z0.to(dev))
+    ref_smp = O.kfac_sample(LA, LG, z0.double())
+    assert smp.shape == (4096, 4097)
+    assert relerr(smp.cpu(), ref_smp) < tol
+    # MC forward, S = 2, implicit=None (the heuristic the bench uses picks implicit for l0, materialised for l1)
+    S, B = 2, 256
+    xt = torch.randn(B, 4096, generator=gen)
+    zs = [torch.stack([torch.randn(4097, 4096, generator=gen) for _ in range(S)]),
+          torch.stack([torch.randn(4097, 10, generator=gen) for _ in range(S)])]
+    got = mc_logits(est, xt.to(dev), S, noise=[t.to(dev) for t in zs])
+    LA1, LG1 = (t.double().cpu() for t in est.inv_state[l1])
+    W0, b0 = l0.weight.detach().double().cpu(), l0.bias.detach().double().cpu()
+    W1, b1 = l1.weight.detach().double().cpu(), l1.bias.detach().double().cpu()
+    ref = []
+    for s in range(S):
+        w0s, b0s = O.replace(O.kfac_sample(LA, LG, zs[0][s].double()), W0, b0)
+        w1s, b1s = O.replace(O.kfac_sample(LA1, LG1, zs[1][s].double()), W1, b1)
+        h = torch.relu(xt.double() @ w0s.t() + b0s)
+        ref.append(h @ w1s.t() + b1s)
+    ref = torch.stack(ref)
+    assert relerr(got.cpu(), ref) < tol
+    assert relerr(torch.softmax(got, -1).mean(0).cpu(), torch.softmax(ref, -1).mean(0)) < tol
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_mc_forward_mixed_materialised_implicit_vs_oracle(dev, precision):
+    """a materialised Linear layer followed by an implicit one, chosen by the automatic
+    heuristic (implicit=None): MLP 256-1024-1024-10 at 64 test inputs runs layer 0 materialised (min dim < 700),
+    layer 1 implicit, layer 2 materialised.  The padding / ones columns of the K-concatenated buffer lie inside
+    the GEMMs' K range and must be initialised."""
+    from bnn_kfac_b200.predictive import mc_logits
+    from bnn_kfac_b200.wrapper import MLP as WMLP
+    cm, gm, oest, gest = _pair(lambda: WMLP([256, 1024, 1024, 10]), dev, 0.05, precision=precision)
+    gen = torch.Generator().manual_seed(5)
+    xb = torch.rand(128, 256, generator=gen)
+    labels = O.fisher_backward(cm, xb.double(), generator=gen)
+    oest.update()
+    _fisher_step(gm, xb.to(dev), labels.to(dev))
+    gest.update(128)
+    oest.invert(1e4, 1e6)
+    gest.invert(1e4, 1e6)
+    S, B = 3, 64
+    zs = [[torch.randn(oest.inv_state[l][0].shape[0], oest.inv_state[l][1].shape[0], generator=gen,
+                       dtype=torch.float64) for l in oest.layers] for _ in range(S)]
+    xt = torch.rand(B, 256, generator=gen)
+    ref = []
+    with torch.no_grad():
+        for s in range(S):
+            oest.sample_and_replace(zs[s])
+            ref.append(cm(xt.double()))
+    cm.load_state_dict(oest.map_state)
+    ref = torch.stack(ref)
+    noise = [torch.stack([zs[s][li] for s in range(S)]).float().to(dev) for li in range(3)]
+    # poison the caching allocator so that an uninitialised column reads NaN, not a lucky zero
+    junk = torch.full((64 << 20,), float("nan"), device=dev)
+    del junk
+    got = mc_logits(gest, xt.to(dev), S, noise=noise, implicit=None)
+    assert torch.isfinite(got).all()
+    assert relerr(got.cpu(), ref) < (TOL if precision == "bf16x3" else 2e-2)
+
+
+# ------------------------------------------------------------------------------------------ (d) bf16 mode
+@pytest.mark.parametrize("width", [1024, 4096])
+def test_bf16_single_pass_factors_A_and_G(dev, width):
+    """precision="bf16" (what bench.py times) on inputs that are NOT bf16-representable: both Kronecker factors of
+    a width-wide hidden layer of a real network (ReLU activations, cross-entropy output gradients) must meet the
+    1e-3 factor tolerance against the fp64 formula (models/curvatures.py:345-356)."""
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.wrapper import MLP as WMLP
+    torch.manual_seed(1)
+    gm = WMLP([width, width, width, 10]).to(dev)
+    est = KFAC(gm, precision="bf16")
+    n = width
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(n, width, generator=gen).to(dev)
+    _fisher_step(gm, x, torch.randint(0, 10, (n,), generator=gen).to(dev))
+    recs = {l: (r[0].detach().double(), r[1].detach().double() * n) for l, r in est.record.items()}
+    est.update(n)
+    for layer in _layers(est)[:2]:
+        a, g = recs[layer]
+        a1 = torch.cat([a, torch.ones(n, 1, device=dev, dtype=torch.float64)], 1)
+        refA = a1.t() @ a1 / n
+        refG = g.t() @ g / n
+        eA = relerr(est.state[layer][0].cpu(), refA.cpu())
+        eG = relerr(est.state[layer][1].cpu(), refG.cpu())
+        assert eA < TOL and eG < TOL, (width, eA, eG)
+
+
+# ------------------------------------------------------------------------------------------ (e) regression MC
+def test_mc_regression_mean_std_vs_oracle(golden_cfg2, dev):
+    """sampling/regression_sampling.py:81-88: per-input mean and std (ddof 0) over S shared-noise samples of the
+    toy regression net; the outputs reach |y| ~ 200 at the edge of the test range, so the std needs the centred
+    second moment."""
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.predictive import mc_predict
+    g, p = golden_cfg2, "reg30"
+    cm = load_params(RegNet(30), g, p, torch.float64)
+    gm = load_params(RegNet(30), g, p, torch.float32).to(dev)
+    oest, gest = O.OracleKFAC(cm), KFAC(gm)
+    x, y = torch.tensor(g[f"{p}_x"]), torch.tensor(g[f"{p}_y"])
+    for _ in range(2):
+        loss = torch.nn.functional.mse_loss(cm(x), y)
+        cm.zero_grad()
+        loss.backward()
+        oest.update()
+        loss = torch.nn.functional.mse_loss(gm(x.float().to(dev)), y.float().to(dev))
+        gm.zero_grad()
+        loss.backward()
+        gest.update(1)
+    oest.invert(1e2, 1e4)
+    gest.invert(1e2, 1e4)
+    S = 12
+    gen = torch.Generator().manual_seed(9)
+    zs = [[torch.randn(oest.inv_state[l][0].shape[0], oest.inv_state[l][1].shape[0], generator=gen,
+                       dtype=torch.float64) for l in oest.layers] for _ in range(S)]
+    xt = torch.tensor(g[f"{p}_xtest"])
+    ref_mean, ref_std = O.mc_predict_regression(cm, oest, xt, zs)
+    noise = [torch.stack([zs[s][li] for s in range(S)]).float().to(dev) for li in range(3)]
+    mean, std = mc_predict(gest, xt.float().to(dev), S, mode="regression", noise=noise)
+    assert relerr(mean.cpu(), ref_mean) < TOL
+    assert relerr(std.cpu(), ref_std) < TOL
+    assert np.abs(std.cpu().numpy() / ref_std - 1).max() < 5e-3      # element-wise, incl. the smallest std
+
+
+def test_predictive_moments_centred_kernel(dev):
+    """mode 2 of bk_predictive_moments: variance 1e-6 on a mean of 200 (E[y^2] - E[y]^2 in fp32 returns noise)."""
+    from bnn_kfac_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(2)
+    S, B = 50, 33
+    y = (200.0 + 1e-3 * torch.randn(S, B, 1, generator=g, dtype=torch.float64)).float().to(dev)
+    mean = torch.empty(B, 1, device=dev)
+    var = torch.empty(B, 1, device=dev)
+    _lib.check(lib.bk_predictive_moments(y.data_ptr(), S, B, 1, 2, mean.data_ptr(), var.data_ptr(),
+                                         _lib.stream_ptr()), "moments")
+    yd = y.double()
+    assert relerr(mean.cpu(), yd.mean(0).cpu()) < 1e-6
+    assert relerr(var.cpu(), yd.var(0, unbiased=False).cpu()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ (f) NCCL parity
+def test_nccl_two_rank_parity():
+    """Sharded accumulation + invert_sharded + mc_predict_sharded over NCCL on 2 GPUs must reproduce the
+    single-GPU result (tools/gpu_dist_check.py asserts it on every rank).  Skipped on a 1-GPU box; bench.py
+    carries the same check in its `parity` field at N > 1."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29731",
+                           str(ROOT / "tools" / "gpu_dist_check.py")], capture_output=True, text=True, env=env,
+                          timeout=600)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "dist check ok" in proc.stdout

@@ -133,6 +133,31 @@ def test_regression_linearised(golden):
     assert relerr(model(xt).detach().squeeze(1), golden["reg_pred_mean"]) < 1e-6
 
 
+@pytest.mark.parametrize("n_hid", [30, 50])
+def test_regression_linearised_cfg2_fp64(n_hid):
+    """BASELINE config 2 (n_hid 30 = the script, 50 = BASELINE.json): the oracle against the reference's own fp64
+    run (tests/golden/make_golden_cfg2.py).  fp64 on both sides: agreement to rounding, both kron forms."""
+    g = dict(np.load(ROOT / "tests" / "golden" / "reference_golden_cfg2.npz"))
+    model = load_params(RegNet(n_hid), g, f"reg{n_hid}", torch.float64)
+    layers = O.selected_layers(model)
+    state = {l: (torch.tensor(g[f"reg{n_hid}_state_{i}_A"]), torch.tensor(g[f"reg{n_hid}_state_{i}_G"]))
+             for i, l in enumerate(layers)}
+    xt = torch.tensor(g[f"reg{n_hid}_xtest"])
+    for use_kron in (True, False):
+        stds = [O.linearised_regression_point(model, layers, state, x_j, 0.01, 30, 3, use_kron) for x_j in xt[::4]]
+        np.testing.assert_allclose(np.array(stds) - 3, g[f"reg{n_hid}_pred_std"][::4] - 3, rtol=1e-7)
+    # one update at the final parameters: oracle factors == the reference's
+    x, y = torch.tensor(g[f"reg{n_hid}_x"]), torch.tensor(g[f"reg{n_hid}_y"])
+    oest = O.OracleKFAC(model)
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    model.zero_grad()
+    loss.backward()
+    oest.update()
+    for i, l in enumerate(oest.layers):
+        assert relerr(oest.state[l][0], g[f"reg{n_hid}_step_{i}_A"]) < 1e-12
+        assert relerr(oest.state[l][1], g[f"reg{n_hid}_step_{i}_G"]) < 1e-12
+
+
 def test_kron_doctest_vector(golden):
     """The reference's only executable check: models/utilities.py:400-407."""
     out = O.kron(torch.tensor(golden["kron_a"]), torch.tensor(golden["kron_b"]))
@@ -321,3 +346,27 @@ def test_inf_dim_reduction_product_host_logic(golden_inf, rank):
         if rank < lam.numel():
             np.testing.assert_array_equal(got[0].numpy(), g[f"inf_r{rank}_lrA_{li}"])
             np.testing.assert_array_equal(got[2].numpy(), g[f"inf_r{rank}_lrlam_{li}"])
+
+
+def test_staged_reference_matches_oracle_port():
+    """oracle/_ref (the unmodified reference modules staged by oracle/make_ref.py, what `bench.py --impl
+    reference` times) and the oracle port compute the same factors from the same hook records."""
+    from oracle import make_ref
+    if not make_ref.available():
+        if not make_ref.REF.exists():
+            pytest.skip("oracle/_ref not staged and /root/reference absent")
+        make_ref.make()
+    ref = make_ref.load()
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(12, 9), torch.nn.ReLU(), torch.nn.Linear(9, 4)).double()
+    est = ref.KFAC(model)
+    x = torch.rand(16, 12, dtype=torch.float64)
+    loss = torch.nn.functional.cross_entropy(model(x), torch.randint(0, 4, (16,)))
+    loss.backward()
+    recs = {l: [r[0].detach().clone(), r[1].detach().clone()] for l, r in est.record.items()}
+    est.update(16)
+    est.update(16)      # state +=
+    for layer, (a, g) in recs.items():
+        f1, f2 = O.kfac_linear_factors(a, g, True)
+        assert torch.allclose(est.state[layer][0], 2 * f1, atol=1e-12)
+        assert torch.allclose(est.state[layer][1], 2 * f2, atol=1e-12)

@@ -26,13 +26,9 @@ def build(dev, widths, seed=0):
     return m.to(dev)
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cuda.matmul.allow_tf32 = False
+def run_check(rank, world, dev):
+    """Runs inside an initialised NCCL process group.  Returns {"inverse_relerr", "predictive_relerr",
+    "identical_on_all_ranks", "ok"} (the error figures are rank 0's; every rank gets the same `ok`)."""
     widths = [300, 520, 260, 10]
     n_per, steps = 64, 2
     g = torch.Generator().manual_seed(1234)
@@ -53,7 +49,7 @@ def main():
     D.invert_sharded(est, 1e2, 1e4)
     S = 2 * world + 1
     pred = D.mc_predict_sharded(est, xt, S)
-    ok = True
+    worst, e_pred = 0.0, 0.0
     if rank == 0:
         ref_model = build(dev, widths)
         ref = KFAC(ref_model, seed=11)
@@ -66,14 +62,14 @@ def main():
         ref_pred = mc_predict(ref, xt, S)
         layers = [l for _, l in est._selected_layers()]
         rlayers = [l for _, l in ref._selected_layers()]
-        worst = 0.0
         for l, rl in zip(layers, rlayers):
             for k in range(2):
                 worst = max(worst, relerr(est.inv_state[l][k], ref.inv_state[rl][k]))
         e_pred = relerr(pred, ref_pred)
-        ok = worst < 1e-3 and e_pred < 1e-3
-        print(f"world={world} inverse relerr (worst factor) {worst:.2e}  predictive relerr {e_pred:.2e}  "
-              f"{'OK' if ok else 'FAIL'}", flush=True)
+        for h in ref.hooks:
+            h.remove()
+    for h in est.hooks:
+        h.remove()
     # every rank must hold the same inverse factors and prediction
     chk = torch.stack([est.inv_state[l][k].double().sum() for _, l in est._selected_layers() for k in range(2)]
                       + [pred.double().sum()])
@@ -81,11 +77,30 @@ def main():
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     same = bool(torch.equal(lo, hi))
+    flag = torch.tensor([1.0 if (worst < 1e-3 and e_pred < 1e-3 and same) else 0.0], device=dev)
+    dist.broadcast(flag, src=0)
+    return {"inverse_relerr": worst, "predictive_relerr": e_pred, "identical_on_all_ranks": same,
+            "ok": bool(flag.item() > 0.5) and same, "tolerance": 1e-3,
+            "what": "sharded accumulation + invert_sharded + mc_predict_sharded vs one GPU on the full batch "
+                    "(MLP 300-520-260-10)"}
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res = run_check(rank, world, dev)
     if rank == 0:
-        print(f"identical on all ranks: {same}", flush=True)
+        print(f"world={world} inverse relerr (worst factor) {res['inverse_relerr']:.2e}  predictive relerr "
+              f"{res['predictive_relerr']:.2e}  identical on all ranks: {res['identical_on_all_ranks']}", flush=True)
+        if res["ok"]:
+            print("dist check ok", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if (ok and same) else 1)
+    sys.exit(0 if res["ok"] else 1)
 
 
 if __name__ == "__main__":
