@@ -419,10 +419,12 @@ def main():
     a_al = (C.c_float * cnt)(*[1.0 / n] * cnt)
     a_be = (C.c_float * cnt)(*[1.0] * cnt)
     reps = 20
+    syrk_flags = _lib.SYRK_LOWER_ONLY if est.lower_only else 0
 
     def syrk():
         _lib.check(L.bk_syrk_accum_staged_grouped(a_states, a_lds, a_hi, a_lo, a_ldt, a_ns, a_ds, a_al, a_be,
-                                                  cnt, prec, _lib.stream_ptr()), "bk_syrk_accum_staged_grouped")
+                                                  cnt, prec, syrk_flags, _lib.stream_ptr()),
+                   "bk_syrk_accum_staged_grouped")
     for _ in range(3):
         syrk()
     torch.cuda.synchronize()

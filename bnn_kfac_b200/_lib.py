@@ -19,6 +19,9 @@ BK_SMALL64_MAX_DIM = 112
 BK_SMALL64_MAX_ELEMS = 12544
 BK_SMALL64_MAX_BATCH = 16
 
+SYRK_LOWER_ONLY = 1
+SYRK_NO_OVERLAP = 2
+
 GEMM_SYRK_LOWER = 1
 GEMM_MIRROR = 2
 GEMM_TRI_A = 4
@@ -62,10 +65,11 @@ SIGNATURES = {
     "bk_syrk_grouped_workspace_bytes": (_sz, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _i]),
     "bk_syrk_accum_grouped": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_ll),
                                    C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f),
-                                   C.POINTER(_f), C.POINTER(_f), _i, _i, _p, _sz, _p]),
+                                   C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _p, _sz, _p]),
+    "bk_sym_finalize": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _f, _p]),
     "bk_syrk_accum_staged_grouped": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_p),
                                           C.POINTER(_ll), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f),
-                                          C.POINTER(_f), _i, _i, _p]),
+                                          C.POINTER(_f), _i, _i, _i, _p]),
     "bk_syrk_accum_staged": (_i, [_p, _ll, _p, _p, _ll, _i, _i, _f, _f, _i, _p]),
     "bk_conv_a_accum": (_i, [_p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
     "bk_conv_g_accum": (_i, [_p, _ll, _p, _i, _i, _i, _f, _f, _f, _p]),

@@ -3,6 +3,7 @@
 // header says so (bk_damp_chol_inv_batched returns a device-computed status).
 #include "../../include/bk_kfac.h"
 
+#include "bk_common.cuh"
 #include "bk_kernels.cuh"
 #include "bk_umma_gemm.cuh"
 
@@ -15,6 +16,7 @@ inline long long round8(long long v) { return (v + 7) / 8 * 8; }
 }  // namespace
 
 #include <atomic>
+#include <mutex>
 
 namespace bk {
 static std::atomic<unsigned long long> g_launches{0};
@@ -200,10 +202,40 @@ size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* 
   return total;
 }
 
+namespace {
+
+// Per-device side stream + events for the staging / SYRK pipeline of bk_syrk_accum_grouped.
+struct StagePipe {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, first = nullptr;
+  cudaEvent_t staged[8] = {};
+  bool ok = false;
+  StagePipe() {
+    ok = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&first, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i)
+      ok = cudaEventCreateWithFlags(&staged[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+};
+
+StagePipe* stage_pipe() {
+  static std::mutex mu;
+  static StagePipe* pipes[bk::kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= bk::kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> g(mu);
+  if (pipes[dev] == nullptr) pipes[dev] = new StagePipe();
+  return pipes[dev]->ok ? pipes[dev] : nullptr;
+}
+
+}  // namespace
+
 int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const float* const* xs,
                           const long long* ldxs, const int* ns, const int* ds, const int* has_bias,
                           const float* in_scales, const float* alphas, const float* betas, int count,
-                          int precision, void* workspace, size_t workspace_bytes, void* stream) {
+                          int precision, int flags, void* workspace, size_t workspace_bytes,
+                          void* stream) {
   if (count <= 0) return BK_OK;
   if (states == nullptr || ld_states == nullptr || xs == nullptr || ldxs == nullptr ||
       ns == nullptr || ds == nullptr || has_bias == nullptr || in_scales == nullptr ||
@@ -213,18 +245,16 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
       (workspace == nullptr && workspace_bytes > 0) ||
       (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return BK_ERR_WORKSPACE;
+  const bool mirror = (flags & BK_SYRK_LOWER_ONLY) == 0;
   cudaStream_t st = as_stream(stream);
   char* base = static_cast<char*>(workspace);
   size_t off = 0;
-  bk::SyrkGroupItem items[64];
-  struct Border {
-    float* state;
-    long long ld;
-    int d;
-    const float* colsum;
-    float alpha, beta, n;
-  } borders[64];
-  int n_items = 0, n_borders = 0;
+  // pass 1: route every factor; the tensor-core items are collected, the others run right away
+  struct Wide {
+    int idx;
+    char* ws;
+  } wide[64];
+  int n_wide = 0;
   for (int i = 0; i < count; ++i) {
     const size_t need = bk_syrk_workspace_bytes(ns[i], ds[i], has_bias[i], precision);
     char* ws = base + off;
@@ -235,7 +265,7 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
     const bool aligned = (ld_states[i] % 4) == 0 && (reinterpret_cast<uintptr_t>(states[i]) & 15) == 0 &&
                          (ldxs[i] % 4) == 0 && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0 &&
                          (betas[i] == 0.f || betas[i] == 1.f) && d >= 192;
-    if (!tensor || !aligned || n_items >= 64) {
+    if (!tensor || !aligned || n_wide >= 64) {
       const int rc = bk_syrk_accum(states[i], ld_states[i], xs[i], ldxs[i], n, d, hb, in_scales[i],
                                    alphas[i], betas[i], precision, ws, need, stream);
       if (rc) return rc;
@@ -243,36 +273,116 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
     }
     if (states[i] == nullptr || xs[i] == nullptr || n <= 0 || ld_states[i] < dp || ldxs[i] < d)
       return BK_ERR_ARG;
-    const long long ldt = round8(n);
-    const size_t one = align_up(static_cast<size_t>(dp) * ldt * 2, 256);
-    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ws);
-    __nv_bfloat16* lo =
-        precision == BK_PREC_BF16X3 ? reinterpret_cast<__nv_bfloat16*>(ws + one) : nullptr;
-    float* colsum =
-        hb ? reinterpret_cast<float*>(ws + (precision == BK_PREC_BF16X3 ? 2 : 1) * one) : nullptr;
-    if (colsum != nullptr &&
-        cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, st) != cudaSuccess)
-      return BK_ERR_CUDA;
-    const int rc = bk::launch_transpose_split(xs[i], ldxs[i], n, d, in_scales[i], 0, hi, lo, ldt, st,
-                                              colsum);
-    if (rc) return rc;
-    bk::SyrkGroupItem& it = items[n_items++];
-    it.X_hi = hi;
-    it.X_lo = lo;
-    it.ldx = ldt;
-    it.d = d;
-    it.n = n;
-    it.alpha = alphas[i];
-    it.beta = betas[i];
-    it.C = states[i];
-    it.ldc = ld_states[i];
-    if (hb) borders[n_borders++] = {states[i], ld_states[i], d, colsum, alphas[i], betas[i],
-                                    static_cast<float>(n)};
+    wide[n_wide++] = {i, ws};
   }
-  for (int g0 = 0; g0 < n_items; g0 += 8) {
-    const int gc = n_items - g0 < 8 ? n_items - g0 : 8;
-    const int rc = bk::launch_umma_syrk_grouped(items + g0, gc, precision, st);
+  if (n_wide == 0) return BK_OK;
+  // pass 2: software pipeline over chunks of wide factors.  The staging pass (fp32 [n, d] -> K-major bf16,
+  // HBM-bound) of chunk c + 1 runs on a side stream underneath the tensor-core SYRK of chunk c (the
+  // lower-only SYRK leaves enough shared memory per SM for a co-resident staging CTA).  Chunk 0 is a single
+  // factor so that the tensor cores start after ONE staging pass; later chunks hold up to 3.
+  StagePipe* pipe = (flags & BK_SYRK_NO_OVERLAP) ? nullptr : stage_pipe();
+  int chunk_begin[66];
+  int n_chunks = 0;
+  if (pipe != nullptr && n_wide > 1) {
+    int b = 0;
+    chunk_begin[n_chunks++] = 0;
+    b = 1;
+    while (b < n_wide) {
+      chunk_begin[n_chunks++] = b;
+      b += (n_wide - b) >= 6 ? 3 : (n_wide - b);   // ... 3, then whatever is left (<= 5)
+      if (n_chunks >= 8) break;
+    }
+    if (b < n_wide) {  // more than the pipeline's events cover: last chunk takes the rest
+      // (groups of 8 are split again at launch)
+    }
+  } else {
+    chunk_begin[n_chunks++] = 0;
+  }
+  chunk_begin[n_chunks] = n_wide;
+  struct Border {
+    float* state;
+    long long ld;
+    int d;
+    const float* colsum;
+    float alpha, beta, n;
+  } borders[64];
+  int n_borders = 0;
+  bk::SyrkGroupItem items[64];
+  auto stage_chunk = [&](int c, cudaStream_t s) -> int {
+    for (int w = chunk_begin[c]; w < chunk_begin[c + 1]; ++w) {
+      const int i = wide[w].idx;
+      const int d = ds[i], n = ns[i], hb = has_bias[i] ? 1 : 0;
+      const long long ldt = round8(n);
+      const size_t one = align_up(static_cast<size_t>(d + hb) * ldt * 2, 256);
+      char* ws = wide[w].ws;
+      __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ws);
+      __nv_bfloat16* lo =
+          precision == BK_PREC_BF16X3 ? reinterpret_cast<__nv_bfloat16*>(ws + one) : nullptr;
+      float* colsum =
+          hb ? reinterpret_cast<float*>(ws + (precision == BK_PREC_BF16X3 ? 2 : 1) * one) : nullptr;
+      if (colsum != nullptr &&
+          cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, s) != cudaSuccess)
+        return BK_ERR_CUDA;
+      const int rc = bk::launch_transpose_split(xs[i], ldxs[i], n, d, in_scales[i], 0, hi, lo, ldt, s,
+                                                colsum);
+      if (rc) return rc;
+      bk::SyrkGroupItem& it = items[w];
+      it.X_hi = hi;
+      it.X_lo = lo;
+      it.ldx = ldt;
+      it.d = d;
+      it.n = n;
+      it.alpha = alphas[i];
+      it.beta = betas[i];
+      it.C = states[i];
+      it.ldc = ld_states[i];
+      if (hb) borders[n_borders++] = {states[i], ld_states[i], d, colsum, alphas[i], betas[i],
+                                      static_cast<float>(n)};
+    }
+    return 0;
+  };
+  auto syrk_chunk = [&](int c) -> int {
+    for (int g0 = chunk_begin[c]; g0 < chunk_begin[c + 1]; g0 += 8) {
+      const int gc = chunk_begin[c + 1] - g0 < 8 ? chunk_begin[c + 1] - g0 : 8;
+      const int rc = bk::launch_umma_syrk_grouped(items + g0, gc, precision, mirror, st);
+      if (rc) return rc;
+    }
+    return 0;
+  };
+  // the pipeline's events are per device, not per caller: one update at a time uses them
+  static std::mutex pipe_mu;
+  std::unique_lock<std::mutex> pipe_lock(pipe_mu, std::defer_lock);
+  if (n_chunks > 1) pipe_lock.lock();
+  if (n_chunks == 1) {
+    int rc = stage_chunk(0, st);
     if (rc) return rc;
+    rc = syrk_chunk(0);
+    if (rc) return rc;
+  } else {
+    // the side stream may touch the workspace only after everything already queued on `st` (the previous
+    // update's SYRKs read the same staging buffers) ...
+    if (cudaEventRecord(pipe->fork, st) != cudaSuccess ||
+        cudaStreamWaitEvent(pipe->side, pipe->fork, 0) != cudaSuccess)
+      return BK_ERR_CUDA;
+    int rc = stage_chunk(0, st);
+    if (rc) return rc;
+    // ... and starts staging chunk 1 when chunk 0 is staged (not before: the first SYRK should not wait
+    // for a staging pass that shares HBM with two others)
+    if (cudaEventRecord(pipe->first, st) != cudaSuccess ||
+        cudaStreamWaitEvent(pipe->side, pipe->first, 0) != cudaSuccess)
+      return BK_ERR_CUDA;
+    for (int c = 1; c < n_chunks; ++c) {
+      rc = stage_chunk(c, pipe->side);
+      if (rc) return rc;
+      if (cudaEventRecord(pipe->staged[c - 1], pipe->side) != cudaSuccess) return BK_ERR_CUDA;
+    }
+    rc = syrk_chunk(0);
+    if (rc) return rc;
+    for (int c = 1; c < n_chunks; ++c) {
+      if (cudaStreamWaitEvent(st, pipe->staged[c - 1], 0) != cudaSuccess) return BK_ERR_CUDA;
+      rc = syrk_chunk(c);
+      if (rc) return rc;
+    }
   }
   for (int b = 0; b < n_borders; ++b) {
     const int rc = bk::launch_bias_border(borders[b].state, borders[b].ld, borders[b].d,
@@ -287,7 +397,7 @@ int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_state
                                  const void* const* xt_his, const void* const* xt_los,
                                  const long long* ldts, const int* ns, const int* ds,
                                  const float* alphas, const float* betas, int count, int precision,
-                                 void* stream) {
+                                 int flags, void* stream) {
   if (count <= 0) return BK_OK;
   if (count > 8 || states == nullptr || ld_states == nullptr || xt_his == nullptr ||
       ldts == nullptr || ns == nullptr || ds == nullptr || alphas == nullptr || betas == nullptr)
@@ -305,7 +415,15 @@ int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_state
     items[i].C = states[i];
     items[i].ldc = ld_states[i];
   }
-  return bk::launch_umma_syrk_grouped(items, count, precision, as_stream(stream));
+  return bk::launch_umma_syrk_grouped(items, count, precision, (flags & BK_SYRK_LOWER_ONLY) == 0,
+                                      as_stream(stream));
+}
+
+int bk_sym_finalize(float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
+                    float scale, void* stream) {
+  if (count < 0 || (count > 0 && (factors_host == nullptr || ld_host == nullptr || dims_host == nullptr)))
+    return BK_ERR_ARG;
+  return bk::launch_sym_finalize(factors_host, ld_host, dims_host, count, scale, as_stream(stream));
 }
 
 int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int c, int h, int w,

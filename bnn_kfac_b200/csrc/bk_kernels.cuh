@@ -94,6 +94,8 @@ int launch_kron(const float* a, int m, int n, const float* b, int p, int q, floa
 // ---- bk_tri.cu  (lower-triangle packing of symmetric factors for the multi-GPU exchange)
 int launch_tri_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
                     cudaStream_t stream);
+int launch_sym_finalize(float* const* mats, const long long* lds, const int* dims, int count, float scale,
+                        cudaStream_t stream);
 int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims, int count, const float* packed,
                       float scale, int mirror, cudaStream_t stream);
 

@@ -74,6 +74,41 @@ tri_unpack_kernel(const __grid_constant__ TriTable t, const float* __restrict__ 
   }
 }
 
+// In place: lower triangle (diagonal included) *= scale, upper triangle = mirror of it.  The tensor-core factor
+// update accumulates lower triangles only (bk_syrk_accum_grouped with BK_SYRK_LOWER_ONLY) and, in the
+// running-average mode, in units of a lazily applied scalar; this pass produces the full symmetric factor
+// the reference's callers read from `state` (models/curvatures.py:363), once per read instead of per update.
+__global__ void __launch_bounds__(256)
+sym_finalize_kernel(const __grid_constant__ TriTable t, float scale) {
+  __shared__ float tile[32][33];
+  const int f = blockIdx.z;
+  const int d = t.d[f];
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti || ti * 32 >= d) return;
+  float* m = t.mat[f];
+  const long long ld = t.ld[f];
+  const int j = tj * 32 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = threadIdx.y + 8 * k;
+    const int i = ti * 32 + r;
+    float v = 0.f;
+    if (i < d && j <= i) {
+      v = scale * m[static_cast<long long>(i) * ld + j];
+      if (scale != 1.f) m[static_cast<long long>(i) * ld + j] = v;
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = threadIdx.y + 8 * k;
+    const int jj = tj * 32 + r;
+    const int ii = ti * 32 + threadIdx.x;
+    if (ii < d && jj < ii) m[static_cast<long long>(jj) * ld + ii] = tile[threadIdx.x][r];
+  }
+}
+
 int run(bool pack, float* const* mats, const long long* lds, const int* dims, int count, float* packed,
         float scale, int mirror, cudaStream_t stream) {
   long long off = 0;
@@ -93,7 +128,8 @@ int run(bool pack, float* const* mats, const long long* lds, const int* dims, in
     }
     const int tiles = (dmax + 31) / 32;
     const dim3 grid(tiles, tiles, n), block(32, 8);
-    if (pack) tri_pack_kernel<<<grid, block, 0, stream>>>(t, packed);
+    if (mirror == 2) sym_finalize_kernel<<<grid, block, 0, stream>>>(t, scale);
+    else if (pack) tri_pack_kernel<<<grid, block, 0, stream>>>(t, packed);
     else tri_unpack_kernel<<<grid, block, 0, stream>>>(t, packed, scale, mirror);
     note_launch();
   }
@@ -105,6 +141,11 @@ int run(bool pack, float* const* mats, const long long* lds, const int* dims, in
 int launch_tri_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
                     cudaStream_t stream) {
   return run(true, const_cast<float* const*>(mats), lds, dims, count, packed, 1.f, 1, stream);
+}
+
+int launch_sym_finalize(float* const* mats, const long long* lds, const int* dims, int count, float scale,
+                        cudaStream_t stream) {
+  return run(false, mats, lds, dims, count, nullptr, scale, 2, stream);
 }
 
 int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims, int count, const float* packed,

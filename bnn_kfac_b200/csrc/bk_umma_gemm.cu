@@ -39,6 +39,7 @@ constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UK = 16;  // K per tcgen05.mma for 16-bit inputs
 constexpr int kAccStages = 2;
+constexpr int kSameAB = 1 << 20;  // internal flag: the A and B operands are the same buffers (SYRK)
 constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
 constexpr uint32_t kBytesA = BM * BK * 2;  // 16 KiB
@@ -56,6 +57,11 @@ struct Cfg {
   static constexpr int kStages = CG == 1 ? 4 : 6;
   static constexpr uint32_t kSmemBytes =
       kStages * kStageBytes + 4 * kEpiStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  // lower-only TMA epilogue (no mirrored tile): half the epilogue staging.  For CTA pairs this leaves
+  // ~22 KB of the SM's shared memory free, enough for a CTA of the operand-staging kernel to be
+  // co-resident (the staging of the next factors then overlaps this kernel, see bk_api.cu).
+  static constexpr uint32_t kSmemBytesLower =
+      kStages * kStageBytes + 4 * (kEpiStageBytes / 2) + 256 + 1024;
 };
 
 struct KParams {
@@ -128,6 +134,7 @@ struct GroupMaps {
 };
 struct GroupParams {
   int count, nparts;
+  int mirror;  // 1: write the transposed tile as well (full symmetric state); 0: lower triangle only
   int tile_begin[kMaxGroup + 1];
   int M[kMaxGroup], K[kMaxGroup];
   float alpha[kMaxGroup];
@@ -208,7 +215,14 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
                                           const GroupParams* gp) {
   const int num_tiles = kGrouped ? gp->tile_begin[gp->count] : p.num_tiles;
   const int nparts = kGrouped ? gp->nparts : p.nparts;
-  const int flags = kGrouped ? (kSyrkLower | kMirror) : p.flags;
+  const int flags = kGrouped ? (kSyrkLower | (gp->mirror ? kMirror : 0)) : p.flags;
+  // per-warp epilogue staging: direct + mirrored 32 x 32 tile, or the direct tile only
+  const uint32_t epi_bytes = (kTmaEpi && (flags & kSyrkLower) && !(flags & kMirror)) ? kEpiStageBytes / 2
+                                                                                    : kEpiStageBytes;
+  // SYRK tile on the diagonal of a CTA-pair schedule: the A rows and the B rows staged by each CTA are
+  // the SAME 128 rows of X^T, so only A is loaded and the B descriptor points at it (saves 1/17 of the
+  // L2 -> SM operand traffic of a 4096-wide factor)
+  const bool diag_dedup = CG == 2 && (flags & kSyrkLower) != 0 && (kGrouped || (flags & kSameAB) != 0);
   constexpr int kStages = Cfg<CG>::kStages;
   constexpr uint32_t kStageBytes = Cfg<CG>::kStageBytes;
   constexpr int kTileM = Cfg<CG>::kTileM;
@@ -218,7 +232,7 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_epi = smem + kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 4 * kEpiStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 4 * epi_bytes);
   uint64_t* full_bar = bars;                       // [kStages]   (CG=2: the leader's are used)
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;        // [kAccStages]
@@ -286,9 +300,10 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
           if (CG == 2) {
             // both CTAs' bytes complete on the LEADER's full barrier, which expects 2 stages' worth
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            const bool same = diag_dedup && tl.m0 == tl.n0 && ia == ib;
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], same ? 2 * kBytesA : 2 * kStageBytes);
             tma_load_3d_2sm(sa, ma, lbar, kb * BK, a_row, tl.b * p.a_bmul);
-            tma_load_3d_2sm(sa + kBytesA, mb, lbar, kb * BK, b_row, tl.b * p.b_bmul);
+            if (!same) tma_load_3d_2sm(sa + kBytesA, mb, lbar, kb * BK, b_row, tl.b * p.b_bmul);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
             tma_load_3d(sa, ma, &full_bar[stage], kb * BK, a_row, tl.b * p.a_bmul);
@@ -320,7 +335,13 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = umma_smem_desc_k_sw128(sa);
-          const uint64_t db = umma_smem_desc_k_sw128(sa + kBytesA);
+          bool same = false;
+          if (diag_dedup && tl.m0 == tl.n0) {
+            int ia, ib;
+            part_pair(it / tl.nkb, ia, ib);
+            same = ia == ib;
+          }
+          const uint64_t db = umma_smem_desc_k_sw128(same ? sa : sa + kBytesA);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
@@ -351,7 +372,7 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp - kEpiWarp0;  // TMEM lane quadrant == warp % 4
-    float* stg = reinterpret_cast<float*>(smem_epi + q * kEpiStageBytes);
+    float* stg = reinterpret_cast<float*>(smem_epi + q * epi_bytes);
     const bool syrk = (flags & kSyrkLower) != 0;
     const bool mirror = (flags & kMirror) != 0;
     const bool relu = (flags & kRelu) != 0;
@@ -644,6 +665,9 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.batch = a.batch;
   p.nparts = a.nparts;
   p.flags = a.flags;
+  if ((a.flags & kSyrkLower) && a.A_hi == a.B_hi && a.A_lo == a.B_lo && a.A_lo2 == a.B_lo2 &&
+      a.lda == a.ldb && a.strideA == a.strideB)
+    p.flags |= kSameAB;
   p.tiles_m = (a.M + kTileM - 1) / kTileM;
   p.tiles_n = (a.N + BN - 1) / BN;
   if (a.flags & kSyrkLower) {
@@ -718,7 +742,7 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts,
+int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, bool mirror,
                              cudaStream_t stream) {
   if (count <= 0) return 0;
   if (count > kMaxGroup || (nparts != 1 && nparts != 3)) return -2;
@@ -733,6 +757,7 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts,
   GroupParams gp{};
   gp.count = count;
   gp.nparts = nparts;
+  gp.mirror = mirror ? 1 : 0;
   int total = 0;
   for (int g = 0; g < count; ++g) {
     const SyrkGroupItem& it = items[g];
@@ -772,7 +797,7 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts,
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * 2));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+  cfg.dynamicSmemBytes = mirror ? Cfg<2>::kSmemBytes : Cfg<2>::kSmemBytesLower;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -63,7 +63,10 @@ struct SyrkGroupItem {
   long long ldc = 0;
 };
 // Up to 8 problems in one persistent CTA-pair launch (see bk_umma_gemm.cu).
-int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, cudaStream_t stream);
+// mirror = false: only the lower triangle of each C is accumulated (the caller mirrors once, when the full
+// symmetric factor is read: bk_sym_finalize).
+int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, bool mirror,
+                             cudaStream_t stream);
 
 // Tuning / bring-up knob: force the tcgen05 cta_group of the contraction core (1 or 2; 0 = automatic).
 void set_umma_cta_group(int cg);

@@ -74,6 +74,50 @@ class _Workspace:
         return self._buf
 
 
+class _FactorState(dict):
+    """`KFAC.state`: the reference's dict (module -> [A, G], models/curvatures.py:363) whose values are brought
+    up to date when they are READ.  The tensor-core factor update accumulates lower triangles only and, in the
+    running-average mode, in units of a lazily applied scalar (see KFAC.update); any public read — `state[layer]`,
+    `.get`, `.items()`, `.values()`, pickling — first runs bk_sym_finalize on the entries that need it, so callers
+    always see the full symmetric factors of the reference.  Membership tests, `len`, iteration over keys and
+    assignment (`state[layer] = [A, G]`, as the regression scripts' fixtures do) never touch the device."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def __getitem__(self, key):
+        self._owner._finalize_state(key)
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        self._owner._finalize_state()
+        return dict.items(self)
+
+    def values(self):
+        self._owner._finalize_state()
+        return dict.values(self)
+
+    def pop(self, key, *default):
+        if key in self:
+            self._owner._finalize_state(key)
+        return dict.pop(self, key, *default)
+
+    def __setitem__(self, key, value):
+        self._owner._state_assigned(key)
+        dict.__setitem__(self, key, value)
+
+    def raw(self, key):
+        """The stored tensors as they are (possibly lower-only / unscaled): for the update path."""
+        return dict.__getitem__(self, key)
+
+    def __reduce__(self):   # pickles (save(), deepcopy) as a plain, finalised dict
+        return (dict, (dict(self.items()),))
+
+
 class Curvature(ABC):
     """Base class: holds the model, a deep copy of its MAP weights, `state` and `inv_state`.
 
@@ -172,7 +216,7 @@ class Curvature(ABC):
         re-instantiating the model."""
         names = self._names()
         torch.save({
-            'state': self.state,
+            'state': dict(self.state.items()),
             'inv_state': self.inv_state,
             'model': self.model,
             'state_by_name': {names[k]: v for k, v in self.state.items() if k in names},
@@ -222,12 +266,20 @@ class Curvature(ABC):
         d.pop("_lib", None)
         d["_ws"] = None
         d["_staged"] = dict()
+        if isinstance(self.state, _FactorState):
+            d["state"] = dict(self.state.items())       # finalised, plain
+            d["_dirty"] = set()
         return d
 
     def __setstate__(self, d):
         self.__dict__.update(d)
         self._lib = _lib.load()
         self._ws = _Workspace()
+        if hasattr(self, "_dirty") and not isinstance(self.state, _FactorState):
+            st = _FactorState(self)
+            for k, v in self.state.items():
+                dict.__setitem__(st, k, v)
+            self.state = st
 
     def _next_sample_id(self) -> int:
         sid = self._sample_counter
@@ -305,8 +357,28 @@ class KFAC(Curvature):
                  layer_types: Union[List[str], str] = None,
                  *,
                  precision: str = "bf16x3",
-                 seed: int = 0):
+                 seed: int = 0,
+                 averaging: str = "sum",
+                 decay: float = 0.95,
+                 lower_only: bool = True):
+        """averaging="sum" (default) is the reference: `state` is the plain sum of the per-batch factors
+        (models/curvatures.py:359-363).  averaging="ema" keeps an exponential running average instead,
+            state_1 = F_1,   state_t = decay * state_{t-1} + (1 - decay) * F_t,
+        at no extra cost per update: the accumulators hold state / c with c = decay^(t-1), a new batch is
+        added with weight (1 - decay) / c by the same `+=` kernels, and c is applied when `state` is read
+        (bk_sym_finalize; also whenever c drops below 2^-20, i.e. every ~14 / (1 - decay) updates).
+        lower_only: the tensor-core SYRK accumulates lower triangles only and `state` reads mirror them
+        (halves the epilogue's reduction traffic per update); False restores the mirrored epilogue."""
         super().__init__(model, layer_types, precision=precision, seed=seed)
+        if averaging not in ("sum", "ema"):
+            raise ValueError('averaging must be "sum" or "ema"')
+        if averaging == "ema" and not (0.0 < decay < 1.0):
+            raise ValueError("decay must lie in (0, 1)")
+        self.averaging, self.decay, self.lower_only = averaging, float(decay), bool(lower_only)
+        self.state = _FactorState(self)
+        self._dirty = set()     # layers whose wide factors currently hold a valid LOWER triangle only
+        self._scale = 1.0       # state = _scale * stored accumulators (running-average mode)
+        self._n_updates = 0
         self.hooks = list()
         self.record = dict()
         self._pending = []
@@ -328,6 +400,39 @@ class KFAC(Curvature):
         # reference stores grad_output[0] * N (curvatures.py:323); the factor N is applied inside the
         # factor kernel instead (in_scale), see update().
         self.record[module][1] = grad_output[0]
+
+    # ------------------------------------------------------------------ lazy state
+    def _raw(self, layer):
+        st = self.state
+        return st.raw(layer) if isinstance(st, _FactorState) else st[layer]
+
+    def _raw_items(self):
+        return dict.items(self.state)
+
+    def _state_assigned(self, key):
+        """A caller replaces `state[key]`: the new tensors are complete and unscaled."""
+        if self._scale != 1.0:
+            self._finalize_state()
+        self._dirty.discard(key)
+
+    def _finalize_state(self, key=None):
+        """Mirror the lower-only accumulators (and apply the running-average scale) in place."""
+        if self._scale == 1.0:
+            todo = [k for k in ([key] if key is not None else list(self._dirty)) if k in self._dirty]
+        else:
+            todo = list(dict.keys(self.state))      # the scale is one scalar for the whole estimator
+        if not todo:
+            return
+        tensors = [t for k in todo for t in self._raw(k)]
+        n = len(tensors)
+        mats = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        lds = (C.c_longlong * n)(*[t.stride(0) for t in tensors])
+        dims = (C.c_int * n)(*[t.shape[0] for t in tensors])
+        _lib.check(self._lib.bk_sym_finalize(mats, lds, dims, n, float(self._scale), _lib.stream_ptr()),
+                   "bk_sym_finalize")
+        for k in todo:
+            self._dirty.discard(k)
+        self._scale = 1.0
 
     # ------------------------------------------------------------------ factor update
     def _syrk(self, state: Tensor, beta: float, x: Tensor, has_bias: bool, in_scale: float,
@@ -355,8 +460,9 @@ class KFAC(Curvature):
         insc = (C.c_float * n)(*[it[4] for it in items])
         alph = (C.c_float * n)(*[it[5] for it in items])
         beta = (C.c_float * n)(*[it[1] for it in items])
+        flags = _lib.SYRK_LOWER_ONLY if self.lower_only else 0
         _lib.check(self._lib.bk_syrk_accum_grouped(states, lds, xs, ldx, ns, ds, hb, insc, alph, beta, n, prec,
-                                                   ws.data_ptr(), nbytes, _lib.stream_ptr()),
+                                                   flags, ws.data_ptr(), nbytes, _lib.stream_ptr()),
                    "bk_syrk_accum_grouped")
 
     def update(self, batch_size: int = None):
@@ -364,6 +470,15 @@ class KFAC(Curvature):
         g = grad_output * N (curvatures.py:325-365).  `batch_size` is ignored, as in the reference."""
         del batch_size
         self._pending = []
+        # weight of this batch in units of the stored accumulators (see __init__): 1 for the plain sum
+        w = 1.0
+        if self.averaging == "ema" and self._n_updates > 0:
+            if self._scale * self.decay < 2.0 ** -20:
+                self._finalize_state()
+            self._scale *= self.decay
+            w = (1.0 - self.decay) / self._scale
+        self._n_updates += 1
+        wide_mode = self.lower_only and self.precision != "fp32"
         for _, layer in self._selected_layers():
             module_class = layer.__class__.__name__
             forward, backward = self.record[layer]
@@ -382,7 +497,7 @@ class KFAC(Curvature):
                 d_a = forward.shape[1] + int(has_bias)
                 d_g = backward.shape[1]
             if layer in self.state:
-                first, second = self.state[layer]
+                first, second = self._raw(layer)
                 beta = 1.0
             else:
                 first = _alloc_factor(d_a, forward.device)
@@ -390,47 +505,49 @@ class KFAC(Curvature):
                 self.state[layer] = [first, second]
                 beta = 0.0
             if module_class == 'Conv2d':
-                self._update_conv(layer, forward, backward, first, second, beta, has_bias, n_batch)
+                self._update_conv(layer, forward, backward, first, second, beta, has_bias, n_batch, w)
             else:
                 x = forward.float().contiguous()
                 g = backward.float().contiguous()
-                self._syrk(first, beta, x, has_bias, 1.0, 1.0 / x.shape[0])
-                self._syrk(second, beta, g, False, float(n_batch), 1.0 / g.shape[0])
+                self._syrk(first, beta, x, has_bias, 1.0, w / x.shape[0])
+                self._syrk(second, beta, g, False, float(n_batch), w / g.shape[0])
+            if wide_mode and max(d_a, d_g) > _lib.BK_SMALL_D_MAX:
+                self._dirty.add(layer)      # the tensor-core SYRK leaves the upper triangle stale
         self._flush_syrks()
 
-    def _update_conv(self, layer, forward, backward, first, second, beta, has_bias, n_batch):
+    def _update_conv(self, layer, forward, backward, first, second, beta, has_bias, n_batch, w=1.0):
         st = _lib.stream_ptr()
         x = forward.float().contiguous()
         g = backward.float().contiguous()
-        n, c, h, w = x.shape
+        n, c, h, wd = x.shape
         kh, kw = layer.kernel_size
         ph, pw = layer.padding if not isinstance(layer.padding, str) else (0, 0)
         sh, sw = layer.stride
         if isinstance(layer.padding, str) or tuple(layer.dilation) != (1, 1) or layer.groups != 1:
             raise NotImplementedError("Conv2d with string padding, dilation or groups")
         oh = (h + 2 * ph - kh) // sh + 1
-        ow = (w + 2 * pw - kw) // sw + 1
+        ow = (wd + 2 * pw - kw) // sw + 1
         cols = n * oh * ow
         d_a = first.shape[0]
         if d_a <= _lib.BK_SMALL_D_MAX:
             _lib.check(self._lib.bk_conv_a_accum(first.data_ptr(), first.stride(0), x.data_ptr(), n, c,
-                                                 h, w, kh, kw, ph, pw, sh, sw, int(has_bias),
-                                                 1.0 / cols, beta, st), "bk_conv_a_accum")
+                                                 h, wd, kh, kw, ph, pw, sh, sw, int(has_bias),
+                                                 w / cols, beta, st), "bk_conv_a_accum")
         else:
             # wide conv layers: explicit patch matrix [N*L, C*kh*kw] staged once, tensor-core SYRK
             u = torch.nn.functional.unfold(x, (kh, kw), padding=(ph, pw), stride=(sh, sw))
             u = u.permute(0, 2, 1).reshape(cols, -1).contiguous()
-            self._syrk(first, beta, u, has_bias, 1.0, 1.0 / cols)
+            self._syrk(first, beta, u, has_bias, 1.0, w / cols)
         o = g.shape[1]
         hw = g.shape[2] * g.shape[3]
         gcols = n * hw
         if o <= _lib.BK_SMALL_D_MAX:
             _lib.check(self._lib.bk_conv_g_accum(second.data_ptr(), second.stride(0), g.data_ptr(), n, o,
-                                                 hw, float(n_batch), 1.0 / gcols, beta, st),
+                                                 hw, float(n_batch), w / gcols, beta, st),
                        "bk_conv_g_accum")
         else:
             g2 = g.permute(0, 2, 3, 1).reshape(gcols, o).contiguous()
-            self._syrk(second, beta, g2, False, float(n_batch), 1.0 / gcols)
+            self._syrk(second, beta, g2, False, float(n_batch), w / gcols)
 
     # ------------------------------------------------------------------ inversion
     def invert(self, add: Union[float, list, tuple] = 0., multiply: Union[float, list, tuple] = 1.):
@@ -456,6 +573,23 @@ class KFAC(Curvature):
 
     def _invalidate_caches(self):
         self._staged = dict()
+
+    def _adopt_loaded_state(self):
+        """`load` / `load_by_name` replaced `state` by a plain dict of complete factors."""
+        st = _FactorState(self)
+        for k, v in self.state.items():
+            dict.__setitem__(st, k, v)
+        self.state = st
+        self._dirty = set()
+        self._scale = 1.0
+
+    def load(self, filename):
+        super().load(filename)
+        self._adopt_loaded_state()
+
+    def load_by_name(self, filename):
+        super().load_by_name(filename)
+        self._adopt_loaded_state()
 
     # ------------------------------------------------------------------ sampling
     def _staged_factors(self, layer):

@@ -160,15 +160,24 @@ def reduce_state_copy(est, group=None) -> List[Tensor]:
     of 470 MB; measured dense on 2 x B200: 1.35 ms, against 4.1 ms for per-owner `reduce` calls).
     CPU tensors (gloo tests of the host logic) and non-square states take the dense flat-buffer path."""
     w = world_size(group)
+    # KFAC keeps lower-only (and, in the running-average mode, lazily scaled) accumulators between reads of
+    # `state` (curvatures._FactorState): the packed exchange needs exactly the lower triangles, so it reads them
+    # raw and folds the scale into the unpack instead of paying a mirror pass first
+    raw_items = getattr(est, "_raw_items", None)
+    scale = float(getattr(est, "_scale", 1.0)) if raw_items is not None else 1.0
+    values = [v for _, v in raw_items()] if raw_items is not None else list(est.state.values())
     factors: List[Tensor] = []
-    for v in est.state.values():
+    for v in values:
         factors += list(v) if isinstance(v, (list, tuple)) else [v]
     if not factors:
         return []
     square = all(f.dim() == 2 and f.shape[0] == f.shape[1] and f.stride(1) == 1 and f.dtype == torch.float32
                  for f in factors)
-    if not (factors[0].is_cuda and square and isinstance(next(iter(est.state.values())), (list, tuple))):
-        # one flat buffer, one collective: the copies are the send buffer
+    if not (factors[0].is_cuda and square and isinstance(values[0], (list, tuple))):
+        # one flat buffer, one collective: the copies are the send buffer (complete factors needed)
+        factors = []
+        for v in est.state.values():
+            factors += list(v) if isinstance(v, (list, tuple)) else [v]
         flat, reduced = _flat_views(factors)
         if w > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
@@ -190,7 +199,7 @@ def reduce_state_copy(est, group=None) -> List[Tensor]:
     outs = [torch.empty(f.shape[0], f.shape[0], dtype=torch.float32, device=f.device) for f in factors]
     dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
     ldo = (C.c_longlong * n)(*[o.stride(0) for o in outs])
-    _lib.check(lib.bk_tri_unpack(dst, ldo, dims, n, packed.data_ptr(), 1.0 / w, 1, st), "bk_tri_unpack")
+    _lib.check(lib.bk_tri_unpack(dst, ldo, dims, n, packed.data_ptr(), scale / w, 1, st), "bk_tri_unpack")
     return outs
 
 
@@ -254,14 +263,15 @@ def invert_sharded(est, add=0., multiply=1., group=None,
             n, s = add[index], multiply[index]
         else:
             n, s = float(add), float(multiply)
-        first, second = est.state[layer]
+        # shapes only here: a raw read does not trigger the mirror pass of KFAC's lazy `state`
+        first, second = est._raw(layer) if hasattr(est, "_raw") else est.state[layer]
         factors += [first, second]
         adds += [float(n)] * 2
         mults += [float(s)] * 2
     owners = plan_owners([f.shape[0] for f in factors], w)
     if keep_state_replicated:
         allreduce_state(est, group)
-        reduced = factors
+        reduced = [t for layer in layers for t in est.state[layer]]
     else:
         # reduce scratch copies so that the local partial `state` stays a valid accumulator
         reduced = reduce_state_copy(est, group)

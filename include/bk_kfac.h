@@ -109,17 +109,31 @@ int bk_syrk_accum(float* state, long long ld_state, const float* x, long long ld
  * others take the bk_syrk_accum route one by one. */
 size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* has_bias, int count,
                                        int precision);
+/* flags:
+ *   BK_SYRK_LOWER_ONLY  the tensor-core items accumulate the LOWER triangle only (diagonal included); the upper
+ *                       triangle of those states is unspecified until bk_sym_finalize mirrors it.  Saves the
+ *                       mirrored half of the epilogue's L2 reduction traffic on every update.
+ *   BK_SYRK_NO_OVERLAP  stage every operand first, then run the SYRKs (default: the staging of later factors
+ *                       runs on an internal per-device side stream underneath the SYRK of earlier ones; the
+ *                       call is still ordered on `stream` as a whole). */
+#define BK_SYRK_LOWER_ONLY 1
+#define BK_SYRK_NO_OVERLAP 2
 int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const float* const* xs,
                           const long long* ldxs, const int* ns, const int* ds, const int* has_bias,
                           const float* in_scales, const float* alphas, const float* betas, int count,
-                          int precision, void* workspace, size_t workspace_bytes, void* stream);
+                          int precision, int flags, void* workspace, size_t workspace_bytes, void* stream);
+/* In place: lower triangle (diagonal included) *= scale, upper triangle = its mirror: turns lower-only
+ * (and, for the running-average mode, lazily scaled) accumulators into the full symmetric factors the
+ * reference keeps in `state` (models/curvatures.py:359-363).  Host arrays of device pointers, as bk_tri_pack. */
+int bk_sym_finalize(float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
+                    float scale, void* stream);
 /* The grouped tensor-core launch alone, on operands already staged as K-major bf16 [d, n] (no bias
- * row): up to 8 problems, states 16 B aligned with ld % 4 == 0, beta in {0, 1}. */
+ * row): up to 8 problems, states 16 B aligned with ld % 4 == 0, beta in {0, 1}; flags as above. */
 int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_states,
                                  const void* const* xt_his, const void* const* xt_los,
                                  const long long* ldts, const int* ns, const int* ds,
                                  const float* alphas, const float* betas, int count, int precision,
-                                 void* stream);
+                                 int flags, void* stream);
 /* Same, operand already staged as K-major bf16 [d+has_bias, n] (e.g. by bk_transpose_split). */
 int bk_syrk_accum_staged(float* state, long long ld_state, const void* xt_hi, const void* xt_lo,
                          long long ldt, int n, int dprime, float alpha, float beta, int precision,

@@ -125,8 +125,12 @@ class OracleKFAC:
     """Hook-driven KFAC on a CPU model: same observable behaviour as the reference class
     (models/curvatures.py:295-405), composed from the functions above."""
 
-    def __init__(self, model: torch.nn.Module):
+    def __init__(self, model: torch.nn.Module, averaging: str = "sum", decay: float = 0.95):
+        """averaging="sum": the reference (curvatures.py:359-363).  averaging="ema" is NOT in the reference
+        (BASELINE.json's north_star asks for a "fused running-average update"): state_1 = F_1,
+        state_t = decay * state_{t-1} + (1 - decay) * F_t — the definition the CUDA path is tested against."""
         self.model = model
+        self.averaging, self.decay = averaging, decay
         self.layers = selected_layers(model)
         self.record: Dict[torch.nn.Module, list] = {m: [None, None] for m in self.layers}
         self.state: Dict[torch.nn.Module, list] = {}
@@ -151,7 +155,10 @@ class OracleKFAC:
                 f1, f2 = kfac_conv_factors(a, g, m.kernel_size, m.padding, m.stride, m.bias is not None)
             else:
                 f1, f2 = kfac_linear_factors(a, g, m.bias is not None)
-            if m in self.state:
+            if m in self.state and self.averaging == "ema":
+                self.state[m][0] = self.decay * self.state[m][0] + (1 - self.decay) * f1
+                self.state[m][1] = self.decay * self.state[m][1] + (1 - self.decay) * f2
+            elif m in self.state:
                 self.state[m][0] += f1
                 self.state[m][1] += f2
             else:

@@ -329,6 +329,71 @@ def test_predictive_moments_centred_kernel(dev):
     assert relerr(var.cpu(), yd.var(0, unbiased=False).cpu()) < 1e-3
 
 
+# ------------------------------------------------------------------------------------------ running average
+@pytest.mark.parametrize("decay", [0.95, 0.5])
+def test_running_average_update_vs_oracle(dev, decay):
+    """averaging="ema" (north_star's fused running-average update): state_t = decay state_{t-1} + (1 - decay) F_t
+    realised as lazily scaled `+=` accumulation (no extra pass per update).  8 updates of an MLP with a tensor-core
+    sized and a SIMT sized layer + one conv net, read mid-way (forces a finalize) and at the end; decay 0.5 with a
+    forced renormalisation threshold crossing is covered by 8 halvings of the scale."""
+    from bnn_kfac_b200.curvatures import KFAC
+    from bnn_kfac_b200.wrapper import MLP as WMLP, BaseNet_750
+    for ctor, shape in ((lambda: WMLP([300, 260, 10]), (64, 300)), (BaseNet_750, (32, 1, 28, 28))):
+        torch.manual_seed(0)
+        cm = ctor().double()
+        cm.weight_init_uniform(0.1)
+        gm = ctor()
+        gm.load_state_dict({k: v.float() for k, v in cm.state_dict().items()})
+        gm = gm.to(dev)
+        oest = O.OracleKFAC(cm, averaging="ema", decay=decay)
+        gest = KFAC(gm, averaging="ema", decay=decay)
+        gen = torch.Generator().manual_seed(4)
+        for t in range(8):
+            xb = torch.rand(*shape, generator=gen)
+            labels = O.fisher_backward(cm, xb.double(), generator=gen)
+            oest.update()
+            _fisher_step(gm, xb.to(dev), labels.to(dev))
+            gest.update(shape[0])
+            if t in (2, 7):
+                for ol, gl in zip(oest.layers, _layers(gest)):
+                    for k in range(2):
+                        got = gest.state[gl][k]
+                        assert relerr(got.cpu(), oest.state[ol][k]) < 1e-5, (t, k)
+                        assert (got - got.t()).abs().max().item() == 0.0
+        oest.invert(0.5, 50.0)
+        gest.invert(0.5, 50.0)
+        for ol, gl in zip(oest.layers, _layers(gest)):
+            for k in range(2):
+                assert relerr(gest.inv_state[gl][k].cpu(), oest.inv_state[ol][k]) < TOL
+
+
+def test_lower_only_state_reads_and_mirrored_mode_agree(dev):
+    """`state` reads of the lower-only accumulators (default) equal the mirrored-epilogue mode bit for bit in the
+    lower triangle, are exactly symmetric, survive further updates after a read, and save()/load() round-trips the
+    finalised factors."""
+    from bnn_kfac_b200.curvatures import KFAC
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(512, 384).to(dev)
+    model = torch.nn.Sequential(lin)
+    ests = [KFAC(model, lower_only=True), KFAC(model, lower_only=False)]
+    gen = torch.Generator().manual_seed(1)
+    for t in range(3):
+        x = torch.randn(256, 512, generator=gen).to(dev)
+        _fisher_step(model, x, torch.randint(0, 384, (256,), generator=gen).to(dev))
+        for e in ests:
+            e.update(256)
+        if t == 1:
+            A0 = ests[0].state[lin][0].clone()          # read in the middle, then keep accumulating
+            assert (A0 - A0.t()).abs().max().item() == 0.0
+    (A0, G0), (A1, G1) = ests[0].state[lin], ests[1].state[lin]
+    assert torch.equal(torch.tril(A0), torch.tril(A1)) and torch.equal(torch.tril(G0), torch.tril(G1))
+    assert (A0 - A0.t()).abs().max().item() == 0.0 and (G0 - G0.t()).abs().max().item() == 0.0
+    assert relerr(A0.cpu(), A1.cpu()) < 1e-7
+    for e in ests:
+        for h in e.hooks:
+            h.remove()
+
+
 # ------------------------------------------------------------------------------------------ (f) NCCL parity
 def test_nccl_two_rank_parity():
     """Sharded accumulation + invert_sharded + mc_predict_sharded over NCCL on 2 GPUs must reproduce the

@@ -206,27 +206,39 @@ def t_syrk_edges():
     # grouped call with mixed shapes (wide + small + unaligned)
     shapes = [(64, 400, 1), (64, 256, 0), (64, 20, 1), (50, 301, 1), (64, 1024, 1)]
     xs = [torch.randn(n_, d_, generator=g).to(dev) for n_, d_, _ in shapes]
-    sts = []
-    for (n_, d_, hb_) in shapes:
-        dp = d_ + hb_
-        pitch = (dp + 3) // 4 * 4 if dp > 176 else dp
-        sts.append(torch.zeros(dp, pitch, device=dev)[:, :dp])
     cnt = len(shapes)
     ns = (C.c_int * cnt)(*[s_[0] for s_ in shapes]); ds = (C.c_int * cnt)(*[s_[1] for s_ in shapes])
     hbs = (C.c_int * cnt)(*[s_[2] for s_ in shapes])
     nb = L.bk_syrk_grouped_workspace_bytes(ns, ds, hbs, cnt, 3)
     ws = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
-    for beta in (0.0, 1.0):
-        rc = L.bk_syrk_accum_grouped((C.c_void_p * cnt)(*[t.data_ptr() for t in sts]),
-                                     (C.c_longlong * cnt)(*[t.stride(0) for t in sts]),
-                                     (C.c_void_p * cnt)(*[t.data_ptr() for t in xs]),
-                                     (C.c_longlong * cnt)(*[t.stride(0) for t in xs]), ns, ds, hbs,
-                                     (C.c_float * cnt)(*[1.0] * cnt), (C.c_float * cnt)(*[1.0 / s_[0] for s_ in shapes]),
-                                     (C.c_float * cnt)(*[beta] * cnt), cnt, 3, ws.data_ptr(), nb, _lib.stream_ptr())
-        _lib.check(rc, "bk_syrk_accum_grouped")
-    torch.cuda.synchronize()
-    for (n_, d_, hb_), x_, st_ in zip(shapes, xs, sts):
-        report(f"grouped syrk n={n_} d={d_} bias={hb_} (beta 0 then 1)", relerr(st_, 2 * syrk_ref(x_, hb_, 1.0, 1.0 / n_)), 3e-5)
+    # flags: 0 = mirrored epilogue, staging overlapped; 1 = lower-only (+ bk_sym_finalize); 3 = lower-only, no overlap
+    for flags in (0, 1, 3, 2):
+        sts = []
+        for (n_, d_, hb_) in shapes:
+            dp = d_ + hb_
+            pitch = (dp + 3) // 4 * 4 if dp > 176 else dp
+            sts.append(torch.zeros(dp, pitch, device=dev)[:, :dp])
+        for beta in (0.0, 1.0):
+            rc = L.bk_syrk_accum_grouped((C.c_void_p * cnt)(*[t.data_ptr() for t in sts]),
+                                         (C.c_longlong * cnt)(*[t.stride(0) for t in sts]),
+                                         (C.c_void_p * cnt)(*[t.data_ptr() for t in xs]),
+                                         (C.c_longlong * cnt)(*[t.stride(0) for t in xs]), ns, ds, hbs,
+                                         (C.c_float * cnt)(*[1.0] * cnt), (C.c_float * cnt)(*[1.0 / s_[0] for s_ in shapes]),
+                                         (C.c_float * cnt)(*[beta] * cnt), cnt, 3, flags, ws.data_ptr(), nb,
+                                         _lib.stream_ptr())
+            _lib.check(rc, "bk_syrk_accum_grouped")
+        scale = 1.0
+        if flags & 1:
+            scale = 0.5
+            _lib.check(L.bk_sym_finalize((C.c_void_p * cnt)(*[t.data_ptr() for t in sts]),
+                                         (C.c_longlong * cnt)(*[t.stride(0) for t in sts]),
+                                         (C.c_int * cnt)(*[t.shape[0] for t in sts]), cnt, scale, _lib.stream_ptr()),
+                       "bk_sym_finalize")
+        torch.cuda.synchronize()
+        for (n_, d_, hb_), x_, st_ in zip(shapes, xs, sts):
+            report(f"grouped syrk flags={flags} n={n_} d={d_} bias={hb_} (beta 0 then 1)",
+                   relerr(st_, 2 * scale * syrk_ref(x_, hb_, 1.0, 1.0 / n_)), 3e-5)
+            report(f"grouped syrk flags={flags} d={d_} symmetric", (st_ - st_.t()).abs().max().item(), 0.0)
 
 
 def t_chol_small():
