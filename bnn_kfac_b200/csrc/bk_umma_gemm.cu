@@ -135,6 +135,14 @@ struct GroupMaps {
 struct GroupParams {
   int count, nparts;
   int mirror;  // 1: write the transposed tile as well (full symmetric state); 0: lower triangle only
+  // stream-K schedule: the launch's work is the concatenation of every tile's main-loop iterations
+  // (iters[g] = k-blocks x precision passes per tile of problem g); cluster c of P processes iterations
+  // [c W / P, (c + 1) W / P) of it, rounded to kWorkGrain, wherever the tile boundaries fall.  A tile cut
+  // by a boundary is finished by two clusters; both add their partial sums to C through the TMA reduction,
+  // so no fix-up pass exists and every cluster carries the same load (no wave quantisation: 136 tiles per
+  // 4096-wide factor on 74 CTA pairs would otherwise idle 8 % of a one-factor launch).
+  int iters[kMaxGroup];
+  int work_begin[kMaxGroup + 1];
   int tile_begin[kMaxGroup + 1];
   int M[kMaxGroup], K[kMaxGroup];
   float alpha[kMaxGroup];
@@ -174,6 +182,8 @@ __device__ __forceinline__ void part_pair(int part, int& ia, int& ib) {
   ib = (part == 1) ? 1 : (part == 3) ? 2 : (part == 5) ? 1 : 0;
 }
 
+constexpr int kWorkGrain = 8;  // stream-K boundaries are multiples of this many main-loop iterations
+
 // Per-tile view of "which problem": tensor maps, extents and scale.
 struct Work {
   Tile tl;
@@ -209,6 +219,61 @@ __device__ __forceinline__ Work get_work(int t, const KParams& p, const OpMaps* 
   }
   return w;
 }
+
+// One unit of work of a role loop: main-loop iterations [it0, it1) of one output tile.
+struct Seg {
+  Work wk;
+  int it0, it1;
+};
+
+// Enumerates the segments of this cluster: whole tiles round-robin (single problems) or its stream-K range
+// (grouped SYRK).  Every role (producer, MMA, epilogue) walks its own copy and sees the same sequence.
+template <int CG, bool kGrouped>
+struct WorkIter {
+  const KParams& p;
+  const OpMaps* om;
+  const GroupMaps* gm;
+  const GroupParams* gp;
+  int nparts;
+  int t, step, num_tiles;  // tile striding
+  int u, u_end;            // stream-K cursor (iterations)
+  __device__ __forceinline__ WorkIter(const KParams& p_, const OpMaps* om_, const GroupMaps* gm_,
+                                      const GroupParams* gp_, int nparts_, int first, int step_,
+                                      int num_tiles_)
+      : p(p_), om(om_), gm(gm_), gp(gp_), nparts(nparts_), t(first), step(step_), num_tiles(num_tiles_) {
+    u = u_end = 0;
+    if (kGrouped) {
+      const long long W = gp->work_begin[gp->count];
+      long long a = W * first / step, b = W * (first + 1) / step;
+      a -= a % kWorkGrain;
+      if (first + 1 < step) b -= b % kWorkGrain;
+      u = static_cast<int>(a);
+      u_end = static_cast<int>(b);
+    }
+  }
+  __device__ __forceinline__ bool next(Seg& s) {
+    if (kGrouped) {
+      if (u >= u_end) return false;
+      int g = 0;
+      while (u >= gp->work_begin[g + 1]) ++g;
+      const int iters = gp->iters[g];
+      const int rel = u - gp->work_begin[g];
+      const int tile = rel / iters;
+      s.it0 = rel - tile * iters;
+      const int n = min(iters - s.it0, u_end - u);
+      s.it1 = s.it0 + n;
+      u += n;
+      s.wk = get_work<CG, true>(gp->tile_begin[g] + tile, p, om, gm, gp);
+      return true;
+    }
+    if (t >= num_tiles) return false;
+    s.wk = get_work<CG, false>(t, p, om, gm, gp);
+    s.it0 = 0;
+    s.it1 = s.wk.tl.nkb * nparts;
+    t += step;
+    return true;
+  }
+};
 
 template <int CG, bool kTmaEpi, bool kGrouped>
 __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, const GroupMaps* gm,
@@ -281,14 +346,15 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = first_tile; t < num_tiles; t += tile_step) {
-        const Work wk = get_work<CG, kGrouped>(t, p, om, gm, gp);
+      WorkIter<CG, kGrouped> wi(p, om, gm, gp, nparts, first_tile, tile_step, num_tiles);
+      Seg sg;
+      while (wi.next(sg)) {
+        const Work& wk = sg.wk;
         const Tile tl = wk.tl;
-        const int iters = tl.nkb * nparts;
         // this CTA's slice of the cluster tile: its own 128 rows of A, its share of the B rows
         const int a_row = tl.m0 + static_cast<int>(cta_rank) * BM;
         const int b_row = tl.n0 + static_cast<int>(cta_rank) * kRowsB;
-        for (int it = 0; it < iters; ++it) {
+        for (int it = sg.it0; it < sg.it1; ++it) {
           const int part = it / tl.nkb;
           const int kb = tl.kb0 + it - part * tl.nkb;
           int ia, ib;
@@ -324,13 +390,14 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = first_tile; t < num_tiles; t += tile_step) {
-        const Tile tl = get_work<CG, kGrouped>(t, p, om, gm, gp).tl;
-        const int iters = tl.nkb * nparts;
+      WorkIter<CG, kGrouped> wi(p, om, gm, gp, nparts, first_tile, tile_step, num_tiles);
+      Seg sg;
+      while (wi.next(sg)) {
+        const Tile tl = sg.wk.tl;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int it = 0; it < iters; ++it) {
+        for (int it = sg.it0; it < sg.it1; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -347,10 +414,12 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
             // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
             if (CG == 2)
               umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(k * 2),
-                               db + static_cast<uint64_t>(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+                               db + static_cast<uint64_t>(k * 2), idesc,
+                               (it != sg.it0 || k != 0) ? 1u : 0u);
             else
               umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2),
-                           db + static_cast<uint64_t>(k * 2), idesc, (it | k) != 0 ? 1u : 0u);
+                           db + static_cast<uint64_t>(k * 2), idesc,
+                           (it != sg.it0 || k != 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
           if (CG == 2) umma_commit_2sm(&empty_bar[stage], 3);
@@ -380,8 +449,10 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader0 = (CG == 2) ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u;
-    for (int t = first_tile; t < num_tiles; t += tile_step) {
-      const Work wk = get_work<CG, kGrouped>(t, p, om, gm, gp);
+    WorkIter<CG, kGrouped> wi(p, om, gm, gp, nparts, first_tile, tile_step, num_tiles);
+    Seg sg;
+    while (wi.next(sg)) {
+      const Work& wk = sg.wk;
       const Tile tl = wk.tl;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -759,6 +830,7 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
   gp.nparts = nparts;
   gp.mirror = mirror ? 1 : 0;
   int total = 0;
+  long long work = 0;
   for (int g = 0; g < count; ++g) {
     const SyrkGroupItem& it = items[g];
     if (it.X_hi == nullptr || it.C == nullptr || it.d <= 0 || it.n <= 0) return -2;
@@ -781,12 +853,18 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
       return -5;
     const int tm = (it.d + 255) / 256;
     gp.tile_begin[g] = total;
+    gp.iters[g] = (it.n + BK - 1) / BK * nparts;
+    gp.work_begin[g] = work;
+    work += static_cast<long long>(tm) * (tm + 1) / 2 * gp.iters[g];
+    if (work > 0x7fffffffLL) return -2;
     total += tm * (tm + 1) / 2;
     gp.M[g] = it.d;
     gp.K[g] = it.n;
     gp.alpha[g] = it.alpha;
   }
   for (int g = count; g <= kMaxGroup; ++g) gp.tile_begin[g] = total;
+  for (int g = count; g <= kMaxGroup; ++g) gp.work_begin[g] = static_cast<int>(work);
+  for (int g = count; g < kMaxGroup; ++g) gp.iters[g] = 1;
   for (int g = count; g < kMaxGroup; ++g) {
     maps.a0[g] = maps.a0[0];
     maps.a1[g] = maps.a1[0];
