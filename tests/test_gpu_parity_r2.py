@@ -110,9 +110,9 @@ def test_spd_inverse_f64_and_quadform_vs_numpy(dev):
     Q = torch.randn(dinp, dinp, generator=g, dtype=torch.float64)
     H = torch.randn(dout, dout, generator=g, dtype=torch.float64)
     out = torch.full((B,), 2.0, device=dev)
-    Vd = V.to(dev)
-    _lib.check(lib.bk_kron_quadform_f64(Vd.data_ptr(), dinp * dout, B, dinp, dout, Q.to(dev).data_ptr(),
-                                        H.to(dev).data_ptr(), out.data_ptr(), 1, _lib.stream_ptr()), "quadform")
+    Vd, Qd, Hd = V.to(dev), Q.to(dev), H.to(dev)
+    _lib.check(lib.bk_kron_quadform_f64(Vd.data_ptr(), dinp * dout, B, dinp, dout, Qd.data_ptr(),
+                                        Hd.data_ptr(), out.data_ptr(), 1, _lib.stream_ptr()), "quadform")
     ref = 2.0 + torch.einsum("bik,ij,bjl,kl->b", V.double(), Q, V.double(), H).abs()
     assert relerr(out.cpu(), ref) < 1e-6
 
