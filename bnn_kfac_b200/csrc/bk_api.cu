@@ -41,6 +41,8 @@ int bk_device_check(void) {
 
 void bk_set_cta_group(int cta_group) { bk::set_umma_cta_group(cta_group); }
 
+void bk_set_syrk_tuning(int flags) { bk::set_syrk_tuning(flags); }
+
 void bk_set_eigh_mode(int mode) { bk::set_eigh_mode(mode); }
 
 void bk_set_eigh_pair_width(int width) { bk::set_eigh_pair_width(width); }

@@ -146,6 +146,7 @@ struct GroupParams {
   // 3-factor launch reads 708 MB instead of 100 MB from DRAM.)
   int iters[kMaxGroup];
   int full_tiles, tail_work;
+  int no_dedup;
   int tile_begin[kMaxGroup + 1];
   int M[kMaxGroup], K[kMaxGroup];
   float alpha[kMaxGroup];
@@ -297,7 +298,8 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
   // SYRK tile on the diagonal of a CTA-pair schedule: the A rows and the B rows staged by each CTA are
   // the SAME 128 rows of X^T, so only A is loaded and the B descriptor points at it (saves 1/17 of the
   // L2 -> SM operand traffic of a 4096-wide factor)
-  const bool diag_dedup = CG == 2 && (flags & kSyrkLower) != 0 && (kGrouped || (flags & kSameAB) != 0);
+  const bool diag_dedup = CG == 2 && (flags & kSyrkLower) != 0 &&
+                          (kGrouped ? gp->no_dedup == 0 : (flags & kSameAB) != 0);
   constexpr int kStages = Cfg<CG>::kStages;
   constexpr uint32_t kStageBytes = Cfg<CG>::kStageBytes;
   constexpr int kTileM = Cfg<CG>::kTileM;
@@ -351,55 +353,82 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // The two single-thread role loops below are the critical path of the kernel: one iteration per 64-wide
+  // k-block, i.e. per 512 tensor-core cycles.  (Measured, profiles/r02_syrk_role_loops.md: with ~110 SASS
+  // instructions per iteration — an integer division for the precision pass, operand-map lookups through
+  // local memory, descriptor re-encoding — the producer and the MMA issuer were ISSUE-bound and held the
+  // tensor pipe at 56 % active.)  Everything that is constant per tile or per precision pass is hoisted; the
+  // hot loops work on raw shared-memory addresses.
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full_base = smem_u32(full_bar);
+  const uint32_t empty_base = smem_u32(empty_bar);
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    // The WHOLE warp walks the loop (warp-uniform control flow and addresses stay in uniform registers);
+    // one elected lane issues.  Under `if (lane == 0)` every operand of every TMA / MMA instruction went
+    // through an ELECT + R2UR.BROADCAST waterfall: ~20 extra instructions per issued instruction.
+    {
+      uint32_t stage = 0, phase = 0;
+      // CTA pairs: both CTAs' bytes complete on the LEADER's full barrier, which expects 2 stages' worth
+      const uint32_t lfull_base = (CG == 2) ? mapa_u32(full_base, 0) : full_base;
       WorkIter<CG, kGrouped> wi(p, om, gm, gp, nparts, first_tile, tile_step, num_tiles);
       Seg sg;
       while (wi.next(sg)) {
-        const Work& wk = sg.wk;
-        const Tile tl = wk.tl;
+        const Tile tl = sg.wk.tl;
         // this CTA's slice of the cluster tile: its own 128 rows of A, its share of the B rows
         const int a_row = tl.m0 + static_cast<int>(cta_rank) * BM;
         const int b_row = tl.n0 + static_cast<int>(cta_rank) * kRowsB;
-        for (int it = sg.it0; it < sg.it1; ++it) {
-          const int part = it / tl.nkb;
-          const int kb = tl.kb0 + it - part * tl.nkb;
+        const int a_b = tl.b * p.a_bmul, b_b = tl.b * p.b_bmul;
+        const bool diag_tile = diag_dedup && tl.m0 == tl.n0;
+        int it = sg.it0;
+        int part = it / tl.nkb;            // once per segment
+        int kb = it - part * tl.nkb;
+        while (it < sg.it1) {
           int ia, ib;
           part_pair(part, ia, ib);
-          const CUtensorMap* ma = wk.a[ia];
-          const CUtensorMap* mb = wk.b[ib];
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
-          if (CG == 2) {
-            // both CTAs' bytes complete on the LEADER's full barrier, which expects 2 stages' worth
-            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            const bool same = diag_dedup && tl.m0 == tl.n0 && ia == ib;
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], same ? 2 * kBytesA : 2 * kStageBytes);
-            tma_load_3d_2sm(sa, ma, lbar, kb * BK, a_row, tl.b * p.a_bmul);
-            if (!same) tma_load_3d_2sm(sa + kBytesA, mb, lbar, kb * BK, b_row, tl.b * p.b_bmul);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_3d(sa, ma, &full_bar[stage], kb * BK, a_row, tl.b * p.a_bmul);
-            tma_load_3d(sa + kBytesA, mb, &full_bar[stage], kb * BK, b_row, tl.b * p.b_bmul);
+          const CUtensorMap* ma = ia == 0 ? sg.wk.a[0] : (ia == 1 ? sg.wk.a[1] : sg.wk.a[2]);
+          const CUtensorMap* mb = ib == 0 ? sg.wk.b[0] : (ib == 1 ? sg.wk.b[1] : sg.wk.b[2]);
+          const bool same = diag_tile && ia == ib;
+          const uint32_t tx = (CG == 2) ? (same ? 2 * kBytesA : 2 * kStageBytes) : kStageBytes;
+          const int kend = min(tl.nkb, kb + (sg.it1 - it));
+          it += kend - kb;
+          int kcoord = (tl.kb0 + kb) * BK;
+          for (; kb < kend; ++kb, kcoord += BK) {     // ---- hot loop
+            mbar_wait_addr(empty_base + stage * 8u, phase ^ 1u);
+            const uint32_t sa = smem_base + stage * kStageBytes;
+            const uint32_t fb = lfull_base + stage * 8u;
+            if (elect_one()) {
+              if (CG == 2) {
+                if (cta_rank == 0) mbar_arrive_expect_tx_addr(full_base + stage * 8u, tx);
+                tma_load_3d_2sm_addr(sa, ma, fb, kcoord, a_row, a_b);
+                if (!same) tma_load_3d_2sm_addr(sa + kBytesA, mb, fb, kcoord, b_row, b_b);
+              } else {
+                mbar_arrive_expect_tx_addr(fb, tx);
+                tma_load_3d_addr(sa, ma, fb, kcoord, a_row, a_b);
+                tma_load_3d_addr(sa + kBytesA, mb, fb, kcoord, b_row, b_b);
+              }
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(kStages)) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          kb = 0;
+          ++part;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, see above)
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // descriptor of stage 0's A tile; stage s and the B tile are plain offsets in the (address >> 4) field
+      const uint64_t desc0 = umma_smem_desc_k_sw128(smem_base);
+      const uint32_t tfull_base = smem_u32(tfull_bar);
       WorkIter<CG, kGrouped> wi(p, om, gm, gp, nparts, first_tile, tile_step, num_tiles);
       Seg sg;
       while (wi.next(sg)) {
@@ -407,41 +436,53 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int it = sg.it0; it < sg.it1; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t da = umma_smem_desc_k_sw128(sa);
-          bool same = false;
-          if (diag_dedup && tl.m0 == tl.n0) {
-            int ia, ib;
-            part_pair(it / tl.nkb, ia, ib);
-            same = ia == ib;
-          }
-          const uint64_t db = umma_smem_desc_k_sw128(same ? sa : sa + kBytesA);
+        const bool diag_tile = diag_dedup && tl.m0 == tl.n0;
+        uint32_t accumulate = 0;           // the first MMA of a segment overwrites the accumulator
+        int it = sg.it0;
+        int part = it / tl.nkb;
+        int kb = it - part * tl.nkb;
+        while (it < sg.it1) {
+          int ia, ib;
+          part_pair(part, ia, ib);
+          const uint64_t b_off = (diag_tile && ia == ib) ? 0ull : static_cast<uint64_t>(kBytesA >> 4);
+          const int kend = min(tl.nkb, kb + (sg.it1 - it));
+          it += kend - kb;
+          for (; kb < kend; ++kb) {                   // ---- hot loop
+            mbar_wait_addr(full_base + stage * 8u, phase);
+            tc_fence_after();
+            const uint64_t da = desc0 + static_cast<uint64_t>(stage * (kStageBytes >> 4));
+            const uint64_t db = da + b_off;
+            if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-            if (CG == 2)
-              umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(k * 2),
-                               db + static_cast<uint64_t>(k * 2), idesc,
-                               (it != sg.it0 || k != 0) ? 1u : 0u);
-            else
-              umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2),
-                           db + static_cast<uint64_t>(k * 2), idesc,
-                           (it != sg.it0 || k != 0) ? 1u : 0u);
+              for (int k = 0; k < BK / UK; ++k) {
+                // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
+                if (CG == 2)
+                  umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                                   idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
+                else
+                  umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
+                               idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
+              }
+              // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+              if (CG == 2) umma_commit_2sm_addr(empty_base + stage * 8u, 3);
+              else umma_commit_addr(empty_base + stage * 8u);
+            }
+            __syncwarp();
+            accumulate = 1;
+            if (++stage == static_cast<uint32_t>(kStages)) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if (CG == 2) umma_commit_2sm(&empty_bar[stage], 3);
-          else umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          kb = 0;
+          ++part;
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if (CG == 2) umma_commit_2sm(&tfull_bar[acc], 3);
-        else umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if (CG == 2) umma_commit_2sm_addr(tfull_base + static_cast<uint32_t>(acc) * 8u, 3);
+          else umma_commit_addr(tfull_base + static_cast<uint32_t>(acc) * 8u);
+        }
+        __syncwarp();
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
@@ -506,7 +547,8 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
           uint8_t* sm = sd + 32 * 32 * 4;                 // mirrored tile [32 cols][32 rows]
           const bool diag = syrk && c0 == r0;
           const bool do_mirror = syrk && mirror;
-          if (lane == 0) tma_store_wait_read0();  // previous chunk's stores have drained the buffer
+          // (bulk groups belong to the issuing thread: elect.sync with a full mask always elects the same lane)
+          if (elect_one()) tma_store_wait_read0();  // previous chunk's stores have drained the buffer
           __syncwarp();
           // direct: lane = row, eight 16 B chunks per row at swizzled position (chunk ^ (row & 7))
 #pragma unroll
@@ -529,7 +571,7 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             tma_reduce_add_3d(wk.c, sd, c0, r0, tl.b * p.c_bmul);
             if (do_mirror) tma_reduce_add_3d(wk.c, sm, r0, c0, tl.b * p.c_bmul);
             tma_store_commit();
@@ -624,7 +666,7 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
     }
   }
 
-  if (kTmaEpi && warp >= kEpiWarp0 && lane == 0) tma_store_wait_read0();  // smem outlives stores
+  if (kTmaEpi && warp >= kEpiWarp0 && elect_one()) tma_store_wait_read0();  // smem outlives stores
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // the peer may still be reading its TMEM / receiving commits
   else __syncthreads();
@@ -712,6 +754,7 @@ int make_output_map(CUtensorMap* map, float* base, int rows, int cols, long long
 
 // bring-up / A-B timing switch for the TMA-reduce epilogue (1 = allowed)
 int g_allow_tma_epilogue = 1;
+int g_syrk_tuning_flags = 0;  // see set_syrk_tuning()
 
 int sm_count() {
   static std::mutex mu;
@@ -877,7 +920,8 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
   }
   // every CTA pair of the device takes part: whole tiles round-robin, then an equal share of the tail
   const int clusters = sm_count() / 2;
-  gp.full_tiles = total / clusters * clusters;
+  gp.full_tiles = (g_syrk_tuning_flags & 2) ? total : total / clusters * clusters;
+  gp.no_dedup = (g_syrk_tuning_flags & 1) ? 1 : 0;
   long long tail = 0;
   for (int g = 0, t = 0; g < count; ++g) {
     const int tiles_g = gp.tile_begin[g + 1] - gp.tile_begin[g];
@@ -902,6 +946,10 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
   note_launch();
   return (err == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -5;
 }
+
+// A/B switches of the grouped SYRK (bring-up / profiling): bit 0 = no diagonal-tile operand dedup,
+// bit 1 = no stream-K tail (whole tiles only).
+void set_syrk_tuning(int flags) { g_syrk_tuning_flags = flags; }
 
 // cta_group override for bring-up / A-B timing: 0 = automatic, 1 or 2 = forced; +16 disables the
 // TMA-reduce epilogue (register read-modify-write epilogue everywhere).

@@ -57,6 +57,9 @@ int bk_device_check(void);
  * SM (128 x 256 tiles), 2 = CTA pairs (256 x 256 tiles, tcgen05.mma.cta_group::2), 0 = automatic
  * (pairs whenever the problem has at least 192 rows and 129 columns).  Results do not depend on it. */
 void bk_set_cta_group(int cta_group);
+/* A/B switches of the grouped factor SYRK (profiling only): bit 0 = load both operands of diagonal tiles,
+ * bit 1 = whole tiles only (no stream-K split of the last partial wave). */
+void bk_set_syrk_tuning(int flags);
 
 /* ---------------------------------------------------------------------------------------------
  * Contraction core.  D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]; bf16 (uint16 storage) K-major
