@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip inversion / predictive extras")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s back-to-back leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -288,6 +289,14 @@ def main():
     from bnn_kfac_b200.wrapper import MLP
     L = _lib.load()
     _lib.require_device()
+
+    # N > 1: the sharded path must reproduce the single-GPU result before anything is timed (same check as
+    # tests/test_gpu_parity_r2.py::test_nccl_two_rank_parity; its outcome travels in the JSON line)
+    parity = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import gpu_dist_check
+        parity = gpu_dist_check.run_check(rank, world, dev)
 
     torch.manual_seed(0)
     model = MLP(WIDTHS).to(dev)
@@ -386,6 +395,18 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps, reduce_after)
 
+    # ---- sustained leg: the same device-resident step back to back for >= 2 s (the headline's timed region is
+    # ~10 ms, a burst-clock figure; under seconds of load the part sits at its 1 kW power cap and the SM clock
+    # settles near 1.3 - 1.5 GHz).  Own clock record; compared with the SUSTAINED cuBLAS peak.
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(2.2 / (ms_dev / args.steps * 1e-3)))
+        with ClockSampler(local_rank) as clocks_sus:
+            ms_sus = timed(lambda: step_device(resident), n_sus)
+        sustained = {"seconds": ms_sus * 1e-3, "steps": n_sus, "ms_per_step": ms_sus / n_sus,
+                     "value": BATCH * n_sus * world / (ms_sus * 1e-3), "unit": "samples/s",
+                     "clocks": clocks_sus.summary()}
+
     total_samples = BATCH * args.steps * world
     value = total_samples / (ms_dev * 1e-3)
     e2e_value = total_samples / (ms_e2e * 1e-3)
@@ -439,12 +460,25 @@ def main():
     syrk_ms = e0.elapsed_time(e1) / reps
     syrk_flops = sum(t[4] * (t[4] + 1) * n for t in grp)   # one multiply-add per lower-triangle entry per sample
     achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
+    syrk_sus = None
+    if not args.no_sustained:      # the kernel alone, back to back for >= 2 s
+        n_k = int(2.2 / (syrk_ms * 1e-3))
+        e0.record()
+        for _ in range(n_k):
+            syrk()
+        e1.record()
+        torch.cuda.synchronize()
+        syrk_sus = syrk_flops / (e0.elapsed_time(e1) / n_k * 1e-3) / 1e12
     roofline = {"bound": "tensor",
-                "kernel": f"umma_syrk_grouped_kernel (cta_group::2, TMA-reduce epilogue; {cnt} SYRKs 4096x4096x4096 "
-                          "lower+mirror in one launch)",
+                "kernel": f"umma_syrk_grouped_kernel (cta_group::2, TMA-reduce epilogue; {cnt} SYRKs 4096x4096x4096, "
+                          f"{'lower triangle only' if est.lower_only else 'lower + mirror'}, in one launch)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)",
                 "us_per_launch": syrk_ms * 1e3, "flops_per_launch": syrk_flops, "traffic": None}
+    if syrk_sus is not None and peaks.get("bf16_tflops_sustained"):
+        roofline["sustained"] = {"achieved": syrk_sus, "peak": peaks["bf16_tflops_sustained"],
+                                 "frac": syrk_sus / peaks["bf16_tflops_sustained"],
+                                 "note": "same launch back to back for >= 2 s, vs the sustained cuBLAS figure"}
     prof = os.path.join(ROOT, "profiles", "syrk_traffic.json")
     if os.path.exists(prof):
         try:
@@ -462,6 +496,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": checksum_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": None, "roofline": roofline, "clocks": clocks.summary()}
+    line["e2e"]["d2h_note"] = ("the result of a step is the device-resident factor state (0.47 GB, consumed on the device "
+                               "by invert()); the per-step read-back is a 32-byte checksum (trace of every factor)")
+    if sustained is not None:
+        sustained["algorithmic_tflops"] = sustained["value"] * algorithmic_flops_per_sample(WIDTHS) / 1e12
+        if peaks.get("bf16_tflops_sustained"):
+            sustained["frac_of_sustained_peak"] = sustained["algorithmic_tflops"] / world / peaks["bf16_tflops_sustained"]
+        line["sustained"] = sustained
+    line["step_frac_of_burst_peak"] = line["algorithmic_tflops"] / world / peaks["bf16_tflops"]
+    if parity is not None:
+        line["parity"] = parity
     if reduce_ms is not None:
         state_bytes = sum(t.numel() * 4 for l in layers for t in est.state[l])
         wire_bytes = sum(t.shape[0] * (t.shape[0] + 1) // 2 * 4 for l in layers for t in est.state[l])

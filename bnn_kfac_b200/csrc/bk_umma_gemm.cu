@@ -135,15 +135,16 @@ struct GroupMaps {
 struct GroupParams {
   int count, nparts;
   int mirror;  // 1: write the transposed tile as well (full symmetric state); 0: lower triangle only
-  // Schedule: tiles [0, full_tiles) (a multiple of the P CTA pairs) are taken whole, round-robin, so the
-  // pairs that run at the same time work on neighbouring tiles and share operand panels in L2.  The
-  // remaining T mod P tiles would leave pairs idle for a whole tile time (136 tiles of a 4096-wide factor on
-  // 74 pairs: 1.84 waves); they are scheduled stream-K instead: their main-loop iterations (iters[g] =
-  // k-blocks x precision passes per tile of problem g), concatenated, are cut into P equal ranges (multiples
-  // of kWorkGrain).  A tile cut by a boundary is finished by two pairs; both add their partial sums to C
-  // through the TMA reduction, so there is no fix-up pass.  (Stream-K over the WHOLE launch was measured:
-  // every pair then walks its own region of the triangle, the L2 hit rate falls from 73 % to 53 %, and a
-  // 3-factor launch reads 708 MB instead of 100 MB from DRAM.)
+  // Schedule: tiles [0, full_tiles) are taken whole, round-robin over the P CTA pairs, so the pairs that run
+  // at the same time work on neighbouring tiles and share operand panels in L2.  Default: full_tiles = all.
+  // Optional (set_syrk_tuning bit 1): the last T mod P tiles, which leave pairs idle for a tile time (136 tiles
+  // of a 4096-wide factor on 74 pairs: 1.84 waves), are scheduled stream-K — their main-loop iterations
+  // (iters[g] = k-blocks x precision passes per tile of problem g), concatenated, are cut into P equal ranges
+  // (multiples of kWorkGrain); a tile cut by a boundary is finished by two pairs, both adding their partial
+  // sums to C through the TMA reduction.  MEASURED SLOWER (profiles/r02_syrk_ab.md): 7 factors 364.6 vs
+  // 344.2 us, 1 factor 75.1 vs 65.0 us — kept as a switch, off.  Stream-K over the WHOLE launch is worse
+  // still: every pair then walks its own region of the triangle, the L2 hit rate falls from 73 % to 53 %, and
+  // a 3-factor launch reads 708 MB instead of 100 MB from DRAM.
   int iters[kMaxGroup];
   int full_tiles, tail_work;
   int no_dedup;
@@ -920,7 +921,7 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
   }
   // every CTA pair of the device takes part: whole tiles round-robin, then an equal share of the tail
   const int clusters = sm_count() / 2;
-  gp.full_tiles = (g_syrk_tuning_flags & 2) ? total : total / clusters * clusters;
+  gp.full_tiles = (g_syrk_tuning_flags & 2) ? total / clusters * clusters : total;
   gp.no_dedup = (g_syrk_tuning_flags & 1) ? 1 : 0;
   long long tail = 0;
   for (int g = 0, t = 0; g < count; ++g) {
@@ -948,7 +949,7 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
 }
 
 // A/B switches of the grouped SYRK (bring-up / profiling): bit 0 = no diagonal-tile operand dedup,
-// bit 1 = no stream-K tail (whole tiles only).
+// bit 1 = stream-K split of the last partial wave (default: whole tiles only).
 void set_syrk_tuning(int flags) { g_syrk_tuning_flags = flags; }
 
 // cta_group override for bring-up / A-B timing: 0 = automatic, 1 or 2 = forced; +16 disables the

@@ -68,7 +68,7 @@ struct SyrkGroupItem {
 int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, bool mirror,
                              cudaStream_t stream);
 
-// A/B switches of the grouped SYRK: bit 0 = no diagonal-tile operand dedup, bit 1 = no stream-K tail.
+// A/B switches of the grouped SYRK: bit 0 = no diagonal-tile operand dedup, bit 1 = stream-K tail on.
 void set_syrk_tuning(int flags);
 // Tuning / bring-up knob: force the tcgen05 cta_group of the contraction core (1 or 2; 0 = automatic).
 void set_umma_cta_group(int cg);

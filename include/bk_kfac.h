@@ -58,7 +58,7 @@ int bk_device_check(void);
  * (pairs whenever the problem has at least 192 rows and 129 columns).  Results do not depend on it. */
 void bk_set_cta_group(int cta_group);
 /* A/B switches of the grouped factor SYRK (profiling only): bit 0 = load both operands of diagonal tiles,
- * bit 1 = whole tiles only (no stream-K split of the last partial wave). */
+ * bit 1 = stream-K split of the last partial wave (default off: measured slower). */
 void bk_set_syrk_tuning(int flags);
 
 /* ---------------------------------------------------------------------------------------------

@@ -50,6 +50,6 @@ for cnt in (7, 3, 1):
     L.bk_set_syrk_tuning(0)
     for (tune, flags), v in sorted(res.items()):
         us = min(v)
-        print(f"factors={cnt} tuning={tune} (dedup={'off' if tune & 1 else 'on'}, tail-split={'off' if tune & 2 else 'on'}) "
+        print(f"factors={cnt} tuning={tune} (dedup={'off' if tune & 1 else 'on'}, tail-split={'on' if tune & 2 else 'off'}) "
               f"{'lower-only' if flags else 'mirrored'}: best {us:7.1f} us  all {[round(x, 1) for x in v]}  "
               f"{cnt * d * (d + 1) * n / us / 1e6:7.1f} TFLOP/s alg", flush=True)
