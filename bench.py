@@ -268,6 +268,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip inversion / predictive extras")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s back-to-back leg")
+    ap.add_argument("--inputs", default="fp32", choices=["fp32", "bf16"],
+                    help="dtype of the (a, g) tensors handed to KFAC.update: fp32 (what the reference's hooks see on an "
+                         "fp32 model; staged to bf16 by the library) or bf16 (a model under bf16 autocast; consumed "
+                         "directly).  BASELINE config 5's values are bf16-representable: both carry the same numbers")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -303,7 +307,8 @@ def main():
     est = KFAC(model, precision=args.precision)
     layers = [l for _, l in est._selected_layers()]
     gen = torch.Generator().manual_seed(1234 + rank)
-    host = [(a.pin_memory(), g.pin_memory()) for a, g in synth_batch(gen, BATCH, WIDTHS)]
+    in_dtype = torch.bfloat16 if args.inputs == "bf16" else torch.float32
+    host = [(a.to(in_dtype).pin_memory(), g.to(in_dtype).pin_memory()) for a, g in synth_batch(gen, BATCH, WIDTHS)]
     resident = [(a.to(dev), g.to(dev)) for a, g in host]
     # e2e: two sets of device input buffers; the H2D copy of step i + 1 (copy stream) overlaps the kernels of step i
     staging2 = [[(torch.empty_like(a), torch.empty_like(g)) for a, g in resident] for _ in range(2)]
@@ -311,7 +316,7 @@ def main():
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"next": 0, "primed": False}
-    h2d_bytes = sum(a.numel() * 4 + g.numel() * 4 for a, g in host)
+    h2d_bytes = sum(a.numel() * a.element_size() + g.numel() * g.element_size() for a, g in host)
     checksum_host = torch.empty(2 * len(layers), dtype=torch.float32).pin_memory()
 
     def step_device(bufs):
@@ -425,10 +430,13 @@ def main():
             d = x.shape[1]
             if d <= 176:
                 continue
-            hi = torch.empty(d, n, dtype=torch.bfloat16, device=dev)
-            lo = torch.empty_like(hi)
-            L.bk_transpose_split(x.data_ptr(), d, n, d, 1.0, 0, hi.data_ptr(), lo.data_ptr(), n,
-                                 _lib.stream_ptr())
+            if args.inputs == "bf16":      # the launch reads the activations themselves
+                hi, lo = x, x
+            else:
+                hi = torch.empty(d, n, dtype=torch.bfloat16, device=dev)
+                lo = torch.empty_like(hi)
+                L.bk_transpose_split(x.data_ptr(), d, n, d, 1.0, 0, hi.data_ptr(), lo.data_ptr(), n,
+                                     _lib.stream_ptr())
             scratch = torch.zeros(st_t.shape[0], st_t.stride(0), device=dev)
             grp.append((scratch, st_t.stride(0), hi, lo, d))
     cnt = len(grp)
@@ -436,13 +444,15 @@ def main():
     a_lds = (C.c_longlong * cnt)(*[t[1] for t in grp])
     a_hi = (C.c_void_p * cnt)(*[t[2].data_ptr() for t in grp])
     a_lo = (C.c_void_p * cnt)(*[t[3].data_ptr() for t in grp])
-    a_ldt = (C.c_longlong * cnt)(*[n] * cnt)
+    a_ldt = (C.c_longlong * cnt)(*[t[2].stride(0) for t in grp])
     a_ns = (C.c_int * cnt)(*[n] * cnt)
     a_ds = (C.c_int * cnt)(*[t[4] for t in grp])
     a_al = (C.c_float * cnt)(*[1.0 / n] * cnt)
     a_be = (C.c_float * cnt)(*[1.0] * cnt)
     reps = 20
-    syrk_flags = _lib.SYRK_LOWER_ONLY if est.lower_only else 0
+    syrk_flags = (_lib.SYRK_LOWER_ONLY if est.lower_only else 0) | (_lib.SYRK_ROW_MAJOR if args.inputs == "bf16" else 0)
+    if args.inputs == "bf16":
+        prec = 1
 
     def syrk():
         _lib.check(L.bk_syrk_accum_staged_grouped(a_states, a_lds, a_hi, a_lo, a_ldt, a_ns, a_ds, a_al, a_be,
@@ -490,7 +500,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[args.precision],
-            "data": "synthetic",
+            "data": "synthetic", "inputs": args.inputs,
             "config": bench_config(world),
             "algorithmic_tflops": value * algorithmic_flops_per_sample(WIDTHS) / 1e12,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,

@@ -21,6 +21,7 @@ BK_SMALL64_MAX_BATCH = 16
 
 SYRK_LOWER_ONLY = 1
 SYRK_NO_OVERLAP = 2
+SYRK_ROW_MAJOR = 4
 
 GEMM_SYRK_LOWER = 1
 GEMM_MIRROR = 2
@@ -64,7 +65,7 @@ SIGNATURES = {
     "bk_syrk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "bk_syrk_accum": (_i, [_p, _ll, _p, _ll, _i, _i, _i, _f, _f, _f, _i, _p, _sz, _p]),
     "bk_syrk_grouped_workspace_bytes": (_sz, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _i, _i]),
-    "bk_syrk_accum_grouped": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_ll),
+    "bk_syrk_accum_grouped": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_p), C.POINTER(_i), C.POINTER(_ll),
                                    C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f),
                                    C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _p, _sz, _p]),
     "bk_sym_finalize": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _f, _p]),

@@ -233,11 +233,11 @@ StagePipe* stage_pipe() {
 
 }  // namespace
 
-int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const float* const* xs,
-                          const long long* ldxs, const int* ns, const int* ds, const int* has_bias,
-                          const float* in_scales, const float* alphas, const float* betas, int count,
-                          int precision, int flags, void* workspace, size_t workspace_bytes,
-                          void* stream) {
+int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const void* const* xs,
+                          const int* x_is_bf16, const long long* ldxs, const int* ns, const int* ds,
+                          const int* has_bias, const float* in_scales, const float* alphas,
+                          const float* betas, int count, int precision, int flags, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   if (count <= 0) return BK_OK;
   if (states == nullptr || ld_states == nullptr || xs == nullptr || ldxs == nullptr ||
       ns == nullptr || ds == nullptr || has_bias == nullptr || in_scales == nullptr ||
@@ -255,8 +255,8 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
   struct Wide {
     int idx;
     char* ws;
-  } wide[64];
-  int n_wide = 0;
+  } wide[64], direct[64];
+  int n_wide = 0, n_direct = 0;
   for (int i = 0; i < count; ++i) {
     const size_t need = bk_syrk_workspace_bytes(ns[i], ds[i], has_bias[i], precision);
     char* ws = base + off;
@@ -264,12 +264,22 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
     const int d = ds[i], n = ns[i], hb = has_bias[i] ? 1 : 0;
     const int dp = d + hb;
     const bool tensor = dp > BK_SMALL_D_MAX && precision != BK_PREC_FP32;
+    const bool bf16_in = x_is_bf16 != nullptr && x_is_bf16[i] != 0;
     const bool aligned = (ld_states[i] % 4) == 0 && (reinterpret_cast<uintptr_t>(states[i]) & 15) == 0 &&
-                         (ldxs[i] % 4) == 0 && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0 &&
+                         (ldxs[i] % (bf16_in ? 8 : 4)) == 0 && (reinterpret_cast<uintptr_t>(xs[i]) & 15) == 0 &&
                          (betas[i] == 0.f || betas[i] == 1.f) && d >= 192;
+    if (bf16_in) {
+      // bf16 activations feed the tensor cores as they are (row-major = MN-major operand of X^T X): the
+      // caller converts the factors this path cannot take (narrow / unaligned) to fp32 first
+      if (!tensor || !aligned || n_direct >= 64) return BK_ERR_ARG;
+      if (states[i] == nullptr || xs[i] == nullptr || n <= 0 || ld_states[i] < dp || ldxs[i] < d)
+        return BK_ERR_ARG;
+      direct[n_direct++] = {i, ws};
+      continue;
+    }
     if (!tensor || !aligned || n_wide >= 64) {
-      const int rc = bk_syrk_accum(states[i], ld_states[i], xs[i], ldxs[i], n, d, hb, in_scales[i],
-                                   alphas[i], betas[i], precision, ws, need, stream);
+      const int rc = bk_syrk_accum(states[i], ld_states[i], static_cast<const float*>(xs[i]), ldxs[i], n, d,
+                                   hb, in_scales[i], alphas[i], betas[i], precision, ws, need, stream);
       if (rc) return rc;
       continue;
     }
@@ -277,12 +287,87 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
       return BK_ERR_ARG;
     wide[n_wide++] = {i, ws};
   }
-  if (n_wide == 0) return BK_OK;
+  struct Border {
+    float* state;
+    long long ld;
+    int d;
+    const float* colsum;
+    float alpha, beta, n;
+  } borders[128];
+  int n_borders = 0;
+  StagePipe* pipe = (flags & BK_SYRK_NO_OVERLAP) ? nullptr : stage_pipe();
+  // the pipeline's events are per device, not per caller: one update at a time uses them
+  static std::mutex pipe_mu;
+  std::unique_lock<std::mutex> pipe_lock(pipe_mu, std::defer_lock);
+  if (pipe != nullptr) pipe_lock.lock();
+  bool forked = false;
+  auto fork_side = [&]() -> int {
+    // the side stream may touch the workspace only after everything already queued on `st` (the previous
+    // update's SYRKs read the same staging buffers)
+    if (forked) return 0;
+    if (cudaEventRecord(pipe->fork, st) != cudaSuccess ||
+        cudaStreamWaitEvent(pipe->side, pipe->fork, 0) != cudaSuccess)
+      return BK_ERR_CUDA;
+    forked = true;
+    return 0;
+  };
+  // pass 1b: bf16 activations — no staging at all.  The column sums for the bias row run on the side stream
+  // (HBM-bound, 33 MB per 4096^2 operand) underneath the tensor-core launch; the input scale of the second
+  // factor (grad_output * N, models/curvatures.py:323) moves into alpha: (s g)(s g)^T = s^2 g g^T.
+  if (n_direct > 0) {
+    bk::SyrkGroupItem ditems[64];
+    cudaStream_t cs = pipe != nullptr ? pipe->side : st;
+    bool any_sum = false;
+    for (int w = 0; w < n_direct; ++w) {
+      const int i = direct[w].idx;
+      const int d = ds[i], n = ns[i], hb = has_bias[i] ? 1 : 0;
+      bk::SyrkGroupItem& it = ditems[w];
+      it.X_hi = static_cast<const __nv_bfloat16*>(xs[i]);
+      it.X_lo = nullptr;
+      it.ldx = ldxs[i];
+      it.d = d;
+      it.n = n;
+      it.alpha = alphas[i] * in_scales[i] * in_scales[i];
+      it.beta = betas[i];
+      it.C = states[i];
+      it.ldc = ld_states[i];
+      if (hb) {
+        float* colsum = reinterpret_cast<float*>(direct[w].ws);
+        if (pipe != nullptr) {
+          const int rc = fork_side();
+          if (rc) return rc;
+        }
+        if (cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, cs) != cudaSuccess) return BK_ERR_CUDA;
+        const int rc = bk::launch_colsum_bf16(it.X_hi, it.ldx, n, d, in_scales[i], colsum, cs);
+        if (rc) return rc;
+        any_sum = true;
+        borders[n_borders++] = {states[i], ld_states[i], d, colsum, alphas[i], betas[i], static_cast<float>(n)};
+      }
+    }
+    if (any_sum && pipe != nullptr && cudaEventRecord(pipe->staged[7], pipe->side) != cudaSuccess)
+      return BK_ERR_CUDA;
+    for (int g0 = 0; g0 < n_direct; g0 += 8) {
+      const int gc = n_direct - g0 < 8 ? n_direct - g0 : 8;
+      const int rc = bk::launch_umma_syrk_grouped(ditems + g0, gc, 1, mirror, st, true);
+      if (rc) return rc;
+    }
+    if (any_sum && pipe != nullptr && cudaStreamWaitEvent(st, pipe->staged[7], 0) != cudaSuccess)
+      return BK_ERR_CUDA;
+  }
+  auto finish_borders = [&]() -> int {
+    for (int b = 0; b < n_borders; ++b) {
+      const int rc = bk::launch_bias_border(borders[b].state, borders[b].ld, borders[b].d,
+                                            borders[b].colsum, borders[b].alpha, borders[b].beta,
+                                            borders[b].n, st);
+      if (rc) return rc;
+    }
+    return BK_OK;
+  };
+  if (n_wide == 0) return finish_borders();
   // pass 2: software pipeline over chunks of wide factors.  The staging pass (fp32 [n, d] -> K-major bf16,
   // HBM-bound) of chunk c + 1 runs on a side stream underneath the tensor-core SYRK of chunk c (the
   // lower-only SYRK leaves enough shared memory per SM for a co-resident staging CTA).  Chunk 0 is a single
   // factor so that the tensor cores start after ONE staging pass; later chunks hold up to 3.
-  StagePipe* pipe = (flags & BK_SYRK_NO_OVERLAP) ? nullptr : stage_pipe();
   int chunk_begin[66];
   int n_chunks = 0;
   if (pipe != nullptr && n_wide > 1) {
@@ -292,7 +377,7 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
     while (b < n_wide) {
       chunk_begin[n_chunks++] = b;
       b += (n_wide - b) >= 6 ? 3 : (n_wide - b);   // ... 3, then whatever is left (<= 5)
-      if (n_chunks >= 8) break;
+      if (n_chunks >= 7) break;
     }
     if (b < n_wide) {  // more than the pipeline's events cover: last chunk takes the rest
       // (groups of 8 are split again at launch)
@@ -301,14 +386,6 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
     chunk_begin[n_chunks++] = 0;
   }
   chunk_begin[n_chunks] = n_wide;
-  struct Border {
-    float* state;
-    long long ld;
-    int d;
-    const float* colsum;
-    float alpha, beta, n;
-  } borders[64];
-  int n_borders = 0;
   bk::SyrkGroupItem items[64];
   auto stage_chunk = [&](int c, cudaStream_t s) -> int {
     for (int w = chunk_begin[c]; w < chunk_begin[c + 1]; ++w) {
@@ -325,8 +402,8 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
       if (colsum != nullptr &&
           cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, s) != cudaSuccess)
         return BK_ERR_CUDA;
-      const int rc = bk::launch_transpose_split(xs[i], ldxs[i], n, d, in_scales[i], 0, hi, lo, ldt, s,
-                                                colsum);
+      const int rc = bk::launch_transpose_split(static_cast<const float*>(xs[i]), ldxs[i], n, d, in_scales[i],
+                                                0, hi, lo, ldt, s, colsum);
       if (rc) return rc;
       bk::SyrkGroupItem& it = items[w];
       it.X_hi = hi;
@@ -351,22 +428,15 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
     }
     return 0;
   };
-  // the pipeline's events are per device, not per caller: one update at a time uses them
-  static std::mutex pipe_mu;
-  std::unique_lock<std::mutex> pipe_lock(pipe_mu, std::defer_lock);
-  if (n_chunks > 1) pipe_lock.lock();
   if (n_chunks == 1) {
     int rc = stage_chunk(0, st);
     if (rc) return rc;
     rc = syrk_chunk(0);
     if (rc) return rc;
   } else {
-    // the side stream may touch the workspace only after everything already queued on `st` (the previous
-    // update's SYRKs read the same staging buffers) ...
-    if (cudaEventRecord(pipe->fork, st) != cudaSuccess ||
-        cudaStreamWaitEvent(pipe->side, pipe->fork, 0) != cudaSuccess)
-      return BK_ERR_CUDA;
-    int rc = stage_chunk(0, st);
+    int rc = fork_side();
+    if (rc) return rc;
+    rc = stage_chunk(0, st);
     if (rc) return rc;
     // ... and starts staging chunk 1 when chunk 0 is staged (not before: the first SYRK should not wait
     // for a staging pass that shares HBM with two others)
@@ -386,13 +456,7 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
       if (rc) return rc;
     }
   }
-  for (int b = 0; b < n_borders; ++b) {
-    const int rc = bk::launch_bias_border(borders[b].state, borders[b].ld, borders[b].d,
-                                          borders[b].colsum, borders[b].alpha, borders[b].beta,
-                                          borders[b].n, st);
-    if (rc) return rc;
-  }
-  return BK_OK;
+  return finish_borders();
 }
 
 int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_states,
@@ -418,7 +482,7 @@ int bk_syrk_accum_staged_grouped(float* const* states, const long long* ld_state
     items[i].ldc = ld_states[i];
   }
   return bk::launch_umma_syrk_grouped(items, count, precision, (flags & BK_SYRK_LOWER_ONLY) == 0,
-                                      as_stream(stream));
+                                      as_stream(stream), (flags & BK_SYRK_ROW_MAJOR) != 0);
 }
 
 int bk_sym_finalize(float* const* factors_host, const long long* ld_host, const int* dims_host, int count,

@@ -199,6 +199,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same for an MN-major operand (the M / N index is the contiguous one): rows of 64 bf16 (128 B) along M / N for
+// one k, 8-k-row swizzle atoms 1024 B apart (stride byte offset), 64-element M / N chunks `lbo_bytes` apart
+// (leading byte offset).  CUTLASS's canonical Major-MN SW128 layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes = 8192) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: bf16 A/B (K-major), fp32 accumulator, shape M x N x 16.
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K)      [16] B major (0 = K)        [17,23) N >> 3   [24,29) M >> 4

@@ -20,6 +20,8 @@ int launch_transpose_split3(const float* X, long long ldx, int rows, int cols, _
                             __nv_bfloat16* T1, __nv_bfloat16* T2, long long ldt,
                             cudaStream_t stream);
 // Row / column d of a bias-augmented factor from the column sums (see bk_prep.cu).
+int launch_colsum_bf16(const __nv_bfloat16* X, long long ldx, int rows, int cols, float scale, float* colsum,
+                       cudaStream_t stream);
 int launch_bias_border(float* state, long long ld, int d, const float* colsum, float alpha,
                        float beta, float n, cudaStream_t stream);
 int launch_convert_split(const float* X, long long ldx, int rows, int cols, float scale,

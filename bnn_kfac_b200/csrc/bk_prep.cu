@@ -136,6 +136,39 @@ transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, i
   }
 }
 
+// colsum[j] += scale * sum_n X[n][j] for row-major bf16 activations (the bias row / column of the first
+// Kronecker factor when the SYRK consumes the activations directly, models/curvatures.py:346-349).
+// Block: 8 warps x 32 lanes, lane = column PAIR (one bf16x2 load), warps stride over the rows of the block's
+// row chunk; fp32 partial sums, one atomic per column per block.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx, int rows, int cols, float scale,
+                   int rows_per_block, float* __restrict__ colsum) {
+  __shared__ float part[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c + 1 < cols) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(X + static_cast<long long>(r) * ldx + c);
+      s0 += __bfloat162float(v.x);
+      s1 += __bfloat162float(v.y);
+    }
+  } else if (c < cols) {
+    for (int r = r0 + warp; r < r1; r += 8) s0 += __bfloat162float(X[static_cast<long long>(r) * ldx + c]);
+  }
+  part[warp][2 * lane] = s0;
+  part[warp][2 * lane + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+    atomicAdd(&colsum[blockIdx.x * 64 + threadIdx.x], scale * t);
+  }
+}
+
 __global__ void fill_ones_row_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                      int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,6 +377,18 @@ int launch_transpose_split(const float* X, long long ldx, int rows, int cols, fl
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_split_kernel<<<grid, block, 0, stream>>>(X, ldx, rows, cols, scale, ones_row, Thi, Tlo,
                                                      ldt);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_colsum_bf16(const __nv_bfloat16* X, long long ldx, int rows, int cols, float scale, float* colsum,
+                       cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if ((ldx & 1) != 0 || (reinterpret_cast<uintptr_t>(X) & 3) != 0) return -2;
+  int by = (rows + 127) / 128;
+  if (by > 32) by = 32;
+  const int rpb = (rows + by - 1) / by;
+  colsum_bf16_kernel<<<dim3((cols + 63) / 64, by), 256, 0, stream>>>(X, ldx, rows, cols, scale, rpb, colsum);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

@@ -287,7 +287,12 @@ struct WorkIter {
   }
 };
 
-template <int CG, bool kTmaEpi, bool kGrouped>
+// kMN (grouped SYRK only): the operand is the ROW-major activation matrix X [n, d] itself (bf16, feature index
+// contiguous) — "MN-major" for X^T X.  TMA boxes of 64 features x 64 samples land as [64 k-rows][128 B]; a
+// 128-row operand tile is two such boxes 8 KB apart.  The UMMA descriptor then reads: 8-k-row swizzle atoms
+// 1024 B apart (SBO), 64-feature chunks 8192 B apart (LBO), and one K = 16 MMA step advances two atoms
+// (2048 B).  No transposed / converted copy of the activations exists on this path.
+template <int CG, bool kTmaEpi, bool kGrouped, bool kMN = false>
 __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, const GroupMaps* gm,
                                           const GroupParams* gp) {
   const int num_tiles = kGrouped ? gp->tile_begin[gp->count] : p.num_tiles;
@@ -399,7 +404,16 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
             const uint32_t sa = smem_base + stage * kStageBytes;
             const uint32_t fb = lfull_base + stage * 8u;
             if (elect_one()) {
-              if (CG == 2) {
+              if (kMN) {
+                // X [n, d]: coordinates (feature, sample); two 64-feature boxes per 128-row operand tile
+                if (cta_rank == 0) mbar_arrive_expect_tx_addr(full_base + stage * 8u, tx);
+                tma_load_3d_2sm_addr(sa, ma, fb, a_row, kcoord, 0);
+                tma_load_3d_2sm_addr(sa + kBytesA / 2, ma, fb, a_row + 64, kcoord, 0);
+                if (!same) {
+                  tma_load_3d_2sm_addr(sa + kBytesA, mb, fb, b_row, kcoord, 0);
+                  tma_load_3d_2sm_addr(sa + kBytesA + kBytesA / 2, mb, fb, b_row + 64, kcoord, 0);
+                }
+              } else if (CG == 2) {
                 if (cta_rank == 0) mbar_arrive_expect_tx_addr(full_base + stage * 8u, tx);
                 tma_load_3d_2sm_addr(sa, ma, fb, kcoord, a_row, a_b);
                 if (!same) tma_load_3d_2sm_addr(sa + kBytesA, mb, fb, kcoord, b_row, b_b);
@@ -423,12 +437,14 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, see above)
     if (cta_rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN);
+      // MN-major operands: bits 15 / 16 of the instruction descriptor
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kTileM, BN) | (kMN ? ((1u << 15) | (1u << 16)) : 0u);
+      constexpr uint64_t kStep = kMN ? 128 : 2;  // descriptor address advance per K = 16 MMA (>> 4 units)
       uint32_t stage = 0, phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       // descriptor of stage 0's A tile; stage s and the B tile are plain offsets in the (address >> 4) field
-      const uint64_t desc0 = umma_smem_desc_k_sw128(smem_base);
+      const uint64_t desc0 = kMN ? umma_smem_desc_mn_sw128(smem_base) : umma_smem_desc_k_sw128(smem_base);
       const uint32_t tfull_base = smem_u32(tfull_bar);
       WorkIter<CG, kGrouped> wi(p, om, gm, gp, nparts, first_tile, tile_step, num_tiles);
       Seg sg;
@@ -458,11 +474,13 @@ __device__ __forceinline__ void gemm_body(const OpMaps* om, const KParams& p, co
               for (int k = 0; k < BK / UK; ++k) {
                 // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
                 if (CG == 2)
-                  umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                                   idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
+                  umma_bf16_ss_2sm(tmem_d, da + static_cast<uint64_t>(k) * kStep,
+                                   db + static_cast<uint64_t>(k) * kStep, idesc,
+                                   (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
                 else
-                  umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                               idesc, (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
+                  umma_bf16_ss(tmem_d, da + static_cast<uint64_t>(k) * kStep,
+                               db + static_cast<uint64_t>(k) * kStep, idesc,
+                               (accumulate | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
               }
               // frees the smem slot (in both CTAs of a pair) when these MMAs retire
               if (CG == 2) umma_commit_2sm_addr(empty_base + stage * 8u, 3);
@@ -691,6 +709,14 @@ umma_syrk_grouped_kernel(const __grid_constant__ GroupMaps maps,
   gemm_body<2, true, true>(nullptr, p, &maps, &gp);
 }
 
+// Same, operands = the row-major bf16 activation matrices themselves (no staging pass): see gemm_body.
+__global__ void __launch_bounds__(kThreads, 1)
+umma_syrk_grouped_mn_kernel(const __grid_constant__ GroupMaps maps,
+                            const __grid_constant__ GroupParams gp) {
+  KParams p{};
+  gemm_body<2, true, true, true>(nullptr, p, &maps, &gp);
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -726,6 +752,22 @@ int make_operand_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int 
                                                           : stride) *
                                2};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(static_cast<const void*>(base)), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -4;
+}
+
+// Row-major activations X [n][d] bf16 (row pitch ld): 128B-swizzled boxes of 64 features x 64 samples.
+int make_operand_map_mn(CUtensorMap* map, const __nv_bfloat16* base, int d, int n, long long ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return -3;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0 || ld < d) return -2;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(n), 1};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * n};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(BK), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(static_cast<const void*>(base)), dims, strides, box, estr,
@@ -868,12 +910,16 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, bool mirror,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, bool mn_major) {
   if (count <= 0) return 0;
   if (count > kMaxGroup || (nparts != 1 && nparts != 3)) return -2;
+  if (mn_major && nparts != 1) return -2;  // bf16 activations are exact in one pass: there is no lo part
   static DeviceOnce attr_once;
   if (!attr_once([] {
         return cudaFuncSetAttribute(umma_syrk_grouped_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(Cfg<2>::kSmemBytes)) == cudaSuccess &&
+               cudaFuncSetAttribute(umma_syrk_grouped_mn_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(Cfg<2>::kSmemBytes)) == cudaSuccess;
       }))
@@ -890,7 +936,8 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
     if (nparts == 3 && it.X_lo == nullptr) return -2;
     if ((it.ldc % 4) != 0 || (reinterpret_cast<uintptr_t>(it.C) & 15) != 0) return -2;
     if (it.beta != 0.f && it.beta != 1.f) return -2;
-    int rc = make_operand_map(&maps.a0[g], it.X_hi, it.d, it.n, it.ldx, 0, 1, BM);
+    int rc = mn_major ? make_operand_map_mn(&maps.a0[g], it.X_hi, it.d, it.n, it.ldx)
+                      : make_operand_map(&maps.a0[g], it.X_hi, it.d, it.n, it.ldx, 0, 1, BM);
     if (rc) return rc;
     if (nparts == 3) {
       rc = make_operand_map(&maps.a1[g], it.X_lo, it.d, it.n, it.ldx, 0, 1, BM);
@@ -943,7 +990,8 @@ int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t err = cudaLaunchKernelEx(&cfg, umma_syrk_grouped_kernel, maps, gp);
+  const cudaError_t err = mn_major ? cudaLaunchKernelEx(&cfg, umma_syrk_grouped_mn_kernel, maps, gp)
+                                   : cudaLaunchKernelEx(&cfg, umma_syrk_grouped_kernel, maps, gp);
   note_launch();
   return (err == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -5;
 }

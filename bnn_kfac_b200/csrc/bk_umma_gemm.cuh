@@ -65,8 +65,10 @@ struct SyrkGroupItem {
 // Up to 8 problems in one persistent CTA-pair launch (see bk_umma_gemm.cu).
 // mirror = false: only the lower triangle of each C is accumulated (the caller mirrors once, when the full
 // symmetric factor is read: bk_sym_finalize).
+// mn_major = true: X_hi is the ROW-major activation matrix [n, d] itself (bf16, ldx = its row pitch, a multiple
+// of 8): no staged K-major copy is needed; one precision pass (nparts == 1).
 int launch_umma_syrk_grouped(const SyrkGroupItem* items, int count, int nparts, bool mirror,
-                             cudaStream_t stream);
+                             cudaStream_t stream, bool mn_major = false);
 
 // A/B switches of the grouped SYRK: bit 0 = no diagonal-tile operand dedup, bit 1 = stream-K tail on.
 void set_syrk_tuning(int flags);

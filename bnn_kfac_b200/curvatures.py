@@ -440,13 +440,28 @@ class KFAC(Curvature):
         """Queue state = beta*state + alpha*[in_scale*x ; 1]^T[...]; issued by _flush_syrks()."""
         self._pending.append((state, beta, x, has_bias, in_scale, alpha))
 
+    def _direct_ok(self, state: Tensor, x: Tensor, has_bias: bool) -> bool:
+        """Can this bf16 activation matrix feed the tensor cores as it is (no staging pass)?"""
+        d = x.shape[1]
+        return (x.dtype == torch.bfloat16 and self.precision != "fp32" and d >= 192
+                and d + int(has_bias) > _lib.BK_SMALL_D_MAX and x.stride(1) == 1 and x.stride(0) % 8 == 0
+                and x.data_ptr() % 16 == 0 and state.stride(0) % 4 == 0 and state.data_ptr() % 16 == 0)
+
     def _flush_syrks(self):
         """All queued factor updates of this update() in ONE grouped library call: the wide factors
-        share one persistent tensor-core launch (bk_syrk_accum_grouped)."""
+        share persistent tensor-core launches (bk_syrk_accum_grouped).  bf16 activations (a model under
+        bf16 autocast) are consumed directly — row-major X is the MN-major operand of X^T X — where the factor
+        is wide enough; everything else is handed over as fp32."""
         items, self._pending = self._pending, []
         n = len(items)
         if n == 0:
             return
+        fixed = []
+        for (state, beta, x, has_bias, in_scale, alpha) in items:
+            if x.dtype != torch.float32 and not self._direct_ok(state, x, has_bias):
+                x = x.float()
+            fixed.append((state, beta, x.contiguous() if x.stride(-1) != 1 else x, has_bias, in_scale, alpha))
+        items = fixed
         prec = _PRECISIONS[self.precision]
         ns = (C.c_int * n)(*[it[2].shape[0] for it in items])
         ds = (C.c_int * n)(*[it[2].shape[1] for it in items])
@@ -456,12 +471,13 @@ class KFAC(Curvature):
         states = (C.c_void_p * n)(*[it[0].data_ptr() for it in items])
         lds = (C.c_longlong * n)(*[it[0].stride(0) for it in items])
         xs = (C.c_void_p * n)(*[it[2].data_ptr() for it in items])
+        bf = (C.c_int * n)(*[int(it[2].dtype == torch.bfloat16) for it in items])
         ldx = (C.c_longlong * n)(*[it[2].stride(0) for it in items])
         insc = (C.c_float * n)(*[it[4] for it in items])
         alph = (C.c_float * n)(*[it[5] for it in items])
         beta = (C.c_float * n)(*[it[1] for it in items])
         flags = _lib.SYRK_LOWER_ONLY if self.lower_only else 0
-        _lib.check(self._lib.bk_syrk_accum_grouped(states, lds, xs, ldx, ns, ds, hb, insc, alph, beta, n, prec,
+        _lib.check(self._lib.bk_syrk_accum_grouped(states, lds, xs, bf, ldx, ns, ds, hb, insc, alph, beta, n, prec,
                                                    flags, ws.data_ptr(), nbytes, _lib.stream_ptr()),
                    "bk_syrk_accum_grouped")
 
@@ -507,8 +523,9 @@ class KFAC(Curvature):
             if module_class == 'Conv2d':
                 self._update_conv(layer, forward, backward, first, second, beta, has_bias, n_batch, w)
             else:
-                x = forward.float().contiguous()
-                g = backward.float().contiguous()
+                # fp32 or bf16 as the model produced them (other dtypes are widened in _flush_syrks)
+                x = forward if forward.stride(-1) == 1 else forward.contiguous()
+                g = backward if backward.stride(-1) == 1 else backward.contiguous()
                 self._syrk(first, beta, x, has_bias, 1.0, w / x.shape[0])
                 self._syrk(second, beta, g, False, float(n_batch), w / g.shape[0])
             if wide_mode and max(d_a, d_g) > _lib.BK_SMALL_D_MAX:

@@ -118,13 +118,22 @@ size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* 
  *                       mirrored half of the epilogue's L2 reduction traffic on every update.
  *   BK_SYRK_NO_OVERLAP  stage every operand first, then run the SYRKs (default: the staging of later factors
  *                       runs on an internal per-device side stream underneath the SYRK of earlier ones; the
- *                       call is still ordered on `stream` as a whole). */
+ *                       call is still ordered on `stream` as a whole).
+ *   BK_SYRK_ROW_MAJOR   (bk_syrk_accum_staged_grouped only) the operands are row-major bf16 activations [n, d]
+ *                       (ldt = their row pitch, a multiple of 8), not staged K-major copies.
+ * x_is_bf16 (nullable = all fp32): xs[i] is a bf16 matrix [n, d] (row pitch ldxs[i] % 8 == 0, 16 B aligned base).
+ * Such activations (a model running under bf16 autocast) feed the tensor cores directly - no staging pass, the
+ * products of bf16 values are exact in the fp32 accumulator, so one pass is the full-precision result; only wide
+ * factors (d + has_bias > BK_SMALL_D_MAX, d >= 192) qualify, anything else returns BK_ERR_ARG (convert it to
+ * fp32 first). */
 #define BK_SYRK_LOWER_ONLY 1
 #define BK_SYRK_NO_OVERLAP 2
-int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const float* const* xs,
-                          const long long* ldxs, const int* ns, const int* ds, const int* has_bias,
-                          const float* in_scales, const float* alphas, const float* betas, int count,
-                          int precision, int flags, void* workspace, size_t workspace_bytes, void* stream);
+#define BK_SYRK_ROW_MAJOR 4
+int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const void* const* xs,
+                          const int* x_is_bf16, const long long* ldxs, const int* ns, const int* ds,
+                          const int* has_bias, const float* in_scales, const float* alphas,
+                          const float* betas, int count, int precision, int flags, void* workspace,
+                          size_t workspace_bytes, void* stream);
 /* In place: lower triangle (diagonal included) *= scale, upper triangle = its mirror: turns lower-only
  * (and, for the running-average mode, lazily scaled) accumulators into the full symmetric factors the
  * reference keeps in `state` (models/curvatures.py:359-363).  Host arrays of device pointers, as bk_tri_pack. */

@@ -418,6 +418,36 @@ def test_lower_only_state_reads_and_mirrored_mode_agree(dev):
             h.remove()
 
 
+@pytest.mark.parametrize("shape", [(300, 512, 384), (4096, 4096, 4096), (257, 200, 264)])
+def test_bf16_activations_direct_path(dev, shape):
+    """bf16 activations / output gradients (a model under bf16 autocast) feed the tcgen05 SYRK as they are
+    (row-major X = MN-major operand of X^T X, no staging pass).  Products of bf16 values are exact in the fp32
+    accumulator, so against the fp64 formula on the SAME bf16 values (models/curvatures.py:345-356) the factors
+    must agree to fp32 rounding — sample counts that are not a multiple of the 64-sample TMA box and widths that
+    are not a multiple of the 64-feature box included; two updates exercise `+=`."""
+    from bnn_kfac_b200.curvatures import KFAC
+    n, d_in, d_out = shape
+    lin = torch.nn.Linear(d_in, d_out).to(dev)
+    est = KFAC(torch.nn.Sequential(lin))
+    gen = torch.Generator().manual_seed(n + d_in)
+    refA = refG = 0
+    for _ in range(2):
+        a = torch.randn(n, d_in, generator=gen).to(dev).bfloat16()
+        g = (torch.randn(n, d_out, generator=gen) / n).to(dev).bfloat16()
+        est.record[lin] = [a, g]
+        est.update(n)
+        a1 = torch.cat([a.double(), torch.ones(n, 1, device=dev, dtype=torch.float64)], 1)
+        gs = g.double() * n
+        refA = refA + a1.t() @ a1 / n
+        refG = refG + gs.t() @ gs / n
+    A, G = est.state[lin]
+    assert relerr(A.cpu(), refA.cpu()) < 2e-6 and relerr(G.cpu(), refG.cpu()) < 2e-6
+    assert (A - A.t()).abs().max().item() == 0.0
+    assert abs(A[-1, -1].item() - 2.0) < 1e-6
+    for h in est.hooks:
+        h.remove()
+
+
 # ------------------------------------------------------------------------------------------ (f) NCCL parity
 def test_nccl_two_rank_parity():
     """Sharded accumulation + invert_sharded + mc_predict_sharded over NCCL on 2 GPUs must reproduce the

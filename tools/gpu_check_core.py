@@ -221,7 +221,7 @@ def t_syrk_edges():
         for beta in (0.0, 1.0):
             rc = L.bk_syrk_accum_grouped((C.c_void_p * cnt)(*[t.data_ptr() for t in sts]),
                                          (C.c_longlong * cnt)(*[t.stride(0) for t in sts]),
-                                         (C.c_void_p * cnt)(*[t.data_ptr() for t in xs]),
+                                         (C.c_void_p * cnt)(*[t.data_ptr() for t in xs]), None,
                                          (C.c_longlong * cnt)(*[t.stride(0) for t in xs]), ns, ds, hbs,
                                          (C.c_float * cnt)(*[1.0] * cnt), (C.c_float * cnt)(*[1.0 / s_[0] for s_ in shapes]),
                                          (C.c_float * cnt)(*[beta] * cnt), cnt, 3, flags, ws.data_ptr(), nb,

@@ -21,11 +21,18 @@ def make(cnt):
              hi=(C.c_void_p * cnt)(*[t.data_ptr() for t in his]), lo=(C.c_void_p * cnt)(*[t.data_ptr() for t in his]),
              ldt=(C.c_longlong * cnt)(*[n] * cnt), ns=(C.c_int * cnt)(*[n] * cnt), ds=(C.c_int * cnt)(*[d] * cnt),
              al=(C.c_float * cnt)(*[1.0 / n] * cnt), be=(C.c_float * cnt)(*[1.0] * cnt), keep=(his, sts))
+    xs = [torch.randn(n, d, device=dev).to(torch.bfloat16) for _ in range(cnt)]      # row-major activations
+    a["x"] = (C.c_void_p * cnt)(*[t.data_ptr() for t in xs])
+    a["ldx"] = (C.c_longlong * cnt)(*[d] * cnt)
+    a["keep2"] = xs
     return a
 
 
 def timed(a, cnt, flags, reps=10):
-    f = lambda: _lib.check(L.bk_syrk_accum_staged_grouped(a["states"], a["lds"], a["hi"], a["lo"], a["ldt"], a["ns"],
+    row_major = bool(flags & 4)
+    f = lambda: _lib.check(L.bk_syrk_accum_staged_grouped(a["states"], a["lds"], a["x"] if row_major else a["hi"],
+                                                          a["x"] if row_major else a["lo"],
+                                                          a["ldx"] if row_major else a["ldt"], a["ns"],
                                                           a["ds"], a["al"], a["be"], cnt, 1, flags,
                                                           _lib.stream_ptr()), "grouped")
     f()
@@ -43,13 +50,13 @@ for cnt in (7, 3, 1):
     a = make(cnt)
     res = {}
     for rnd in range(3):
-        for tune in (0, 1, 2, 3):
-            for flags in (1, 0):
+        for tune in (0, 1):
+            for flags in (1, 0, 5):
                 L.bk_set_syrk_tuning(tune)
                 res.setdefault((tune, flags), []).append(timed(a, cnt, flags))
     L.bk_set_syrk_tuning(0)
     for (tune, flags), v in sorted(res.items()):
         us = min(v)
         print(f"factors={cnt} tuning={tune} (dedup={'off' if tune & 1 else 'on'}, tail-split={'on' if tune & 2 else 'off'}) "
-              f"{'lower-only' if flags else 'mirrored'}: best {us:7.1f} us  all {[round(x, 1) for x in v]}  "
+              f"{'lower-only' if flags & 1 else 'mirrored'}{' ROW-MAJOR bf16 activations (no staging)' if flags & 4 else ''}: best {us:7.1f} us  all {[round(x, 1) for x in v]}  "
               f"{cnt * d * (d + 1) * n / us / 1e6:7.1f} TFLOP/s alg", flush=True)
