@@ -18,6 +18,7 @@ BK_SMALL_D_MAX = 176
 BK_SMALL64_MAX_DIM = 112
 BK_SMALL64_MAX_ELEMS = 12544
 BK_SMALL64_MAX_BATCH = 16
+BK_BLOCK_INV_MAX_DIM = 160
 
 SYRK_LOWER_ONLY = 1
 SYRK_NO_OVERLAP = 2
@@ -92,6 +93,8 @@ SIGNATURES = {
     "bk_ger_accum": (_i, [_p, _ll, _p, _i, _f, _f, _p]),
     "bk_kron": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "bk_dominance": (_i, [_p, _ll, _i, _f, _p, _p, _i, _p, _p]),
+    "bk_band_mask": (_i, [_p, _ll, _i, _f, _i, _p, _p, _p, _ll, _p]),
+    "bk_block_inverse": (_i, [_p, _ll, _i, _p, _p, _i, _i, C.c_double, _p, _ll, _i, _p, _p]),
     "bk_tri_pack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _p]),
     "bk_tri_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _f, _i, _p]),
     "bk_inf_regularise": (_i, [_p, _ll, _p, _ll, _f, _f, _p, _p, _p]),

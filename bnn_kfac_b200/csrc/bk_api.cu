@@ -700,5 +700,17 @@ int bk_kron_quadform_f64(const float* v, long long stride_v, int batch, int d_in
                                       as_stream(stream));
 }
 
+int bk_band_mask(float* h, long long ld, int p, float tau, int add_tau_in_place, const int* row_lo,
+                 const int* row_hi, float* out, long long ldo, void* stream) {
+  return bk::launch_band_mask(h, ld, p, tau, add_tau_in_place, row_lo, row_hi, out, ldo, as_stream(stream));
+}
+
+int bk_block_inverse(const float* res, long long ld, int p, const int* comp_begin, const int* comp_end,
+                     int ncomp, int max_dim, double scale, float* out, long long ldo, int zero_fill, int* status,
+                     void* stream) {
+  return bk::launch_block_inverse(res, ld, p, comp_begin, comp_end, ncomp, max_dim, scale, out, ldo, zero_fill,
+                                  status, as_stream(stream));
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

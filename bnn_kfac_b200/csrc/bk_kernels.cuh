@@ -93,6 +93,14 @@ int launch_ger_accum(float* state, long long ld, const float* g, int P, float al
 int launch_kron(const float* a, int m, int n, const float* b, int p, int q, float* out,
                 cudaStream_t stream);
 
+// ---- bk_blockdiag.cu  (kernel-block-diagonal masks and per-component inverses of a dense Fisher)
+constexpr int kBlockInvMaxDim = 160;      // one [d][d+1] fp64 matrix in one CTA's shared memory
+int launch_band_mask(float* H, long long ld, int P, float tau, int in_place, const int* row_lo,
+                     const int* row_hi, float* out, long long ldo, cudaStream_t stream);
+int launch_block_inverse(const float* R, long long ld, int P, const int* comp_begin, const int* comp_end,
+                         int ncomp, int max_dim, double scale, float* out, long long ldo, int zero_fill,
+                         int* status, cudaStream_t stream);
+
 // ---- bk_tri.cu  (lower-triangle packing of symmetric factors for the multi-GPU exchange)
 int launch_tri_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
                     cudaStream_t stream);

@@ -232,6 +232,24 @@ int bk_ger_accum(float* state, long long ld, const float* g, int p, float alpha,
  * (models/utilities.py:387-409, sampling_free/utils.py:279-290). */
 int bk_kron(const float* a, int m, int n, const float* b, int p, int q, float* out, void* stream);
 
+/* Kernel-block-diagonal approximation of a dense Fisher (sampling_free/utils.py:63-211,
+ * generate_kernel_diag_15080 / _748 / _141 / generate_kernel_diag):
+ *     H += tau I;  res = 0;  res[a:b, a:b] = H[a:b, a:b] for every block;  return res, inverse(n * res)
+ * bk_band_mask: out[i][j] = H[i][j] (+ tau on the diagonal) for row_lo[i] <= j < row_hi[i], else 0; row_lo /
+ * row_hi (device int [p]) are the extreme bounds of the blocks that contain row i (0, 0 for a row in no block) -
+ * for interval blocks, overlapping ones included, that is exactly the union of the squares.
+ * add_tau_in_place != 0 also performs the reference's in-place H += tau I.  h and out must not alias.
+ * bk_block_inverse: out[a:b, a:b] = inverse(scale * res[a:b, a:b]) for each CONNECTED component [a, b) of the
+ * block union (device int arrays, b - a <= BK_BLOCK_INV_MAX_DIM = max_dim bound): fp64 Gauss-Jordan with partial
+ * pivoting, one CTA per component; zero_fill != 0 clears the rest of out first.  status (device int, nullable):
+ * 0 or 65536 * component + (1-based step) of the first exactly singular pivot. */
+#define BK_BLOCK_INV_MAX_DIM 160
+int bk_band_mask(float* h, long long ld, int p, float tau, int add_tau_in_place, const int* row_lo,
+                 const int* row_hi, float* out, long long ldo, void* stream);
+int bk_block_inverse(const float* res, long long ld, int p, const int* comp_begin, const int* comp_end,
+                     int ncomp, int max_dim, double scale, float* out, long long ldo, int zero_fill, int* status,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU factor exchange (no counterpart in the single-device reference).  The accumulated
  * factors are symmetric, so ranks exchange packed lower triangles: factor after factor in one flat fp32

@@ -402,6 +402,42 @@ def dense_variance(J: Tensor, H_inv: Tensor) -> float:
     return torch.abs(J @ H_inv @ J.t()).item()
 
 
+def kernel_coords(P: int, n_hid: Optional[int] = None) -> List[Tuple[int, int]]:
+    """Block ranges of sampling_free/utils.py: P = 15080 (:65-93), 748 (:108-129), 141 (:146-167); n_hid given:
+    the regression variant (:181-201), whose first loop advances by 1 while its blocks are n_hid wide."""
+    if n_hid is not None:
+        groups = ((n_hid, n_hid, 1, n_hid), (n_hid, n_hid, n_hid, n_hid), (1, n_hid, n_hid, 1))
+    else:
+        groups = {15080: ((5, 25, 25, 5), (10, 125, 125, 10), (80, 160, 160, 80), (10, 80, 80, 10)),
+                  748: ((3, 9, 9, 3), (6, 27, 27, 6), (10, 54, 54, 10)),
+                  141: ((10, 1, 1, 10), (10, 10, 10, 10), (1, 10, 10, 1))}[P]
+    coords, curr = [], 0
+    for count, size, step, bias in groups:
+        for _ in range(count):
+            coords.append((curr, curr + size))
+            curr += step
+        coords.append((curr, curr + bias))
+        curr += bias
+    return coords
+
+
+def kernel_diag(H: Tensor, coords: Sequence[Tuple[int, int]], tau: float = 0.0, n: float = 1.0
+                ) -> Tuple[Tensor, Tensor]:
+    """H += tau I (in place); res[a:b, a:b] = H[a:b, a:b] per block; (res, inverse(n * res)).
+    sampling_free/utils.py:95-103 (same body at :131-138, :169-177, :203-211)."""
+    res = torch.zeros_like(H)
+    H += tau * torch.eye(H.shape[0], dtype=H.dtype)
+    for (a, b) in coords:
+        res[a:b, a:b] = H[a:b, a:b]
+    return res, torch.inverse(n * res)
+
+
+def diag_approximation(H: Tensor, tau: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """(diag(diag(H) + tau), diag(1 / (diag(H) + tau))).  sampling_free/utils.py:42-45."""
+    h = torch.diag(H) + tau
+    return torch.diag(h), torch.diag(torch.reciprocal(h))
+
+
 # =============================================================================== eigen-decomposition
 def factor_eigenvectors(xxt: Tensor, ggt: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Eigen-decomposition of F + F^T (SUM, not mean) in ascending order; restated with

@@ -370,3 +370,24 @@ def test_staged_reference_matches_oracle_port():
         f1, f2 = O.kfac_linear_factors(a, g, True)
         assert torch.allclose(est.state[layer][0], 2 * f1, atol=1e-12)
         assert torch.allclose(est.state[layer][1], 2 * f2, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["kd748", "kd141", "kdreg5", "kdreg30"])
+def test_kernel_diag_oracle_vs_reference(name):
+    """oracle.kernel_diag / kernel_coords against outputs of the reference's generate_kernel_diag* functions
+    (tests/golden/make_golden_kernel_diag.py)."""
+    g = dict(np.load(ROOT / "tests" / "golden" / "reference_golden_kernel_diag.npz"))
+    P, n, tau, scale, n_hid = g[f"{name}_meta"]
+    P, n_hid = int(P), (None if n_hid < 0 else int(n_hid))
+    G = torch.tensor(g[f"{name}_G"]).double()
+    H = G.t() @ G / G.shape[0]
+    H0 = H.clone()
+    res, inv = O.kernel_diag(H, O.kernel_coords(P, n_hid), float(tau), float(scale))
+    assert torch.equal(H, H0 + float(tau) * torch.eye(P, dtype=torch.float64))     # in-place side effect
+    assert relerr(res, g[f"{name}_res"]) < 1e-6
+    assert relerr(inv, g[f"{name}_inv"]) < 1e-5
+    if name == "kd141":
+        d_res, d_inv = O.diag_approximation(H0, float(tau))
+        assert relerr(d_res, g["kd141_diag_res"]) < 1e-12 and relerr(d_inv, g["kd141_diag_inv"]) < 1e-12
+        assert relerr(O.dense_inverse(H0, float(tau)), g["kd141_H_inv"]) < 1e-6
+        assert abs(O.dominance(H0, [], 1e-5)[0] - float(g["kd141_dominance"])) < 1e-12
