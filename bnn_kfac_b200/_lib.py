@@ -93,8 +93,10 @@ SIGNATURES = {
     "bk_ger_accum": (_i, [_p, _ll, _p, _i, _f, _f, _p]),
     "bk_kron": (_i, [_p, _i, _i, _p, _i, _i, _p, _p]),
     "bk_dominance": (_i, [_p, _ll, _i, _f, _p, _p, _i, _p, _p]),
+    "bk_chol_trinv_f64": (_i, [_p, _ll, _i, C.c_double, _p, _ll, _p, _p]),
     "bk_band_mask": (_i, [_p, _ll, _i, _f, _i, _p, _p, _p, _ll, _p]),
     "bk_block_inverse": (_i, [_p, _ll, _i, _p, _p, _i, _i, C.c_double, _p, _ll, _i, _p, _p]),
+    "bk_dominance_rows": (_i, [_p, _ll, _i, _i, _i, _f, _p, _p, _i, _p, _p]),
     "bk_tri_pack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _p]),
     "bk_tri_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _f, _i, _p]),
     "bk_inf_regularise": (_i, [_p, _ll, _p, _ll, _f, _f, _p, _p, _p]),

@@ -568,7 +568,15 @@ int bk_dominance(const float* h, long long ld, int p, float tau, const int* bloc
                  const int* block_end, int nblocks, double* out3, void* stream) {
   if (h == nullptr || out3 == nullptr || ld < p) return BK_ERR_ARG;
   if (nblocks > 0 && (block_begin == nullptr || block_end == nullptr)) return BK_ERR_ARG;
-  return bk::launch_dominance(h, ld, p, tau, block_begin, block_end, nblocks, out3,
+  return bk::launch_dominance(h, ld, 0, p, p, tau, block_begin, block_end, nblocks, out3,
+                              as_stream(stream));
+}
+
+int bk_dominance_rows(const float* rows, long long ld, int row0, int nrows, int p, float tau,
+                      const int* block_begin, const int* block_end, int nblocks, double* out3, void* stream) {
+  if (rows == nullptr || out3 == nullptr || ld < p || row0 < 0 || nrows < 0 || row0 + nrows > p) return BK_ERR_ARG;
+  if (nblocks > 0 && (block_begin == nullptr || block_end == nullptr)) return BK_ERR_ARG;
+  return bk::launch_dominance(rows, ld, row0, nrows, p, tau, block_begin, block_end, nblocks, out3,
                               as_stream(stream));
 }
 
@@ -698,6 +706,11 @@ int bk_kron_quadform_f64(const float* v, long long stride_v, int batch, int d_in
   if (batch > 0 && (v == nullptr || q == nullptr || h == nullptr || out == nullptr)) return BK_ERR_ARG;
   return bk::launch_kron_quadform_f64(v, stride_v, batch, d_in_p, d_out, q, h, out, accumulate,
                                       as_stream(stream));
+}
+
+int bk_chol_trinv_f64(const float* f, long long ldf, int d, double add, float* w, long long ldw, int* status,
+                      void* stream) {
+  return bk::launch_chol_trinv_f64(f, ldf, d, add, w, ldw, status, as_stream(stream));
 }
 
 int bk_band_mask(float* h, long long ld, int p, float tau, int add_tau_in_place, const int* row_lo,

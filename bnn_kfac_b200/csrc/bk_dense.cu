@@ -15,14 +15,15 @@ namespace bk {
 namespace {
 
 __global__ void __launch_bounds__(256)
-dominance_kernel(const float* __restrict__ H, long long ld, int P, float tau,
+dominance_kernel(const float* __restrict__ H, long long ld, int row0, int nrows, int P, float tau,
                  const int* __restrict__ block_begin, const int* __restrict__ block_end, int nblocks,
                  double* __restrict__ out) {
   __shared__ double red[3][8];
   double s_diag = 0.0, s_all = 0.0, s_blk = 0.0;
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(H) & 15) == 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = blockIdx.x; i < P; i += gridDim.x) {
+  // H points at global row `row0`; this launch covers the global rows [row0, row0 + nrows)
+  for (int i = row0 + blockIdx.x; i < row0 + nrows; i += gridDim.x) {
     // diagonal block that contains row i (blocks are disjoint, ascending): binary search
     int lo = 0, hi = nblocks - 1, b0 = 0, b1 = 0;
     while (lo <= hi) {
@@ -36,7 +37,7 @@ dominance_kernel(const float* __restrict__ H, long long ld, int P, float tau,
         break;
       }
     }
-    const float* row = H + static_cast<long long>(i) * ld;
+    const float* row = H + static_cast<long long>(i - row0) * ld;
     float a_all = 0.f, a_blk = 0.f;  // fp32 per-thread partials over <= P/256 addends, fp64 above
     auto take = [&](float x, int jj) {
       if (jj == i) {
@@ -163,12 +164,12 @@ int launch_kron(const float* a, int m, int n, const float* b, int p, int q, floa
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
-int launch_dominance(const float* H, long long ld, int P, float tau, const int* block_begin,
+int launch_dominance(const float* H, long long ld, int row0, int nrows, int P, float tau, const int* block_begin,
                      const int* block_end, int nblocks, double* out3, cudaStream_t stream) {
-  if (P <= 0) return 0;
   if (cudaMemsetAsync(out3, 0, 3 * sizeof(double), stream) != cudaSuccess) return -5;
-  int grid = P < kNumSMsB200 * 16 ? P : kNumSMsB200 * 16;
-  dominance_kernel<<<grid, 256, 0, stream>>>(H, ld, P, tau, block_begin, block_end, nblocks, out3);
+  if (P <= 0 || nrows <= 0) return 0;
+  int grid = nrows < kNumSMsB200 * 16 ? nrows : kNumSMsB200 * 16;
+  dominance_kernel<<<grid, 256, 0, stream>>>(H, ld, row0, nrows, P, tau, block_begin, block_end, nblocks, out3);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

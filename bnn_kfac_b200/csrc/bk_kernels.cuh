@@ -85,7 +85,8 @@ void set_eigh_mode(int mode);
 void set_eigh_pair_width(int p);  // 0 = automatic, 64 or 128
 
 // ---- bk_dense.cu
-int launch_dominance(const float* H, long long ld, int P, float tau, const int* block_begin,
+// H points at global row row0 of the P x P matrix; rows [row0, row0 + nrows) are summed.
+int launch_dominance(const float* H, long long ld, int row0, int nrows, int P, float tau, const int* block_begin,
                      const int* block_end, int nblocks, double* out3, cudaStream_t stream);
 
 int launch_ger_accum(float* state, long long ld, const float* g, int P, float alpha, float beta,
@@ -150,6 +151,9 @@ constexpr int kSmall64MaxBatch = 16;      // factors per launch
 int launch_spd_inverse_f64(const float* const* factors, const long long* lds, const int* dims,
                            const double* add, const double* mult, double* const* outs, int count,
                            int* status, cudaStream_t stream);
+// W = chol(sym_lower(F) + add I)^-1 (fp32 lower-triangular, d <= kSmall64MaxDim); status: atomicCAS(0 -> pivot).
+int launch_chol_trinv_f64(const float* F, long long ldf, int d, double add, float* W, long long ldw,
+                          int* status, cudaStream_t stream);
 int launch_kron_quadform_f64(const float* V, long long stride_v, int batch, int dinp, int dout,
                              const double* Q, const double* H, float* out, int accumulate,
                              cudaStream_t stream);

@@ -31,32 +31,14 @@ struct Inv64Batch {
   double add[kSmall64MaxBatch], mult[kSmall64MaxBatch];
 };
 
-// shared memory: A [d][d+1] doubles (R, then L in the lower triangle), X [d][d+1] (L^-1)
-__global__ void __launch_bounds__(kInvThreads)
-spd_inverse_f64_kernel(const __grid_constant__ Inv64Batch p, int* __restrict__ status) {
-  extern __shared__ double sm64[];
-  const int b = blockIdx.x;
-  const int d = p.d[b];
-  const int ld = d + 1;
-  double* A = sm64;
-  double* X = sm64 + static_cast<size_t>(d) * ld;
-  const float* F = p.f[b];
-  const long long ldf = p.ld[b];
-  const int tid = threadIdx.x;
-  __shared__ int bad;
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < d * d; e += kInvThreads) {
-    const int i = e / d, j = e - i * d;
-    const double s = 0.5 * (static_cast<double>(F[i * ldf + j]) + static_cast<double>(F[j * ldf + i]));
-    A[i * ld + j] = p.mult[b] * s + (i == j ? p.add[b] : 0.0);
-    X[i * ld + j] = 0.0;
-  }
-  __syncthreads();
+// In shared memory: A (SPD, [d][ld]) -> L in its lower triangle; X (zero-filled) -> L^-1 (lower triangular).
+// *bad receives the 1-based index of the first non-positive pivot.  All threads of the CTA call it.
+__device__ void chol_trinv_shared(double* A, double* X, int d, int ld, int tid, int* bad) {
   // right-looking Cholesky, one column per step
   for (int k = 0; k < d; ++k) {
     if (tid == 0) {
       const double v = A[k * ld + k];
-      if (!(v > 0.0)) bad = k + 1;
+      if (!(v > 0.0) && *bad == 0) *bad = k + 1;
       A[k * ld + k] = sqrt(v > 0.0 ? v : 1.0);
     }
     __syncthreads();
@@ -79,6 +61,30 @@ spd_inverse_f64_kernel(const __grid_constant__ Inv64Batch p, int* __restrict__ s
     }
   }
   __syncthreads();
+}
+
+// shared memory: A [d][d+1] doubles (R, then L in the lower triangle), X [d][d+1] (L^-1)
+__global__ void __launch_bounds__(kInvThreads)
+spd_inverse_f64_kernel(const __grid_constant__ Inv64Batch p, int* __restrict__ status) {
+  extern __shared__ double sm64[];
+  const int b = blockIdx.x;
+  const int d = p.d[b];
+  const int ld = d + 1;
+  double* A = sm64;
+  double* X = sm64 + static_cast<size_t>(d) * ld;
+  const float* F = p.f[b];
+  const long long ldf = p.ld[b];
+  const int tid = threadIdx.x;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < d * d; e += kInvThreads) {
+    const int i = e / d, j = e - i * d;
+    const double s = 0.5 * (static_cast<double>(F[i * ldf + j]) + static_cast<double>(F[j * ldf + i]));
+    A[i * ld + j] = p.mult[b] * s + (i == j ? p.add[b] : 0.0);
+    X[i * ld + j] = 0.0;
+  }
+  __syncthreads();
+  chol_trinv_shared(A, X, d, ld, tid, &bad);
   // R^-1 = X^T X  (X lower triangular: sum over t >= max(i, j))
   double* out = p.out[b];
   for (int e = tid; e < d * d; e += kInvThreads) {
@@ -88,6 +94,34 @@ spd_inverse_f64_kernel(const __grid_constant__ Inv64Batch p, int* __restrict__ s
     out[e] = s;
   }
   if (tid == 0 && bad != 0 && status != nullptr) atomicCAS(status, 0, b * 65536 + bad);
+}
+
+// One diagonal block of the sharded dense-Fisher Cholesky (distributed.dense_fisher_sharded): R = sym(F) + add I,
+// W = chol(R)^-1 written as an fp32 lower-triangular matrix (zero upper triangle), one CTA.
+__global__ void __launch_bounds__(kInvThreads)
+chol_trinv_f64_kernel(const float* __restrict__ F, long long ldf, int d, double add, float* __restrict__ W,
+                      long long ldw, int* __restrict__ status) {
+  extern __shared__ double sm64[];
+  const int ld = d + 1;
+  double* A = sm64;
+  double* X = sm64 + static_cast<size_t>(d) * ld;
+  const int tid = threadIdx.x;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  for (int e = tid; e < d * d; e += kInvThreads) {
+    const int i = e / d, j = e - i * d;
+    // lower triangle is authoritative (the trailing updates of the blocked factorisation touch it only)
+    const double s = static_cast<double>(i >= j ? F[i * ldf + j] : F[j * ldf + i]);
+    A[i * ld + j] = s + (i == j ? add : 0.0);
+    X[i * ld + j] = 0.0;
+  }
+  __syncthreads();
+  chol_trinv_shared(A, X, d, ld, tid, &bad);
+  for (int e = tid; e < d * d; e += kInvThreads) {
+    const int i = e / d, j = e - i * d;
+    W[i * ldw + j] = (j <= i) ? static_cast<float>(X[i * ld + j]) : 0.f;
+  }
+  if (tid == 0 && bad != 0 && status != nullptr) atomicCAS(status, 0, bad);
 }
 
 // one CTA per test point: Vs [dinp][dout], U = Q V [dinp][dout] in shared memory
@@ -159,6 +193,23 @@ int launch_spd_inverse_f64(const float* const* factors, const long long* lds, co
     return -5;
   if (status != nullptr && cudaMemsetAsync(status, 0, sizeof(int), stream) != cudaSuccess) return -5;
   spd_inverse_f64_kernel<<<count, kInvThreads, smem, stream>>>(p, status);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_chol_trinv_f64(const float* F, long long ldf, int d, double add, float* W, long long ldw,
+                          int* status, cudaStream_t stream) {
+  if (d <= 0) return 0;
+  if (F == nullptr || W == nullptr || d > kSmall64MaxDim || ldf < d || ldw < d) return -2;
+  const size_t smem = 2ull * d * (d + 1) * sizeof(double);
+  static DeviceOnce attr_once;
+  if (!attr_once([] {
+        return cudaFuncSetAttribute(chol_trinv_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(2ull * kSmall64MaxDim * (kSmall64MaxDim + 1) *
+                                                     sizeof(double))) == cudaSuccess;
+      }))
+    return -5;
+  chol_trinv_f64_kernel<<<1, kInvThreads, smem, stream>>>(F, ldf, d, add, W, ldw, status);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

@@ -224,6 +224,10 @@ int bk_eigh_batched(const float* const* factors_host, const long long* ld_host,
  */
 int bk_dominance(const float* h, long long ld, int p, float tau, const int* block_begin,
                  const int* block_end, int nblocks, double* out3, void* stream);
+/* The same sums over the global rows [row0, row0 + nrows) only; `rows` points at row row0 (a row-block shard of
+ * the dense Fisher, bnn_kfac_b200/dense_sharded.py: the ranks' partial sums are added by one all-reduce). */
+int bk_dominance_rows(const float* rows, long long ld, int row0, int nrows, int p, float tau,
+                      const int* block_begin, const int* block_end, int nblocks, double* out3, void* stream);
 /* Rank-1 accumulation state = beta*state + alpha * g g^T, state [p, p] fp32 (row pitch ld), g [p]:
  * BlockDiagonal.update (models/curvatures.py:228-232, `torch.ger(grads, grads) * batch_size`, `+=`). */
 int bk_ger_accum(float* state, long long ld, const float* g, int p, float alpha, float beta,
@@ -348,6 +352,14 @@ int bk_spd_inverse_f64(const float* const* factors_host, const long long* ld_hos
                        int count, int* status, void* stream);
 int bk_kron_quadform_f64(const float* v, long long stride_v, int batch, int d_in_p, int d_out,
                          const double* q, const double* h, float* out, int accumulate, void* stream);
+
+/* One diagonal block of the blocked Cholesky of the SHARDED dense Fisher (no counterpart in the
+ * single-device reference, whose `pinverse(H + tau I)` is sampling_free/classification/classification_ll_dense.py:
+ * 108-109): w (fp32 [d, ldw], lower triangular, zero upper part) = chol(sym_lower(f) + add I)^-1, computed in fp64
+ * by one CTA, d <= BK_SMALL64_MAX_DIM; only the lower triangle of f is read.  status (device int, nullable, NOT
+ * cleared by the call) receives the 1-based pivot index if the block is not positive definite. */
+int bk_chol_trinv_f64(const float* f, long long ldf, int d, double add, float* w, long long ldw, int* status,
+                      void* stream);
 
 #ifdef __cplusplus
 }

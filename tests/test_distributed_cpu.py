@@ -148,6 +148,91 @@ def _worker(rank, world, port, tmp):
         D.allreduce_mean_grads(m)
         for p in m.parameters():
             assert torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2))
+
+        # 6) Diagonal update with the batch sharded: all-reduce of the mean gradient, global batch size
+        class _Diag:
+            def __init__(self, model):
+                self.model, self.seen = model, None
+
+            def update(self, batch_size):
+                self.seen = (batch_size, [p.grad.clone() for p in self.model.parameters()])
+
+        m = torch.nn.Linear(3, 2)
+        for p in m.parameters():
+            p.grad = torch.full_like(p, float(2 * rank + 1))
+        dg = _Diag(m)
+        D.diagonal_update_sharded(dg, 16)
+        assert dg.seen[0] == 16 * world
+        assert all(torch.allclose(g, torch.full_like(g, float(world))) for g in dg.seen[1])   # mean of 1, 3
+
+        # 7) linearised predictive, test inputs / test batches sharded
+        xt = torch.linspace(-6, 6, 7).view(7, 1)
+        got = D.linearised_kfac_regression_sharded(None, xt, 0.01, 30.0, 3.0,
+                                                   fn=lambda e, x, tau, N, sigma: (x[:, 0] ** 2 * N + sigma))
+        assert torch.allclose(got, xt[:, 0] ** 2 * 30.0 + 3.0)
+        batches = [torch.full((3 + i, 4), float(i)) for i in range(5)]
+        fn = lambda e, x: (x[:, :2] + 1, float(x[0, 0]) * 2, float(x[0, 0]) - 1)   # noqa: E731
+        pm, ps, pe = D.linearised_kfac_classification_sharded(None, batches, fn=fn)
+        assert torch.equal(pm, torch.cat([b[:, :2] + 1 for b in batches]))
+        assert ps.tolist() == [0.0, 2.0, 4.0, 6.0, 8.0] and pe.tolist() == [-1.0, 0.0, 1.0, 2.0, 3.0]
+        a5, b5 = D.row_slice(5, world, rank)
+        Jl = torch.arange(a5, b5, dtype=torch.float32).view(-1, 1).repeat(1, 3)
+        got = D.linearised_diag_sharded(None, Jl, 5, fn=lambda e, J: (J * J).sum(1))
+        assert torch.equal(got, 3 * torch.arange(5, dtype=torch.float32) ** 2)
+        # more ranks than rows: empty shards still take part in the collectives
+        got = D.linearised_kfac_regression_sharded(None, xt[:1], 0.01, 30.0, 3.0,
+                                                   fn=lambda e, x, tau, N, sigma: x[:, 0] * 0 + 5.0)
+        assert got.tolist() == [5.0]
+
+        # 8) dense Fisher: gradient rows split, reduce-scatter by row block (block-cyclic), dominance from the
+        #    shards, bordered blocked Cholesky on the sharded rows for |J (H + tau I)^-1 J^T|
+        from bnn_kfac_b200 import dense_sharded as DS
+
+        class TorchOps:
+            """fp64 torch stand-ins for the four CUDA operations (test infrastructure only)."""
+
+            def syrk(self, grads, normalise):
+                return grads.t() @ grads / normalise
+
+            def chol_trinv(self, blk, add, status):
+                a = torch.tril(blk) + torch.tril(blk, -1).t() + add * torch.eye(blk.shape[0], dtype=blk.dtype)
+                return torch.linalg.inv(torch.linalg.cholesky(a))
+
+            def gemm_nt(self, a, b, out, alpha, beta):
+                if a.shape[0] and b.shape[0]:
+                    out.copy_(alpha * (a.clone() @ b.clone().t()) + beta * out)
+
+            def rownorm2(self, y):
+                return (y * y).sum(1)
+
+            def dominance_rows(self, rows, row0, P, tau, coords):
+                reg = rows[:, :P].clone()
+                idx = torch.arange(rows.shape[0])
+                reg[idx, row0 + idx] += tau
+                blk = sum(reg[max(a, row0) - row0:max(min(b, row0 + rows.shape[0]) - row0, 0), a:b].abs().sum()
+                          for a, b in coords)
+                return torch.stack([reg[idx, row0 + idx].abs().sum(), reg.abs().sum(),
+                                    torch.as_tensor(blk, dtype=reg.dtype)])
+
+        for P, nb in ((23, 4), (16, 4), (5, 8)):
+            gen = torch.Generator().manual_seed(77)
+            G = torch.randn(12, P, generator=gen, dtype=torch.float64)
+            J = torch.randn(5, P, generator=gen, dtype=torch.float64)
+            ga, gb = D.row_slice(12, world, rank)
+            ja, jb = D.row_slice(5, world, rank)
+            sh = DS.dense_fisher_sharded(G[ga:gb], 12, nb=nb, ops=TorchOps())
+            H = G.t() @ G / 12
+            for l, g in enumerate(sh.mine):                     # each rank holds exactly its block rows of H
+                n = min(nb, P - g * nb)
+                assert torch.allclose(sh.rows[l * nb:l * nb + n, :P], H[g * nb:g * nb + n], atol=1e-12)
+            coords = [(0, 3), (3, 5)] if P > 5 else [(0, 2)]
+            d1, d2 = sh.dominance(coords, 1e-5)
+            r1, r2 = O.dominance(H, coords, 1e-5)
+            assert abs(d1 - r1) < 1e-12 and abs(d2 - r2) < 1e-12
+            var = sh.variance(J[ja:jb], 0.04, n_rows=5)
+            ref = torch.stack([torch.as_tensor(O.dense_variance(J[i:i + 1], O.dense_inverse(H, 0.04)), dtype=torch.float64)
+                               for i in range(5)])
+            assert torch.allclose(var, ref.to(var.dtype), rtol=1e-9), (P, nb, var, ref)
         Path(tmp, f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()

@@ -88,3 +88,55 @@ def test_kernel_diag_15080_blocks_vs_fp64(dev):
     assert not res[~mask].any() and not inv[~mask].any()
     with pytest.raises(NotImplementedError):
         dense.generate_kernel_diag_15080(H[:100, :100].contiguous(), 0.04)
+
+
+# ------------------------------------------------------------------------------------------ e5 (world size 1)
+@pytest.mark.parametrize("P,nb", [(1500, 112), (700, 64)])
+def test_dense_fisher_sharded_single_rank_vs_oracle(dev, P, nb):
+    """dense_sharded (row-block-cyclic H, bordered blocked Cholesky through bk_chol_trinv_f64 + tensor-core panel /
+    trailing GEMMs) at world size 1 against the fp64 oracle: hessian/utils.py:4-23 (dominance) and
+    classification_ll_dense.py:108-109,160-161 (|J pinv(H + tau I) J^T|).  The same code runs under NCCL in
+    tools/gpu_dist_check.py (2+ GPUs)."""
+    from bnn_kfac_b200 import dense, dense_sharded
+    n, B, tau = 256, 24, 0.04
+    gen = torch.Generator().manual_seed(31)
+    G = 0.3 * torch.randn(n, P, generator=gen)
+    J = torch.randn(B, P, generator=gen)
+    sh = dense_sharded.dense_fisher_sharded(G.to(dev), n, nb=nb)
+    H64 = O.dense_fisher(G.double())
+    coords = [(i, min(i + 50, P)) for i in range(0, P, 50)]
+    d = sh.dominance(coords, 1e-5)
+    r = O.dominance(H64, coords, 1e-5)
+    assert abs(d[0] - r[0]) < 1e-5 * r[0] + 1e-9 and abs(d[1] - r[1]) < 1e-4 * r[1]
+    var = sh.variance(J.to(dev), tau)
+    Hinv = O.dense_inverse(H64, tau)
+    ref = torch.tensor([O.dense_variance(J[i:i + 1].double(), Hinv) for i in range(B)])
+    assert relerr(var.cpu(), ref) < TOL
+    assert float(((var.cpu().double() - ref).abs() / ref).max()) < TOL
+    # and against the replicated single-GPU path of dense.py
+    H = dense.dense_fisher(G.to(dev))
+    var1 = dense.dense_variance(J.to(dev), dense.dense_inverse(H, tau))
+    assert relerr(var.cpu(), var1.cpu()) < TOL
+
+
+def test_sharded_entry_points_world1(dev):
+    """e4 / e6 entry points without a process group (world size 1) equal the plain calls."""
+    from bnn_kfac_b200 import distributed as D
+    from bnn_kfac_b200.curvatures import Diagonal
+    from bnn_kfac_b200.wrapper import MLP
+    torch.manual_seed(3)
+    m = MLP([20, 16, 5]).to(dev)
+    x = torch.rand(8, 20, device=dev)
+    y = torch.randint(0, 5, (8,), device=dev)
+    est_a, est_b = Diagonal(m), Diagonal(m)
+    loss = torch.nn.functional.cross_entropy(m(x), y)
+    m.zero_grad()
+    loss.backward()
+    est_a.update(8)
+    D.diagonal_update_sharded(est_b, 8)
+    for (la, va), (lb, vb) in zip(est_a.state.items(), est_b.state.items()):
+        assert torch.equal(va, vb)
+    est_a.invert(1.0, 10.0)
+    J = torch.randn(6, sum(p.numel() for p in m.parameters()), device=dev)
+    from bnn_kfac_b200.predictive import linearised_diag
+    assert torch.equal(D.linearised_diag_sharded(est_a, J, 6), linearised_diag(est_a, J))
