@@ -301,6 +301,10 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import gpu_dist_check
         parity = gpu_dist_check.run_check(rank, world, dev)
+        # SURVEY 8(e) rows 4-6 (linearised predictive, Diagonal, dense Fisher at BASELINE config 3's P = 15 080)
+        # under NCCL: parity against one GPU + a device-timed figure each
+        sharded_rows = gpu_dist_check.run_check_rows(rank, world, dev, dense_p=15080)
+        parity["ok"] = parity["ok"] and sharded_rows["ok"]
 
     torch.manual_seed(0)
     model = MLP(WIDTHS).to(dev)
@@ -516,6 +520,7 @@ def main():
     line["step_frac_of_burst_peak"] = line["algorithmic_tflops"] / world / peaks["bf16_tflops"]
     if parity is not None:
         line["parity"] = parity
+        line["sharded_rows"] = sharded_rows
     if reduce_ms is not None:
         state_bytes = sum(t.numel() * 4 for l in layers for t in est.state[l])
         wire_bytes = sum(t.shape[0] * (t.shape[0] + 1) // 2 * 4 for l in layers for t in est.state[l])

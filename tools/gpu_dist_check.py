@@ -85,6 +85,99 @@ def run_check(rank, world, dev):
                     "(MLP 300-520-260-10)"}
 
 
+def _ev_ms(fn, dev):
+    """Device time of fn(), max over ranks, after a barrier (collectives inside must start together)."""
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return out, t.item()
+
+
+def run_check_rows(rank, world, dev, dense_p=3000):
+    """SURVEY 8(e) rows 4-6 under NCCL against the single-GPU result, with a device-timed figure each:
+    linearised predictive with the test inputs sharded, Diagonal update with the batch sharded (mean gradient
+    all-reduced before squaring), dense Fisher with the gradient rows split (reduce-scatter by row block,
+    dominance from the shards, bordered blocked Cholesky on the sharded rows)."""
+    from bnn_kfac_b200 import dense, dense_sharded
+    from bnn_kfac_b200.curvatures import Diagonal
+    from bnn_kfac_b200.predictive import linearised_diag, linearised_kfac_regression
+    out = {}
+    # ---- e4: sampling-free regression predictive (regression_ll_block.py:120-140), test points sharded
+    torch.manual_seed(2)
+    net = MLP([1, 50, 50, 1]).to(dev)      # the toy regression net of BASELINE config 2
+    est = KFAC(net, seed=3)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(30, 1, generator=g) * 8 - 4).to(dev)
+    y = x ** 3
+    loss = torch.nn.functional.mse_loss(net(x), y)
+    net.zero_grad()
+    loss.backward()
+    est.update(30)
+    xt = torch.linspace(-6, 6, 100, device=dev).view(-1, 1)
+    got, ms = _ev_ms(lambda: D.linearised_kfac_regression_sharded(est, xt, 0.01, 30.0, 3.0), dev)
+    ref = linearised_kfac_regression(est, xt, 0.01, 30.0, 3.0)
+    out["linearised_regression"] = {"relerr": relerr(got, ref), "ms": ms, "test_points": 100}
+    for h in est.hooks:
+        h.remove()
+    # ---- e6: Diagonal, batch sharded
+    widths = [300, 520, 260, 10]
+    n_per = 64
+    gen = torch.Generator().manual_seed(99)
+    X = torch.rand(world * n_per, widths[0], generator=gen).to(dev)
+    Y = torch.randint(0, 10, (world * n_per,), generator=gen).to(dev)
+    model = build(dev, widths)
+    dg = Diagonal(model)
+    loss = torch.nn.functional.cross_entropy(model(X[rank * n_per:(rank + 1) * n_per]), Y[rank * n_per:(rank + 1) * n_per])
+    model.zero_grad()
+    loss.backward()
+    _, ms = _ev_ms(lambda: D.diagonal_update_sharded(dg, n_per), dev)
+    ref_model = build(dev, widths)
+    rd = Diagonal(ref_model)
+    loss = torch.nn.functional.cross_entropy(ref_model(X), Y)
+    ref_model.zero_grad()
+    loss.backward()
+    rd.update(world * n_per)
+    worst = max(relerr(a, b) for a, b in zip(dg.state.values(), rd.state.values()))
+    dg.invert(1.0, 10.0)
+    rd.invert(1.0, 10.0)
+    P = sum(p.numel() for p in model.parameters())
+    Jall = torch.randn(40, P, generator=torch.Generator().manual_seed(7)).to(dev)
+    a, b = D.row_slice(40, world, rank)
+    v = D.linearised_diag_sharded(dg, Jall[a:b].contiguous(), 40)
+    worst = max(worst, relerr(v, linearised_diag(rd, Jall)))
+    out["diagonal"] = {"relerr": worst, "update_ms": ms, "params": P}
+    # ---- e5: dense Fisher, gradient rows split
+    P, n, B, tau = dense_p, 64 * world, 8 * world, 0.04
+    gen = torch.Generator().manual_seed(13)
+    G = (0.3 * torch.randn(n, P, generator=gen)).to(dev)
+    J = torch.randn(B, P, generator=gen).to(dev)
+    ga, gb = D.row_slice(n, world, rank)
+    ja, jb = D.row_slice(B, world, rank)
+    sh, ms_acc = _ev_ms(lambda: dense_sharded.dense_fisher_sharded(G[ga:gb].contiguous(), n), dev)
+    coords = [(i, min(i + 100, P)) for i in range(0, P, 100)]
+    dom, ms_dom = _ev_ms(lambda: sh.dominance(coords, 1e-5), dev)
+    var, ms_var = _ev_ms(lambda: sh.variance(J[ja:jb].contiguous(), tau, n_rows=B), dev)
+    H = dense.dense_fisher(G)
+    dom1 = dense.dominance(H, coords, 1e-5)
+    var1 = dense.dense_variance(J, dense.dense_inverse(H, tau))
+    out["dense_fisher"] = {"relerr": relerr(var, var1), "dominance_err": max(abs(dom[0] - dom1[0]), abs(dom[1] - dom1[1])),
+                           "accumulate_exchange_ms": ms_acc, "dominance_ms": ms_dom, "cholesky_variance_ms": ms_var,
+                           "P": P, "gradients": n, "test_rows": B}
+    ok = (out["linearised_regression"]["relerr"] < 1e-3 and out["diagonal"]["relerr"] < 1e-3
+          and out["dense_fisher"]["relerr"] < 1e-3 and out["dense_fisher"]["dominance_err"] < 1e-5)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok"] = bool(flag.item() > 0.5)
+    out["tolerance"] = 1e-3
+    return out
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -93,6 +186,10 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     res = run_check(rank, world, dev)
+    rows = run_check_rows(rank, world, dev, dense_p=int(os.environ.get("BK_DENSE_P", "3000")))
+    if rank == 0:
+        print("rows", rows, flush=True)
+    res["ok"] = res["ok"] and rows["ok"]
     if rank == 0:
         print(f"world={world} inverse relerr (worst factor) {res['inverse_relerr']:.2e}  predictive relerr "
               f"{res['predictive_relerr']:.2e}  identical on all ranks: {res['identical_on_all_ranks']}", flush=True)
