@@ -404,18 +404,6 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps, reduce_after)
 
-    # ---- sustained leg: the same device-resident step back to back for >= 2 s (the headline's timed region is
-    # ~10 ms, a burst-clock figure; under seconds of load the part sits at its 1 kW power cap and the SM clock
-    # settles near 1.3 - 1.5 GHz).  Own clock record; compared with the SUSTAINED cuBLAS peak.
-    sustained = None
-    if not args.no_sustained:
-        n_sus = max(args.steps, int(2.2 / (ms_dev / args.steps * 1e-3)))
-        with ClockSampler(local_rank) as clocks_sus:
-            ms_sus = timed(lambda: step_device(resident), n_sus)
-        sustained = {"seconds": ms_sus * 1e-3, "steps": n_sus, "ms_per_step": ms_sus / n_sus,
-                     "value": BATCH * n_sus * world / (ms_sus * 1e-3), "unit": "samples/s",
-                     "clocks": clocks_sus.summary()}
-
     total_samples = BATCH * args.steps * world
     value = total_samples / (ms_dev * 1e-3)
     e2e_value = total_samples / (ms_e2e * 1e-3)
@@ -474,25 +462,12 @@ def main():
     syrk_ms = e0.elapsed_time(e1) / reps
     syrk_flops = sum(t[4] * (t[4] + 1) * n for t in grp)   # one multiply-add per lower-triangle entry per sample
     achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
-    syrk_sus = None
-    if not args.no_sustained:      # the kernel alone, back to back for >= 2 s
-        n_k = int(2.2 / (syrk_ms * 1e-3))
-        e0.record()
-        for _ in range(n_k):
-            syrk()
-        e1.record()
-        torch.cuda.synchronize()
-        syrk_sus = syrk_flops / (e0.elapsed_time(e1) / n_k * 1e-3) / 1e12
     roofline = {"bound": "tensor",
                 "kernel": f"umma_syrk_grouped_kernel (cta_group::2, TMA-reduce epilogue; {cnt} SYRKs 4096x4096x4096, "
                           f"{'lower triangle only' if est.lower_only else 'lower + mirror'}, in one launch)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + " (burst)",
                 "us_per_launch": syrk_ms * 1e3, "flops_per_launch": syrk_flops, "traffic": None}
-    if syrk_sus is not None and peaks.get("bf16_tflops_sustained"):
-        roofline["sustained"] = {"achieved": syrk_sus, "peak": peaks["bf16_tflops_sustained"],
-                                 "frac": syrk_sus / peaks["bf16_tflops_sustained"],
-                                 "note": "same launch back to back for >= 2 s, vs the sustained cuBLAS figure"}
     prof = os.path.join(ROOT, "profiles", "syrk_traffic.json")
     if os.path.exists(prof):
         try:
@@ -512,11 +487,6 @@ def main():
             "gpu_launches": None, "roofline": roofline, "clocks": clocks.summary()}
     line["e2e"]["d2h_note"] = ("the result of a step is the device-resident factor state (0.47 GB, consumed on the device "
                                "by invert()); the per-step read-back is a 32-byte checksum (trace of every factor)")
-    if sustained is not None:
-        sustained["algorithmic_tflops"] = sustained["value"] * algorithmic_flops_per_sample(WIDTHS) / 1e12
-        if peaks.get("bf16_tflops_sustained"):
-            sustained["frac_of_sustained_peak"] = sustained["algorithmic_tflops"] / world / peaks["bf16_tflops_sustained"]
-        line["sustained"] = sustained
     line["step_frac_of_burst_peak"] = line["algorithmic_tflops"] / world / peaks["bf16_tflops"]
     if parity is not None:
         line["parity"] = parity
@@ -538,6 +508,38 @@ def main():
 
     if not args.no_extras:
         line["extras"] = extras(est, model, layers, dev, world, rank)
+    # ---- sustained legs LAST: seconds of full load leave the part power-capped (SM clock ~1.5 GHz) for a while,
+    # which would colour every figure measured after them (the predictive extras read 35 % low in r02a)
+    # ---- sustained leg: the same device-resident step back to back for >= 2 s (the headline's timed region is
+    # ~10 ms, a burst-clock figure; under seconds of load the part sits at its 1 kW power cap and the SM clock
+    # settles near 1.3 - 1.5 GHz).  Own clock record; compared with the SUSTAINED cuBLAS peak.
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(2.2 / (ms_dev / args.steps * 1e-3)))
+        with ClockSampler(local_rank) as clocks_sus:
+            ms_sus = timed(lambda: step_device(resident), n_sus)
+        sustained = {"seconds": ms_sus * 1e-3, "steps": n_sus, "ms_per_step": ms_sus / n_sus,
+                     "value": BATCH * n_sus * world / (ms_sus * 1e-3), "unit": "samples/s",
+                     "clocks": clocks_sus.summary()}
+
+    syrk_sus = None
+    if not args.no_sustained:      # the kernel alone, back to back for >= 2 s
+        n_k = int(2.2 / (syrk_ms * 1e-3))
+        e0.record()
+        for _ in range(n_k):
+            syrk()
+        e1.record()
+        torch.cuda.synchronize()
+        syrk_sus = syrk_flops / (e0.elapsed_time(e1) / n_k * 1e-3) / 1e12
+    if syrk_sus is not None and peaks.get("bf16_tflops_sustained"):
+        line["roofline"]["sustained"] = {"achieved": syrk_sus, "peak": peaks["bf16_tflops_sustained"],
+                                 "frac": syrk_sus / peaks["bf16_tflops_sustained"],
+                                 "note": "same launch back to back for >= 2 s, vs the sustained cuBLAS figure"}
+    if sustained is not None:
+        sustained["algorithmic_tflops"] = sustained["value"] * algorithmic_flops_per_sample(WIDTHS) / 1e12
+        if peaks.get("bf16_tflops_sustained"):
+            sustained["frac_of_sustained_peak"] = sustained["algorithmic_tflops"] / world / peaks["bf16_tflops_sustained"]
+        line["sustained"] = sustained
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
         if "extras" in line and "posterior_predictive" in line["extras"]:
@@ -603,14 +605,16 @@ def extras(est, model, layers, dev, world, rank):
     for _ in range(2):
         mc_moments(est, x, S, sample0=rank * S)
     # best of 3 x (4 repetitions): launch-heavy as well, see the inversion above
-    ms = min(ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=4) for _ in range(3))
+    with ClockSampler(dev.index or 0) as pclk:
+        ms = min(ev_ms(lambda: mc_moments(est, x, S, sample0=rank * S), reps=4) for _ in range(3))
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out["posterior_predictive"] = {"value": S * world * B / (t.item() * 1e-3),
                                    "unit": "(weight samples x test inputs)/s",
                                    "weight_samples_per_s": S * world / (t.item() * 1e-3),
-                                   "config": {"samples_per_gpu": S, "test_inputs": B}}
+                                   "config": {"samples_per_gpu": S, "test_inputs": B},
+                                   "clocks": pclk.summary()}
     return out
 
 

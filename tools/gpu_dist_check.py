@@ -85,8 +85,11 @@ def run_check(rank, world, dev):
                     "(MLP 300-520-260-10)"}
 
 
-def _ev_ms(fn, dev):
-    """Device time of fn(), max over ranks, after a barrier (collectives inside must start together)."""
+def _ev_ms(fn, dev, warm=True):
+    """Device time of the second call of fn(), max over ranks, after a barrier (collectives inside must start
+    together; the first call pays one-off costs: workspace growth, autograd's batched-gradient tracing)."""
+    if warm:
+        fn()
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -136,7 +139,7 @@ def run_check_rows(rank, world, dev, dense_p=3000):
     loss = torch.nn.functional.cross_entropy(model(X[rank * n_per:(rank + 1) * n_per]), Y[rank * n_per:(rank + 1) * n_per])
     model.zero_grad()
     loss.backward()
-    _, ms = _ev_ms(lambda: D.diagonal_update_sharded(dg, n_per), dev)
+    _, ms = _ev_ms(lambda: D.diagonal_update_sharded(dg, n_per), dev, warm=False)     # accumulates: once
     ref_model = build(dev, widths)
     rd = Diagonal(ref_model)
     loss = torch.nn.functional.cross_entropy(ref_model(X), Y)
