@@ -289,7 +289,7 @@ def main():
 
     from bnn_kfac_b200 import _lib
     from bnn_kfac_b200.curvatures import KFAC
-    from bnn_kfac_b200.distributed import reduce_state_copy
+    from bnn_kfac_b200.distributed import plan_owners, reduce_scatter_to_owners, reduce_state_copy
     from bnn_kfac_b200.wrapper import MLP
     L = _lib.load()
     _lib.require_device()
@@ -378,27 +378,35 @@ def main():
         return ms.item()
 
     # the exchange invert_sharded() performs: one all-reduce of (copies of) the accumulated factors
-    reduce_after = (lambda: reduce_state_copy(est)) if world > 1 else None
+    # (a reduce-scatter of the packed lower triangles to the owning ranks, as invert_sharded issues it)
+    def exchange():
+        owners = plan_owners([t.shape[0] for l in layers for t in est._raw(l)], world)
+        return reduce_scatter_to_owners(est, owners)
+    reduce_after = exchange if world > 1 else None
     for _ in range(args.warmup):
         step_device(resident)
     if reduce_after is not None:
         reduce_after()          # warm the NCCL channels: the timed region holds exactly one reduction
     with ClockSampler(local_rank) as clocks:
         ms_dev = timed(lambda: step_device(resident), args.steps, reduce_after)
-    reduce_ms = None
+    reduce_ms = scatter_ms = None
     if world > 1:
-        best = None
-        for _ in range(3):
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            reduce_state_copy(est)
-            e1.record()
-            barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            best = t.item() if best is None else min(best, t.item())
-        reduce_ms = best
+        def best_of3(fn):
+            best = None
+            for _ in range(3):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                barrier()
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = t.item() if best is None else min(best, t.item())
+            return best
+        reduce_state_copy(est)
+        reduce_ms = best_of3(lambda: reduce_state_copy(est))
+        scatter_ms = best_of3(exchange)
 
     for _ in range(args.warmup):
         step_e2e()
@@ -497,8 +505,15 @@ def main():
         line["factor_allreduce"] = {
             "ms": reduce_ms, "state_bytes": state_bytes, "wire_bytes": wire_bytes,
             "algbw_GBps": wire_bytes / (reduce_ms * 1e-3) / 1e9,
-            "note": "one per timed region (deferred: state is a plain sum of batch means); bk_tri_pack -> ONE NCCL "
-                    "all-reduce of the packed lower triangles -> bk_tri_unpack (mirror, 1/world)"}
+            "note": "the replicated variant (callers that read .state afterwards): bk_tri_pack -> ONE NCCL "
+                    "all-reduce of the packed lower triangles -> bk_tri_unpack (mirror, 1/world); NOT in the timed region"}
+        sent = wire_bytes * (world - 1) / world
+        line["factor_exchange"] = {
+            "ms": scatter_ms, "wire_bytes": wire_bytes, "bytes_sent_per_rank": sent,
+            "busbw_GBps": sent / (scatter_ms * 1e-3) / 1e9,
+            "note": "one per timed region (deferred: state is a plain sum of batch means); packed lower triangles in "
+                    "owner order -> ONE NCCL reduce-scatter -> bk_tri_unpack of the owned factors (what invert_sharded "
+                    "issues)"}
 
     # kernels launched by this library inside the device-timed region (counted by the library itself)
     c0 = L.bk_launch_count()

@@ -75,6 +75,7 @@ SIGNATURES = {
                                           C.POINTER(_f), _i, _i, _i, _p]),
     "bk_syrk_accum_staged": (_i, [_p, _ll, _p, _p, _ll, _i, _i, _f, _f, _i, _p]),
     "bk_conv_a_accum": (_i, [_p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "bk_im2col_split": (_i, [_p] + [_i] * 10 + [_f, _i, _p, _p, _ll, _p]),
     "bk_conv_g_accum": (_i, [_p, _ll, _p, _i, _i, _i, _f, _f, _f, _p]),
     "bk_diag_accum": (_i, [_p, _p, _p, _i, _i, _f, _f, _p]),
     "bk_diag_invert": (_i, [_p, _p, _ll, _f, _f, _p]),

@@ -500,6 +500,14 @@ int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int
                                 stride_w, has_bias, alpha, beta, as_stream(stream));
 }
 
+int bk_im2col_split(const float* x, int n, int c, int h, int w, int kh, int kw, int pad_h, int pad_w,
+                    int stride_h, int stride_w, float scale, int ones_row, void* t_hi, void* t_lo, long long ldt,
+                    void* stream) {
+  return bk::launch_im2col_split(x, n, c, h, w, kh, kw, pad_h, pad_w, stride_h, stride_w, scale, ones_row,
+                                 static_cast<__nv_bfloat16*>(t_hi), static_cast<__nv_bfloat16*>(t_lo), ldt,
+                                 as_stream(stream));
+}
+
 int bk_conv_g_accum(float* state, long long ld_state, const float* g, int n, int o, int hw,
                     float in_scale, float alpha, float beta, void* stream) {
   if (state == nullptr || g == nullptr) return BK_ERR_ARG;

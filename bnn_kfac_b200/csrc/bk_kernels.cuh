@@ -41,6 +41,11 @@ int launch_conv_a_syrk(float* state, long long ld_state, const float* x, int n, 
 int launch_conv_g_syrk(float* state, long long ld_state, const float* g, int n, int o, int hw,
                        float in_scale, float alpha, float beta, cudaStream_t stream);
 
+// ---- bk_im2col.cu  (NCHW fp32 -> K-major bf16 patch-matrix operand of the tensor-core SYRK, wide conv factors)
+int launch_im2col_split(const float* X, int n, int c, int h, int w, int kh, int kw, int ph, int pw, int sh,
+                        int sw, float scale, int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo,
+                        long long ldt, cudaStream_t stream);
+
 // ---- bk_syrk_fp32.cu  (full-fp32 SIMT SYRK, any d; parity mode for ill-conditioned factors)
 int launch_syrk_fp32(float* state, long long ld_state, const float* x, long long ldx, int n, int d,
                      int has_bias, float in_scale, float alpha, float beta, cudaStream_t stream);

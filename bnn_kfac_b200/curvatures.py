@@ -550,11 +550,16 @@ class KFAC(Curvature):
             _lib.check(self._lib.bk_conv_a_accum(first.data_ptr(), first.stride(0), x.data_ptr(), n, c,
                                                  h, wd, kh, kw, ph, pw, sh, sw, int(has_bias),
                                                  w / cols, beta, st), "bk_conv_a_accum")
-        else:
-            # wide conv layers: explicit patch matrix [N*L, C*kh*kw] staged once, tensor-core SYRK
+        elif self.precision == "fp32":
+            # full-fp32 parity mode: the SIMT SYRK consumes an explicit fp32 patch matrix [N*L, C*kh*kw]
             u = torch.nn.functional.unfold(x, (kh, kw), padding=(ph, pw), stride=(sh, sw))
             u = u.permute(0, 2, 1).reshape(cols, -1).contiguous()
             self._syrk(first, beta, u, has_bias, 1.0, w / cols)
+        else:
+            # wide conv layers: the K-major bf16 patch operand straight from NCHW (bk_im2col_split: no fp32
+            # unfold / permute / contiguous round trips), then the tensor-core SYRK
+            self._staged_conv_syrk(first, beta, x, (n, c, h, wd, kh, kw, ph, pw, sh, sw), cols, has_bias, 1.0,
+                                   w / cols)
         o = g.shape[1]
         hw = g.shape[2] * g.shape[3]
         gcols = n * hw
@@ -562,9 +567,31 @@ class KFAC(Curvature):
             _lib.check(self._lib.bk_conv_g_accum(second.data_ptr(), second.stride(0), g.data_ptr(), n, o,
                                                  hw, float(n_batch), w / gcols, beta, st),
                        "bk_conv_g_accum")
-        else:
+        elif self.precision == "fp32":
             g2 = g.permute(0, 2, 3, 1).reshape(gcols, o).contiguous()
             self._syrk(second, beta, g2, False, float(n_batch), w / gcols)
+        else:
+            # [N, O, H'W'] -> [O, N*H'W'] is the 1 x 1 case of the same staging kernel
+            self._staged_conv_syrk(second, beta, g, (n, o, g.shape[2], g.shape[3], 1, 1, 0, 0, 1, 1), gcols, False,
+                                   float(n_batch), w / gcols)
+
+    def _staged_conv_syrk(self, state: Tensor, beta: float, x: Tensor, shape, cols: int, has_bias: bool,
+                          in_scale: float, alpha: float):
+        """state = beta*state + alpha * U U^T with U = [in_scale * unfold(x) ; 1] staged K-major in bf16."""
+        n, c, h, wd, kh, kw, ph, pw, sh, sw = shape
+        lib, st = self._lib, _lib.stream_ptr()
+        x3 = self.precision == "bf16x3"
+        rows = c * kh * kw + int(has_bias)
+        ldt = _round8(cols)
+        nbytes = rows * ldt * 2
+        buf = self._ws.get((2 if x3 else 1) * nbytes + 256, x.device)
+        t_hi = buf.data_ptr()
+        t_lo = t_hi + (nbytes + 255) // 256 * 256 if x3 else 0
+        _lib.check(lib.bk_im2col_split(x.data_ptr(), n, c, h, wd, kh, kw, ph, pw, sh, sw, float(in_scale),
+                                       int(has_bias), t_hi, t_lo, ldt, st), "bk_im2col_split")
+        _lib.check(lib.bk_syrk_accum_staged(state.data_ptr(), state.stride(0), t_hi, t_lo, ldt, cols, rows,
+                                            float(alpha), float(beta), _PRECISIONS[self.precision], st),
+                   "bk_syrk_accum_staged")
 
     # ------------------------------------------------------------------ inversion
     def invert(self, add: Union[float, list, tuple] = 0., multiply: Union[float, list, tuple] = 1.):

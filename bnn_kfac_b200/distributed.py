@@ -25,6 +25,7 @@ collectives is always the CUDA library.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -203,6 +204,54 @@ def reduce_state_copy(est, group=None) -> List[Tensor]:
     return outs
 
 
+def reduce_scatter_to_owners(est, owners: Sequence[int], group=None) -> Dict[int, Tensor]:
+    """The exchange step of the sharded inversion as a REDUCE-SCATTER: every factor ends up, summed over ranks and
+    divided by the world size, on its owner only ({flat factor index: [d, d] tensor} of the factors this rank owns;
+    flat order = layers in `state` order, [A, G] per layer).  The packed lower triangles are laid out in OWNER
+    order - chunk r of the send buffer holds the factors rank r owns, chunks padded to one size - so ONE
+    `reduce_scatter_tensor` delivers each owner exactly its factors: (world - 1) / world x sum d (d + 1) / 2 values
+    leave every rank, half of what the all-reduce of `reduce_state_copy` moves (that one also hands every rank all
+    factors, which only callers that read `.state` afterwards need).  The local `est.state` stays a valid partial
+    accumulator.  Device path only (NCCL); see invert_sharded for the gloo fallback."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    w, me = world_size(group), rank(group)
+    raw_items = getattr(est, "_raw_items", None)
+    scale = float(getattr(est, "_scale", 1.0)) if raw_items is not None else 1.0
+    values = [v for _, v in raw_items()] if raw_items is not None else list(est.state.values())
+    factors = [f for v in values for f in v]
+    tri = [f.shape[0] * (f.shape[0] + 1) // 2 for f in factors]
+    by_rank = [[i for i in range(len(factors)) if owners[i] == r] for r in range(w)]
+    chunk = max(max(sum(tri[i] for i in idx) for idx in by_rank), 1)
+    chunk = (chunk + 3) // 4 * 4                                  # 16-byte chunk boundaries
+    dev = factors[0].device
+    st = _lib.stream_ptr()
+    send = torch.empty(w * chunk, dtype=torch.float32, device=dev)
+    for r, idx in enumerate(by_rank):
+        if not idx:
+            continue
+        n = len(idx)
+        _lib.check(lib.bk_tri_pack((C.c_void_p * n)(*[factors[i].data_ptr() for i in idx]),
+                                   (C.c_longlong * n)(*[factors[i].stride(0) for i in idx]),
+                                   (C.c_int * n)(*[factors[i].shape[0] for i in idx]), n,
+                                   send.data_ptr() + 4 * r * chunk, st), "bk_tri_pack")
+    if w > 1:
+        recv = torch.empty(chunk, dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM, group=group)
+    else:
+        recv = send
+    mine = by_rank[me]
+    outs = {i: torch.empty(factors[i].shape[0], factors[i].shape[0], dtype=torch.float32, device=dev) for i in mine}
+    if mine:
+        n = len(mine)
+        _lib.check(lib.bk_tri_unpack((C.c_void_p * n)(*[outs[i].data_ptr() for i in mine]),
+                                     (C.c_longlong * n)(*[outs[i].stride(0) for i in mine]),
+                                     (C.c_int * n)(*[factors[i].shape[0] for i in mine]), n, recv.data_ptr(),
+                                     scale / w, 1, st), "bk_tri_unpack")
+    return outs
+
+
 def allgather_cholesky(owned: Dict[int, Tensor], dims: Sequence[int], owners: Sequence[int], device,
                        group=None) -> List[Tensor]:
     """Every rank ends up with all Cholesky factors: rank r packs the lower triangles of the factors it owns
@@ -269,9 +318,15 @@ def invert_sharded(est, add=0., multiply=1., group=None,
         adds += [float(n)] * 2
         mults += [float(s)] * 2
     owners = plan_owners([f.shape[0] for f in factors], w)
+    square_cuda = all(f.is_cuda and f.dim() == 2 and f.shape[0] == f.shape[1] and f.stride(1) == 1
+                      and f.dtype == torch.float32 for f in factors)
     if keep_state_replicated:
         allreduce_state(est, group)
         reduced = [t for layer in layers for t in est.state[layer]]
+    elif square_cuda and not os.environ.get("BK_SHARDED_ALLREDUCE"):
+        # reduce-scatter of the packed lower triangles, laid out in owner order: every owner receives exactly the
+        # factors it inverts (half the traffic of an all-reduce; the local partial `state` stays an accumulator)
+        reduced = reduce_scatter_to_owners(est, owners, group)
     else:
         # reduce scratch copies so that the local partial `state` stays a valid accumulator
         reduced = reduce_state_copy(est, group)
@@ -281,7 +336,6 @@ def invert_sharded(est, add=0., multiply=1., group=None,
         res = inverter([reduced[i] for i in mine], [adds[i] for i in mine], [mults[i] for i in mine])
         for i, r in zip(mine, res):
             outs[i] = r.contiguous()    # collectives ship the storage: it must be dense row-major
-    import os
     if w > 1 and factors[0].is_cuda and not os.environ.get("BK_SHARDED_BCAST"):
         # one all-gather of packed lower triangles instead of one broadcast per factor
         outs = allgather_cholesky({i: outs[i] for i in mine}, [f.shape[0] for f in factors], owners,

@@ -156,6 +156,15 @@ int bk_syrk_accum_staged(float* state, long long ld_state, const void* xt_hi, co
 int bk_conv_a_accum(float* state, long long ld_state, const float* x, int n, int c, int h, int w,
                     int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w, int has_bias,
                     float alpha, float beta, void* stream);
+/* Wide Conv2d factors (c*kh*kw + has_bias > BK_SMALL_D_MAX): the K-major bf16 operand of the tensor-core SYRK
+ * straight from the NCHW activations, t[r][col] = scale * patch value with r = (ci*kh + i)*kw + j (unfold's row
+ * order, models/curvatures.py:342-343), col = img*L + oh*OW + ow, plus a row of ones when ones_row != 0
+ * (:346-348); columns [n*L, ldt) are zero.  ldt % 8 == 0, 16 B aligned outputs, t_lo nullable.  Feed the result to
+ * bk_syrk_accum_staged(dprime = c*kh*kw + ones_row, n = n*L).  kh = kw = 1 regroups output gradients
+ * [n, o, h'w'] into [o, n*h'w'] (:353). */
+int bk_im2col_split(const float* x, int n, int c, int h, int w, int kh, int kw, int pad_h, int pad_w,
+                    int stride_h, int stride_w, float scale, int ones_row, void* t_hi, void* t_lo, long long ldt,
+                    void* stream);
 /* Conv2d second factor (models/curvatures.py:353-356): g is [n, o, hw] fp32. */
 int bk_conv_g_accum(float* state, long long ld_state, const float* g, int n, int o, int hw,
                     float in_scale, float alpha, float beta, void* stream);

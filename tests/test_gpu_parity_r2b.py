@@ -140,3 +140,60 @@ def test_sharded_entry_points_world1(dev):
     J = torch.randn(6, sum(p.numel() for p in m.parameters()), device=dev)
     from bnn_kfac_b200.predictive import linearised_diag
     assert torch.equal(D.linearised_diag_sharded(est_a, J, 6), linearised_diag(est_a, J))
+
+
+# ------------------------------------------------------------------------------------------ wide conv factors
+class _WideConvNet(torch.nn.Module):
+    """conv(3->24, 3x3) -> conv(24->200, 3x3, stride 2): the second layer's factors are 217^2 (24*9 + 1) and
+    200^2, both beyond the SIMT path (BK_SMALL_D_MAX = 176)."""
+
+    def __init__(self):
+        super().__init__()
+        self.c1 = torch.nn.Conv2d(3, 24, 3, padding=1)
+        self.c2 = torch.nn.Conv2d(24, 200, 3, stride=2, padding=1)
+        self.fc = torch.nn.Linear(200 * 5 * 5, 10)
+
+    def forward(self, x):
+        x = torch.relu(self.c1(x))
+        x = torch.relu(self.c2(x))
+        return self.fc(torch.flatten(x, 1))
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16", "fp32"])
+def test_wide_conv_factors_vs_oracle(dev, precision):
+    """models/curvatures.py:341-356 for a conv layer whose factors need the tensor cores: the patch operand comes
+    from bk_im2col_split (no F.unfold), second batch accumulates (`+=`).  bf16x3 / fp32: 1e-3 is met with four
+    orders of margin; single-pass bf16: operand rounding 2^-9 relative per element -> 1e-3 relative Frobenius is the
+    bound the BASELINE tolerance allows and what is asserted."""
+    from bnn_kfac_b200.curvatures import KFAC
+    torch.manual_seed(4)
+    cm = _WideConvNet().double()
+    gm = _WideConvNet()
+    gm.load_state_dict({k: v.float() for k, v in cm.state_dict().items()})
+    gm = gm.to(dev)
+    oest, gest = O.OracleKFAC(cm), KFAC(gm, precision=precision)
+    gen = torch.Generator().manual_seed(8)
+    for _ in range(2):
+        x = torch.rand(6, 3, 10, 10, generator=gen)
+        labels = O.fisher_backward(cm, x.double(), generator=gen)
+        oest.update()
+        loss = torch.nn.functional.cross_entropy(gm(x.to(dev)), labels.to(dev))
+        gm.zero_grad()
+        loss.backward()
+        gest.update(6)
+    glayers = [l for _, l in gest._selected_layers()]
+    tol = TOL if precision == "bf16" else 2e-5
+    for ol, gl in zip(oest.layers, glayers):
+        for k in range(2):
+            got, ref = gest.state[gl][k], oest.state[ol][k]
+            assert got.shape == ref.shape
+            assert relerr(got.cpu(), ref.numpy()) < tol, (precision, gl, k)
+            assert torch.equal(got, got.t())
+    # the wide layer really took the tensor-core path
+    assert gest.state[glayers[1]][0].shape[0] == 217 and gest.state[glayers[1]][1].shape[0] == 200
+    oest.invert(0.5, 50.0)
+    gest.invert(0.5, 50.0)
+    if precision != "bf16":
+        for ol, gl in zip(oest.layers, glayers):
+            for k in range(2):
+                assert relerr(gest.inv_state[gl][k].cpu(), oest.inv_state[ol][k].numpy()) < TOL
