@@ -289,7 +289,10 @@ def main():
 
     from bnn_kfac_b200 import _lib
     from bnn_kfac_b200.curvatures import KFAC
-    from bnn_kfac_b200.distributed import plan_owners, reduce_scatter_to_owners, reduce_state_copy
+    from bnn_kfac_b200.distributed import (bind_to_gpu_numa_node, plan_owners, reduce_scatter_to_owners,
+                                           reduce_state_copy)
+    # N > 1: each rank runs on (and allocates its pinned e2e buffers from) the NUMA node next to its GPU
+    numa_cores = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     from bnn_kfac_b200.wrapper import MLP
     L = _lib.load()
     _lib.require_device()
@@ -310,52 +313,61 @@ def main():
     model = MLP(WIDTHS).to(dev)
     est = KFAC(model, precision=args.precision)
     layers = [l for _, l in est._selected_layers()]
-    gen = torch.Generator().manual_seed(1234 + rank)
-    in_dtype = torch.bfloat16 if args.inputs == "bf16" else torch.float32
-    host = [(a.to(in_dtype).pin_memory(), g.to(in_dtype).pin_memory()) for a, g in synth_batch(gen, BATCH, WIDTHS)]
-    resident = [(a.to(dev), g.to(dev)) for a, g in host]
-    # e2e: two sets of device input buffers; the H2D copy of step i + 1 (copy stream) overlaps the kernels of step i
-    staging2 = [[(torch.empty_like(a), torch.empty_like(g)) for a, g in resident] for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    e2e_state = {"next": 0, "primed": False}
-    h2d_bytes = sum(a.numel() * a.element_size() + g.numel() * g.element_size() for a, g in host)
-    checksum_host = torch.empty(2 * len(layers), dtype=torch.float32).pin_memory()
+    synth = synth_batch(torch.Generator().manual_seed(1234 + rank), BATCH, WIDTHS)
 
-    def step_device(bufs):
-        for layer, (a, g) in zip(layers, bufs):
-            est.record[layer] = [a, g]
-        est.update(BATCH)
+    def make_legs(in_dtype):
+        """Device-resident and end-to-end step closures for (a, g) tensors of one container dtype."""
+        host = [(a.to(in_dtype).pin_memory(), g.to(in_dtype).pin_memory()) for a, g in synth]
+        resident = [(a.to(dev), g.to(dev)) for a, g in host]
+        # e2e: two sets of device input buffers; the H2D copy of step i + 1 (copy stream) overlaps the kernels of step i
+        staging2 = [[(torch.empty_like(a), torch.empty_like(g)) for a, g in resident] for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        e2e_state = {"next": 0, "primed": False}
+        h2d_bytes = sum(a.numel() * a.element_size() + g.numel() * g.element_size() for a, g in host)
+        checksum_host = torch.empty(2 * len(layers), dtype=torch.float32).pin_memory()
 
-    def enqueue_h2d(slot):
-        """this step's inputs: pinned host buffers -> device set `slot`, on the copy stream"""
-        copy_stream.wait_event(consumed[slot])            # the kernels that last read this set are done
-        with torch.cuda.stream(copy_stream):
-            for (ha, hg), (da, dg) in zip(host, staging2[slot]):
-                da.copy_(ha, non_blocking=True)
-                dg.copy_(hg, non_blocking=True)
-            copied[slot].record(copy_stream)
+        def step_device(bufs):
+            for layer, (a, g) in zip(layers, bufs):
+                est.record[layer] = [a, g]
+            est.update(BATCH)
 
-    def step_e2e():
-        """One end-to-end step: H2D of the step's host inputs, KFAC.update, D2H of a checksum of the result.
-        Every step copies its own 0.47 GB; the copy of the NEXT step is issued before this step's kernels so that
-        the two overlap (software pipelining over the timed steps; the first call primes the pipeline)."""
-        cur = e2e_state["next"]
-        if not e2e_state["primed"]:
-            enqueue_h2d(cur)
-            e2e_state["primed"] = True
-        enqueue_h2d(cur ^ 1)                               # prefetch the next step's inputs
-        torch.cuda.current_stream().wait_event(copied[cur])
-        step_device(staging2[cur])
-        consumed[cur].record(torch.cuda.current_stream())
-        # checksum of the accumulators: trace of every factor (the diagonal is valid in the lower-only accumulators,
-        # so this read does not trigger the mirror pass a public `state` read would run)
-        cs = torch.stack([est._raw(l)[k].diagonal().sum() for l in layers for k in range(2)])
-        checksum_host.copy_(cs, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        e2e_state["next"] = cur ^ 1
-        return checksum_host
+        def enqueue_h2d(slot):
+            """this step's inputs: pinned host buffers -> device set `slot`, on the copy stream"""
+            copy_stream.wait_event(consumed[slot])            # the kernels that last read this set are done
+            with torch.cuda.stream(copy_stream):
+                for (ha, hg), (da, dg) in zip(host, staging2[slot]):
+                    da.copy_(ha, non_blocking=True)
+                    dg.copy_(hg, non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        def step_e2e():
+            """One end-to-end step: H2D of the step's host inputs, KFAC.update, D2H of a checksum of the result.
+            Every step copies its own inputs; the copy of the NEXT step is issued before this step's kernels so
+            that the two overlap (software pipelining over the timed steps; the first call primes the pipeline)."""
+            cur = e2e_state["next"]
+            if not e2e_state["primed"]:
+                enqueue_h2d(cur)
+                e2e_state["primed"] = True
+            enqueue_h2d(cur ^ 1)                               # prefetch the next step's inputs
+            torch.cuda.current_stream().wait_event(copied[cur])
+            step_device(staging2[cur])
+            consumed[cur].record(torch.cuda.current_stream())
+            # checksum of the accumulators: trace of every factor (the diagonal is valid in the lower-only
+            # accumulators, so this read does not trigger the mirror pass a public `state` read would run)
+            cs = torch.stack([est._raw(l)[k].diagonal().sum() for l in layers for k in range(2)])
+            checksum_host.copy_(cs, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            e2e_state["next"] = cur ^ 1
+            return checksum_host
+
+        return {"resident": resident, "step_device": step_device, "step_e2e": step_e2e, "h2d_bytes": h2d_bytes,
+                "checksum_host": checksum_host}
+
+    legs = make_legs(torch.bfloat16 if args.inputs == "bf16" else torch.float32)
+    resident, step_device, step_e2e = legs["resident"], legs["step_device"], legs["step_e2e"]
+    h2d_bytes, checksum_host = legs["h2d_bytes"], legs["checksum_host"]
 
     def barrier():
         if world > 1:
@@ -493,6 +505,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": checksum_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": None, "roofline": roofline, "clocks": clocks.summary()}
+    if numa_cores is not None:
+        line["e2e"]["host_cores_bound"] = len(numa_cores)
     line["e2e"]["d2h_note"] = ("the result of a step is the device-resident factor state (0.47 GB, consumed on the device "
                                "by invert()); the per-step read-back is a 32-byte checksum (trace of every factor)")
     line["step_frac_of_burst_peak"] = line["algorithmic_tflops"] / world / peaks["bf16_tflops"]
@@ -523,6 +537,25 @@ def main():
 
     if not args.no_extras:
         line["extras"] = extras(est, model, layers, dev, world, rank)
+    # ---- the same workload with bf16 (a, g) containers (a model under bf16 autocast; BASELINE config 5's values are
+    # bf16-representable, so the numbers are identical): the tensor cores read the activations as they are (no
+    # staging pass) and an end-to-end step moves half the bytes over the host link
+    if args.inputs == "fp32" and not args.no_extras:
+        alt = make_legs(torch.bfloat16)
+        for _ in range(args.warmup):
+            alt["step_device"](alt["resident"])
+        ms_alt = timed(lambda: alt["step_device"](alt["resident"]), args.steps)
+        for _ in range(args.warmup):
+            alt["step_e2e"]()
+        ms_alt_e2e = timed(alt["step_e2e"], args.steps)
+        line.setdefault("extras", {})["bf16_inputs"] = {
+            "value": total_samples / (ms_alt * 1e-3), "ms_per_step": ms_alt / args.steps,
+            "e2e": {"value": total_samples / (ms_alt_e2e * 1e-3), "ms_per_step": ms_alt_e2e / args.steps,
+                    "h2d_bytes_per_step": alt["h2d_bytes"]},
+            "unit": "samples/s",
+            "note": "(a, g) handed to KFAC.update as bf16 tensors: direct MN-major tcgen05 operands, no staging pass; "
+                    "no factor exchange in this timed region"}
+        del alt
     # ---- sustained legs LAST: seconds of full load leave the part power-capped (SM clock ~1.5 GHz) for a while,
     # which would colour every figure measured after them (the predictive extras read 35 % low in r02a)
     # ---- sustained leg: the same device-resident step back to back for >= 2 s (the headline's timed region is

@@ -21,6 +21,7 @@ inline long long round8(long long v) { return (v + 7) / 8 * 8; }
 namespace bk {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+unsigned long long launch_count() { return g_launches.load(); }
 }  // namespace bk
 
 #pragma GCC visibility push(default)
@@ -42,6 +43,8 @@ int bk_device_check(void) {
 void bk_set_cta_group(int cta_group) { bk::set_umma_cta_group(cta_group); }
 
 void bk_set_syrk_tuning(int flags) { bk::set_syrk_tuning(flags); }
+
+void bk_set_chol_graph(int enabled) { bk::set_chol_graph(enabled); }
 
 void bk_set_eigh_mode(int mode) { bk::set_eigh_mode(mode); }
 

@@ -25,6 +25,7 @@
 #include "bk_kernels.cuh"
 #include "bk_umma_gemm.cuh"
 
+#include <mutex>
 #include <vector>
 
 namespace bk {
@@ -424,12 +425,14 @@ inline size_t staging_bytes(int max_pad) {
 // block column k of C (final after the panel of Cholesky step k) and its own step k - 1, nothing else.
 struct Pipeline {
   cudaStream_t side = nullptr;
+  cudaStream_t cap = nullptr;  // origin stream of graph captures (the caller's stream may be the legacy default)
   cudaEvent_t fork = nullptr, join = nullptr;
   std::vector<cudaEvent_t> panel_done;
   bool ok = false;
   explicit Pipeline(bool) {}  // inert instance (no device)
   Pipeline() {
     ok = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
   }
@@ -529,58 +532,28 @@ int outer_update(const CholProb& p, int c0, bool phase2, __nv_bfloat16* sa, __nv
 
 }  // namespace
 
-int chol_inv_batched(const float* const* factors, float* const* outs, const int* dims,
-                     const float* add, const float* multiply, int count, void* workspace,
-                     size_t workspace_bytes, cudaStream_t stream) {
-  if (count <= 0) return 0;
-  if (workspace == nullptr || workspace_bytes < chol_inv_workspace_bytes(dims, count) ||
-      (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
-    return -6;
-  static DeviceOnce attr_once;
-  const int smem = sizeof(float) * NB * ((TM + kPad) + (TN + kPad));
-  if (!attr_once([&] {
-        return cudaFuncSetAttribute(rank64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ==
-               cudaSuccess;
-      }))
-    return -5;
-  char* w = static_cast<char*>(workspace);
-  CholProb* d_tab = reinterpret_cast<CholProb*>(w);
-  w += align_up(sizeof(CholProb) * static_cast<size_t>(count), 256);
-  int* d_info = reinterpret_cast<int*>(w);
-  w += align_up(sizeof(int) * static_cast<size_t>(count), 256);
-  CholProb* h_tab = new CholProb[count];
-  int max_pad = 0;
-  for (int f = 0; f < count; ++f) {
-    if (dims[f] <= 0 || factors[f] == nullptr || outs[f] == nullptr || add[f] < 0.f ||
-        multiply[f] < 0.f) {
-      delete[] h_tab;
-      return -2;
-    }
-    CholProb& p = h_tab[f];
-    p.F = factors[f];
-    p.out = outs[f];
-    p.d = dims[f];
-    p.dpad = pad_dim(dims[f]);
-    p.nb = p.dpad / NB;
-    p.sqrt_s = sqrtf(multiply[f]);
-    p.sqrt_n = sqrtf(add[f]);
-    const size_t mat = align_up(static_cast<size_t>(p.dpad) * p.dpad * 4, 256);
-    p.R = reinterpret_cast<float*>(w);
-    w += mat;
-    p.X = reinterpret_cast<float*>(w);
-    w += mat;
-    p.Dinv = reinterpret_cast<float*>(w);
-    w += align_up(static_cast<size_t>(p.nb) * NB * NB * 4, 256);
-    if (p.dpad > max_pad) max_pad = p.dpad;
-  }
-  cudaError_t e = cudaMemcpyAsync(d_tab, h_tab, sizeof(CholProb) * count, cudaMemcpyHostToDevice,
-                                  stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_info, 0, sizeof(int) * count, stream);
-  // the table copy is from pageable memory: it has been staged when the call returns
-  std::vector<CholProb> h_tab2(h_tab, h_tab + count);
-  delete[] h_tab;
-  if (e != cudaSuccess) return -5;
+namespace {
 
+int g_chol_graph = 1;
+
+struct GraphKey {
+  void* workspace;
+  int dev;
+  std::vector<int> dims;
+  bool operator==(const GraphKey& o) const { return workspace == o.workspace && dev == o.dev && dims == o.dims; }
+};
+struct CachedGraph {
+  GraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+std::mutex g_graph_mu;
+std::vector<CachedGraph> g_graphs;
+
+// The whole step sequence (damp / flip, both phases, flip-out) enqueued on `stream` (+ the pipeline's side stream,
+// forked from and joined back into it).  Depends on the workspace layout and the dims only.
+int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, CholProb* d_tab, int* d_info,
+                  __nv_bfloat16* stage_a, Pipeline& pipe, bool pipelined, int smem, cudaStream_t stream) {
   const int max_nb = max_pad / NB;
   const CholProb* cd_tab = d_tab;
   const dim3 tb(32, 8);
@@ -591,15 +564,12 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   // block; the update of everything beyond it is ONE fp32-class (bf16x6) tensor-core GEMM per factor.
   const bool two_level = max_pad >= kTwoLevelMin;
   const int inner_per_outer = kOuter / NB;
-  __nv_bfloat16* stage_a = reinterpret_cast<__nv_bfloat16*>(w);
   const size_t part_stride = align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) / 2;
   __nv_bfloat16* stage_b = stage_a + 3 * part_stride;
   __nv_bfloat16* stage_a2 = stage_a + 6 * part_stride;  // L21 staging of the inverse phase
   // Wide problems: the inverse phase (X = C^-1 by block forward substitution on the identity) is pipelined one
   // step behind the Cholesky phase on a side stream; both are chains of latency-bound steps that leave most
   // of the GPU idle on their own.
-  Pipeline& pipe = device_pipeline();
-  const bool pipelined = max_nb >= 4 && pipe.ok && pipe.reserve(max_nb);
   cudaStream_t s2 = pipelined ? pipe.side : stream;
   if (pipelined) {
     if (cudaEventRecord(pipe.fork, stream) != cudaSuccess || cudaStreamWaitEvent(s2, pipe.fork, 0) != cudaSuccess)
@@ -681,6 +651,120 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   }
   flip_out_kernel<<<tg, tb, 0, stream>>>(d_tab);
   note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+}  // namespace
+
+void set_chol_graph(int enabled) { g_chol_graph = enabled; }
+
+int chol_inv_batched(const float* const* factors, float* const* outs, const int* dims,
+                     const float* add, const float* multiply, int count, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  if (workspace == nullptr || workspace_bytes < chol_inv_workspace_bytes(dims, count) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return -6;
+  static DeviceOnce attr_once;
+  const int smem = sizeof(float) * NB * ((TM + kPad) + (TN + kPad));
+  if (!attr_once([&] {
+        return cudaFuncSetAttribute(rank64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ==
+               cudaSuccess;
+      }))
+    return -5;
+  char* w = static_cast<char*>(workspace);
+  CholProb* d_tab = reinterpret_cast<CholProb*>(w);
+  w += align_up(sizeof(CholProb) * static_cast<size_t>(count), 256);
+  int* d_info = reinterpret_cast<int*>(w);
+  w += align_up(sizeof(int) * static_cast<size_t>(count), 256);
+  CholProb* h_tab = new CholProb[count];
+  int max_pad = 0;
+  for (int f = 0; f < count; ++f) {
+    if (dims[f] <= 0 || factors[f] == nullptr || outs[f] == nullptr || add[f] < 0.f ||
+        multiply[f] < 0.f) {
+      delete[] h_tab;
+      return -2;
+    }
+    CholProb& p = h_tab[f];
+    p.F = factors[f];
+    p.out = outs[f];
+    p.d = dims[f];
+    p.dpad = pad_dim(dims[f]);
+    p.nb = p.dpad / NB;
+    p.sqrt_s = sqrtf(multiply[f]);
+    p.sqrt_n = sqrtf(add[f]);
+    const size_t mat = align_up(static_cast<size_t>(p.dpad) * p.dpad * 4, 256);
+    p.R = reinterpret_cast<float*>(w);
+    w += mat;
+    p.X = reinterpret_cast<float*>(w);
+    w += mat;
+    p.Dinv = reinterpret_cast<float*>(w);
+    w += align_up(static_cast<size_t>(p.nb) * NB * NB * 4, 256);
+    if (p.dpad > max_pad) max_pad = p.dpad;
+  }
+  cudaError_t e = cudaMemcpyAsync(d_tab, h_tab, sizeof(CholProb) * count, cudaMemcpyHostToDevice,
+                                  stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_info, 0, sizeof(int) * count, stream);
+  // the table copy is from pageable memory: it has been staged when the call returns
+  std::vector<CholProb> h_tab2(h_tab, h_tab + count);
+  delete[] h_tab;
+  if (e != cudaSuccess) return -5;
+
+  Pipeline& pipe = device_pipeline();
+  const int max_nb = max_pad / NB;
+  const bool pipelined = max_nb >= 4 && pipe.ok && pipe.reserve(max_nb);
+  __nv_bfloat16* stage_a = reinterpret_cast<__nv_bfloat16*>(w);
+  // Every kernel argument below is derived from the workspace address and the dims (factor / output pointers and
+  // the damping scalars are read from the device table just refreshed): the sequence is captured once per
+  // (workspace, dims) into a CUDA graph and replayed - one graph launch instead of ~450 (one 4097-wide factor) to
+  // ~1200 (the 8 factors of the wide MLP) host-issued dependent launches on two streams.
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool use_graph = g_chol_graph != 0 && pipe.ok && max_nb >= 4;
+  if (use_graph) {
+    GraphKey key{workspace, dev, std::vector<int>(dims, dims + count)};
+    std::lock_guard<std::mutex> guard(g_graph_mu);
+    CachedGraph* hit = nullptr;
+    for (auto& c : g_graphs)
+      if (c.key == key) hit = &c;
+    if (hit == nullptr) {
+      CachedGraph fresh;
+      fresh.key = key;
+      const unsigned long long before = launch_count();
+      bool ok = cudaStreamBeginCapture(pipe.cap, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      int rc_enq = -5;
+      if (ok) {
+        rc_enq = enqueue_steps(h_tab2, count, max_pad, d_tab, d_info, stage_a, pipe, pipelined, smem, pipe.cap);
+        cudaGraph_t graph = nullptr;
+        ok = cudaStreamEndCapture(pipe.cap, &graph) == cudaSuccess && rc_enq == 0 && graph != nullptr;
+        if (ok) ok = cudaGraphInstantiate(&fresh.exec, graph, 0) == cudaSuccess;
+        if (graph != nullptr) cudaGraphDestroy(graph);
+      }
+      fresh.launches = static_cast<int>(launch_count() - before);
+      note_launch(-fresh.launches);  // counted per replay below
+      if (ok) {
+        if (g_graphs.size() >= 16) {
+          for (auto& c : g_graphs) cudaGraphExecDestroy(c.exec);
+          g_graphs.clear();
+        }
+        g_graphs.push_back(fresh);
+        hit = &g_graphs.back();
+      } else {
+        cudaGetLastError();  // capture unsupported here: fall through to the direct path
+        if (rc_enq < 0 && rc_enq != -5) return rc_enq;
+      }
+    }
+    if (hit != nullptr) {
+      if (cudaGraphLaunch(hit->exec, stream) != cudaSuccess) return -5;
+      note_launch(hit->launches);
+    } else {
+      const int rc_enq = enqueue_steps(h_tab2, count, max_pad, d_tab, d_info, stage_a, pipe, pipelined, smem, stream);
+      if (rc_enq) return rc_enq;
+    }
+  } else {
+    const int rc_enq = enqueue_steps(h_tab2, count, max_pad, d_tab, d_info, stage_a, pipe, pipelined, smem, stream);
+    if (rc_enq) return rc_enq;
+  }
   if (cudaGetLastError() != cudaSuccess) return -5;
 
   int* h_info = new int[count];

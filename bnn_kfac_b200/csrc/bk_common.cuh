@@ -41,6 +41,7 @@ struct DeviceOnce {
 // Host side: every kernel launch of this library is counted (bk_launch_count in the C ABI reports
 // the total, which is how bench.py states how many of OUR kernels ran inside a timed region).
 void note_launch(int n = 1);
+unsigned long long launch_count();
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

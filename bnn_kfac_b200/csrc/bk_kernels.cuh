@@ -70,6 +70,10 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
                      size_t workspace_bytes, cudaStream_t stream);
 
 
+// 1 (default): the launch sequence of a given (workspace, dims) problem is captured once into a CUDA graph and
+// replayed; 0: every call enqueues its kernels one by one.
+void set_chol_graph(int enabled);
+
 // ---- bk_eigh.cu  (batched one-sided Jacobi eigensolver)
 size_t eigh_workspace_bytes(const int* dims, int count);
 // Returns 0, the 1-based index of the first factor that did not converge, or a negative error.

@@ -425,25 +425,36 @@ int launch_convert_split(const float* X, long long ldx, int rows, int cols, floa
 namespace {
 
 // Matrix element (r, c) of sample s is lane c % 4 of the Philox block with counter
-// (c / 4, r, sample0 + s, stream_id) under key = seed: one thread produces 4 consecutive columns of one
-// row (one Philox call, two Box-Muller pairs) and stores them as one 8-byte bf16x4 (rows are 16 B
-// aligned because ldz % 8 == 0).  No 64-bit index arithmetic, no dependence on the launch geometry.
-__global__ void __launch_bounds__(256)
+// (c / 4, r, sample0 + s, stream_id) under key = seed: one thread produces 8 consecutive columns of one
+// row (two Philox calls, four Box-Muller pairs) and stores them as one 16-byte bf16x8 (rows are 16 B
+// aligned because ldz % 8 == 0).  The values do not depend on the launch geometry.
+//
+// PERSISTENT launch: one CTA per SM, 512 threads, grid-stride over the (row, column-group) items of each sample.
+// The generator is ALU / MUFU work (~30 instructions per normal) and its consumers are tensor-bound persistent
+// GEMMs that occupy every SM with one CTA of ~225 KB shared memory: a conventional grid of 200 000 small blocks
+// never shares an SM with such a CTA (each resident block reserves 1 KB of shared memory, eight of them leave no
+// room for the GEMM CTA, and blocks keep arriving), so generator and GEMM ran strictly one after the other even on
+// different streams (measured: tools/gpu_philox_ab.py).  ONE generator CTA per SM (no shared memory of its own:
+// 1 KB reserved) fits beside the GEMM CTA in either launch order, and the two use different pipes.
+__global__ void __launch_bounds__(512, 1)
 philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_id, int rows,
                      int cols, int nsamples, float* __restrict__ Zf, long long ldf,
                      long long stridef, __nv_bfloat16* __restrict__ Zhi,
                      __nv_bfloat16* __restrict__ Zlo, long long ldz, long long stridez) {
   const int groups = (cols + 3) >> 2;  // column groups (Philox blocks) per row
-  const int pairs = (groups + 1) >> 1; // each thread produces two adjacent groups = 8 columns
+  const uint32_t pairs = static_cast<uint32_t>((groups + 1) >> 1);  // two adjacent groups = 8 columns per thread
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   // 16-byte stores of 8 bf16 need 16 B aligned rows
   const bool vec = (Zhi != nullptr) && ((ldz & 7) == 0) && ((stridez & 7) == 0) &&
                    ((reinterpret_cast<uintptr_t>(Zhi) & 15) == 0) &&
                    (Zlo == nullptr || (reinterpret_cast<uintptr_t>(Zlo) & 15) == 0);
-  // grid: x -> column-group pairs, y -> rows (grid-stride), z -> samples (grid-stride)
-  for (int s = blockIdx.z; s < nsamples; s += gridDim.z) {
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-      for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += gridDim.x * blockDim.x) {
+  const uint32_t items = static_cast<uint32_t>(rows) * pairs;       // per sample (host checks < 2^32)
+  const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int s = 0; s < nsamples; ++s) {
+    {
+      for (uint32_t it = first; it < items; it += stride) {
+        const int r = static_cast<int>(it / pairs);
+        const int t = static_cast<int>(it - static_cast<uint32_t>(r) * pairs);
         // two independent Philox blocks per thread: the 10-round dependency chains interleave
         uint32_t ca[4] = {static_cast<uint32_t>(2 * t), static_cast<uint32_t>(r), sample0 + s, stream_id};
         uint32_t cb[4] = {static_cast<uint32_t>(2 * t + 1), static_cast<uint32_t>(r), sample0 + s,
@@ -504,9 +515,19 @@ int launch_philox_normal(unsigned long long seed, unsigned sample0, unsigned str
                          __nv_bfloat16* Zhi, __nv_bfloat16* Zlo, long long ldz, long long stridez,
                          cudaStream_t stream) {
   if (rows <= 0 || cols <= 0 || nsamples <= 0) return 0;
-  const int pairs = ((cols + 3) / 4 + 1) / 2;
-  dim3 grid((pairs + 255) / 256, rows < 4096 ? rows : 4096, nsamples < 16 ? nsamples : 16);
-  philox_normal_kernel<<<grid, 256, 0, stream>>>(seed, sample0, stream_id, rows, cols, nsamples, Zf,
+  const long long pairs = ((cols + 3) / 4 + 1) / 2;
+  if (pairs * rows >= (1ll << 32)) return -2;
+  static DeviceOnce carve_once;
+  // same shared-memory carveout as the GEMM CTAs it is meant to run beside (no reconfiguration between the two)
+  carve_once([] {
+    cudaFuncSetAttribute(philox_normal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    return true;
+  });
+  const long long total = pairs * rows * nsamples;
+  int grid = static_cast<int>((total + 511) / 512);
+  if (grid > kNumSMsB200) grid = kNumSMsB200;
+  philox_normal_kernel<<<grid, 512, 0, stream>>>(seed, sample0, stream_id, rows, cols, nsamples, Zf,
                                                  ldf, stridef, Zhi, Zlo, ldz, stridez);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;

@@ -506,3 +506,26 @@ def linearised_diag_sharded(est, J_local: Tensor, n_rows: int, group=None,
     w = world_size(group)
     local = fn(est, J_local) if J_local.shape[0] else torch.empty(0, dtype=torch.float32, device=J_local.device)
     return _gather_var(local, [hi - lo for lo, hi in (row_slice(n_rows, w, r) for r in range(w))], group)
+
+
+# ------------------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPU cores NVML reports as closest to GPU `device_index` (its NUMA node), so
+    that pinned host buffers allocated afterwards are placed on that node (first touch) and the per-rank host ->
+    device copies of an end-to-end step do not all cross one socket's memory controllers.  Returns the core list,
+    or None when NVML / the affinity call is unavailable (nothing is changed then).  Call it BEFORE allocating
+    pinned memory; one process per GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cores = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

@@ -194,6 +194,11 @@ int bk_diag_quadform(float* out, const float* j, long long ldj, const float* h, 
  * call also returns after synchronising the stream.
  */
 size_t bk_chol_inv_workspace_bytes(const int* dims_host, int count);
+/* Process-wide switch (default 1): the step sequence of bk_damp_chol_inv_batched - ~450 dependent launches on two
+ * streams for one 4097-wide factor - depends only on (workspace address, dims), so it is captured ONCE into a CUDA
+ * graph and replayed by later calls (factor / output pointers and the damping scalars travel through a device
+ * table that is refreshed outside the graph).  0 = enqueue every kernel on every call. */
+void bk_set_chol_graph(int enabled);
 int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* outs_host,
                              const int* dims_host, const float* add_host,
                              const float* multiply_host, int count, void* workspace,
