@@ -177,3 +177,24 @@ def ptr(t) -> int:
 def stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def nvtx_range(name: str):
+    """Decorator: wraps a stage entry point in an NVTX range `bk/<name>` (one range per stage
+    of the path - factor update, inversion, sampling, predictive - so that an Nsight Systems / ncu --nvtx timeline
+    of a user's run shows them by name).  A push/pop pair costs ~100 ns; no-op without CUDA."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            import torch
+            if not torch.cuda.is_available():
+                return fn(*args, **kwargs)
+            torch.cuda.nvtx.range_push("bk/" + name)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco

@@ -290,6 +290,7 @@ class Curvature(ABC):
 class Diagonal(Curvature):
     """Diagonal Fisher / GGN.  Reference: curvatures.py:146-207."""
 
+    @_lib.nvtx_range("Diagonal.update")
     def update(self, batch_size: int):
         """state += [W.grad | b.grad]^2 * batch_size  (curvatures.py:155-172)."""
         st = _lib.stream_ptr()
@@ -481,6 +482,7 @@ class KFAC(Curvature):
                                                    flags, ws.data_ptr(), nbytes, _lib.stream_ptr()),
                    "bk_syrk_accum_grouped")
 
+    @_lib.nvtx_range("KFAC.update")
     def update(self, batch_size: int = None):
         """Accumulates A = [a;1][a;1]^T / cols and G = g g^T / cols per selected layer, with
         g = grad_output * N (curvatures.py:325-365).  `batch_size` is ignored, as in the reference."""
@@ -594,6 +596,7 @@ class KFAC(Curvature):
                    "bk_syrk_accum_staged")
 
     # ------------------------------------------------------------------ inversion
+    @_lib.nvtx_range("KFAC.invert")
     def invert(self, add: Union[float, list, tuple] = 0., multiply: Union[float, list, tuple] = 1.):
         """inv_state[layer] = (chol(inv(R_A)), chol(inv(R_G))) with R = sqrt(s) F + sqrt(n) I,
         symmetrised (curvatures.py:367-398).  One batched launch sequence for all factors."""
@@ -682,6 +685,7 @@ class KFAC(Curvature):
         assert self.inv_state, "Inverse state dict is empty. Did you call 'invert' prior to this?"
         return self.sample_batch(layer, 1, z=None if z is None else z.unsqueeze(0))[0]
 
+    @_lib.nvtx_range("KFAC.sample_batch")
     def sample_batch(self, layer: Module, n_samples: int, z: Optional[Tensor] = None,
                      sample0: Optional[int] = None) -> Tensor:
         """`n_samples` posterior samples of one layer in one batched launch: [S, d_out, d_in'].

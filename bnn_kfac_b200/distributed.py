@@ -292,6 +292,12 @@ def allgather_cholesky(owned: Dict[int, Tensor], dims: Sequence[int], owners: Se
     return outs
 
 
+def _nvtx(name):
+    from . import _lib
+    return _lib.nvtx_range(name)
+
+
+@_nvtx("invert_sharded")
 def invert_sharded(est, add=0., multiply=1., group=None,
                    inverter: Optional[Callable[[List[Tensor], List[float], List[float]], List[Tensor]]] = None,
                    keep_state_replicated: bool = False) -> None:

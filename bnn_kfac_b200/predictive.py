@@ -410,6 +410,7 @@ def mc_logits(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0,
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
 
+@_lib.nvtx_range("mc_moments")
 def mc_moments(est: KFAC, x: Tensor, n_samples: int, sample0: int = 0, mode: str = "classification",
                program=None, noise=None) -> Tuple[Tensor, Tensor]:
     """(E_s[p], E_s[p^2]) over `n_samples` samples starting at global sample id `sample0`;
@@ -542,6 +543,7 @@ def argmax_grad_outputs(pred_mean: Tensor) -> Tensor:
     return go
 
 
+@_lib.nvtx_range("linearised_kfac_classification")
 def linearised_kfac_classification(est: KFAC, x: Tensor) -> Tuple[Tensor, float, float]:
     """One test batch of the sampling-free KFAC predictive: (pred_mean [B, C], pred_std, entropy).
     classification_ll_block.py:114-135, including its quirks (Cholesky factors used as Q_i / H_i, flat
@@ -561,6 +563,7 @@ def linearised_kfac_classification(est: KFAC, x: Tensor) -> Tuple[Tensor, float,
     return pred_mean.detach(), pred_std, float(entropy)
 
 
+@_lib.nvtx_range("linearised_kfac_regression")
 def linearised_kfac_regression(est: KFAC, x_test: Tensor, tau: float, N: float, sigma: float) -> Tensor:
     """Predictive std per test point: sqrt(sum_layers |J (q_inv (x) h_inv) J^T|) + sigma with
     q_inv = (N (A + tau I))^-1, h_inv = (N (G + tau I))^-1 taken from `state`.
