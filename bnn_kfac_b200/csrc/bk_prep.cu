@@ -450,11 +450,19 @@ philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_
                    (Zlo == nullptr || (reinterpret_cast<uintptr_t>(Zlo) & 15) == 0);
   const uint32_t items = static_cast<uint32_t>(rows) * pairs;       // per sample (host checks < 2^32)
   const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  // (row, column group) of an item advance incrementally: one division per thread, none per item
+  const uint32_t dr = stride / pairs, dt = stride - dr * pairs;
+  const bool hi_only = vec && Zlo == nullptr && Zf == nullptr;      // single-pass bf16 operand: no lo parts at all
   for (int s = 0; s < nsamples; ++s) {
     {
-      for (uint32_t it = first; it < items; it += stride) {
-        const int r = static_cast<int>(it / pairs);
-        const int t = static_cast<int>(it - static_cast<uint32_t>(r) * pairs);
+      uint32_t r_u = first / pairs, t_u = first - r_u * pairs;
+      for (uint32_t it = first; it < items; it += stride, r_u += dr, t_u += dt) {
+        if (t_u >= pairs) {
+          t_u -= pairs;
+          ++r_u;
+        }
+        const int r = static_cast<int>(r_u);
+        const int t = static_cast<int>(t_u);
         // two independent Philox blocks per thread: the 10-round dependency chains interleave
         uint32_t ca[4] = {static_cast<uint32_t>(2 * t), static_cast<uint32_t>(r), sample0 + s, stream_id};
         uint32_t cb[4] = {static_cast<uint32_t>(2 * t + 1), static_cast<uint32_t>(r), sample0 + s,
@@ -471,6 +479,21 @@ philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_
         if (Zf != nullptr) {
           float* dst = Zf + s * stridef + static_cast<long long>(r) * ldf + c0;
           for (int j = 0; j < nv; ++j) dst[j] = z[j];
+        }
+        if (hi_only && c0 + 7 < ldz) {
+          // padding columns [cols, ldz) are written as zeros
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j >= nv) z[j] = 0.f;
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(z[0], z[1]), p1 = __floats2bfloat162_rn(z[2], z[3]);
+          const __nv_bfloat162 p2 = __floats2bfloat162_rn(z[4], z[5]), p3 = __floats2bfloat162_rn(z[6], z[7]);
+          uint4 ph;
+          ph.x = *reinterpret_cast<const uint32_t*>(&p0);
+          ph.y = *reinterpret_cast<const uint32_t*>(&p1);
+          ph.z = *reinterpret_cast<const uint32_t*>(&p2);
+          ph.w = *reinterpret_cast<const uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(Zhi + s * stridez + static_cast<long long>(r) * ldz + c0) = ph;
+          continue;
         }
         if (Zhi != nullptr) {
           __nv_bfloat16 h[8], l[8];
