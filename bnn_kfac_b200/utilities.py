@@ -235,3 +235,80 @@ def binned_kl_distance(dist1, dist2, smooth: float = 1e-7, bins=None) -> float:
         pdfs.append(h / h.sum())
     p, q = pdfs
     return float(np.sum(p * np.log(p / q)) + np.sum(q * np.log(q / p)))
+
+
+# ------------------------------------------------------------------------------------------------------
+# Script helpers of models/utilities.py:22-118, 366-386, 410-430 (the same functions are duplicated in
+# sampling_free/utils.py:213-236) that the linearised-predictive and dense-Fisher scripts call.
+def gradient(y: Tensor, x: Tensor, grad_outputs: Optional[Tensor] = None) -> Tensor:
+    """dy/dx contracted with grad_outputs (ones by default), graph kept (models/utilities.py:29-34)."""
+    if grad_outputs is None:
+        grad_outputs = torch.ones_like(y)
+    return torch.autograd.grad(y, [x], grad_outputs=grad_outputs, create_graph=True, retain_graph=True,
+                               allow_unused=True)[0]
+
+
+def jacobian(y: Tensor, x: Tensor, device=None) -> Tensor:
+    """[classes, numel(x)]: row i = gradient of sum_b y[b, i] w.r.t. x (models/utilities.py:36-47, which runs one
+    backward pass per class; here the classes are one batched backward, `is_grads_batched`, same values)."""
+    n_cls = y.shape[1]
+    go = torch.zeros((n_cls,) + tuple(y.shape), dtype=y.dtype, device=y.device)
+    idx = torch.arange(n_cls, device=y.device)
+    go[idx, :, idx] = 1
+    try:
+        g = torch.autograd.grad(y, [x], grad_outputs=go, retain_graph=True, allow_unused=True,
+                                is_grads_batched=True)[0]
+        jac = g.reshape(n_cls, -1)
+    except RuntimeError:        # an op without a batching rule: the reference's loop
+        jac = torch.stack([torch.flatten(gradient(y, x, go[i])) for i in range(n_cls)])
+    return jac.detach().to(device if device is not None else y.device)
+
+
+def get_near_psd(A: Tensor, epsilon: float) -> Tensor:
+    """Nearest-PSD repair: eigenvalues of (A + A^T)/2 below epsilon are raised to epsilon
+    (models/utilities.py:22-26).  The reference calls the GENERAL eigensolver on the symmetric part in fp64 and
+    returns a complex tensor; the symmetric part has a real orthogonal eigenbasis, so this returns the real fp32
+    matrix V max(w, eps) V^T from the Jacobi eigensolver (documented deviation: dtype)."""
+    from .curvatures import mm_nt
+    (w,), (v,) = eigh_factors([A], sym_scale=0.5)
+    w = torch.where(w < epsilon, torch.full_like(w, float(epsilon)), w)
+    return mm_nt((v * w.unsqueeze(0)).contiguous(), v)
+
+
+def generate_kernel_coords() -> List[Tuple[int, int]]:
+    """Per-kernel diagonal block ranges of BaseNet_15k (models/utilities.py:93-118, hessian/utils.py:67-95)."""
+    from .dense import kernel_block_coords_basenet15k
+    return kernel_block_coords_basenet15k()
+
+
+def calculateDominance(H: Tensor, regParam: float = 0.00001) -> Tuple[float, float]:
+    """(diagonal dominance, kernel-block dominance) of H + regParam I for BaseNet_15k's 15 080 x 15 080 Fisher
+    (models/utilities.py:50-70; other sizes raise NotImplementedError like the reference), one pass on the device."""
+    from .dense import dominance
+    if H.numel() != 15080 ** 2:
+        raise NotImplementedError
+    return dominance(H, generate_kernel_coords(), regParam)
+
+
+def ram() -> float:
+    """Utilised system memory in percent (models/utilities.py:369-375)."""
+    import psutil
+    return psutil.virtual_memory()[2]
+
+
+def vram() -> float:
+    """Device memory allocated by this process in GB (models/utilities.py:378-384)."""
+    return torch.cuda.memory_allocated() / (1024.0 ** 3)
+
+
+def seed_all_rng(seed: Optional[int] = None) -> None:
+    """Seeds torch, numpy and python RNGs (models/utilities.py:389-407).  The engine's own noise is Philox keyed by
+    the estimator's `seed=` argument and does not depend on these global generators."""
+    import os
+    import random
+    from datetime import datetime
+    if seed is None:
+        seed = os.getpid() + int(datetime.now().strftime("%S%f")) + int.from_bytes(os.urandom(2), "big")
+    np.random.seed(seed % (2 ** 32))
+    torch.manual_seed(seed)
+    random.seed(seed)

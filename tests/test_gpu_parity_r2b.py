@@ -200,3 +200,32 @@ def test_wide_conv_factors_vs_oracle(dev, precision):
         for ol, gl in zip(oest.layers, glayers):
             for k in range(2):
                 assert relerr(gest.inv_state[gl][k].cpu(), oest.inv_state[ol][k].numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------ script helpers
+def test_utilities_script_helpers(dev):
+    """gradient / jacobian / get_near_psd / calculateDominance of models/utilities.py:22-70 against plain fp64
+    torch restatements of the cited lines."""
+    from bnn_kfac_b200 import utilities as U
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(7, 4).to(dev)
+    xin = torch.rand(5, 7, device=dev)
+    y = torch.softmax(lin(xin), dim=1)
+    jac = U.jacobian(y, lin.weight, dev)
+    ref = torch.stack([torch.flatten(torch.autograd.grad(y[:, i].sum(), lin.weight, retain_graph=True)[0])
+                       for i in range(4)])
+    assert jac.shape == (4, 28) and relerr(jac.cpu(), ref.cpu()) < 1e-6
+    g = U.gradient(y, lin.bias)
+    assert relerr(g.detach().cpu(), torch.autograd.grad(y.sum(), lin.bias, retain_graph=True)[0].cpu()) < 1e-6
+    gen = torch.Generator().manual_seed(2)
+    A = torch.randn(60, 60, generator=gen)
+    C64 = ((A + A.t()) / 2).double()
+    w, v = torch.linalg.eigh(C64)
+    ref_psd = v @ torch.diag(torch.clamp(w, min=0.05)) @ v.t()
+    got = U.get_near_psd(A.to(dev), 0.05)
+    assert relerr(got.cpu(), ref_psd) < TOL
+    with pytest.raises(NotImplementedError):
+        U.calculateDominance(torch.eye(10, device=dev))
+    assert len(U.generate_kernel_coords()) == 109 and U.generate_kernel_coords()[-1] == (15070, 15080)
+    U.seed_all_rng(3)
+    assert U.vram() >= 0.0 and 0.0 <= U.ram() <= 100.0
