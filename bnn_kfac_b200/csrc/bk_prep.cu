@@ -450,17 +450,27 @@ philox_normal_kernel(unsigned long long seed, uint32_t sample0, uint32_t stream_
                    (Zlo == nullptr || (reinterpret_cast<uintptr_t>(Zlo) & 15) == 0);
   const uint32_t items = static_cast<uint32_t>(rows) * pairs;       // per sample (host checks < 2^32)
   const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-  // (row, column group) of an item advance incrementally: one division per thread, none per item
-  const uint32_t dr = stride / pairs, dt = stride - dr * pairs;
+  // The (sample, row, column group) index of an item advances INCREMENTALLY by the grid stride: a few divisions per
+  // thread, none per item, and small matrices with many samples (conv layers, S = 100) fill the grid because the
+  // samples are part of the flattened index instead of a serial outer loop.
+  const uint32_t ds = stride / items, rem = stride - ds * items;
+  const uint32_t dr = rem / pairs, dt = rem - dr * pairs;
   const bool hi_only = vec && Zlo == nullptr && Zf == nullptr;      // single-pass bf16 operand: no lo parts at all
-  for (int s = 0; s < nsamples; ++s) {
+  {
     {
-      uint32_t r_u = first / pairs, t_u = first - r_u * pairs;
-      for (uint32_t it = first; it < items; it += stride, r_u += dr, t_u += dt) {
+      uint32_t s_u = first / items;
+      const uint32_t q0 = first - s_u * items;
+      uint32_t r_u = q0 / pairs, t_u = q0 - r_u * pairs;
+      for (; s_u < static_cast<uint32_t>(nsamples); s_u += ds, r_u += dr, t_u += dt) {
         if (t_u >= pairs) {
           t_u -= pairs;
           ++r_u;
         }
+        if (r_u >= static_cast<uint32_t>(rows)) {
+          r_u -= static_cast<uint32_t>(rows);
+          if (++s_u >= static_cast<uint32_t>(nsamples)) break;
+        }
+        const int s = static_cast<int>(s_u);
         const int r = static_cast<int>(r_u);
         const int t = static_cast<int>(t_u);
         // two independent Philox blocks per thread: the 10-round dependency chains interleave
