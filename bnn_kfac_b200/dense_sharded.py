@@ -58,21 +58,41 @@ class CudaDenseOps:
                                                    status.data_ptr(), self._lib.stream_ptr()), "bk_chol_trinv_f64")
         return w
 
+    def _staged(self, slot: int, x: Tensor):
+        """bf16 (hi, lo) K-major copies of an fp32 (possibly strided) matrix in a grow-only staging buffer: two
+        operands per GEMM, 270 GEMMs per factorisation - no allocation, no zero-fill, no contiguous() copy."""
+        _lib = self._lib
+        rows, cols = x.shape
+        ld = (cols + 7) // 8 * 8
+        need = rows * ld
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            pool = self._pool = {}
+        buf = pool.get(slot)
+        if buf is None or buf.numel() < 2 * need or buf.device != x.device:
+            buf = pool[slot] = torch.zeros(2 * max(need, 1 << 20), dtype=torch.bfloat16, device=x.device)
+        if ld != cols:
+            buf[:2 * need].zero_()      # padding columns take part in the TMA boxes
+        hi, lo = buf.data_ptr(), buf.data_ptr() + 2 * need
+        assert x.stride(1) == 1 and x.dtype == torch.float32
+        _lib.check(self.lib.bk_convert_split(x.data_ptr(), x.stride(0), rows, cols, 1.0, 0, hi, lo, ld,
+                                             _lib.stream_ptr()), "bk_convert_split")
+        return hi, lo, ld
+
     def gemm_nt(self, a: Tensor, b: Tensor, out: Tensor, alpha: float, beta: float) -> None:
-        """out = alpha * a b^T + beta * out (fp32 views, split-bf16 tensor-core passes)."""
-        from .curvatures import stage_operand
+        """out = alpha * a b^T + beta * out (fp32 views, split-bf16 tensor-core passes).  `out` may alias `a`:
+        the operands are staged copies."""
         _lib = self._lib
         m, k = a.shape
         n = b.shape[0]
         if m == 0 or n == 0:
             return
-        a_hi, a_lo, lda = stage_operand(a)
-        b_hi, b_lo, ldb = stage_operand(b)
+        a_hi, a_lo, lda = self._staged(0, a)
+        b_hi, b_lo, ldb = self._staged(1, b)
         assert out.stride(1) == 1
-        _lib.check(self.lib.bk_gemm_nt(a_hi.data_ptr(), a_lo.data_ptr(), lda, 0, b_hi.data_ptr(), b_lo.data_ptr(),
-                                       ldb, 0, m, n, k, 1, _lib.BK_PREC_BF16X3, 0, float(alpha), float(beta),
-                                       out.data_ptr(), out.stride(0), 0, 0, 0, 0, 0, 0, 0, _lib.stream_ptr()),
-                   "bk_gemm_nt")
+        _lib.check(self.lib.bk_gemm_nt(a_hi, a_lo, lda, 0, b_hi, b_lo, ldb, 0, m, n, k, 1, _lib.BK_PREC_BF16X3, 0,
+                                       float(alpha), float(beta), out.data_ptr(), out.stride(0), 0, 0, 0, 0, 0, 0, 0,
+                                       _lib.stream_ptr()), "bk_gemm_nt")
 
     def rownorm2(self, y: Tensor) -> Tensor:
         _lib = self._lib
@@ -155,7 +175,14 @@ class ShardedDenseFisher:
         A[:nloc * nb].copy_(self.rows)
         A[nloc * nb:, :self.P].copy_(J_local)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        counts_after = lambda k, r: len([g for g in range(r, nblk, w) if g > k])  # noqa: E731
+        owned = [len(range(r, nblk, w)) for r in range(w)]
+
+        def counts_after(k, r):      # blocks g = r, r + w, ... with k < g < nblk
+            return owned[r] - (0 if k < r else (k - r) // w + 1)
+
+        slots_max = (nblk - 1) // w + 1
+        send_full = torch.zeros(slots_max * nb, nb, device=dev, dtype=A.dtype) if w > 1 else None
+        recv_full = torch.empty(w * slots_max * nb, nb, device=dev, dtype=A.dtype) if w > 1 else None
         for k in range(nblk):
             owner, lk = k % w, k // w
             c0, c1 = k * nb, (k + 1) * nb
@@ -172,22 +199,20 @@ class ShardedDenseFisher:
             ops.gemm_nt(panel, W, panel, 1.0, 0.0)        # X = A[:, k] W^T (operands are staged copies: in place)
             if k == nblk - 1:
                 break
-            # all-gather of the block rows of the panel, reordered to global block order
-            cnt = [counts_after(k, r) for r in range(w)]
-            cmax = max(cnt)
             if w > 1:
-                send = torch.zeros(cmax * nb, nb, device=dev, dtype=A.dtype)
-                send[:cnt[me] * nb].copy_(A[l0 * nb:nloc * nb, c0:c1])
-                recv = torch.empty(w * cmax * nb, nb, device=dev, dtype=A.dtype)
+                # all-gather of the panel's block rows.  Every rank places block g = l * w + r at slot l - base
+                # (base = the local index of block k + 1 on its owner), so the gathered [rank][slot] buffer read in
+                # [slot][rank] order IS the global block order: one strided copy, no index tensors.  The slots in
+                # front of block k + 1 and behind the last block hold stale data and are sliced away.
+                base = (k + 1) // w
+                cm = slots_max - base
+                send = send_full[:cm * nb]
+                if nloc > l0:
+                    send[(l0 - base) * nb:(nloc - base) * nb].copy_(A[l0 * nb:nloc * nb, c0:c1])
+                recv = recv_full[:w * cm * nb]
                 dist.all_gather_into_tensor(recv, send, group=self.group)
-                order = []
-                for g in range(k + 1, nblk):
-                    r = g % w
-                    # rank r holds g at local slot g // w and sent its slots from (n_owned - cnt[r]) on
-                    slot = g // w - (len(range(r, nblk, w)) - cnt[r])
-                    order.append(r * cmax + slot)
-                idx = torch.tensor(order, dtype=torch.long, device=dev)
-                x_all = recv.view(w * cmax, nb, nb).index_select(0, idx).reshape(-1, nb)
+                ordered = recv.view(w, cm, nb * nb).permute(1, 0, 2).reshape(cm * w * nb, nb)
+                x_all = ordered[(k + 1 - base * w) * nb:(nblk - base * w) * nb]
             else:
                 x_all = A[l0 * nb:nloc * nb, c0:c1]
             # trailing update of my rows (block rows and Jacobian rows): A[:, k+1:] -= X X_all^T

@@ -166,11 +166,14 @@ def run_check_rows(rank, world, dev, dense_p=3000):
     coords = [(i, min(i + 100, P)) for i in range(0, P, 100)]
     dom, ms_dom = _ev_ms(lambda: sh.dominance(coords, 1e-5), dev)
     var, ms_var = _ev_ms(lambda: sh.variance(J[ja:jb].contiguous(), tau, n_rows=B), dev)
-    H = dense.dense_fisher(G)
+    def single_gpu():
+        H1 = dense.dense_fisher(G)
+        return H1, dense.dense_variance(J, dense.dense_inverse(H1, tau))
+    (H, var1), ms_single = _ev_ms(single_gpu, dev)
     dom1 = dense.dominance(H, coords, 1e-5)
-    var1 = dense.dense_variance(J, dense.dense_inverse(H, tau))
     out["dense_fisher"] = {"relerr": relerr(var, var1), "dominance_err": max(abs(dom[0] - dom1[0]), abs(dom[1] - dom1[1])),
                            "accumulate_exchange_ms": ms_acc, "dominance_ms": ms_dom, "cholesky_variance_ms": ms_var,
+                           "single_gpu_replicated_ms": ms_single,
                            "P": P, "gradients": n, "test_rows": B}
     ok = (out["linearised_regression"]["relerr"] < 1e-3 and out["diagonal"]["relerr"] < 1e-3
           and out["dense_fisher"]["relerr"] < 1e-3 and out["dense_fisher"]["dominance_err"] < 1e-5)
