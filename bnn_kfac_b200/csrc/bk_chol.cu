@@ -33,7 +33,6 @@ namespace bk {
 namespace {
 
 constexpr int NB = 64;
-constexpr int TM = 128, TN = 128;
 constexpr int kPad = 4;
 
 struct CholProb {
@@ -110,117 +109,152 @@ __global__ void damp_flip_kernel(const CholProb* __restrict__ tab) {
 }
 
 // ------------------------------------------------------------------ diagonal block: potrf + inverse
-// One CTA factorises the 64 x 64 diagonal block AND inverts the factor, both in REGISTERS and in the
-// same sweep.  Thread (c, rq) owns column c, rows 16 rq .. 16 rq + 15 of the block A and of X (X = I
-// initially).  Step j: the owners of column j of A and of row j of X publish them through
-// double-buffered shared vectors, ONE barrier, then
-//     c > j :  A[i][c] -= L[i][j] L[c][j]              (i > j)    right-looking Cholesky
-//     c <= j:  X[i][c] -= L[i][j] X[j][c]              (i > j)    forward substitution on I
-// (X[j][c] is zero for c > j and columns c < j of A are final, so a thread does ONE of the two), with
-// L[i][j] L[c][j] = colj[i] colj[c] / piv.  Rows are blocked, not cyclic: warps whose 16 rows are all
-// <= j have nothing left to do and fall through to the barrier, so the work shrinks with j, and the
-// published column is read with 128-bit loads.
-// (Earlier versions: block in shared memory, two barriers and a dependent load-modify-store chain per
-// step, inverse afterwards by one thread per column: ~64-75 us per block, a third of a 4097-wide
-// inversion, all of it serial latency.)
-__global__ void __launch_bounds__(256)
+// One CTA factorises the 64 x 64 diagonal block AND inverts the factor, in REGISTERS and in the same sweep.
+// Thread (c, h) owns column c, rows 32 h .. 32 h + 31, in ONE register array v[]: column c of A until step
+// j = c (right-looking Cholesky), column c of X = L^-1 afterwards (forward substitution on I) - X[j][c] is zero
+// for c > j and columns c < j of A are final, so a column is in exactly one of the two states:
+//     step j:  owners publish column j of A and row j of X (double-buffered shared vectors), ONE barrier, then
+//     c > j :  A[i][c] -= L[i][j] L[c][j]              (i > j)     L[i][j] L[c][j] = colj[i] colj[c] / piv
+//     c == j:  L[:, j] goes to a shared tile; X[i][j] = -colj[i] / piv, X[j][j] = 1 / L[j][j]
+//     c < j :  X[i][c] -= L[i][j] X[j][c]              (i > j)
+// i.e. v[r] = fma(-colj[i], f, v[r]) with a per-thread scalar f for everybody.  Rows are blocked, not cyclic: the
+// warps of the upper half have nothing left to do in the second half of the sweep and fall through to the barrier.
+// The sweep is a chain of 64 dependent steps, so what counts is the latency of one step: four warps (one per
+// scheduler) with 32 independent FMAs each behind every published column, shared memory addressed through
+// precomputed 32-bit offsets (the compiler re-derived generic addresses from S2R SR_CgaCtaId / SR_TID inside
+// every step of the C++ version, on the critical path in front of the publishing stores and the broadcast loads),
+// a bare MUFU.RSQ (pivots are >= the damping term, no denormal fix-up), no divergent A / X paths.
+// History: block in shared memory, two barriers per step, inverse afterwards: 64-75 us per block; registers,
+// 8 warps x 16 rows, separate A and X arrays: 23.3 us (~670 cycles per step, 70 instructions per warp per
+// step); this version: see profiles/r02_potrf_diag.md.
+constexpr int kDiagThreads = 128;
+constexpr int kLsPitch = NB + 1;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kDiagThreads)
 potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ info) {
   pdl_wait_then_trigger();
   const CholProb p = tab[blockIdx.x];
   if (k >= p.nb) return;
-  __shared__ __align__(16) float colj[2][NB];
-  __shared__ float xrow[2][NB];
+  // [0, 512): colj[2][64]   [512, 1024): xrow[2][64]   [1024, ...): L tile [64][65]
+  __shared__ __align__(16) float sh[4 * NB + NB * kLsPitch];
   __shared__ int bad;
+  uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sh));
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register (no S2R re-derivation per step)
   const int tid = threadIdx.x;
   float* blk = p.R + static_cast<long long>(k) * NB * p.dpad + k * NB;
   if (tid == 0) bad = 0;
-  const int c = tid % NB, rq = tid / NB;  // column, row block (0..3)
-  constexpr int R = NB / 4;
-  const int i0 = R * rq;
-  float a[R], x[R];
+  const int c = tid % NB, h = tid / NB;  // column, row half (0..1)
+  constexpr int R = NB / 2;
+  const int i0 = R * h;
+  float v[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    a[r] = blk[static_cast<long long>(i0 + r) * p.dpad + c];
-    x[r] = (i0 + r == c) ? 1.f : 0.f;
-  }
-  // The column loop is unrolled by the 16 rows a thread owns: row j of X is then the STATICALLY indexed register
-  // x[jj] of its owners.  (With a rolled loop the compiler turned the select chain that picked x[j & 15] into a
-  // dynamic load from a local-memory copy of x[] — 64 bytes of stack, an STL per update and an LDL on the
-  // critical path in front of every barrier; ncu source view, round 1.)
+  for (int r = 0; r < R; ++r) v[r] = blk[static_cast<long long>(i0 + r) * p.dpad + c];
+  const uint32_t a_col = sbase + 4u * static_cast<uint32_t>(i0);  // + 256 * buffer: this thread's rows of colj
+  const uint32_t a_c = sbase + 4u * static_cast<uint32_t>(c);     // + 256 * buffer: colj[c]; + 512: xrow[c]
+  const uint32_t a_ls = sbase + 4u * (4 * NB + static_cast<uint32_t>(c) * kLsPitch);  // L tile row c
+  bool nonpos = false;
+  // The column loop is unrolled by the 32 rows a thread owns: row j of X is then the STATICALLY indexed register
+  // v[jj] of its owners (a rolled loop makes the compiler index a local-memory copy of v[] dynamically).
 #pragma unroll 1
   for (int jb = 0; jb < NB / R; ++jb) {
-    const bool row_owner = jb == rq;  // this thread holds rows 16 jb .. 16 jb + 15 (warp-uniform)
-    // row i0 + r lies below row j = 16 jb + jj  <=>  rq > jb (warp-uniform) or, for the owners of block jb,
-    // r > jj — a compile-time fact in the unrolled body: no per-element compare
-    const bool below = rq > jb;
+    const bool row_owner = jb == h;  // this thread holds rows 32 jb .. 32 jb + 31 (warp-uniform)
+    // row i0 + r lies below row j = 32 jb + jj  <=>  h > jb (warp-uniform) or, for the owners of half jb,
+    // r > jj - a compile-time fact in the unrolled body: no per-element compare
+    const bool below = h > jb;
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) {
     const int j = jb * R + jj;
-    float* cj = colj[jj & 1];
-    float* xj = xrow[jj & 1];
-    if (c == j && rq >= jb) {
-#pragma unroll
-      for (int r = 0; r < R; r += 4)
-        *reinterpret_cast<float4*>(&cj[i0 + r]) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
-    }
-    if (row_owner) xj[c] = x[jj];  // X[j][c] before the division by L[j][j]
-    __syncthreads();
-    if (rq < jb) continue;  // all rows of this warp are final (warp-uniform)
-    float piv = cj[j];
-    if (!(piv > 0.f)) {  // not positive definite (or NaN)
-      if (tid == 0 || c == j) bad = 1;
-      piv = 1.f;
-    }
-    const float rs = rsqrtf(piv);  // 1 / L[j][j]
-    const float ipiv = rs * rs;
-    const float4 q0 = *reinterpret_cast<const float4*>(&cj[i0]);
-    const float4 q1 = *reinterpret_cast<const float4*>(&cj[i0 + 4]);
-    const float4 q2 = *reinterpret_cast<const float4*>(&cj[i0 + 8]);
-    const float4 q3 = *reinterpret_cast<const float4*>(&cj[i0 + 12]);
-    const float cv[R] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
-                         q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-    if (c > j) {
-      const float lc = cj[c] * ipiv;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (below || r > jj) a[r] = fmaf(-cv[r], lc, a[r]);
-    } else {
-      const float xc = xj[c] * ipiv;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (below || r > jj) x[r] = fmaf(-cv[r], xc, x[r]);
+    const uint32_t buf = 256u * (jj & 1);
+    if (h >= jb) {
       if (c == j) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (below || r > jj) a[r] = cv[r] * rs;
-          else if (row_owner && r == jj) a[r] = piv * rs;
-        }
+        for (int r = 0; r < R; r += 4) sts128(a_col + buf + 4u * r, v[r], v[r + 1], v[r + 2], v[r + 3]);
       }
+      if (row_owner) sts32(a_c + 512u + buf, v[jj]);  // X[j][c] before the division by L[j][j] (c < j)
     }
-    if (row_owner) x[jj] = xj[c] * rs;  // final X[j][c]
+    __syncthreads();
+    if (h < jb) continue;  // all rows of this warp are final (warp-uniform)
+    float piv = lds32(sbase + buf + 4u * j);
+    const float fc = lds32(a_c + buf);          // A[c][j]  (meaningful for c > j)
+    const float fx = lds32(a_c + 512u + buf);   // X[j][c]  (meaningful for c < j)
+    float cv[R];
+#pragma unroll
+    for (int r = 0; r < R; r += 4) {
+      const float4 q = lds128(a_col + buf + 4u * r);
+      cv[r] = q.x; cv[r + 1] = q.y; cv[r + 2] = q.z; cv[r + 3] = q.w;
+    }
+    if (!(piv > 0.f)) {  // not positive definite (or NaN)
+      nonpos = true;
+      piv = 1.f;
+    }
+    const float rs = rsqrt_fast(piv);  // 1 / L[j][j]
+    const float ipiv = rs * rs;
+    float f = ((c > j) ? fc : fx) * ipiv;
+    if (c == j) {  // the column changes state: X[:, j] starts from zero, f = X[j][j] / piv = 1 / piv
+      f = ipiv;
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = 0.f;
+    }
+    if (h == 1) {  // column j of L (rows c >= j) into the shared tile; these two warps are active to the end
+      const float lcj = (c == j) ? piv * rs : fc * rs;
+      if (c >= j) sts32(a_ls + 4u * j, lcj);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (below || r > jj) v[r] = fmaf(-cv[r], f, v[r]);
+    if (row_owner && c <= j) v[jj] = (c == j) ? rs : fx * rs;  // final X[j][c]
   }
   }
+  if (nonpos) bad = 1;
+  __syncthreads();
   float* di = p.Dinv + static_cast<long long>(k) * NB * NB;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int i = i0 + r;
-    if (c <= i) blk[static_cast<long long>(i) * p.dpad + c] = a[r];
-    di[i * NB + c] = (c <= i) ? x[r] : 0.f;
+    if (c <= i) blk[static_cast<long long>(i) * p.dpad + c] = sh[4 * NB + i * kLsPitch + c];
+    di[i * NB + c] = (c <= i) ? v[r] : 0.f;
   }
-  __syncthreads();
   if (tid == 0 && bad) atomicCAS(&info[blockIdx.x], 0, k + 1);
 }
 
 // ------------------------------------------------------------------ rank-64 update
 enum Mode : int { kPanel = 0, kTrail = 1, kRowScale = 2, kXUpdate = 3 };
 
-// C[m x n] = beta*C + alpha * A[m x 64] * (NT ? B[n x 64]^T : B[64 x n]);  one 128x128 tile / CTA.
+// C[m x n] = beta*C + alpha * A[m x 64] * (NT ? B[n x 64]^T : B[64 x n]);  one T x T tile / CTA, T = 128 (8 x 8
+// outputs per thread) or 64 (4 x 4).  The steps are latency-bound chains: whenever the 128-wide tiling would leave
+// most SMs without a CTA the host picks T = 64 - four times the CTAs, a quarter of the loads and FMAs in front of
+// each CTA's stores (panel of a 4097-wide factor: 32 CTAs x ~15 us -> 64+ CTAs x ~6 us).
 // `limit` (two-level blocking, 0 = none): the rank-64 update only reaches up to row / column `limit`
 // of the matrix (the end of the current 256-wide outer block); everything beyond it receives the
 // whole outer block at once from the tensor-core GEMM (see chol_inv_batched).
+template <int T>
 __global__ void __launch_bounds__(256)
 rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
   pdl_wait_then_trigger();
+  constexpr int TT = T / 16;  // outputs per thread and dimension; also 128-bit loads per thread and operand
+  constexpr int V = TT / 4;
   const CholProb p = tab[blockIdx.y];
   if (k >= p.nb) return;
   const long long ld = p.dpad;
@@ -253,13 +287,13 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
     alpha = -1.f; beta = 1.f;
   }
   if (m <= 0 || n <= 0) return;
-  const int tiles_m = (m + TM - 1) / TM, tiles_n = (n + TN - 1) / TN;
+  const int tiles_m = (m + T - 1) / T, tiles_n = (n + T - 1) / T;
   int ti, tj;
   if (lower && limit > 0) {
     // rectangular m x n region (n <= 192) of the lower triangle: plain enumeration + masking
     ti = blockIdx.x / tiles_n;
     tj = blockIdx.x - ti * tiles_n;
-    if (ti >= tiles_m || tj * TN > ti * TM + TM - 1) return;
+    if (ti >= tiles_m || tj * T > ti * T + T - 1) return;
   } else if (lower) {
     const int t = blockIdx.x;
     ti = static_cast<int>((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
@@ -272,27 +306,27 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
     tj = blockIdx.x - ti * tiles_n;
     if (ti >= tiles_m) return;
   }
-  const int r0 = ti * TM, c0 = tj * TN;
+  const int r0 = ti * T, c0 = tj * T;
 
   extern __shared__ float sm[];
-  float(*As)[TM + kPad] = reinterpret_cast<float(*)[TM + kPad]>(sm);
-  float(*Bs)[TN + kPad] = reinterpret_cast<float(*)[TN + kPad]>(sm + NB * (TM + kPad));
+  float(*As)[T + kPad] = reinterpret_cast<float(*)[T + kPad]>(sm);
+  float(*Bs)[T + kPad] = reinterpret_cast<float(*)[T + kPad]>(sm + NB * (T + kPad));
   const int tid = threadIdx.x;
-  // Operand tiles: every thread issues ALL of its 128-bit loads (8 per operand) before the first
-  // shared-memory store, so one DRAM / L2 round trip is exposed per tile instead of 32.
+  // Operand tiles: every thread issues ALL of its 128-bit loads (TT per operand) before the first
+  // shared-memory store, so one DRAM / L2 round trip is exposed per tile instead of 4 TT.
   {
-    float4 va[8];
+    float4 va[TT];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < TT; ++u) {
       const int q = tid + 256 * u;
       const int i = q >> 4, k4 = (q & 15) << 2;
       va[u] = (r0 + i < m) ? __ldg(reinterpret_cast<const float4*>(A + (r0 + i) * lda + k4))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float4 vb[8];
+    float4 vb[TT];
     if (nt) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < TT; ++u) {
         const int q = tid + 256 * u;
         const int j = q >> 4, k4 = (q & 15) << 2;
         vb[u] = (c0 + j < n) ? __ldg(reinterpret_cast<const float4*>(B + (c0 + j) * ldb + k4))
@@ -300,16 +334,16 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < TT; ++u) {
         const int q = tid + 256 * u;
-        const int kk = q >> 5, j4 = (q & 31) << 2;
-        // n and c0 are multiples of 64 / 128 here (k1 = (k+1)*64), so a float4 is all-in or all-out
+        const int kk = q / (T / 4), j4 = (q % (T / 4)) << 2;
+        // n and c0 are multiples of 64 here (k1 = (k+1)*64), so a float4 is all-in or all-out
         vb[u] = (c0 + j4 < n) ? __ldg(reinterpret_cast<const float4*>(B + kk * ldb + c0 + j4))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < TT; ++u) {
       const int q = tid + 256 * u;
       const int i = q >> 4, k4 = (q & 15) << 2;
       As[k4 + 0][i] = va[u].x;
@@ -319,7 +353,7 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
     }
     if (nt) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < TT; ++u) {
         const int q = tid + 256 * u;
         const int j = q >> 4, k4 = (q & 15) << 2;
         Bs[k4 + 0][j] = vb[u].x;
@@ -329,60 +363,88 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < TT; ++u) {
         const int q = tid + 256 * u;
-        const int kk = q >> 5, j4 = (q & 31) << 2;
+        const int kk = q / (T / 4), j4 = (q % (T / 4)) << 2;
         *reinterpret_cast<float4*>(&Bs[kk][j4]) = vb[u];
       }
     }
   }
   __syncthreads();
   const int ty = tid / 16, tx = tid % 16;
-  float acc[8][8];
+  float acc[TT][TT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TT; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TT; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
   for (int kk = 0; kk < NB; ++kk) {
-    const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-    const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
-    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float a[TT], b[TT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int v = 0; v < V; ++v) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TT + 4 * v]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * TT + 4 * v]);
+      a[4 * v] = av.x; a[4 * v + 1] = av.y; a[4 * v + 2] = av.z; a[4 * v + 3] = av.w;
+      b[4 * v] = bv.x; b[4 * v + 1] = bv.y; b[4 * v + 2] = bv.z; b[4 * v + 3] = bv.w;
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    for (int i = 0; i < TT; ++i)
+#pragma unroll
+      for (int j = 0; j < TT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
   }
-  // Read-modify-write of the 8 x 8 register tile: ALL old values are loaded (as float4 pairs) before
-  // the first store - a load / store pair per element would expose one L2 round trip 64 times.
-  // Row starts are 16 B aligned (ld and c0 are multiples of 64 / 128, tx * 8 floats = 32 B).
-  float4 old[8][2];
+  // Read-modify-write of the TT x TT register tile: ALL old values are loaded (as float4) before
+  // the first store - a load / store pair per element would expose one L2 round trip TT^2 times.
+  // Row starts are 16 B aligned (ld and c0 are multiples of 64, tx * TT floats = 16 / 32 B).
+  float4 old[TT][V];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = r0 + ty * 8 + i;
-    const int col = c0 + tx * 8;
+  for (int i = 0; i < TT; ++i) {
+    const int row = r0 + ty * TT + i;
+    const int col = c0 + tx * TT;
     const bool live = beta != 0.f && row < m && col < n && !(lower && col > row);
     const float4* src = reinterpret_cast<const float4*>(C + row * ld + col);
-    old[i][0] = live ? src[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-    old[i][1] = (live && col + 4 < n) ? src[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      old[i][v] = (live && col + 4 * v < n) ? src[v] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = r0 + ty * 8 + i;
+  for (int i = 0; i < TT; ++i) {
+    const int row = r0 + ty * TT + i;
     if (row >= m) continue;
     float* crow = C + row * ld;
-    const float o[8] = {old[i][0].x, old[i][0].y, old[i][0].z, old[i][0].w,
-                        old[i][1].x, old[i][1].y, old[i][1].z, old[i][1].w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = c0 + tx * 8 + j;
-      if (col >= n || (lower && col > row)) continue;
-      crow[col] = fmaf(alpha, acc[i][j], beta * o[j]);
+    for (int v = 0; v < V; ++v) {
+      const float o[4] = {old[i][v].x, old[i][v].y, old[i][v].z, old[i][v].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = c0 + tx * TT + 4 * v + j;
+        if (col >= n || (lower && col > row)) continue;
+        crow[col] = fmaf(alpha, acc[i][4 * v + j], beta * o[j]);
+      }
     }
   }
+}
+
+constexpr int rank64_smem(int T) { return static_cast<int>(sizeof(float)) * NB * 2 * (T + kPad); }
+
+// Tile edge for a rank-64 launch: 128 when the grid fills the GPU anyway, 64 when the launch is a latency-bound
+// link of the chain (few tiles).
+inline int pick_tile(long long tiles128_total) { return tiles128_total >= 2 * 148 ? 128 : 64; }
+
+// grid.x of a rank-64 launch over an m x n region with tile edge T
+inline int rank64_tiles(int m, int n, int T, bool lower_full) {
+  const int tm = (m + T - 1) / T, tn = (n + T - 1) / T;
+  return lower_full ? tm * (tm + 1) / 2 : tm * tn;
+}
+
+inline void launch_rank64(int m, int n, bool lower_full, int count, cudaStream_t stream, const CholProb* tab, int k,
+                          int mode, int limit) {
+  const int T = pick_tile(static_cast<long long>(rank64_tiles(m, n, 128, lower_full)) * count);
+  const dim3 grid(rank64_tiles(m, n, T, lower_full), count);
+  if (T == 128)
+    launch_chained(rank64_kernel<128>, grid, dim3(256), static_cast<size_t>(rank64_smem(128)), stream, tab, k, mode, limit);
+  else
+    launch_chained(rank64_kernel<64>, grid, dim3(256), static_cast<size_t>(rank64_smem(64)), stream, tab, k, mode, limit);
+  note_launch();
 }
 
 // ------------------------------------------------------------------ un-flip + transpose to output
@@ -553,7 +615,7 @@ std::vector<CachedGraph> g_graphs;
 // The whole step sequence (damp / flip, both phases, flip-out) enqueued on `stream` (+ the pipeline's side stream,
 // forked from and joined back into it).  Depends on the workspace layout and the dims only.
 int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, CholProb* d_tab, int* d_info,
-                  __nv_bfloat16* stage_a, Pipeline& pipe, bool pipelined, int smem, cudaStream_t stream) {
+                  __nv_bfloat16* stage_a, Pipeline& pipe, bool pipelined, int /*smem*/, cudaStream_t stream) {
   const int max_nb = max_pad / NB;
   const CholProb* cd_tab = d_tab;
   const dim3 tb(32, 8);
@@ -579,16 +641,10 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
   auto inverse_step = [&](int k) -> int {
     const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
     const int n = (k + 1) * NB;
-    const int tn = (n + TN - 1) / TN;
-    launch_chained(rank64_kernel, dim3(tn, count), dim3(256), smem, s2, cd_tab, k, static_cast<int>(kRowScale), 0);
-    note_launch();
+    launch_rank64(NB, n, false, count, s2, cd_tab, k, static_cast<int>(kRowScale), 0);
     int m = max_pad - (k + 1) * NB;
     if (two_level) m = (limit < max_pad ? limit : max_pad) - (k + 1) * NB;
-    if (m > 0) {
-      const int tm = (m + TM - 1) / TM;
-      launch_chained(rank64_kernel, dim3(tm * tn, count), dim3(256), smem, s2, cd_tab, k, static_cast<int>(kXUpdate), limit);
-      note_launch();
-    }
+    if (m > 0) launch_rank64(m, n, false, count, s2, cd_tab, k, static_cast<int>(kXUpdate), limit);
     if (two_level && (k + 1) % inner_per_outer == 0) {
       const int c0 = (k + 1 - inner_per_outer) * NB;
       for (int f = 0; f < count; ++f) {
@@ -601,14 +657,10 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
   // ---- phase 1: right-looking Cholesky of the flipped damped matrix (+ the pipelined inverse steps)
   for (int k = 0; k < max_nb; ++k) {
     const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
-    launch_chained(potrf_diag_kernel, dim3(count), dim3(256), 0, stream, cd_tab, k, d_info);
+    launch_chained(potrf_diag_kernel, dim3(count), dim3(kDiagThreads), 0, stream, cd_tab, k, d_info);
     note_launch();
     const int m = max_pad - (k + 1) * NB;
-    if (m > 0) {
-      const int tm = (m + TM - 1) / TM;
-      launch_chained(rank64_kernel, dim3(tm, count), dim3(256), smem, stream, cd_tab, k, static_cast<int>(kPanel), 0);
-      note_launch();
-    }
+    if (m > 0) launch_rank64(m, NB, false, count, stream, cd_tab, k, static_cast<int>(kPanel), 0);
     if (pipelined) {
       // block column k of C and Dinv[k] are final: inverse step k may run
       if (cudaEventRecord(pipe.panel_done[k], stream) != cudaSuccess ||
@@ -618,17 +670,11 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
       if (rc) return rc;
     }
     if (m > 0) {
-      const int tm = (m + TM - 1) / TM;
       if (!two_level) {
-        launch_chained(rank64_kernel, dim3(tm * (tm + 1) / 2, count), dim3(256), smem, stream, cd_tab, k, static_cast<int>(kTrail), 0);
-        note_launch();
+        launch_rank64(m, m, true, count, stream, cd_tab, k, static_cast<int>(kTrail), 0);
       } else {
         const int ncols = limit - (k + 1) * NB;  // columns of the outer block right of this step
-        if (ncols > 0) {
-          const int tn = (ncols + TN - 1) / TN;
-          launch_chained(rank64_kernel, dim3(tm * tn, count), dim3(256), smem, stream, cd_tab, k, static_cast<int>(kTrail), limit);
-          note_launch();
-        }
+        if (ncols > 0) launch_rank64(m, ncols, false, count, stream, cd_tab, k, static_cast<int>(kTrail), limit);
       }
     }
     if (two_level && (k + 1) % inner_per_outer == 0) {
@@ -666,10 +712,12 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
       (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return -6;
   static DeviceOnce attr_once;
-  const int smem = sizeof(float) * NB * ((TM + kPad) + (TN + kPad));
+  const int smem = rank64_smem(128);
   if (!attr_once([&] {
-        return cudaFuncSetAttribute(rank64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ==
-               cudaSuccess;
+        return cudaFuncSetAttribute(rank64_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    rank64_smem(128)) == cudaSuccess &&
+               cudaFuncSetAttribute(rank64_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    rank64_smem(64)) == cudaSuccess;
       }))
     return -5;
   char* w = static_cast<char*>(workspace);
