@@ -477,10 +477,14 @@ inline int pad_dim(int d) { return (d + NB - 1) / NB * NB; }
 constexpr int kOuter = 256;       // outer block width of the two-level algorithm (4 inner blocks)
 constexpr int kTwoLevelMin = 2048;  // padded size from which the tensor-core trailing updates pay off
 
-inline size_t staging_bytes(int max_pad) {
-  // three operands (L21 for the Cholesky phase; L21 again and the transposed X block for the inverse phase,
-  // which runs concurrently on its own stream), three bf16 parts each, [max_pad, kOuter]
-  return max_pad >= kTwoLevelMin ? 3 * 3 * align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) : 0;
+inline size_t staging_bytes(int max_pad, int count) {
+  // per factor (the outer updates of different factors run concurrently on auxiliary streams) and per parity of
+  // the outer block (the FAR part of one block's update is still reading its operands while the next block's
+  // are staged): three operands (L21 for the Cholesky phase; L21 again and the transposed X block for the
+  // inverse phase, which runs concurrently on its own stream), three bf16 parts each, [max_pad, kOuter]
+  return max_pad >= kTwoLevelMin
+             ? static_cast<size_t>(count) * 2 * 3 * 3 * align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256)
+             : 0;
 }
 
 // The triangular-inverse phase runs one step behind the Cholesky phase on a second stream: its step k needs
@@ -489,6 +493,11 @@ struct Pipeline {
   cudaStream_t side = nullptr;
   cudaStream_t cap = nullptr;  // origin stream of graph captures (the caller's stream may be the legacy default)
   cudaEvent_t fork = nullptr, join = nullptr;
+  // outer (tensor-core) updates of the factors of a batch: up to kAux streams per phase, forked from / joined into
+  // the phase's stream, so that the partial waves of one factor's GEMM are filled by another factor's
+  static constexpr int kAux = 4;
+  cudaStream_t aux[2][kAux] = {};
+  cudaEvent_t aux_fork[2] = {}, aux_join[2][kAux] = {};
   std::vector<cudaEvent_t> panel_done;
   bool ok = false;
   explicit Pipeline(bool) {}  // inert instance (no device)
@@ -497,6 +506,12 @@ struct Pipeline {
          cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+    for (int ph = 0; ph < 2 && ok; ++ph) {
+      ok = cudaEventCreateWithFlags(&aux_fork[ph], cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < kAux && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&aux[ph][i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&aux_join[ph][i], cudaEventDisableTiming) == cudaSuccess;
+    }
   }
   bool reserve(int n) {
     while (ok && static_cast<int>(panel_done.size()) < n) {
@@ -531,63 +546,92 @@ size_t chol_inv_workspace_bytes(const int* dims, int count) {
     bytes += align_up(dp * dp * 4, 256) * 2 + align_up((dp / NB) * NB * NB * 4, 256);
     if (static_cast<int>(dp) > max_pad) max_pad = static_cast<int>(dp);
   }
-  return bytes + staging_bytes(max_pad);
+  return bytes + staging_bytes(max_pad, count);
 }
 
 namespace {
 
-// One 256-wide outer block of factor p is final in `src` (R for phase 1, R again for phase 2): hand
-// its contribution to everything beyond the block to the tensor cores as an fp32-class bf16x6 GEMM
-// (hi/lo/lo2 splits carry 24 mantissa bits, six accumulating passes; a plain bf16 or bf16x3 update
-// would perturb the Schur complement by 1e-3 .. 1e-5 and the inverse by cond(R) times that).
+// One 256-wide outer block of factor p is final in R: hand its contribution to everything beyond the block to the
+// tensor cores as fp32-class bf16x6 GEMMs (hi/lo/lo2 splits carry 24 mantissa bits, six accumulating passes; a
+// plain bf16 or bf16x3 update would perturb the Schur complement by 1e-3 .. 1e-5 and the inverse by cond(R)
+// times that).
 //   phase 1:  R[c1:, c1:]  -= L21 L21^T          (SYRK, lower tiles only)
 //   phase 2:  X[c1:, :c1]  -= L21 X[c0:c1, :c1]
-int outer_update(const CholProb& p, int c0, bool phase2, __nv_bfloat16* sa, __nv_bfloat16* sb,
-                 size_t part_stride, cudaStream_t stream) {
+// Each update is issued in two parts.  NEAR = what the inner steps of the NEXT outer block touch (phase 1: the
+// next 256 columns; phase 2: the next 256 rows): it stays on the chain.  FAR = the rest: it only has to be
+// complete before the outer block after next starts, so it runs beside the next block's (latency-bound, nearly
+// empty) inner steps.  Both parts add into their target through the TMA reduction, so a FAR part and the next
+// block's updates of the same region commute.
+struct OuterStage {
+  __nv_bfloat16* a;  // L21 as three bf16 parts, [m2, kOuter] each
+  __nv_bfloat16* b;  // phase 2: X[c0:c1, :c1]^T as three parts, [c1, kOuter] each
+  size_t part_stride;
+};
+
+int outer_stage(const CholProb& p, int c0, bool phase2, const OuterStage& st, cudaStream_t stream) {
   const int c1 = c0 + kOuter;
   if (c1 >= p.dpad) return 0;
   const int m2 = p.dpad - c1;
   const long long ld = p.dpad;
-  __nv_bfloat16* a0 = sa;
-  __nv_bfloat16* a1 = sa + part_stride;
-  __nv_bfloat16* a2 = sa + 2 * part_stride;
-  int rc = launch_convert_split3(p.R + static_cast<long long>(c1) * ld + c0, ld, m2, kOuter, a0, a1, a2,
-                                 kOuter, stream);
-  if (rc) return rc;
+  int rc = launch_convert_split3(p.R + static_cast<long long>(c1) * ld + c0, ld, m2, kOuter, st.a,
+                                 st.a + st.part_stride, st.a + 2 * st.part_stride, kOuter, stream);
+  if (rc == 0 && phase2)
+    rc = launch_transpose_split3(p.X + static_cast<long long>(c0) * ld, ld, kOuter, c1, st.b, st.b + st.part_stride,
+                                 st.b + 2 * st.part_stride, kOuter, stream);
+  return rc;
+}
+
+int g_chol_far_sms = 64;  // SMs all concurrently running FAR parts of one phase may occupy together
+
+int outer_gemm(const CholProb& p, int c0, bool phase2, bool far, const OuterStage& st, int concurrent,
+               cudaStream_t stream) {
+  const int c1 = c0 + kOuter;
+  if (c1 >= p.dpad) return 0;
+  const int m2 = p.dpad - c1;
+  const int near_rows = m2 < kOuter ? m2 : kOuter;
+  if (far && m2 <= kOuter) return 0;
+  const long long ld = p.dpad;
+  const long long skip = far ? static_cast<long long>(kOuter) * kOuter : 0;  // FAR: rows from kOuter of L21 on
   GemmArgs g;
-  g.A_hi = a0;
-  g.A_lo = a1;
-  g.A_lo2 = a2;
+  g.A_hi = st.a + skip;
+  g.A_lo = st.a + st.part_stride + skip;
+  g.A_lo2 = st.a + 2 * st.part_stride + skip;
   g.lda = kOuter;
   g.K = kOuter;
-  g.M = m2;
   g.batch = 1;
   g.nparts = 6;
   g.alpha = -1.f;
   g.beta = 1.f;
   g.ldc = ld;
+  g.ldb = kOuter;
+  // a FAR part is background work: it must leave SMs to the chain kernels it runs beside (a CTA of the
+  // contraction core owns its SM's shared memory; the chain would queue behind whole tiles otherwise)
+  if (far && g_chol_far_sms > 0) g.max_sms = (g_chol_far_sms / (2 * concurrent)) * 2;
   if (!phase2) {
-    g.B_hi = a0;
-    g.B_lo = a1;
-    g.B_lo2 = a2;
-    g.ldb = kOuter;
-    g.N = m2;
-    g.flags = kSyrkLower;
-    g.C = p.R + static_cast<long long>(c1) * ld + c1;
+    if (far) {  // R[c1 + 256:, c1 + 256:] -= L21' L21'^T, lower tiles
+      g.B_hi = g.A_hi;
+      g.B_lo = g.A_lo;
+      g.B_lo2 = g.A_lo2;
+      g.M = g.N = m2 - kOuter;
+      g.flags = kSyrkLower;
+      g.C = p.R + static_cast<long long>(c1 + kOuter) * ld + (c1 + kOuter);
+    } else {  // R[c1:, c1 : c1 + 256] -= L21 L21[:256]^T (the upper part of the first tile is never read)
+      g.B_hi = st.a;
+      g.B_lo = st.a + st.part_stride;
+      g.B_lo2 = st.a + 2 * st.part_stride;
+      g.M = m2;
+      g.N = near_rows;
+      g.flags = 0;
+      g.C = p.R + static_cast<long long>(c1) * ld + c1;
+    }
   } else {
-    __nv_bfloat16* b0 = sb;
-    __nv_bfloat16* b1 = sb + part_stride;
-    __nv_bfloat16* b2 = sb + 2 * part_stride;
-    rc = launch_transpose_split3(p.X + static_cast<long long>(c0) * ld, ld, kOuter, c1, b0, b1, b2,
-                                 kOuter, stream);
-    if (rc) return rc;
-    g.B_hi = b0;
-    g.B_lo = b1;
-    g.B_lo2 = b2;
-    g.ldb = kOuter;
+    g.B_hi = st.b;
+    g.B_lo = st.b + st.part_stride;
+    g.B_lo2 = st.b + 2 * st.part_stride;
     g.N = c1;
     g.flags = 0;
-    g.C = p.X + static_cast<long long>(c1) * ld;
+    g.M = far ? m2 - kOuter : near_rows;
+    g.C = p.X + static_cast<long long>(far ? c1 + kOuter : c1) * ld;
   }
   return launch_umma_gemm(g, stream);
 }
@@ -600,9 +644,11 @@ int g_chol_graph = 1;
 
 struct GraphKey {
   void* workspace;
-  int dev;
+  int dev, far_sms;
   std::vector<int> dims;
-  bool operator==(const GraphKey& o) const { return workspace == o.workspace && dev == o.dev && dims == o.dims; }
+  bool operator==(const GraphKey& o) const {
+    return workspace == o.workspace && dev == o.dev && far_sms == o.far_sms && dims == o.dims;
+  }
 };
 struct CachedGraph {
   GraphKey key;
@@ -624,11 +670,50 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
   note_launch();
   // Two-level blocking for wide factors: rank-64 SIMT updates stay inside the current 256-wide outer
   // block; the update of everything beyond it is ONE fp32-class (bf16x6) tensor-core GEMM per factor.
-  const bool two_level = max_pad >= kTwoLevelMin;
+  const bool two_level = max_pad >= kTwoLevelMin && pipelined;
   const int inner_per_outer = kOuter / NB;
   const size_t part_stride = align_up(static_cast<size_t>(max_pad) * kOuter * 2, 256) / 2;
-  __nv_bfloat16* stage_b = stage_a + 3 * part_stride;
-  __nv_bfloat16* stage_a2 = stage_a + 6 * part_stride;  // L21 staging of the inverse phase
+  // all factors' outer updates for the 256-wide block at c0, issued from stream `s` of phase `ph` (0: Cholesky,
+  // 1: inverse).  Staging + NEAR parts: on the auxiliary streams of the phase (factor f on stream f mod nst),
+  // joined back into `s`.  FAR parts: queued behind them on the same auxiliary streams and NOT joined - the next
+  // boundary's staging / NEAR parts line up behind them in stream order, which is exactly the dependency the
+  // outer block after next has on them.
+  auto outer_all = [&](int c0, int ph, cudaStream_t s) -> int {
+    const int nst = count < Pipeline::kAux ? count : Pipeline::kAux;
+    const int parity = (c0 / kOuter) & 1;
+    if (cudaEventRecord(pipe.aux_fork[ph], s) != cudaSuccess) return -5;
+    for (int i = 0; i < nst; ++i)
+      if (cudaStreamWaitEvent(pipe.aux[ph][i], pipe.aux_fork[ph], 0) != cudaSuccess) return -5;
+    auto stage_of = [&](int f) {
+      // per factor: [parity][ 0..3: L21 (Cholesky phase) | 3..6: X^T block | 6..9: L21 (inverse phase) ]
+      __nv_bfloat16* base = stage_a + (static_cast<size_t>(f) * 2 + parity) * 9 * part_stride;
+      return OuterStage{ph == 1 ? base + 6 * part_stride : base, base + 3 * part_stride, part_stride};
+    };
+    for (int f = 0; f < count; ++f) {
+      const OuterStage st = stage_of(f);
+      int rc = outer_stage(h_tab2[f], c0, ph == 1, st, pipe.aux[ph][f % nst]);
+      if (rc == 0) rc = outer_gemm(h_tab2[f], c0, ph == 1, false, st, nst, pipe.aux[ph][f % nst]);
+      if (rc) return rc;
+    }
+    for (int i = 0; i < nst; ++i)
+      if (cudaEventRecord(pipe.aux_join[ph][i], pipe.aux[ph][i]) != cudaSuccess ||
+          cudaStreamWaitEvent(s, pipe.aux_join[ph][i], 0) != cudaSuccess)
+        return -5;
+    for (int f = 0; f < count; ++f) {
+      const int rc = outer_gemm(h_tab2[f], c0, ph == 1, true, stage_of(f), nst, pipe.aux[ph][f % nst]);
+      if (rc) return rc;
+    }
+    return 0;
+  };
+  // the FAR parts still in flight on the auxiliary streams of phase `ph` must land before `s` continues
+  auto outer_drain = [&](int ph, cudaStream_t s) -> int {
+    const int nst = count < Pipeline::kAux ? count : Pipeline::kAux;
+    for (int i = 0; i < nst; ++i)
+      if (cudaEventRecord(pipe.aux_join[ph][i], pipe.aux[ph][i]) != cudaSuccess ||
+          cudaStreamWaitEvent(s, pipe.aux_join[ph][i], 0) != cudaSuccess)
+        return -5;
+    return 0;
+  };
   // Wide problems: the inverse phase (X = C^-1 by block forward substitution on the identity) is pipelined one
   // step behind the Cholesky phase on a side stream; both are chains of latency-bound steps that leave most
   // of the GPU idle on their own.
@@ -646,11 +731,8 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
     if (two_level) m = (limit < max_pad ? limit : max_pad) - (k + 1) * NB;
     if (m > 0) launch_rank64(m, n, false, count, s2, cd_tab, k, static_cast<int>(kXUpdate), limit);
     if (two_level && (k + 1) % inner_per_outer == 0) {
-      const int c0 = (k + 1 - inner_per_outer) * NB;
-      for (int f = 0; f < count; ++f) {
-        const int rc = outer_update(h_tab2[f], c0, true, stage_a2, stage_b, part_stride, s2);
-        if (rc) return rc;
-      }
+      const int rc = outer_all((k + 1 - inner_per_outer) * NB, 1, s2);
+      if (rc) return rc;
     }
     return 0;
   };
@@ -678,11 +760,8 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
       }
     }
     if (two_level && (k + 1) % inner_per_outer == 0) {
-      const int c0 = (k + 1 - inner_per_outer) * NB;
-      for (int f = 0; f < count; ++f) {
-        const int rc = outer_update(h_tab2[f], c0, false, stage_a, stage_b, part_stride, stream);
-        if (rc) return rc;
-      }
+      const int rc = outer_all((k + 1 - inner_per_outer) * NB, 0, stream);
+      if (rc) return rc;
     }
   }
   // ---- phase 2 (not pipelined: small problems): X = C^-1 by block forward substitution on the identity
@@ -692,6 +771,7 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
       if (rc) return rc;
     }
   } else {
+    if (two_level && (outer_drain(0, stream) != 0 || outer_drain(1, s2) != 0)) return -5;
     if (cudaEventRecord(pipe.join, s2) != cudaSuccess || cudaStreamWaitEvent(stream, pipe.join, 0) != cudaSuccess)
       return -5;
   }
@@ -703,6 +783,7 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
 }  // namespace
 
 void set_chol_graph(int enabled) { g_chol_graph = enabled; }
+void set_chol_far_sms(int sms) { g_chol_far_sms = sms; }
 
 int chol_inv_batched(const float* const* factors, float* const* outs, const int* dims,
                      const float* add, const float* multiply, int count, void* workspace,
@@ -770,7 +851,7 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   cudaGetDevice(&dev);
   const bool use_graph = g_chol_graph != 0 && pipe.ok && max_nb >= 4;
   if (use_graph) {
-    GraphKey key{workspace, dev, std::vector<int>(dims, dims + count)};
+    GraphKey key{workspace, dev, g_chol_far_sms, std::vector<int>(dims, dims + count)};
     std::lock_guard<std::mutex> guard(g_graph_mu);
     CachedGraph* hit = nullptr;
     for (auto& c : g_graphs)

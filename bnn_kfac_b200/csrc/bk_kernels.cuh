@@ -73,6 +73,8 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
 // 1 (default): the launch sequence of a given (workspace, dims) problem is captured once into a CUDA graph and
 // replayed; 0: every call enqueues its kernels one by one.
 void set_chol_graph(int enabled);
+// SMs the background (FAR) outer updates of one phase may occupy together (0 = all)
+void set_chol_far_sms(int sms);
 
 // ---- bk_eigh.cu  (batched one-sided Jacobi eigensolver)
 size_t eigh_workspace_bytes(const int* dims, int count);

@@ -888,7 +888,9 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
           return -5;
     }
   }
-  const int clusters_max = sm_count() / CG;
+  int sms = sm_count();
+  if (a.max_sms > 0 && a.max_sms < sms) sms = a.max_sms < CG ? CG : a.max_sms;
+  const int clusters_max = sms / CG;
   const int clusters = p.num_tiles < clusters_max ? p.num_tiles : clusters_max;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));

@@ -47,6 +47,9 @@ struct GemmArgs {
   __nv_bfloat16* O_lo = nullptr;
   __nv_bfloat16* O_lo2 = nullptr;  // third split of the output (with O_lo): hi + lo + lo2 = 24 mantissa bits
   long long ldo = 0, strideO = 0;
+  // Upper bound on the SMs the persistent launch occupies (0 = all).  A CTA of this kernel takes a whole SM
+  // (shared memory); a background GEMM that runs beside a latency-bound kernel chain leaves SMs to the chain.
+  int max_sms = 0;
 };
 
 // Returns 0 on success, negative on argument / CUDA error (see include/bk_kfac.h error codes).

@@ -199,6 +199,9 @@ size_t bk_chol_inv_workspace_bytes(const int* dims_host, int count);
  * graph and replayed by later calls (factor / output pointers and the damping scalars travel through a device
  * table that is refreshed outside the graph).  0 = enqueue every kernel on every call. */
 void bk_set_chol_graph(int enabled);
+/* Tuning knob (default 64): SMs that the background ("far") tensor-core updates of one inversion phase may occupy
+ * together while the latency-bound diagonal / panel chain of the next outer block runs beside them; 0 = no limit. */
+void bk_set_chol_far_sms(int sms);
 int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* outs_host,
                              const int* dims_host, const float* add_host,
                              const float* multiply_host, int count, void* workspace,
