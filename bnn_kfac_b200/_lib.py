@@ -102,6 +102,17 @@ SIGNATURES = {
     "bk_dominance_rows": (_i, [_p, _ll, _i, _i, _i, _f, _p, _p, _i, _p, _p]),
     "bk_tri_pack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _p]),
     "bk_tri_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _f, _i, _p]),
+    "bk_peer_alloc": (_i, [_sz, C.POINTER(_p)]),
+    "bk_peer_free": (_i, [_p]),
+    "bk_peer_export": (_i, [_p, _p]),
+    "bk_peer_open": (_i, [_p, C.POINTER(_p)]),
+    "bk_peer_close": (_i, [_p]),
+    "bk_peer_read_u32": (_i, [_p, C.POINTER(C.c_uint)]),
+    "bk_tile_packed_floats": (_ll, [C.POINTER(_i), _i]),
+    "bk_tile_pack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, _p, _p]),
+    "bk_peer_tile_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, C.POINTER(_p), _i, _f, _i, _p]),
+    "bk_peer_signal": (_i, [C.POINTER(_p), _i, _i, C.c_uint, _p]),
+    "bk_peer_wait": (_i, [_p, _i, C.c_uint, C.c_double, _p, _p]),
     "bk_inf_regularise": (_i, [_p, _ll, _p, _ll, _f, _f, _p, _p, _p]),
     "bk_inf_presample_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "bk_inf_presample": (_i, [_p, _ll, _i, _i, _p, _ll, _i, _i, _p, _p, _p, _p, _sz, _p]),

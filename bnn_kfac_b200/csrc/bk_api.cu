@@ -622,6 +622,88 @@ int bk_tri_unpack(float* const* outs_host, const long long* ld_host, const int* 
                                as_stream(stream));
 }
 
+// ----------------------------------------------------------------------- peer-memory exchange
+int bk_peer_alloc(size_t bytes, void** ptr) {
+  if (ptr == nullptr || bytes == 0) return BK_ERR_ARG;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return BK_ERR_CUDA;
+  }
+  if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaFree(p);
+    return BK_ERR_CUDA;
+  }
+  *ptr = p;
+  return BK_OK;
+}
+
+int bk_peer_free(void* ptr) { return (ptr == nullptr || cudaFree(ptr) == cudaSuccess) ? BK_OK : BK_ERR_CUDA; }
+
+int bk_peer_export(void* ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (ptr == nullptr || handle64 == nullptr) return BK_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return BK_ERR_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  return BK_OK;
+}
+
+int bk_peer_open(const void* handle64, void** ptr) {
+  if (ptr == nullptr || handle64 == nullptr) return BK_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return BK_ERR_CUDA;
+  }
+  *ptr = p;
+  return BK_OK;
+}
+
+int bk_peer_close(void* ptr) {
+  return (ptr == nullptr || cudaIpcCloseMemHandle(ptr) == cudaSuccess) ? BK_OK : BK_ERR_CUDA;
+}
+
+int bk_peer_read_u32(const void* ptr, unsigned int* out_host) {
+  if (ptr == nullptr || out_host == nullptr) return BK_ERR_ARG;
+  return cudaMemcpy(out_host, ptr, 4, cudaMemcpyDeviceToHost) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
+}
+
+long long bk_tile_packed_floats(const int* dims_host, int count) {
+  if (count <= 0 || dims_host == nullptr) return 0;
+  return bk::tile_packed_floats(dims_host, count);
+}
+
+int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
+                 float* packed, void* stream) {
+  if (count <= 0 || factors_host == nullptr || ld_host == nullptr || dims_host == nullptr || packed == nullptr)
+    return BK_ERR_ARG;
+  return bk::launch_tile_pack(factors_host, ld_host, dims_host, count, packed, as_stream(stream));
+}
+
+int bk_peer_tile_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
+                        const float* const* srcs_host, int nsrc, float scale, int mirror, void* stream) {
+  if (count <= 0 || outs_host == nullptr || ld_host == nullptr || dims_host == nullptr || srcs_host == nullptr)
+    return BK_ERR_ARG;
+  return bk::launch_peer_tile_unpack(outs_host, ld_host, dims_host, count, srcs_host, nsrc, scale, mirror ? 1 : 0,
+                                     as_stream(stream));
+}
+
+int bk_peer_signal(unsigned int* const* flags_host, int world, int me, unsigned int epoch, void* stream) {
+  if (flags_host == nullptr) return BK_ERR_ARG;
+  return bk::launch_peer_signal(flags_host, world, me, epoch, as_stream(stream));
+}
+
+int bk_peer_wait(const unsigned int* flags_local, int world, unsigned int epoch, double timeout_s, int* err,
+                 void* stream) {
+  return bk::launch_peer_wait(flags_local, world, epoch, timeout_s, err, as_stream(stream));
+}
+
 // ----------------------------------------------------------------------- INF curvature
 int bk_inf_regularise(float* correction, long long nm, const float* lambda, long long r, float add,
                       float multiply, float* reg_inv_correction, float* reg_lambda, void* stream) {

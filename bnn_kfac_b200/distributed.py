@@ -221,6 +221,9 @@ def reduce_scatter_to_owners(est, owners: Sequence[int], group=None) -> Dict[int
     scale = float(getattr(est, "_scale", 1.0)) if raw_items is not None else 1.0
     values = [v for _, v in raw_items()] if raw_items is not None else list(est.state.values())
     factors = [f for v in values for f in v]
+    ctx = peer_context([f.shape[0] for f in factors], owners, factors[0].device, group)
+    if ctx is not None:
+        return reduce_scatter_to_owners_peer(ctx, factors, owners, scale)
     tri = [f.shape[0] * (f.shape[0] + 1) // 2 for f in factors]
     by_rank = [[i for i in range(len(factors)) if owners[i] == r] for r in range(w)]
     chunk = max(max(sum(tri[i] for i in idx) for idx in by_rank), 1)
@@ -262,6 +265,9 @@ def allgather_cholesky(owned: Dict[int, Tensor], dims: Sequence[int], owners: Se
     from . import _lib
     lib = _lib.load()
     w, me = world_size(group), rank(group)
+    ctx = peer_context(dims, owners, device, group)
+    if ctx is not None:
+        return allgather_cholesky_peer(ctx, owned, dims, owners, device)
     tri = [d * (d + 1) // 2 for d in dims]
     seg = [sum(tri[i] for i in range(len(dims)) if owners[i] == r) for r in range(w)]
     maxlen = max(max(seg), 1)
@@ -290,6 +296,223 @@ def allgather_cholesky(owned: Dict[int, Tensor], dims: Sequence[int], owners: Se
         _lib.check(lib.bk_tri_unpack(dst, ldo, dm, n, recv.data_ptr() + 4 * r * maxlen, 1.0, 0, st),
                    "bk_tri_unpack")
     return outs
+
+
+# ------------------------------------------------------------------- exchange over peer memory
+class PeerExchange:
+    """Peer-memory context of one process group on ONE node (<= 8 ranks, one process per GPU): every rank owns a
+    cudaMalloc buffer exported through CUDA IPC and maps the buffers of all peers (csrc/bk_peer.cu).  The buffer
+    holds a 1 KB header - four flag arrays (ready / done for the factor exchange, ready / done for the return of the
+    Cholesky factors) and an error word - followed by the data region.  Collective: construct / grow it on all
+    ranks of the group with the same size.  `torch.distributed` only carries the 64-byte handles."""
+
+    HEADER = 1024
+    READY_A, DONE_A, READY_B, DONE_B, ERR = 0, 64, 128, 192, 256
+    _cache: Dict[Tuple[int, int], "PeerExchange"] = {}
+
+    def __init__(self, nbytes: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.group, self.device = group, torch.device(device)
+        self.world, self.me = world_size(group), rank(group)
+        self.capacity = int(nbytes)
+        self.epoch = {"A": 0, "B": 0}
+        self.local = C.c_void_p()
+        self.ptrs: List[int] = []
+        self._opened: List[int] = []
+        ok = self.lib.bk_peer_alloc(self.HEADER + self.capacity, C.byref(self.local)) == 0
+        handle = (C.c_ubyte * 64)()
+        if ok:
+            ok = self.lib.bk_peer_export(self.local, handle) == 0
+        mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world * 65, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = allh.cpu().view(self.world, 65)
+        ok = bool(allh[:, 64].min().item())
+        if ok:
+            for r in range(self.world):
+                if r == self.me:
+                    self.ptrs.append(self.local.value)
+                    continue
+                buf = (C.c_ubyte * 64)(*allh[r, :64].tolist())
+                q = C.c_void_p()
+                if self.lib.bk_peer_open(buf, C.byref(q)) != 0:
+                    ok = False
+                    break
+                self.ptrs.append(q.value)
+                self._opened.append(q.value)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # also: every rank has mapped every buffer
+        self.ok = bool(flag.item())
+        if not self.ok:
+            self.close()
+
+    # -- lookup / growth (collective) ------------------------------------------------------------
+    @classmethod
+    def get(cls, nbytes: int, device, group=None) -> Optional["PeerExchange"]:
+        """The context of (group, device), created or grown to `nbytes` of data region; None when peer memory is
+        not usable here (other backend, more than 8 ranks, several nodes, BK_NO_PEER set, IPC refused)."""
+        w = world_size(group)
+        if (w < 2 or w > 8 or os.environ.get("BK_NO_PEER") or not torch.device(device).type == "cuda"
+                or dist.get_backend(group) != "nccl"
+                or int(os.environ.get("LOCAL_WORLD_SIZE", w)) != dist.get_world_size()):
+            return None
+        key = (id(group) if group is not None else 0, torch.device(device).index or 0)
+        ctx = cls._cache.get(key)
+        if ctx is not None and (not ctx.ok or ctx.capacity >= nbytes):
+            return ctx if ctx.ok else None
+        if ctx is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=group)          # nobody still reads the buffer that is about to go away
+            ctx.close()
+        ctx = cls(max(int(nbytes * 1.25), 1 << 20), device, group)
+        cls._cache[key] = ctx
+        return ctx if ctx.ok else None
+
+    def close(self) -> None:
+        for q in self._opened:
+            self.lib.bk_peer_close(q)
+        self._opened, self.ptrs = [], []
+        if self.local:
+            self.lib.bk_peer_free(self.local)
+            self.local = None
+        self.ok = False
+
+    # -- flags -----------------------------------------------------------------------------------
+    def _signal(self, which: int, epoch: int) -> None:
+        import ctypes as C
+        from . import _lib
+        arr = (C.c_void_p * self.world)(*[q + which for q in self.ptrs])
+        _lib.check(self.lib.bk_peer_signal(arr, self.world, self.me, epoch, _lib.stream_ptr()), "bk_peer_signal")
+
+    def _wait(self, which: int, epoch: int, timeout_s: float = 10.0) -> None:
+        from . import _lib
+        _lib.check(self.lib.bk_peer_wait(self.ptrs[self.me] + which, self.world, epoch, timeout_s,
+                                         self.ptrs[self.me] + self.ERR, _lib.stream_ptr()), "bk_peer_wait")
+
+    def data(self, r: int, float_offset: int = 0) -> int:
+        return self.ptrs[r] + self.HEADER + 4 * float_offset
+
+    def error(self) -> int:
+        """0, or 1 + the rank a wait gave up on (synchronises the device)."""
+        import ctypes as C
+        from . import _lib
+        torch.cuda.synchronize()
+        out = C.c_uint(0)
+        _lib.check(self.lib.bk_peer_read_u32(self.ptrs[self.me] + self.ERR, C.byref(out)), "bk_peer_read_u32")
+        return int(out.value)
+
+
+def _tile_floats(lib, dims: Sequence[int]) -> int:
+    import ctypes as C
+    return int(lib.bk_tile_packed_floats((C.c_int * len(dims))(*dims), len(dims))) if dims else 0
+
+
+def _peer_layout(dims: Sequence[int], owners: Sequence[int], w: int, lib):
+    """Data-region layout shared by both exchange steps: region A = w chunks (chunk r: the tile-packed factors rank
+    r owns, index order), region B = the tile-packed Cholesky factors of the local rank."""
+    by_rank = [[i for i in range(len(dims)) if owners[i] == r] for r in range(w)]
+    chunk = max(max(_tile_floats(lib, [dims[i] for i in idx]) for idx in by_rank), 1024)
+    return by_rank, chunk
+
+
+def reduce_scatter_to_owners_peer(ctx: "PeerExchange", factors: Sequence[Tensor], owners: Sequence[int],
+                                  scale: float) -> Dict[int, Tensor]:
+    """reduce_scatter_to_owners over peer memory: pack (local) -> flags -> ONE kernel on each owner that pulls its
+    chunk from all ranks' buffers over NVLink, adds them in rank order, scales and writes the mirrored dense
+    factors.  No collective library call, no receive buffer, no separate unpack pass."""
+    import ctypes as C
+    from . import _lib
+    lib, w, me = ctx.lib, ctx.world, ctx.me
+    dims = [f.shape[0] for f in factors]
+    by_rank, chunk = _peer_layout(dims, owners, w, lib)
+    st = _lib.stream_ptr()
+    ctx.epoch["A"] += 1
+    e = ctx.epoch["A"]
+    ctx._wait(ctx.DONE_A, e - 1)                  # every peer has finished reading my previous send region
+    for r, idx in enumerate(by_rank):
+        for b0 in range(0, len(idx), 16):
+            part = idx[b0:b0 + 16]
+            n = len(part)
+            off = _tile_floats(lib, [dims[i] for i in idx[:b0]])
+            _lib.check(lib.bk_tile_pack((C.c_void_p * n)(*[factors[i].data_ptr() for i in part]),
+                                        (C.c_longlong * n)(*[factors[i].stride(0) for i in part]),
+                                        (C.c_int * n)(*[dims[i] for i in part]), n,
+                                        ctx.data(me, r * chunk + off), st), "bk_tile_pack")
+    ctx._signal(ctx.READY_A, e)
+    ctx._wait(ctx.READY_A, e)                     # every rank's send region is complete
+    mine = by_rank[me]
+    dev = factors[0].device
+    outs = {i: torch.empty(dims[i], dims[i], dtype=torch.float32, device=dev) for i in mine}
+    for b0 in range(0, len(mine), 16):
+        part = mine[b0:b0 + 16]
+        n = len(part)
+        off = _tile_floats(lib, [dims[i] for i in mine[:b0]])
+        srcs = (C.c_void_p * w)(*[ctx.data(r, me * chunk + off) for r in range(w)])
+        _lib.check(lib.bk_peer_tile_unpack((C.c_void_p * n)(*[outs[i].data_ptr() for i in part]),
+                                           (C.c_longlong * n)(*[outs[i].stride(0) for i in part]),
+                                           (C.c_int * n)(*[dims[i] for i in part]), n, srcs, w, scale / w, 1, st),
+                   "bk_peer_tile_unpack")
+    ctx._signal(ctx.DONE_A, e)
+    return outs
+
+
+def allgather_cholesky_peer(ctx: "PeerExchange", owned: Dict[int, Tensor], dims: Sequence[int],
+                            owners: Sequence[int], device) -> List[Tensor]:
+    """allgather_cholesky over peer memory: each owner tile-packs its Cholesky factors into region B of its
+    buffer; every rank then pulls the other owners' factors straight into dense lower-triangular matrices
+    (zero upper triangle) - one kernel per owner, no all-gather, no staging on the receiving side."""
+    import ctypes as C
+    from . import _lib
+    lib, w, me = ctx.lib, ctx.world, ctx.me
+    by_rank, chunk = _peer_layout(dims, owners, w, lib)
+    region_b = w * chunk
+    st = _lib.stream_ptr()
+    ctx.epoch["B"] += 1
+    e = ctx.epoch["B"]
+    ctx._wait(ctx.DONE_B, e - 1)
+    mine = by_rank[me]
+    for b0 in range(0, len(mine), 16):
+        part = mine[b0:b0 + 16]
+        n = len(part)
+        off = _tile_floats(lib, [dims[i] for i in mine[:b0]])
+        _lib.check(lib.bk_tile_pack((C.c_void_p * n)(*[owned[i].data_ptr() for i in part]),
+                                    (C.c_longlong * n)(*[owned[i].stride(0) for i in part]),
+                                    (C.c_int * n)(*[dims[i] for i in part]), n, ctx.data(me, region_b + off), st),
+                   "bk_tile_pack")
+    ctx._signal(ctx.READY_B, e)
+    ctx._wait(ctx.READY_B, e)
+    outs: List[Optional[Tensor]] = [None] * len(dims)
+    for i in mine:
+        outs[i] = owned[i]
+    for r, idx in enumerate(by_rank):
+        if r == me:
+            continue
+        for b0 in range(0, len(idx), 16):
+            part = idx[b0:b0 + 16]
+            n = len(part)
+            off = _tile_floats(lib, [dims[i] for i in idx[:b0]])
+            for i in part:
+                outs[i] = torch.empty(dims[i], dims[i], dtype=torch.float32, device=device)
+            srcs = (C.c_void_p * 1)(ctx.data(r, region_b + off))
+            _lib.check(lib.bk_peer_tile_unpack((C.c_void_p * n)(*[outs[i].data_ptr() for i in part]),
+                                               (C.c_longlong * n)(*[outs[i].stride(0) for i in part]),
+                                               (C.c_int * n)(*[dims[i] for i in part]), n, srcs, 1, 1.0, 0, st),
+                       "bk_peer_tile_unpack")
+    ctx._signal(ctx.DONE_B, e)
+    return outs
+
+
+def peer_context(dims: Sequence[int], owners: Sequence[int], device, group=None) -> Optional["PeerExchange"]:
+    """The peer-memory context sized for exchanging factors of these dims (collective; None = use NCCL)."""
+    w = world_size(group)
+    if w < 2 or torch.device(device).type != "cuda":
+        return None
+    from . import _lib
+    lib = _lib.load()
+    _, chunk = _peer_layout(dims, owners, w, lib)
+    return PeerExchange.get(4 * (w * chunk + chunk), device, group)
 
 
 def _nvtx(name):

@@ -286,6 +286,36 @@ int bk_tri_unpack(float* const* outs_host, const long long* ld_host, const int* 
                   const float* packed, float scale, int mirror, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Factor exchange over NVLink / NVSwitch PEER MEMORY (one process per GPU; no counterpart in the reference).
+ * Buffers are cudaMalloc allocations exported through CUDA IPC; the 64-byte handles travel through the caller's
+ * process group.  "Tile-packed" layout of a lower triangle: its 32 x 32 tiles, tile (ti, tj <= ti) at index
+ * ti (ti + 1) / 2 + tj, 1024 floats each, row-major (factor after factor; bk_tile_packed_floats values in total).
+ */
+int bk_peer_alloc(size_t bytes, void** ptr);                    /* zero-filled device allocation */
+int bk_peer_free(void* ptr);
+int bk_peer_export(void* ptr, void* handle64);                  /* cudaIpcGetMemHandle: 64 bytes out */
+int bk_peer_open(const void* handle64, void** ptr);             /* maps another process's allocation */
+int bk_peer_close(void* ptr);
+int bk_peer_read_u32(const void* ptr, unsigned int* out_host);   /* synchronous 4-byte read (error word) */
+long long bk_tile_packed_floats(const int* dims_host, int count);
+/* dense [d, ld] lower triangles -> tile-packed buffer (count <= 16) */
+int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
+                 float* packed, void* stream);
+/* ONE kernel = collective + unpack: out = scale * sum over the nsrc (<= 8) tile-packed buffers srcs_host[r] (local
+ * or peer memory, the same factor layout in each), summed in index order; mirror != 0 writes the symmetric matrix
+ * (reduce-scatter of accumulated factors, nsrc = world), mirror == 0 a zero upper triangle (all-gather of the
+ * Cholesky factors, nsrc = 1). */
+int bk_peer_tile_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
+                        const float* const* srcs_host, int nsrc, float scale, int mirror, void* stream);
+/* Cross-GPU ordering.  flags_host[r]: a flag array (world 32-bit slots) inside rank r's exported buffer.
+ * bk_peer_signal: system-scope fence, then slot `me` of every rank's array = epoch.  bk_peer_wait: returns (in
+ * stream order) once all `world` slots of the local array have reached epoch; after timeout_s seconds it stores
+ * 1 + the missing rank into *err (device int) instead of spinning on. */
+int bk_peer_signal(unsigned int* const* flags_host, int world, int me, unsigned int epoch, void* stream);
+int bk_peer_wait(const unsigned int* flags_local, int world, unsigned int epoch, double timeout_s, int* err,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * INF curvature: low-rank eigenbasis + diagonal correction (models/curvatures.py:476-682).
  */
 /* INF.invert :537-539.  correction[correction < 0] = 0 IN PLACE (nm values);
