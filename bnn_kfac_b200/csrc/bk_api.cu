@@ -679,11 +679,11 @@ long long bk_tile_packed_floats(const int* dims_host, int count) {
   return bk::tile_packed_floats(dims_host, count);
 }
 
-int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
-                 float* packed, void* stream) {
+int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host,
+                 const long long* offsets_host, int count, float* packed, void* stream) {
   if (count <= 0 || factors_host == nullptr || ld_host == nullptr || dims_host == nullptr || packed == nullptr)
     return BK_ERR_ARG;
-  return bk::launch_tile_pack(factors_host, ld_host, dims_host, count, packed, as_stream(stream));
+  return bk::launch_tile_pack(factors_host, ld_host, dims_host, offsets_host, count, packed, as_stream(stream));
 }
 
 int bk_peer_tile_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
@@ -692,6 +692,10 @@ int bk_peer_tile_unpack(float* const* outs_host, const long long* ld_host, const
     return BK_ERR_ARG;
   return bk::launch_peer_tile_unpack(outs_host, ld_host, dims_host, count, srcs_host, nsrc, scale, mirror ? 1 : 0,
                                      as_stream(stream));
+}
+
+int bk_peer_copy(void* dst, const void* src, long long bytes, int vec_bytes, int ctas, void* stream) {
+  return bk::launch_peer_copy(dst, src, bytes, vec_bytes, ctas, as_stream(stream));
 }
 
 int bk_peer_signal(unsigned int* const* flags_host, int world, int me, unsigned int epoch, void* stream) {

@@ -123,10 +123,11 @@ int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims,
 
 // ---- bk_peer.cu  (factor exchange over peer memory: tile-packed triangles, fused pull + reduce + unpack, flags)
 long long tile_packed_floats(const int* dims, int count);
-int launch_tile_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
-                     cudaStream_t stream);
+int launch_tile_pack(const float* const* mats, const long long* lds, const int* dims, const long long* offs,
+                     int count, float* packed, cudaStream_t stream);
 int launch_peer_tile_unpack(float* const* mats, const long long* lds, const int* dims, int count,
                             const float* const* srcs, int nsrc, float scale, int mirror, cudaStream_t stream);
+int launch_peer_copy(void* dst, const void* src, long long bytes, int vec_bytes, int ctas, cudaStream_t stream);
 int launch_peer_signal(unsigned int* const* flags, int world, int me, unsigned int epoch, cudaStream_t stream);
 int launch_peer_wait(const unsigned int* mine, int world, unsigned int epoch, double timeout_s, int* err,
                      cudaStream_t stream);

@@ -42,7 +42,7 @@ struct TileTable {
 };
 
 struct SrcTable {
-  const float* p[kMaxPeers];
+  const float* p[kMaxTri][kMaxPeers];  // per factor: the buffers that hold its tile-packed triangle
 };
 
 __device__ __forceinline__ void decode(const TileTable& t, int b, int& f, int& ti, int& tj) {
@@ -85,7 +85,7 @@ peer_tile_unpack_kernel(const __grid_constant__ TileTable t, const __grid_consta
   const int d = t.d[f];
   float* m = t.mat[f];
   const long long ld = t.ld[f];
-  const long long base = t.off[f] + static_cast<long long>(blockIdx.x - t.tile0[f]) * 1024;
+  const long long base = static_cast<long long>(blockIdx.x - t.tile0[f]) * 1024;
   const int j = tj * 32 + threadIdx.x;
   float v[4][NSRC];
   // all loads first: NSRC x 4 independent 4-byte loads per thread (128 B per warp and load), L1 bypassed - the
@@ -94,7 +94,7 @@ peer_tile_unpack_kernel(const __grid_constant__ TileTable t, const __grid_consta
   for (int s = 0; s < NSRC; ++s)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      v[k][s] = (s < nsrc) ? __ldcg(src.p[s] + base + (threadIdx.y + 8 * k) * 32 + threadIdx.x) : 0.f;
+      v[k][s] = (s < nsrc) ? __ldcg(src.p[f][s] + base + (threadIdx.y + 8 * k) * 32 + threadIdx.x) : 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int r = threadIdx.y + 8 * k;
@@ -147,7 +147,25 @@ __global__ void peer_wait_kernel(const unsigned int* __restrict__ mine, int worl
   }
 }
 
-int fill_table(TileTable& t, float* const* mats, const long long* lds, const int* dims, int count) {
+// bring-up / measurement: plain copy with 4- or 16-byte accesses, `unroll` independent accesses per thread in flight;
+// whether it is a pull or a push is decided by which of the two pointers is peer memory
+template <typename V, int U>
+__global__ void __launch_bounds__(256) peer_copy_kernel(V* __restrict__ dst, const V* __restrict__ src, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < n; i += U * stride) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldcg(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) dst[i + u * stride] = v[u];
+  }
+  for (; i < n; i += stride) dst[i] = __ldcg(src + i);
+}
+
+// offs == nullptr: factors back to back from float 0
+int fill_table(TileTable& t, float* const* mats, const long long* lds, const int* dims, const long long* offs,
+               int count) {
   if (count <= 0 || count > kMaxTri) return -2;
   long long off = 0;
   int tiles = 0;
@@ -157,7 +175,7 @@ int fill_table(TileTable& t, float* const* mats, const long long* lds, const int
     t.mat[k] = mats[k];
     t.ld[k] = lds[k];
     t.d[k] = dims[k];
-    t.off[k] = off;
+    t.off[k] = offs != nullptr ? offs[k] : off;
     t.tile0[k] = tiles;
     off += static_cast<long long>(T) * (T + 1) / 2 * 1024;
     tiles += T * (T + 1) / 2;
@@ -178,10 +196,10 @@ long long tile_packed_floats(const int* dims, int count) {
   return n;
 }
 
-int launch_tile_pack(const float* const* mats, const long long* lds, const int* dims, int count, float* packed,
-                     cudaStream_t stream) {
+int launch_tile_pack(const float* const* mats, const long long* lds, const int* dims, const long long* offs,
+                     int count, float* packed, cudaStream_t stream) {
   TileTable t{};
-  const int tiles = fill_table(t, const_cast<float* const*>(mats), lds, dims, count);
+  const int tiles = fill_table(t, const_cast<float* const*>(mats), lds, dims, offs, count);
   if (tiles < 0 || packed == nullptr) return -2;
   tile_pack_kernel<<<tiles, dim3(32, 8), 0, stream>>>(t, packed);
   note_launch();
@@ -191,18 +209,31 @@ int launch_tile_pack(const float* const* mats, const long long* lds, const int* 
 int launch_peer_tile_unpack(float* const* mats, const long long* lds, const int* dims, int count,
                             const float* const* srcs, int nsrc, float scale, int mirror, cudaStream_t stream) {
   TileTable t{};
-  const int tiles = fill_table(t, mats, lds, dims, count);
+  const int tiles = fill_table(t, mats, lds, dims, nullptr, count);
   if (tiles < 0 || nsrc < 1 || nsrc > kMaxPeers) return -2;
   SrcTable s{};
-  for (int r = 0; r < nsrc; ++r) {
-    if (srcs[r] == nullptr) return -2;
-    s.p[r] = srcs[r];
-  }
+  for (int k = 0; k < count; ++k)
+    for (int r = 0; r < nsrc; ++r) {
+      if (srcs[k * nsrc + r] == nullptr) return -2;
+      s.p[k][r] = srcs[k * nsrc + r];
+    }
   const dim3 block(32, 8);
   if (nsrc == 1) peer_tile_unpack_kernel<1><<<tiles, block, 0, stream>>>(t, s, nsrc, scale, mirror);
   else if (nsrc == 2) peer_tile_unpack_kernel<2><<<tiles, block, 0, stream>>>(t, s, nsrc, scale, mirror);
   else if (nsrc <= 4) peer_tile_unpack_kernel<4><<<tiles, block, 0, stream>>>(t, s, nsrc, scale, mirror);
   else peer_tile_unpack_kernel<8><<<tiles, block, 0, stream>>>(t, s, nsrc, scale, mirror);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+int launch_peer_copy(void* dst, const void* src, long long bytes, int vec_bytes, int ctas, cudaStream_t stream) {
+  if (dst == nullptr || src == nullptr || bytes <= 0 || bytes % 16 != 0 || ctas <= 0) return -2;
+  if (vec_bytes == 16)
+    peer_copy_kernel<float4, 8><<<ctas, 256, 0, stream>>>(static_cast<float4*>(dst), static_cast<const float4*>(src),
+                                                        bytes / 16);
+  else
+    peer_copy_kernel<float, 8><<<ctas, 256, 0, stream>>>(static_cast<float*>(dst), static_cast<const float*>(src),
+                                                       bytes / 4);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

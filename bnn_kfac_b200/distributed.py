@@ -411,45 +411,53 @@ def _tile_floats(lib, dims: Sequence[int]) -> int:
 
 def _peer_layout(dims: Sequence[int], owners: Sequence[int], w: int, lib):
     """Data-region layout shared by both exchange steps: region A = w chunks (chunk r: the tile-packed factors rank
-    r owns, index order), region B = the tile-packed Cholesky factors of the local rank."""
+    r owns, index order), region B = the tile-packed Cholesky factors of the local rank.  Returns (factors by
+    owner, chunk size in floats, float offset of every factor inside its owner's chunk)."""
     by_rank = [[i for i in range(len(dims)) if owners[i] == r] for r in range(w)]
-    chunk = max(max(_tile_floats(lib, [dims[i] for i in idx]) for idx in by_rank), 1024)
-    return by_rank, chunk
+    within = [0] * len(dims)
+    chunk = 1024
+    for idx in by_rank:
+        off = 0
+        for i in idx:
+            within[i] = off
+            off += _tile_floats(lib, [dims[i]])
+        chunk = max(chunk, off)
+    return by_rank, chunk, within
+
+
+def _batches(idx: Sequence[int], n: int = 16):
+    return [idx[b:b + n] for b in range(0, len(idx), n)]
 
 
 def reduce_scatter_to_owners_peer(ctx: "PeerExchange", factors: Sequence[Tensor], owners: Sequence[int],
                                   scale: float) -> Dict[int, Tensor]:
-    """reduce_scatter_to_owners over peer memory: pack (local) -> flags -> ONE kernel on each owner that pulls its
-    chunk from all ranks' buffers over NVLink, adds them in rank order, scales and writes the mirrored dense
-    factors.  No collective library call, no receive buffer, no separate unpack pass."""
+    """reduce_scatter_to_owners over peer memory: pack (local, one launch) -> flags -> ONE kernel on each owner
+    that pulls its chunk from all ranks' buffers over NVLink, adds them in rank order, scales and writes the
+    mirrored dense factors.  No collective library call, no receive buffer, no separate unpack pass."""
     import ctypes as C
     from . import _lib
     lib, w, me = ctx.lib, ctx.world, ctx.me
     dims = [f.shape[0] for f in factors]
-    by_rank, chunk = _peer_layout(dims, owners, w, lib)
+    by_rank, chunk, within = _peer_layout(dims, owners, w, lib)
     st = _lib.stream_ptr()
     ctx.epoch["A"] += 1
     e = ctx.epoch["A"]
     ctx._wait(ctx.DONE_A, e - 1)                  # every peer has finished reading my previous send region
-    for r, idx in enumerate(by_rank):
-        for b0 in range(0, len(idx), 16):
-            part = idx[b0:b0 + 16]
-            n = len(part)
-            off = _tile_floats(lib, [dims[i] for i in idx[:b0]])
-            _lib.check(lib.bk_tile_pack((C.c_void_p * n)(*[factors[i].data_ptr() for i in part]),
-                                        (C.c_longlong * n)(*[factors[i].stride(0) for i in part]),
-                                        (C.c_int * n)(*[dims[i] for i in part]), n,
-                                        ctx.data(me, r * chunk + off), st), "bk_tile_pack")
+    for part in _batches(list(range(len(factors)))):
+        n = len(part)
+        _lib.check(lib.bk_tile_pack((C.c_void_p * n)(*[factors[i].data_ptr() for i in part]),
+                                    (C.c_longlong * n)(*[factors[i].stride(0) for i in part]),
+                                    (C.c_int * n)(*[dims[i] for i in part]),
+                                    (C.c_longlong * n)(*[owners[i] * chunk + within[i] for i in part]), n,
+                                    ctx.data(me), st), "bk_tile_pack")
     ctx._signal(ctx.READY_A, e)
     ctx._wait(ctx.READY_A, e)                     # every rank's send region is complete
     mine = by_rank[me]
     dev = factors[0].device
     outs = {i: torch.empty(dims[i], dims[i], dtype=torch.float32, device=dev) for i in mine}
-    for b0 in range(0, len(mine), 16):
-        part = mine[b0:b0 + 16]
+    for part in _batches(mine):
         n = len(part)
-        off = _tile_floats(lib, [dims[i] for i in mine[:b0]])
-        srcs = (C.c_void_p * w)(*[ctx.data(r, me * chunk + off) for r in range(w)])
+        srcs = (C.c_void_p * (n * w))(*[ctx.data(r, me * chunk + within[i]) for i in part for r in range(w)])
         _lib.check(lib.bk_peer_tile_unpack((C.c_void_p * n)(*[outs[i].data_ptr() for i in part]),
                                            (C.c_longlong * n)(*[outs[i].stride(0) for i in part]),
                                            (C.c_int * n)(*[dims[i] for i in part]), n, srcs, w, scale / w, 1, st),
@@ -462,44 +470,40 @@ def allgather_cholesky_peer(ctx: "PeerExchange", owned: Dict[int, Tensor], dims:
                             owners: Sequence[int], device) -> List[Tensor]:
     """allgather_cholesky over peer memory: each owner tile-packs its Cholesky factors into region B of its
     buffer; every rank then pulls the other owners' factors straight into dense lower-triangular matrices
-    (zero upper triangle) - one kernel per owner, no all-gather, no staging on the receiving side."""
+    (zero upper triangle) in ONE launch - no all-gather, no staging on the receiving side.  Rank `me` walks the
+    owners starting at me + 1, so at any time every buffer is read by one rank, not by all of them."""
     import ctypes as C
     from . import _lib
     lib, w, me = ctx.lib, ctx.world, ctx.me
-    by_rank, chunk = _peer_layout(dims, owners, w, lib)
+    by_rank, chunk, within = _peer_layout(dims, owners, w, lib)
     region_b = w * chunk
     st = _lib.stream_ptr()
     ctx.epoch["B"] += 1
     e = ctx.epoch["B"]
     ctx._wait(ctx.DONE_B, e - 1)
     mine = by_rank[me]
-    for b0 in range(0, len(mine), 16):
-        part = mine[b0:b0 + 16]
+    for part in _batches(mine):
         n = len(part)
-        off = _tile_floats(lib, [dims[i] for i in mine[:b0]])
         _lib.check(lib.bk_tile_pack((C.c_void_p * n)(*[owned[i].data_ptr() for i in part]),
                                     (C.c_longlong * n)(*[owned[i].stride(0) for i in part]),
-                                    (C.c_int * n)(*[dims[i] for i in part]), n, ctx.data(me, region_b + off), st),
+                                    (C.c_int * n)(*[dims[i] for i in part]),
+                                    (C.c_longlong * n)(*[region_b + within[i] for i in part]), n, ctx.data(me), st),
                    "bk_tile_pack")
     ctx._signal(ctx.READY_B, e)
     ctx._wait(ctx.READY_B, e)
     outs: List[Optional[Tensor]] = [None] * len(dims)
     for i in mine:
         outs[i] = owned[i]
-    for r, idx in enumerate(by_rank):
-        if r == me:
-            continue
-        for b0 in range(0, len(idx), 16):
-            part = idx[b0:b0 + 16]
-            n = len(part)
-            off = _tile_floats(lib, [dims[i] for i in idx[:b0]])
-            for i in part:
-                outs[i] = torch.empty(dims[i], dims[i], dtype=torch.float32, device=device)
-            srcs = (C.c_void_p * 1)(ctx.data(r, region_b + off))
-            _lib.check(lib.bk_peer_tile_unpack((C.c_void_p * n)(*[outs[i].data_ptr() for i in part]),
-                                               (C.c_longlong * n)(*[outs[i].stride(0) for i in part]),
-                                               (C.c_int * n)(*[dims[i] for i in part]), n, srcs, 1, 1.0, 0, st),
-                       "bk_peer_tile_unpack")
+    theirs = [i for k in range(1, w) for i in by_rank[(me + k) % w]]
+    for i in theirs:
+        outs[i] = torch.empty(dims[i], dims[i], dtype=torch.float32, device=device)
+    for part in _batches(theirs):
+        n = len(part)
+        srcs = (C.c_void_p * n)(*[ctx.data(owners[i], region_b + within[i]) for i in part])
+        _lib.check(lib.bk_peer_tile_unpack((C.c_void_p * n)(*[outs[i].data_ptr() for i in part]),
+                                           (C.c_longlong * n)(*[outs[i].stride(0) for i in part]),
+                                           (C.c_int * n)(*[dims[i] for i in part]), n, srcs, 1, 1.0, 0, st),
+                   "bk_peer_tile_unpack")
     ctx._signal(ctx.DONE_B, e)
     return outs
 
@@ -511,7 +515,7 @@ def peer_context(dims: Sequence[int], owners: Sequence[int], device, group=None)
         return None
     from . import _lib
     lib = _lib.load()
-    _, chunk = _peer_layout(dims, owners, w, lib)
+    _, chunk, _ = _peer_layout(dims, owners, w, lib)
     return PeerExchange.get(4 * (w * chunk + chunk), device, group)
 
 

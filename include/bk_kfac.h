@@ -298,15 +298,19 @@ int bk_peer_open(const void* handle64, void** ptr);             /* maps another 
 int bk_peer_close(void* ptr);
 int bk_peer_read_u32(const void* ptr, unsigned int* out_host);   /* synchronous 4-byte read (error word) */
 long long bk_tile_packed_floats(const int* dims_host, int count);
-/* dense [d, ld] lower triangles -> tile-packed buffer (count <= 16) */
-int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host, int count,
-                 float* packed, void* stream);
-/* ONE kernel = collective + unpack: out = scale * sum over the nsrc (<= 8) tile-packed buffers srcs_host[r] (local
- * or peer memory, the same factor layout in each), summed in index order; mirror != 0 writes the symmetric matrix
+/* dense [d, ld] lower triangles -> tile-packed buffer (count <= 16); offsets_host[k] = first float of factor k
+ * inside `packed` (a multiple of 1024), NULL = back to back */
+int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host,
+                 const long long* offsets_host, int count, float* packed, void* stream);
+/* ONE kernel = collective + unpack: out[k] = scale * sum over r < nsrc (<= 8) of the tile-packed triangle at
+ * srcs_host[k * nsrc + r] (local or peer memory), summed in index order; mirror != 0 writes the symmetric matrix
  * (reduce-scatter of accumulated factors, nsrc = world), mirror == 0 a zero upper triangle (all-gather of the
  * Cholesky factors, nsrc = 1). */
 int bk_peer_tile_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
                         const float* const* srcs_host, int nsrc, float scale, int mirror, void* stream);
+/* Measurement aid: copy kernel with 4- or 16-byte accesses (bytes % 16 == 0) on `ctas` CTAs of 256 threads; a pull
+ * or a push depending on which pointer is peer memory. */
+int bk_peer_copy(void* dst, const void* src, long long bytes, int vec_bytes, int ctas, void* stream);
 /* Cross-GPU ordering.  flags_host[r]: a flag array (world 32-bit slots) inside rank r's exported buffer.
  * bk_peer_signal: system-scope fence, then slot `me` of every rank's array = epoch.  bk_peer_wait: returns (in
  * stream order) once all `world` slots of the local array have reached epoch; after timeout_s seconds it stores
