@@ -419,6 +419,11 @@ def main():
         reduce_state_copy(est)
         reduce_ms = best_of3(lambda: reduce_state_copy(est))
         scatter_ms = best_of3(exchange)
+        # the same exchange through NCCL (pack -> reduce_scatter_tensor -> unpack), for comparison
+        os.environ["BK_NO_PEER"] = "1"
+        exchange()
+        scatter_nccl_ms = best_of3(exchange)
+        os.environ.pop("BK_NO_PEER", None)
 
     for _ in range(args.warmup):
         step_e2e()
@@ -522,12 +527,18 @@ def main():
             "note": "the replicated variant (callers that read .state afterwards): bk_tri_pack -> ONE NCCL "
                     "all-reduce of the packed lower triangles -> bk_tri_unpack (mirror, 1/world); NOT in the timed region"}
         sent = wire_bytes * (world - 1) / world
+        from bnn_kfac_b200.distributed import PeerExchange
+        peer = PeerExchange.get(0, dev) is not None
         line["factor_exchange"] = {
             "ms": scatter_ms, "wire_bytes": wire_bytes, "bytes_sent_per_rank": sent,
             "busbw_GBps": sent / (scatter_ms * 1e-3) / 1e9,
-            "note": "one per timed region (deferred: state is a plain sum of batch means); packed lower triangles in "
-                    "owner order -> ONE NCCL reduce-scatter -> bk_tri_unpack of the owned factors (what invert_sharded "
-                    "issues)"}
+            "route": "peer memory" if peer else "nccl",
+            "nccl_route_ms": scatter_nccl_ms,
+            "note": "one per timed region (deferred: state is a plain sum of batch means); what invert_sharded issues. "
+                    "peer memory: bk_tile_pack into the rank's CUDA-IPC buffer -> flags -> ONE bk_peer_tile_unpack launch "
+                    "on every owner that pulls its chunk from all ranks over NVLink, adds in rank order and writes the "
+                    "mirrored dense factors (pack and flags included in ms).  nccl route: packed lower triangles in owner "
+                    "order -> reduce_scatter_tensor -> bk_tri_unpack"}
 
     # kernels launched by this library inside the device-timed region (counted by the library itself)
     c0 = L.bk_launch_count()
