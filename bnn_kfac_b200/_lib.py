@@ -22,6 +22,7 @@ BK_BLOCK_INV_MAX_DIM = 160
 
 SYRK_LOWER_ONLY = 1
 SYRK_NO_OVERLAP = 2
+SYRK_STAGE_PERSISTENT = 8
 SYRK_ROW_MAJOR = 4
 
 GEMM_SYRK_LOWER = 1

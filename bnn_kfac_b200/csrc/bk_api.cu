@@ -226,6 +226,14 @@ struct StagePipe {
   }
 };
 
+int device_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    return 148;
+  return n;
+}
+
 StagePipe* stage_pipe() {
   static std::mutex mu;
   static StagePipe* pipes[bk::kMaxDevices] = {};
@@ -407,8 +415,12 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
       if (colsum != nullptr &&
           cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, s) != cudaSuccess)
         return BK_ERR_CUDA;
+      // A/B switch BK_SYRK_STAGE_PERSISTENT: staging passes on the side stream (= underneath a running SYRK) use
+      // the persistent one-CTA-per-SM variant.  MEASURED SLOWER (0.58 vs 0.49 ms per cfg5 step): one tile in
+      // flight per SM is ~1 TB/s, less than the SYRK chunk above it gives it time for; off by default.
       const int rc = bk::launch_transpose_split(static_cast<const float*>(xs[i]), ldxs[i], n, d, in_scales[i],
-                                                0, hi, lo, ldt, s, colsum);
+                                                0, hi, lo, ldt, s, colsum,
+                                                (s != st && (flags & BK_SYRK_STAGE_PERSISTENT)) ? device_sms() : 0);
       if (rc) return rc;
       bk::SyrkGroupItem& it = items[w];
       it.X_hi = hi;

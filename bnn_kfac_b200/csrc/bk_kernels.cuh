@@ -12,7 +12,7 @@ namespace bk {
 // colsum (optional, fp32 [cols], pre-zeroed): receives sum_n scale * X[n, j] (bias row of A).
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
-                           cudaStream_t stream, float* colsum = nullptr);
+                           cudaStream_t stream, float* colsum = nullptr, int persistent_ctas = 0);
 // Three-way bf16 splits (hi + lo + lo2: 24 mantissa bits) for the bf16x6 products of bk_chol.cu.
 int launch_convert_split3(const float* X, long long ldx, int rows, int cols, __nv_bfloat16* O0,
                           __nv_bfloat16* O1, __nv_bfloat16* O2, long long ldo, cudaStream_t stream);

@@ -62,48 +62,54 @@ __global__ void transpose_split_kernel(const float* __restrict__ X, long long ld
 // which makes both phases conflict-free: the load phase writes, per warp instruction, eight 4-float
 // groups of the rows {s0, s0+2, s0+4, s0+6}; the transposed phase reads, for one feature f, the even
 // (then the odd) samples 2*lane (+1).
-__global__ void __launch_bounds__(256)
-transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
-                         __nv_bfloat16* __restrict__ Thi, __nv_bfloat16* __restrict__ Tlo,
-                         long long ldt, float* __restrict__ colsum) {
-  __shared__ float tile[32 * 129];
-  const int c0 = blockIdx.x * 64;
-  const int r0 = blockIdx.y * 64;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  {
-    // unit u = pass * 8 + warp in [0, 32): (half of the 64 features, group of 8 rows, row parity)
-    float4 v[4];
-    int srow[4], fcol[4];
+struct Tile64Regs {
+  float4 v[4];
+};
+
+// loads of one 64 x 64 tile (rows r0.., columns c0..): four independent 16-byte loads per thread
+__device__ __forceinline__ void tile64_load(const float* __restrict__ X, long long ldx, int rows, int cols, int r0,
+                                            int c0, Tile64Regs& t) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // unit u = pass * 8 + warp in [0, 32): (half of the 64 features, group of 8 rows, row parity)
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int u = pass * 8 + warp;
-      const int half = u & 1, parity = (u >> 1) & 1, grp = u >> 2;  // grp in [0, 8)
-      const int s = grp * 8 + parity + 2 * (lane >> 3);             // rows s0, s0+2, s0+4, s0+6
-      const int f = half * 32 + 4 * (lane & 7);
-      srow[pass] = s;
-      fcol[pass] = f;
-      const int r = r0 + s, c = c0 + f;
-      v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows) {
-        const float* src = X + static_cast<long long>(r) * ldx + c;
-        if (c + 3 < cols) {
-          v[pass] = __ldcs(reinterpret_cast<const float4*>(src));
-        } else {
-          if (c < cols) v[pass].x = src[0];
-          if (c + 1 < cols) v[pass].y = src[1];
-          if (c + 2 < cols) v[pass].z = src[2];
-        }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int u = pass * 8 + warp;
+    const int half = u & 1, parity = (u >> 1) & 1, grp = u >> 2;  // grp in [0, 8)
+    const int s = grp * 8 + parity + 2 * (lane >> 3);             // rows s0, s0+2, s0+4, s0+6
+    const int f = half * 32 + 4 * (lane & 7);
+    const int r = r0 + s, c = c0 + f;
+    t.v[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) {
+      const float* src = X + static_cast<long long>(r) * ldx + c;
+      if (c + 3 < cols) {
+        t.v[pass] = __ldcs(reinterpret_cast<const float4*>(src));
+      } else {
+        if (c < cols) t.v[pass].x = src[0];
+        if (c + 1 < cols) t.v[pass].y = src[1];
+        if (c + 2 < cols) t.v[pass].z = src[2];
       }
     }
+  }
+}
+
+// registers -> shared tile -> transposed, split, stored; ends with the tile free again (two barriers)
+__device__ __forceinline__ void tile64_emit(const Tile64Regs& t, float* __restrict__ tile, int rows, int cols, int r0,
+                                            int c0, float scale, __nv_bfloat16* __restrict__ Thi,
+                                            __nv_bfloat16* __restrict__ Tlo, long long ldt,
+                                            float* __restrict__ colsum, bool persistent) {
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      float* d = tile + (srow[pass] >> 1) * 129 + (srow[pass] & 1) * 64 + fcol[pass];
-      d[0] = v[pass].x * scale;
-      d[1] = v[pass].y * scale;
-      d[2] = v[pass].z * scale;
-      d[3] = v[pass].w * scale;
-    }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int u = pass * 8 + warp;
+    const int half = u & 1, parity = (u >> 1) & 1, grp = u >> 2;
+    const int srow = grp * 8 + parity + 2 * (lane >> 3);
+    const int fcol = half * 32 + 4 * (lane & 7);
+    float* d = tile + (srow >> 1) * 129 + (srow & 1) * 64 + fcol;
+    d[0] = t.v[pass].x * scale;
+    d[1] = t.v[pass].y * scale;
+    d[2] = t.v[pass].z * scale;
+    d[3] = t.v[pass].w * scale;
   }
   __syncthreads();
   const int oc = r0 + 2 * lane;  // sample pair written by this lane
@@ -133,6 +139,43 @@ transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, i
     for (int k = 0; k < 32; ++k)  // rows beyond `rows` hold zeros
       sacc += tile[k * 129 + tid] + tile[k * 129 + 64 + tid];
     atomicAdd(&colsum[c0 + tid], sacc);
+  }
+  if (persistent) __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+transpose_split64_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
+                         __nv_bfloat16* __restrict__ Thi, __nv_bfloat16* __restrict__ Tlo,
+                         long long ldt, float* __restrict__ colsum) {
+  __shared__ float tile[32 * 129];
+  const int c0 = blockIdx.x * 64;
+  const int r0 = blockIdx.y * 64;
+  Tile64Regs t;
+  tile64_load(X, ldx, rows, cols, r0, c0, t);
+  tile64_emit(t, tile, rows, cols, r0, c0, scale, Thi, Tlo, ldt, colsum, false);
+}
+
+// PERSISTENT variant for the staging passes that run UNDER a tensor-core SYRK (bk_syrk_accum_grouped, side
+// stream): the SYRK's persistent CTAs own every SM and leave room for exactly one more CTA of this size, so a
+// conventional grid of 4096 tile-CTAs trickles through one slot per SM, each exposing a full load latency before
+// its first store (measured: 62 us of staging hid only 18 us under a 153 us SYRK).  Here one CTA per SM walks the
+// tiles and keeps the NEXT tile's loads in flight while the current one is transposed and stored.
+__global__ void __launch_bounds__(256, 1)
+transpose_split64_persistent_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float scale,
+                                    __nv_bfloat16* __restrict__ Thi, __nv_bfloat16* __restrict__ Tlo,
+                                    long long ldt, float* __restrict__ colsum) {
+  __shared__ float tile[32 * 129];
+  const int tx = (cols + 63) / 64, ty = (rows + 63) / 64;
+  const int ntiles = tx * ty;
+  int t = blockIdx.x;
+  if (t >= ntiles) return;
+  Tile64Regs cur, nxt;
+  tile64_load(X, ldx, rows, cols, (t / tx) * 64, (t % tx) * 64, cur);
+  for (; t < ntiles; t += gridDim.x) {
+    const int tn = t + gridDim.x;
+    if (tn < ntiles) tile64_load(X, ldx, rows, cols, (tn / tx) * 64, (tn % tx) * 64, nxt);
+    tile64_emit(cur, tile, rows, cols, (t / tx) * 64, (t % tx) * 64, scale, Thi, Tlo, ldt, colsum, true);
+    cur = nxt;
   }
 }
 
@@ -355,7 +398,7 @@ int launch_transpose_split3(const float* X, long long ldx, int rows, int cols, _
 
 int launch_transpose_split(const float* X, long long ldx, int rows, int cols, float scale,
                            int ones_row, __nv_bfloat16* Thi, __nv_bfloat16* Tlo, long long ldt,
-                           cudaStream_t stream, float* colsum) {
+                           cudaStream_t stream, float* colsum, int persistent_ctas) {
   if (rows <= 0 || cols <= 0) return 0;
   const bool fast = (ldx % 4 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (ldt % 2 == 0) &&
                     (reinterpret_cast<uintptr_t>(Thi) % 4 == 0) &&
@@ -363,8 +406,11 @@ int launch_transpose_split(const float* X, long long ldx, int rows, int cols, fl
   if (colsum != nullptr && !fast) return -2;  // callers only request sums on the aligned path
   if (fast) {
     dim3 grid((cols + 63) / 64, (rows + 63) / 64);
-    transpose_split64_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo, ldt,
-                                                       colsum);
+    if (persistent_ctas > 0)
+      transpose_split64_persistent_kernel<<<persistent_ctas, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo,
+                                                                               ldt, colsum);
+    else
+      transpose_split64_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, Thi, Tlo, ldt, colsum);
     note_launch();
     if (ones_row) {  // generic operand with an explicit row of ones (bk_transpose_split ABI)
       fill_ones_row_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(

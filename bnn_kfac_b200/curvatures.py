@@ -477,7 +477,7 @@ class KFAC(Curvature):
         insc = (C.c_float * n)(*[it[4] for it in items])
         alph = (C.c_float * n)(*[it[5] for it in items])
         beta = (C.c_float * n)(*[it[1] for it in items])
-        flags = _lib.SYRK_LOWER_ONLY if self.lower_only else 0
+        flags = (_lib.SYRK_LOWER_ONLY if self.lower_only else 0) | int(getattr(self, "_syrk_flags_extra", 0))
         _lib.check(self._lib.bk_syrk_accum_grouped(states, lds, xs, bf, ldx, ns, ds, hb, insc, alph, beta, n, prec,
                                                    flags, ws.data_ptr(), nbytes, _lib.stream_ptr()),
                    "bk_syrk_accum_grouped")

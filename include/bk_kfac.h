@@ -119,6 +119,8 @@ size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* 
  *   BK_SYRK_NO_OVERLAP  stage every operand first, then run the SYRKs (default: the staging of later factors
  *                       runs on an internal per-device side stream underneath the SYRK of earlier ones; the
  *                       call is still ordered on `stream` as a whole).
+ *   BK_SYRK_STAGE_PERSISTENT  A/B switch, off: the overlapped staging passes run as one persistent CTA per SM
+ *                       (measured slower than the tile grid: 0.58 vs 0.49 ms per cfg5 step).
  *   BK_SYRK_ROW_MAJOR   (bk_syrk_accum_staged_grouped only) the operands are row-major bf16 activations [n, d]
  *                       (ldt = their row pitch, a multiple of 8), not staged K-major copies.
  * x_is_bf16 (nullable = all fp32): xs[i] is a bf16 matrix [n, d] (row pitch ldxs[i] % 8 == 0, 16 B aligned base).
@@ -128,6 +130,7 @@ size_t bk_syrk_grouped_workspace_bytes(const int* ns, const int* ds, const int* 
  * fp32 first). */
 #define BK_SYRK_LOWER_ONLY 1
 #define BK_SYRK_NO_OVERLAP 2
+#define BK_SYRK_STAGE_PERSISTENT 8 /* A/B switch (measured slower, off): overlapped staging passes run as one persistent CTA per SM */
 #define BK_SYRK_ROW_MAJOR 4
 int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, const void* const* xs,
                           const int* x_is_bf16, const long long* ldxs, const int* ns, const int* ds,
