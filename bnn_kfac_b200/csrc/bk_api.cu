@@ -416,8 +416,9 @@ int bk_syrk_accum_grouped(float* const* states, const long long* ld_states, cons
           cudaMemsetAsync(colsum, 0, static_cast<size_t>(d) * 4, s) != cudaSuccess)
         return BK_ERR_CUDA;
       // A/B switch BK_SYRK_STAGE_PERSISTENT: staging passes on the side stream (= underneath a running SYRK) use
-      // the persistent one-CTA-per-SM variant.  MEASURED SLOWER (0.58 vs 0.49 ms per cfg5 step): one tile in
-      // flight per SM is ~1 TB/s, less than the SYRK chunk above it gives it time for; off by default.
+      // the persistent one-CTA-per-SM variant.  MEASURED SLOWER than the tile grid (cfg5 step 0.49 ms): 0.58 ms with
+      // one tile's loads in flight per SM, 0.64 ms with three (114 registers) - slower even than no overlap
+      // (0.54 - 0.57 ms); off by default, tools/gpu_time_update_ab.py.
       const int rc = bk::launch_transpose_split(static_cast<const float*>(xs[i]), ldxs[i], n, d, in_scales[i],
                                                 0, hi, lo, ldt, s, colsum,
                                                 (s != st && (flags & BK_SYRK_STAGE_PERSISTENT)) ? device_sms() : 0);

@@ -167,15 +167,28 @@ transpose_split64_persistent_kernel(const float* __restrict__ X, long long ldx, 
   __shared__ float tile[32 * 129];
   const int tx = (cols + 63) / 64, ty = (rows + 63) / 64;
   const int ntiles = tx * ty;
+  const int g = gridDim.x;
+  // three tiles' loads (48 KB per SM) in flight while a fourth is transposed and stored: register ring A..D
+  Tile64Regs A, B, C, D;
+  auto ld = [&](int t, Tile64Regs& r) {
+    if (t < ntiles) tile64_load(X, ldx, rows, cols, (t / tx) * 64, (t % tx) * 64, r);
+  };
+  auto em = [&](int t, const Tile64Regs& r) {
+    if (t < ntiles) tile64_emit(r, tile, rows, cols, (t / tx) * 64, (t % tx) * 64, scale, Thi, Tlo, ldt, colsum, true);
+  };
   int t = blockIdx.x;
-  if (t >= ntiles) return;
-  Tile64Regs cur, nxt;
-  tile64_load(X, ldx, rows, cols, (t / tx) * 64, (t % tx) * 64, cur);
-  for (; t < ntiles; t += gridDim.x) {
-    const int tn = t + gridDim.x;
-    if (tn < ntiles) tile64_load(X, ldx, rows, cols, (tn / tx) * 64, (tn % tx) * 64, nxt);
-    tile64_emit(cur, tile, rows, cols, (t / tx) * 64, (t % tx) * 64, scale, Thi, Tlo, ldt, colsum, true);
-    cur = nxt;
+  ld(t, A);
+  ld(t + g, B);
+  ld(t + 2 * g, C);
+  for (; t < ntiles; t += 4 * g) {
+    ld(t + 3 * g, D);
+    em(t, A);
+    ld(t + 4 * g, A);
+    em(t + g, B);
+    ld(t + 5 * g, B);
+    em(t + 2 * g, C);
+    ld(t + 6 * g, C);
+    em(t + 3 * g, D);
   }
 }
 
