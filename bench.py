@@ -644,7 +644,7 @@ def extras(est, model, layers, dev, world, rank):
     if world > 1:
         from bnn_kfac_b200.distributed import invert_sharded
         inv = lambda: invert_sharded(est, 1.0, 200.0)     # noqa: E731
-        cfg = f"8 factors sharded over {world} ranks: all-reduce, owner inverts, broadcast of L"
+        cfg = f"8 factors sharded over {world} ranks: reduce-scatter to owners over peer memory (NCCL when unavailable), owner inverts, Cholesky factors pulled back over peer memory"
     else:
         inv = lambda: est.invert(1.0, 200.0)              # noqa: E731
         cfg = "one batched launch sequence"

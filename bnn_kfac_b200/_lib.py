@@ -111,6 +111,7 @@ SIGNATURES = {
     "bk_peer_read_u32": (_i, [_p, C.POINTER(C.c_uint)]),
     "bk_tile_packed_floats": (_ll, [C.POINTER(_i), _i]),
     "bk_tile_pack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), C.POINTER(_ll), _i, _p, _p]),
+    "bk_tile_pack_to": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), C.POINTER(_p), _i, _p]),
     "bk_peer_tile_unpack": (_i, [C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i), _i, C.POINTER(_p), _i, _f, _i, _p]),
     "bk_peer_copy": (_i, [_p, _p, _ll, _i, _i, _p]),
     "bk_peer_signal": (_i, [C.POINTER(_p), _i, _i, C.c_uint, _p]),

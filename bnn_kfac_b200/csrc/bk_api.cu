@@ -699,6 +699,13 @@ int bk_tile_pack(const float* const* factors_host, const long long* ld_host, con
   return bk::launch_tile_pack(factors_host, ld_host, dims_host, offsets_host, count, packed, as_stream(stream));
 }
 
+int bk_tile_pack_to(const float* const* factors_host, const long long* ld_host, const int* dims_host,
+                    float* const* dsts_host, int count, void* stream) {
+  if (count <= 0 || factors_host == nullptr || ld_host == nullptr || dims_host == nullptr || dsts_host == nullptr)
+    return BK_ERR_ARG;
+  return bk::launch_tile_pack_to(factors_host, ld_host, dims_host, dsts_host, count, as_stream(stream));
+}
+
 int bk_peer_tile_unpack(float* const* outs_host, const long long* ld_host, const int* dims_host, int count,
                         const float* const* srcs_host, int nsrc, float scale, int mirror, void* stream) {
   if (count <= 0 || outs_host == nullptr || ld_host == nullptr || dims_host == nullptr || srcs_host == nullptr)

@@ -125,6 +125,8 @@ int launch_tri_unpack(float* const* mats, const long long* lds, const int* dims,
 long long tile_packed_floats(const int* dims, int count);
 int launch_tile_pack(const float* const* mats, const long long* lds, const int* dims, const long long* offs,
                      int count, float* packed, cudaStream_t stream);
+int launch_tile_pack_to(const float* const* mats, const long long* lds, const int* dims, float* const* dsts,
+                        int count, cudaStream_t stream);
 int launch_peer_tile_unpack(float* const* mats, const long long* lds, const int* dims, int count,
                             const float* const* srcs, int nsrc, float scale, int mirror, cudaStream_t stream);
 int launch_peer_copy(void* dst, const void* src, long long bytes, int vec_bytes, int ctas, cudaStream_t stream);

@@ -34,6 +34,7 @@ constexpr int kMaxPeers = 8;
 
 struct TileTable {
   float* mat[kMaxTri];
+  float* dst[kMaxTri];     // tile_pack with per-factor destinations (possibly peer memory); else nullptr
   long long ld[kMaxTri];
   long long off[kMaxTri];  // first packed float of the factor inside a source buffer
   int tile0[kMaxTri + 1];  // first CTA of the factor (tiles of all factors concatenated)
@@ -63,7 +64,8 @@ tile_pack_kernel(const __grid_constant__ TileTable t, float* __restrict__ packed
   const int d = t.d[f];
   const float* m = t.mat[f];
   const long long ld = t.ld[f];
-  float* out = packed + t.off[f] + static_cast<long long>(blockIdx.x - t.tile0[f]) * 1024;
+  float* out = (t.dst[f] != nullptr ? t.dst[f] : packed + t.off[f]) +
+               static_cast<long long>(blockIdx.x - t.tile0[f]) * 1024;
   const int j = tj * 32 + threadIdx.x;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -202,6 +204,21 @@ int launch_tile_pack(const float* const* mats, const long long* lds, const int* 
   const int tiles = fill_table(t, const_cast<float* const*>(mats), lds, dims, offs, count);
   if (tiles < 0 || packed == nullptr) return -2;
   tile_pack_kernel<<<tiles, dim3(32, 8), 0, stream>>>(t, packed);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+// per-factor destinations: the pack IS the send when a destination is another rank's buffer (posted NVLink writes)
+int launch_tile_pack_to(const float* const* mats, const long long* lds, const int* dims, float* const* dsts,
+                        int count, cudaStream_t stream) {
+  TileTable t{};
+  const int tiles = fill_table(t, const_cast<float* const*>(mats), lds, dims, nullptr, count);
+  if (tiles < 0 || dsts == nullptr) return -2;
+  for (int k = 0; k < count; ++k) {
+    if (dsts[k] == nullptr) return -2;
+    t.dst[k] = dsts[k];
+  }
+  tile_pack_kernel<<<tiles, dim3(32, 8), 0, stream>>>(t, nullptr);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

@@ -305,6 +305,10 @@ long long bk_tile_packed_floats(const int* dims_host, int count);
  * inside `packed` (a multiple of 1024), NULL = back to back */
 int bk_tile_pack(const float* const* factors_host, const long long* ld_host, const int* dims_host,
                  const long long* offsets_host, int count, float* packed, void* stream);
+/* The same with one destination per factor (dsts_host[k], 4 KB aligned tile-packed area of factor k): a destination
+ * in another rank's exported buffer makes the pack the SEND (posted writes over NVLink). */
+int bk_tile_pack_to(const float* const* factors_host, const long long* ld_host, const int* dims_host,
+                    float* const* dsts_host, int count, void* stream);
 /* ONE kernel = collective + unpack: out[k] = scale * sum over r < nsrc (<= 8) of the tile-packed triangle at
  * srcs_host[k * nsrc + r] (local or peer memory), summed in index order; mirror != 0 writes the symmetric matrix
  * (reduce-scatter of accumulated factors, nsrc = world), mirror == 0 a zero upper triangle (all-gather of the

@@ -39,14 +39,16 @@ def timed(fn, reps=7):
 
 
 def route(peer):
-    if peer:
-        os.environ.pop("BK_NO_PEER", None)
-    else:
+    os.environ.pop("BK_NO_PEER", None)
+    os.environ.pop("BK_PEER_PUSH", None)
+    if peer == "push":
+        os.environ["BK_PEER_PUSH"] = "1"
+    elif not peer:
         os.environ["BK_NO_PEER"] = "1"
 
 
 res = {}
-for peer in (False, True, False, True):
+for peer in (False, True, "push", False, True):
     route(peer)
     D.reduce_scatter_to_owners(est, owners)
     red, t_min, t_med = timed(lambda: D.reduce_scatter_to_owners(est, owners))
@@ -58,7 +60,7 @@ for peer in (False, True, False, True):
     _, i_min, i_med = timed(lambda: D.invert_sharded(est, 1.0, 200.0))
     res[peer] = (red, gat, [est.inv_state[l][k].clone() for l in layers for k in range(2)])
     if rank == 0:
-        print(f"world={world} {'PEER' if peer else 'NCCL'}: reduce-scatter {t_min:.3f} / {t_med:.3f} ms, "
+        print(f"world={world} {'PEER(push)' if peer == 'push' else 'PEER' if peer else 'NCCL'}: reduce-scatter {t_min:.3f} / {t_med:.3f} ms, "
               f"return of the Cholesky factors {g_min:.3f} / {g_med:.3f} ms, invert_sharded {i_min:.2f} / {i_med:.2f} ms "
               f"(min / median)", flush=True)
 bad = 0.0
