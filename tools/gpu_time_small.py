@@ -37,9 +37,9 @@ for name, ctor, shape in [("cfg1 MLP 784-1024-1024-10", lambda: MLP([784, 1024, 
     nl = L.bk_launch_count() - c0
     t_upd = ev(lambda: est.update(shape[0]))
     t_fb = ev(fwdbwd)
-    t_inv = ev(lambda: est.invert(1e2, 1e4), reps=5, warm=1)
+    t_inv = ev(lambda: est.invert(1e2, 1e4), reps=5, warm=2)
     S = 100 if "cfg4" in name else 30
-    t_mc = ev(lambda: mc_predict(est, x, S), reps=5, warm=1)
+    t_mc = ev(lambda: mc_predict(est, x, S), reps=10, warm=3)
     print(f"{name}: update {t_upd[0]*1e3:.0f} us gpu / {t_upd[1]*1e3:.0f} us wall ({nl} launches) -> {shape[0]/t_upd[1]*1e3:.0f} samples/s; "
           f"model fwd+bwd {t_fb[1]*1e3:.0f} us; invert {t_inv[1]:.2f} ms; mc_predict S={S} B={shape[0]}: {t_mc[1]:.2f} ms "
           f"-> {S*shape[0]/t_mc[1]*1e3:.0f} (samples x inputs)/s", flush=True)
