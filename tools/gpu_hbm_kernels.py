@@ -66,6 +66,21 @@ timeit("ger_accum H += bs * g g^T, P = 15080", [lambda i=i: L.bk_ger_accum(H[i].
 lg = [torch.randn(64, 4096, 1000, device=dev) for _ in range(2)]
 mean = torch.empty(4096, 1000, device=dev); msq = torch.empty_like(mean)
 timeit("predictive_moments softmax mean/meansq [64, 4096, 1000]", [lambda i=i: L.bk_predictive_moments(lg[i].data_ptr(), 64, 4096, 1000, 0, mean.data_ptr(), msq.data_ptr(), st) for i in range(2)], 64 * 4096 * 1000 * 4)
+# peer-exchange kernels with every source in LOCAL memory (their HBM side): tile pack of a 4097-wide factor, fused
+# sum-of-8 + unpack (what an owner runs per factor at world size 8, there with 7 of the 8 sources behind NVLink)
+import ctypes as C
+d = 4097
+T = (d + 31) // 32
+tp = T * (T + 1) // 2 * 1024
+facs = [torch.randn(d, d, device=dev) for _ in range(NB)]
+packs = [torch.empty(tp, device=dev) for _ in range(8)]
+one = lambda t: ((C.c_void_p * 1)(t.data_ptr()), (C.c_longlong * 1)(t.stride(0)), (C.c_int * 1)(d))
+timeit("tile_pack lower triangle of [4097, 4097] -> 32x32 tiles", [lambda i=i: L.bk_tile_pack(*one(facs[i]), None, 1, packs[i].data_ptr(), st) for i in range(NB)], d * (d + 1) // 2 * 4 + tp * 4)
+outs = [torch.empty(d, d, device=dev) for _ in range(2)]
+srcs = (C.c_void_p * 8)(*[t.data_ptr() for t in packs])
+timeit("peer_tile_unpack<8> sum of 8 packed sources -> mirrored [4097, 4097]", [lambda i=i: L.bk_peer_tile_unpack(*one(outs[i]), 1, srcs, 8, 0.125, 1, st) for i in range(2)], 8 * tp * 4 + d * d * 4)
+srcs1 = [(C.c_void_p * 1)(packs[i].data_ptr()) for i in range(NB)]
+timeit("peer_tile_unpack<1> packed -> lower-triangular [4097, 4097]", [lambda i=i: L.bk_peer_tile_unpack(*one(outs[i % 2]), 1, srcs1[i], 1, 1.0, 0, st) for i in range(NB)], tp * 4 + d * d * 4)
 with open("gpurun_out/hbm_kernels.md", "w") as f:
     f.write("| kernel (cfg5-sized operands) | algorithmic MB | us | GB/s | of measured HBM peak (%.1f GB/s) |\n|---|---:|---:|---:|---:|\n" % PEAK)
     for r in rows:
