@@ -365,15 +365,21 @@ class PeerExchange:
         if ctx is not None:
             torch.cuda.synchronize()
             dist.barrier(group=group)          # nobody still reads the buffer that is about to go away
+            ctx.close_peers()
+            dist.barrier(group=group)          # every mapping of every buffer is gone before any buffer is freed
             ctx.close()
         ctx = cls(max(int(nbytes * 1.25), 1 << 20), device, group)
         cls._cache[key] = ctx
         return ctx if ctx.ok else None
 
-    def close(self) -> None:
+    def close_peers(self) -> None:
         for q in self._opened:
             self.lib.bk_peer_close(q)
         self._opened, self.ptrs = [], []
+        self.ok = False
+
+    def close(self) -> None:
+        self.close_peers()
         if self.local:
             self.lib.bk_peer_free(self.local)
             self.local = None
