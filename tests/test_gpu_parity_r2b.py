@@ -229,3 +229,46 @@ def test_utilities_script_helpers(dev):
     assert len(U.generate_kernel_coords()) == 109 and U.generate_kernel_coords()[-1] == (15070, 15080)
     U.seed_all_rng(3)
     assert U.vram() >= 0.0 and 0.0 <= U.ram() <= 100.0
+
+
+# ------------------------------------------------------------------------------- inversion chain (a5), round 2b
+def test_inversion_schedule_variants_agree_and_match_fp64(dev):
+    """KFAC.invert's kernel schedule (models/curvatures.py:381-392): the replayed CUDA graph, the kernel-by-kernel
+    route and every SM cap of the background (FAR) outer updates must return the SAME bits (every output tile is
+    produced by one CTA and the NEAR / FAR parts of an update are ordered per target region), and the result must
+    satisfy L L^T R = I and match chol(inv(R)) in fp64 - on a two-level batch (2049 and 2304 wide: outer blocks, NEAR /
+    FAR split, auxiliary streams, 64- and 128-wide rank-64 tiles) and on a small one (single-level path)."""
+    from bnn_kfac_b200 import _lib
+    from bnn_kfac_b200.curvatures import _Workspace, invert_factors
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(21)
+    for dims in ([2049, 2304, 10], [300, 81]):
+        n = 3000
+        fs = []
+        for d in dims:
+            x = torch.relu(torch.randn(n, d, generator=g)).to(dev)
+            fs.append((x.T @ x / n).contiguous())
+        add, mult = [1.0] * len(dims), [50.0] * len(dims)
+        ws = _Workspace()
+        ref = None
+        try:
+            for graph, far in ((1, 64), (0, 64), (1, 0), (1, 16), (1, 64)):
+                lib.bk_set_chol_graph(graph)
+                lib.bk_set_chol_far_sms(far)
+                outs = invert_factors(fs, add, mult, ws)
+                if ref is None:
+                    ref = [o.clone() for o in outs]
+                for a, b in zip(ref, outs):
+                    assert torch.equal(a, b), (dims, graph, far)
+        finally:
+            lib.bk_set_chol_graph(1)
+            lib.bk_set_chol_far_sms(64)
+        for F_, L_ in zip(fs, ref):
+            d = F_.shape[0]
+            R = (50.0 ** 0.5) * 0.5 * (F_ + F_.T).double() + torch.eye(d, dtype=torch.float64, device=dev)
+            want = torch.linalg.cholesky(torch.linalg.inv(R))
+            rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()   # noqa: E731
+            assert rel(L_, want) < TOL, (d, rel(L_, want))
+            eye = torch.eye(d, dtype=torch.float64, device=dev)
+            assert rel(L_.double() @ L_.double().T @ R, eye) < TOL
+            assert torch.triu(L_, 1).abs().max().item() == 0.0
