@@ -59,6 +59,7 @@ SIGNATURES = {
     "bk_set_syrk_tuning": (None, [_i]),
     "bk_set_chol_graph": (None, [_i]),
     "bk_set_chol_far_sms": (None, [_i]),
+    "bk_set_chol_lookahead": (None, [_i]),
     "bk_set_eigh_mode": (None, [_i]),
     "bk_set_eigh_pair_width": (None, [_i]),
     "bk_gemm_nt": (_i, [_p, _p, _ll, _ll, _p, _p, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _f,

@@ -48,6 +48,8 @@ void bk_set_chol_graph(int enabled) { bk::set_chol_graph(enabled); }
 
 void bk_set_chol_far_sms(int sms) { bk::set_chol_far_sms(sms); }
 
+void bk_set_chol_lookahead(int enabled) { bk::set_chol_lookahead(enabled); }
+
 void bk_set_eigh_mode(int mode) { bk::set_eigh_mode(mode); }
 
 void bk_set_eigh_pair_width(int width) { bk::set_eigh_pair_width(width); }

@@ -241,6 +241,9 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
 
 // ------------------------------------------------------------------ rank-64 update
 enum Mode : int { kPanel = 0, kTrail = 1, kRowScale = 2, kXUpdate = 3 };
+// kTrail only (look-ahead): the first 64 x 64 block of the region - the NEXT diagonal block - is updated by a
+// one-CTA launch on the chain (kDiagOnly); everything else (kSkipDiag) runs beside the next diagonal-block kernel.
+constexpr int kModeMask = 3, kDiagOnly = 16, kSkipDiag = 32;
 
 // C[m x n] = beta*C + alpha * A[m x 64] * (NT ? B[n x 64]^T : B[64 x n]);  one T x T tile / CTA, T = 128 (8 x 8
 // outputs per thread) or 64 (4 x 4).  The steps are latency-bound chains: whenever the 128-wide tiling would leave
@@ -251,8 +254,10 @@ enum Mode : int { kPanel = 0, kTrail = 1, kRowScale = 2, kXUpdate = 3 };
 // whole outer block at once from the tensor-core GEMM (see chol_inv_batched).
 template <int T>
 __global__ void __launch_bounds__(256)
-rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
+rank64_kernel(const CholProb* __restrict__ tab, int k, int mode_flags, int limit) {
   pdl_wait_then_trigger();
+  const int mode = mode_flags & kModeMask;
+  const bool diag_only = (mode_flags & kDiagOnly) != 0, skip_diag = (mode_flags & kSkipDiag) != 0;
   constexpr int TT = T / 16;  // outputs per thread and dimension; also 128-bit loads per thread and operand
   constexpr int V = TT / 4;
   const CholProb p = tab[blockIdx.y];
@@ -306,6 +311,8 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
     tj = blockIdx.x - ti * tiles_n;
     if (ti >= tiles_m) return;
   }
+  if (diag_only && (ti != 0 || tj != 0)) return;
+  if (skip_diag && T == NB && ti == 0 && tj == 0) return;
   const int r0 = ti * T, c0 = tj * T;
 
   extern __shared__ float sm[];
@@ -418,6 +425,7 @@ rank64_kernel(const CholProb* __restrict__ tab, int k, int mode, int limit) {
       for (int j = 0; j < 4; ++j) {
         const int col = c0 + tx * TT + 4 * v + j;
         if (col >= n || (lower && col > row)) continue;
+        if (diag_only ? (row >= NB || col >= NB) : (skip_diag && row < NB && col < NB)) continue;
         crow[col] = fmaf(alpha, acc[i][4 * v + j], beta * o[j]);
       }
     }
@@ -438,8 +446,9 @@ inline int rank64_tiles(int m, int n, int T, bool lower_full) {
 
 inline void launch_rank64(int m, int n, bool lower_full, int count, cudaStream_t stream, const CholProb* tab, int k,
                           int mode, int limit) {
-  const int T = pick_tile(static_cast<long long>(rank64_tiles(m, n, 128, lower_full)) * count);
-  const dim3 grid(rank64_tiles(m, n, T, lower_full), count);
+  const bool diag_only = (mode & kDiagOnly) != 0;
+  const int T = diag_only ? 64 : pick_tile(static_cast<long long>(rank64_tiles(m, n, 128, lower_full)) * count);
+  const dim3 grid(diag_only ? 1 : rank64_tiles(m, n, T, lower_full), count);
   if (T == 128)
     launch_chained(rank64_kernel<128>, grid, dim3(256), static_cast<size_t>(rank64_smem(128)), stream, tab, k, mode, limit);
   else
@@ -491,21 +500,24 @@ inline size_t staging_bytes(int max_pad, int count) {
 // block column k of C (final after the panel of Cholesky step k) and its own step k - 1, nothing else.
 struct Pipeline {
   cudaStream_t side = nullptr;
+  cudaStream_t side2 = nullptr;  // wide part of the in-block trailing updates (beside the next diagonal block)
   cudaStream_t cap = nullptr;  // origin stream of graph captures (the caller's stream may be the legacy default)
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
   // outer (tensor-core) updates of the factors of a batch: up to kAux streams per phase, forked from / joined into
   // the phase's stream, so that the partial waves of one factor's GEMM are filled by another factor's
   static constexpr int kAux = 4;
   cudaStream_t aux[2][kAux] = {};
   cudaEvent_t aux_fork[2] = {}, aux_join[2][kAux] = {};
-  std::vector<cudaEvent_t> panel_done;
+  std::vector<cudaEvent_t> panel_done, trail_done;
   bool ok = false;
   explicit Pipeline(bool) {}  // inert instance (no device)
   Pipeline() {
     ok = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&side2, cudaStreamNonBlocking) == cudaSuccess &&
          cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&join2, cudaEventDisableTiming) == cudaSuccess;
     for (int ph = 0; ph < 2 && ok; ++ph) {
       ok = cudaEventCreateWithFlags(&aux_fork[ph], cudaEventDisableTiming) == cudaSuccess;
       for (int i = 0; i < kAux && ok; ++i)
@@ -518,6 +530,11 @@ struct Pipeline {
       cudaEvent_t e;
       ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
       if (ok) panel_done.push_back(e);
+    }
+    while (ok && static_cast<int>(trail_done.size()) < n) {
+      cudaEvent_t e;
+      ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+      if (ok) trail_done.push_back(e);
     }
     return ok;
   }
@@ -641,10 +658,11 @@ int outer_gemm(const CholProb& p, int c0, bool phase2, bool far, const OuterStag
 namespace {
 
 int g_chol_graph = 1;
+int g_chol_lookahead = 1;
 
 struct GraphKey {
   void* workspace;
-  int dev, far_sms;
+  int dev, far_sms;  // far_sms also carries the look-ahead switch (bit 30)
   std::vector<int> dims;
   bool operator==(const GraphKey& o) const {
     return workspace == o.workspace && dev == o.dev && far_sms == o.far_sms && dims == o.dims;
@@ -718,9 +736,15 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
   // step behind the Cholesky phase on a side stream; both are chains of latency-bound steps that leave most
   // of the GPU idle on their own.
   cudaStream_t s2 = pipelined ? pipe.side : stream;
+  // Look-ahead inside the inner loop: of the trailing update of step k only the NEXT diagonal block sits on the chain
+  // (one CTA); the rest runs on a third stream beside the next diagonal-block kernel and is awaited by panel k + 1.
+  const bool lookahead = pipelined && g_chol_lookahead != 0;
+  cudaStream_t s3 = lookahead ? pipe.side2 : stream;
+  std::vector<char> trail_issued(static_cast<size_t>(max_nb), 0);
   if (pipelined) {
     if (cudaEventRecord(pipe.fork, stream) != cudaSuccess || cudaStreamWaitEvent(s2, pipe.fork, 0) != cudaSuccess)
       return -5;
+    if (lookahead && cudaStreamWaitEvent(s3, pipe.fork, 0) != cudaSuccess) return -5;
   }
   // one step of the inverse phase (enqueued on s2)
   auto inverse_step = [&](int k) -> int {
@@ -742,7 +766,13 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
     launch_chained(potrf_diag_kernel, dim3(count), dim3(kDiagThreads), 0, stream, cd_tab, k, d_info);
     note_launch();
     const int m = max_pad - (k + 1) * NB;
-    if (m > 0) launch_rank64(m, NB, false, count, stream, cd_tab, k, static_cast<int>(kPanel), 0);
+    if (m > 0) {
+      // the panel reads block column k below the diagonal block: the wide trailing update of step k - 1 wrote it
+      if (lookahead && k >= 1 && trail_issued[k - 1] &&
+          cudaStreamWaitEvent(stream, pipe.trail_done[k - 1], 0) != cudaSuccess)
+        return -5;
+      launch_rank64(m, NB, false, count, stream, cd_tab, k, static_cast<int>(kPanel), 0);
+    }
     if (pipelined) {
       // block column k of C and Dinv[k] are final: inverse step k may run
       if (cudaEventRecord(pipe.panel_done[k], stream) != cudaSuccess ||
@@ -752,11 +782,21 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
       if (rc) return rc;
     }
     if (m > 0) {
-      if (!two_level) {
-        launch_rank64(m, m, true, count, stream, cd_tab, k, static_cast<int>(kTrail), 0);
-      } else {
-        const int ncols = limit - (k + 1) * NB;  // columns of the outer block right of this step
-        if (ncols > 0) launch_rank64(m, ncols, false, count, stream, cd_tab, k, static_cast<int>(kTrail), limit);
+      const int ncols = two_level ? limit - (k + 1) * NB : m;  // two-level: columns of the outer block right of k
+      if (ncols > 0) {
+        const int lim = two_level ? limit : 0;
+        const bool full_lower = !two_level;
+        if (!lookahead) {
+          launch_rank64(m, ncols, full_lower, count, stream, cd_tab, k, static_cast<int>(kTrail), lim);
+        } else {
+          launch_rank64(m, ncols, full_lower, count, stream, cd_tab, k, static_cast<int>(kTrail) | kDiagOnly, lim);
+          if (m > NB) {
+            if (cudaStreamWaitEvent(s3, pipe.panel_done[k], 0) != cudaSuccess) return -5;
+            launch_rank64(m, ncols, full_lower, count, s3, cd_tab, k, static_cast<int>(kTrail) | kSkipDiag, lim);
+            if (cudaEventRecord(pipe.trail_done[k], s3) != cudaSuccess) return -5;
+            trail_issued[k] = 1;
+          }
+        }
       }
     }
     if (two_level && (k + 1) % inner_per_outer == 0) {
@@ -772,6 +812,9 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
     }
   } else {
     if (two_level && (outer_drain(0, stream) != 0 || outer_drain(1, s2) != 0)) return -5;
+    if (lookahead && (cudaEventRecord(pipe.join2, s3) != cudaSuccess ||
+                      cudaStreamWaitEvent(stream, pipe.join2, 0) != cudaSuccess))
+      return -5;
     if (cudaEventRecord(pipe.join, s2) != cudaSuccess || cudaStreamWaitEvent(stream, pipe.join, 0) != cudaSuccess)
       return -5;
   }
@@ -783,7 +826,8 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
 }  // namespace
 
 void set_chol_graph(int enabled) { g_chol_graph = enabled; }
-void set_chol_far_sms(int sms) { g_chol_far_sms = sms; }
+void set_chol_far_sms(int sms) { g_chol_far_sms = sms < 0 ? g_chol_far_sms : sms; }
+void set_chol_lookahead(int on) { g_chol_lookahead = on; }
 
 int chol_inv_batched(const float* const* factors, float* const* outs, const int* dims,
                      const float* add, const float* multiply, int count, void* workspace,
@@ -851,7 +895,7 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
   cudaGetDevice(&dev);
   const bool use_graph = g_chol_graph != 0 && pipe.ok && max_nb >= 4;
   if (use_graph) {
-    GraphKey key{workspace, dev, g_chol_far_sms, std::vector<int>(dims, dims + count)};
+    GraphKey key{workspace, dev, g_chol_far_sms | (g_chol_lookahead ? 1 << 30 : 0), std::vector<int>(dims, dims + count)};
     std::lock_guard<std::mutex> guard(g_graph_mu);
     CachedGraph* hit = nullptr;
     for (auto& c : g_graphs)

@@ -75,6 +75,8 @@ int chol_inv_batched(const float* const* factors, float* const* outs, const int*
 void set_chol_graph(int enabled);
 // SMs the background (FAR) outer updates of one phase may occupy together (0 = all)
 void set_chol_far_sms(int sms);
+// 1 (default): of each in-block trailing update only the next diagonal block stays on the chain
+void set_chol_lookahead(int on);
 
 // ---- bk_eigh.cu  (batched one-sided Jacobi eigensolver)
 size_t eigh_workspace_bytes(const int* dims, int count);

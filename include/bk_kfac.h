@@ -205,6 +205,10 @@ void bk_set_chol_graph(int enabled);
 /* Tuning knob (default 64): SMs that the background ("far") tensor-core updates of one inversion phase may occupy
  * together while the latency-bound diagonal / panel chain of the next outer block runs beside them; 0 = no limit. */
 void bk_set_chol_far_sms(int sms);
+/* Switch (default 1): look-ahead in the inner loop of the inversion - of the trailing update of step k only the next
+ * 64 x 64 diagonal block is computed on the chain, the rest runs on a third stream beside the next diagonal-block
+ * kernel and is awaited by the panel of step k + 1.  Same bits either way. */
+void bk_set_chol_lookahead(int enabled);
 int bk_damp_chol_inv_batched(const float* const* factors_host, float* const* outs_host,
                              const int* dims_host, const float* add_host,
                              const float* multiply_host, int count, void* workspace,

@@ -252,17 +252,19 @@ def test_inversion_schedule_variants_agree_and_match_fp64(dev):
         ws = _Workspace()
         ref = None
         try:
-            for graph, far in ((1, 64), (0, 64), (1, 0), (1, 16), (1, 64)):
+            for graph, far, look in ((1, 64, 1), (0, 64, 1), (1, 0, 1), (1, 16, 0), (0, 64, 0), (1, 64, 1)):
                 lib.bk_set_chol_graph(graph)
                 lib.bk_set_chol_far_sms(far)
+                lib.bk_set_chol_lookahead(look)
                 outs = invert_factors(fs, add, mult, ws)
                 if ref is None:
                     ref = [o.clone() for o in outs]
                 for a, b in zip(ref, outs):
-                    assert torch.equal(a, b), (dims, graph, far)
+                    assert torch.equal(a, b), (dims, graph, far, look)
         finally:
             lib.bk_set_chol_graph(1)
             lib.bk_set_chol_far_sms(64)
+            lib.bk_set_chol_lookahead(1)
         for F_, L_ in zip(fs, ref):
             d = F_.shape[0]
             R = (50.0 ** 0.5) * 0.5 * (F_ + F_.T).double() + torch.eye(d, dtype=torch.float64, device=dev)

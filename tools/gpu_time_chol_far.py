@@ -15,8 +15,9 @@ ws = _Workspace()
 for dims in ([d], [d, d - 1] * 3 + [d, 10], [1025, 1024, 1025, 1024, 1025, 10], [2049, 2048, 2049, 10]):
     fs = [F_[:k, :k].contiguous() for k in dims]
     outs = None
-    for cap in ([0, 32, 48, 64, 96] if dims[0] >= 2048 else [64]):
+    for cap, look in ([(64, 0), (64, 1), (0, 1)] if dims[0] >= 2048 else [(64, 0), (64, 1)]):
         L.bk_set_chol_far_sms(cap)
+        L.bk_set_chol_lookahead(look)
         for _ in range(2):
             outs = invert_factors(fs, [1.0] * len(fs), [200.0] * len(fs), ws)
         ms = []
@@ -27,5 +28,6 @@ for dims in ([d], [d, d - 1] * 3 + [d, 10], [1025, 1024, 1025, 1024, 1025, 10], 
             outs = invert_factors(fs, [1.0] * len(fs), [200.0] * len(fs), ws)
             e1.record(); torch.cuda.synchronize()
             ms.append(round(e0.elapsed_time(e1), 2))
-        print(f"dims={dims[0]}x{len(dims)} far_sms={cap}: median {sorted(ms)[3]:.2f} ms  min {min(ms):.2f}  max {max(ms):.2f}", flush=True)
+        print(f"dims={dims[0]}x{len(dims)} far_sms={cap} lookahead={look}: median {sorted(ms)[3]:.2f} ms  min {min(ms):.2f}  max {max(ms):.2f}", flush=True)
 L.bk_set_chol_far_sms(64)
+L.bk_set_chol_lookahead(1)
