@@ -153,7 +153,7 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
 }
 
 __global__ void __launch_bounds__(kDiagThreads)
-potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ info) {
+potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ info, int fuse_prev) {
   pdl_wait_then_trigger();
   const CholProb p = tab[blockIdx.x];
   if (k >= p.nb) return;
@@ -171,6 +171,47 @@ potrf_diag_kernel(const CholProb* __restrict__ tab, int k, int* __restrict__ inf
   float v[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) v[r] = blk[static_cast<long long>(i0 + r) * p.dpad + c];
+  if (fuse_prev) {
+    // Look-ahead: the update of THIS block by the previous step, A_kk -= L_k,k-1 L_k,k-1^T, is applied here instead
+    // of by a launch of its own between the panel and this kernel.  L_k,k-1 (64 x 64, just written by the panel
+    // kernel) goes transposed into the (still unused) L tile: Pt[kk][i], so that a thread reads its 32 rows as
+    // eight broadcast float4 and its own column c as one conflict-free word per kk.  Same accumulation order as
+    // rank64_kernel (kk ascending, one fma each, then old - acc): the result has the same bits.
+    float* Pt = sh + 4 * NB;  // [64][64]
+    {
+      const int i = tid % NB, kh = tid / NB;  // row of L_k,k-1, half of its 64 columns
+      const float* src = blk - NB + static_cast<long long>(i) * p.dpad + 32 * kh;
+      float4 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const float4*>(src + 4 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        Pt[(32 * kh + 4 * u + 0) * NB + i] = q[u].x;
+        Pt[(32 * kh + 4 * u + 1) * NB + i] = q[u].y;
+        Pt[(32 * kh + 4 * u + 2) * NB + i] = q[u].z;
+        Pt[(32 * kh + 4 * u + 3) * NB + i] = q[u].w;
+      }
+    }
+    __syncthreads();
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 2
+    for (int kk = 0; kk < NB; ++kk) {
+      const float pc = Pt[kk * NB + c];
+#pragma unroll
+      for (int r = 0; r < R; r += 4) {
+        const float4 pi = *reinterpret_cast<const float4*>(&Pt[kk * NB + i0 + r]);
+        acc[r] = fmaf(pi.x, pc, acc[r]);
+        acc[r + 1] = fmaf(pi.y, pc, acc[r + 1]);
+        acc[r + 2] = fmaf(pi.z, pc, acc[r + 2]);
+        acc[r + 3] = fmaf(pi.w, pc, acc[r + 3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = fmaf(-1.f, acc[r], v[r]);
+    __syncthreads();  // the L tile is written from the first column step on
+  }
   const uint32_t a_col = sbase + 4u * static_cast<uint32_t>(i0);  // + 256 * buffer: this thread's rows of colj
   const uint32_t a_c = sbase + 4u * static_cast<uint32_t>(c);     // + 256 * buffer: colj[c]; + 512: xrow[c]
   const uint32_t a_ls = sbase + 4u * (4 * NB + static_cast<uint32_t>(c) * kLsPitch);  // L tile row c
@@ -763,7 +804,9 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
   // ---- phase 1: right-looking Cholesky of the flipped damped matrix (+ the pipelined inverse steps)
   for (int k = 0; k < max_nb; ++k) {
     const int limit = two_level ? (k / inner_per_outer + 1) * kOuter : 0;
-    launch_chained(potrf_diag_kernel, dim3(count), dim3(kDiagThreads), 0, stream, cd_tab, k, d_info);
+    // look-ahead: step k - 1 left the update of this diagonal block to this kernel's prologue
+    const int fuse_prev = (lookahead && k >= 1 && (!two_level || k % inner_per_outer != 0)) ? 1 : 0;
+    launch_chained(potrf_diag_kernel, dim3(count), dim3(kDiagThreads), 0, stream, cd_tab, k, d_info, fuse_prev);
     note_launch();
     const int m = max_pad - (k + 1) * NB;
     if (m > 0) {
@@ -789,7 +832,7 @@ int enqueue_steps(const std::vector<CholProb>& h_tab2, int count, int max_pad, C
         if (!lookahead) {
           launch_rank64(m, ncols, full_lower, count, stream, cd_tab, k, static_cast<int>(kTrail), lim);
         } else {
-          launch_rank64(m, ncols, full_lower, count, stream, cd_tab, k, static_cast<int>(kTrail) | kDiagOnly, lim);
+          // (the next diagonal block's share of this update is fused into the next diagonal-block kernel)
           if (m > NB) {
             if (cudaStreamWaitEvent(s3, pipe.panel_done[k], 0) != cudaSuccess) return -5;
             launch_rank64(m, ncols, full_lower, count, s3, cd_tab, k, static_cast<int>(kTrail) | kSkipDiag, lim);
