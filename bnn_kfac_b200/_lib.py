@@ -58,6 +58,7 @@ SIGNATURES = {
     "bk_set_cta_group": (None, [_i]),
     "bk_set_syrk_tuning": (None, [_i]),
     "bk_set_chol_graph": (None, [_i]),
+    "bk_set_conv_fast": (None, [_i]),
     "bk_set_chol_far_sms": (None, [_i]),
     "bk_set_chol_lookahead": (None, [_i]),
     "bk_set_eigh_mode": (None, [_i]),

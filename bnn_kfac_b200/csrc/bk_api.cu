@@ -46,6 +46,8 @@ void bk_set_syrk_tuning(int flags) { bk::set_syrk_tuning(flags); }
 
 void bk_set_chol_graph(int enabled) { bk::set_chol_graph(enabled); }
 
+void bk_set_conv_fast(int enabled) { bk::set_conv_fast(enabled); }
+
 void bk_set_chol_far_sms(int sms) { bk::set_chol_far_sms(sms); }
 
 void bk_set_chol_lookahead(int enabled) { bk::set_chol_lookahead(enabled); }

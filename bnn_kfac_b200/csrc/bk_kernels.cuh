@@ -160,6 +160,8 @@ int launch_sample_to_weights(const float* samples, const float* mean_w, const fl
                              int d_out, int d_in, int has_bias, int nsamples, float* w_f32,
                              __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, long long ldw, float* b_f32,
                              cudaStream_t stream);
+// 1 (default): stride-1 3 x 3 / 5 x 5 layers take the register-tiled kernel; 0: always the generic one
+void set_conv_fast(int on);
 int launch_conv2d_relu_pool(const float* in, long long in_sample_stride, const float* w,
                             const float* b, float* out, int S, int N, int C, int H, int W, int O,
                             int KH, int KW, int SH, int SW, int PH, int PW, int relu, int pool,

@@ -380,6 +380,10 @@ int bk_sample_to_weights(const float* samples, const float* mean_w, const float*
 /* Per-sample conv2d (+bias, optional ReLU, optional 2x2 max-pool) for the reference CNNs
  * (models/wrapper.py:53-101): in [nsamples or 1, n, c, h, w] (in_sample_stride 0 = shared input),
  * w [nsamples, o, c, kh, kw], b [nsamples, o] or null, out [nsamples, n, o, oh', ow']. */
+/* Switch (default 1) of bk_conv2d_relu_pool: stride-1 layers with 3 x 3 / 5 x 5 kernels run a register-tiled kernel
+ * (weights staged once per group of 8 images, one (K + 1)^2 input patch per pooled output); 0 = always the generic
+ * one-CTA-per-(sample, image) kernel.  Same values up to the order of the fp32 accumulation. */
+void bk_set_conv_fast(int enabled);
 int bk_conv2d_relu_pool(const float* in, long long in_sample_stride, const float* w, const float* b,
                         float* out, int nsamples, int n, int c, int h, int wd, int o, int kh, int kw,
                         int sh, int sw, int ph, int pw, int relu, int pool, void* stream);

@@ -274,3 +274,50 @@ def test_inversion_schedule_variants_agree_and_match_fp64(dev):
             eye = torch.eye(d, dtype=torch.float64, device=dev)
             assert rel(L_.double() @ L_.double().T @ R, eye) < TOL
             assert torch.triu(L_, 1).abs().max().item() == 0.0
+
+
+def test_conv_forward_fast_path_matches_generic_and_torch(dev):
+    """bk_conv2d_relu_pool (per-sample weights; models/wrapper.py:53-101 under S weight samples): the register-tiled
+    fast path for stride-1 3 x 3 / 5 x 5 layers against the generic kernel and against torch's conv2d + relu +
+    max_pool2d, on the reference CNNs' layer shapes (padding, pooling, shared and per-sample inputs, a ragged image
+    count, odd pre-pool extents)."""
+    import torch.nn.functional as F
+    from bnn_kfac_b200 import _lib
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(4)
+    cases = [  # (S, N, C, H, W, O, K, pad, pool, shared input)
+        (5, 19, 1, 28, 28, 6, 5, 2, 1, True),     # LeNet-5 conv1
+        (5, 19, 6, 14, 14, 16, 5, 0, 1, False),   # LeNet-5 conv2
+        (3, 8, 1, 28, 28, 5, 5, 0, 1, True),      # BaseNet_15k conv1
+        (3, 9, 5, 12, 12, 10, 5, 0, 1, False),    # BaseNet_15k conv2
+        (4, 7, 1, 28, 28, 3, 3, 0, 1, True),      # BaseNet_750 conv1
+        (2, 5, 3, 9, 11, 4, 3, 1, 0, False),      # no pooling, odd extents
+        (2, 5, 2, 11, 9, 3, 5, 1, 1, False),      # odd pre-pool extent (last row / column dropped)
+    ]
+    try:
+        for S, N, C, H, W, O, K, pad, pool, shared in cases:
+            x = torch.randn((N, C, H, W) if shared else (S, N, C, H, W), generator=g).to(dev)
+            w = (0.3 * torch.randn(S, O, C, K, K, generator=g)).to(dev)
+            b = torch.randn(S, O, generator=g).to(dev)
+            oh, ow = H + 2 * pad - K + 1, W + 2 * pad - K + 1
+            qh, qw = (oh // 2, ow // 2) if pool else (oh, ow)
+            outs = []
+            for fast in (1, 0):
+                lib.bk_set_conv_fast(fast)
+                out = torch.full((S, N, O, qh, qw), float("nan"), device=dev)
+                _lib.check(lib.bk_conv2d_relu_pool(x.data_ptr(), 0 if shared else N * C * H * W, w.data_ptr(),
+                                                   b.data_ptr(), out.data_ptr(), S, N, C, H, W, O, K, K, 1, 1, pad,
+                                                   pad, 1, pool, st), "bk_conv2d_relu_pool")
+                outs.append(out)
+            ref = []
+            for s in range(S):
+                y = F.relu(F.conv2d((x if shared else x[s]).double(), w[s].double(), b[s].double(), padding=pad))
+                ref.append(F.max_pool2d(y, 2, 2) if pool else y)
+            ref = torch.stack(ref)
+            for out in outs:
+                assert torch.isfinite(out).all()
+                assert (out.double() - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+            assert (outs[0] - outs[1]).abs().max().item() < 1e-4
+    finally:
+        lib.bk_set_conv_fast(1)
