@@ -105,26 +105,34 @@ __global__ void conv2d_relu_pool_kernel(const float* __restrict__ in, long long 
 //   * fully unrolled taps.  (LeNet-5, S = 100, batch 256: the generic kernel ran at 3.9 TFLOP/s and was 87 % of
 //     the MC predictive.)
 constexpr int kConvGroup = 8;
+__host__ __device__ constexpr int conv_kkp(int K) { return (K * K + 3) / 4 * 4; }  // taps padded to float4
 template <int K, bool POOL>
 __global__ void __launch_bounds__(256)
 conv2d_fast_kernel(const float* __restrict__ in, long long in_sample_stride, const float* __restrict__ w,
                    const float* __restrict__ b, float* __restrict__ out, int N, int C, int H, int W, int O, int PH,
                    int PW, int relu) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int s = blockIdx.y, n0 = blockIdx.x * kConvGroup;
   const int imgs = min(kConvGroup, N - n0);
-  const int HP = H + 2 * PH, WP = W + 2 * PW;
-  const int OH = HP - K + 1, OW = WP - K + 1;
+  const int HP = H + 2 * PH, WPr = W + 2 * PW;
+  const int WP = WPr + (WPr & 1);  // even row pitch: 8-byte patch loads
+  const int OH = HP - K + 1, OW = WPr - K + 1;
   const int QH = POOL ? OH / 2 : OH, QW = POOL ? OW / 2 : OW;
   constexpr int NP = POOL ? 2 : 1;   // pre-pool outputs per item and dimension
   constexpr int PS = K + NP - 1;     // input patch edge
-  float* ws = sm;                               // [O][C][K*K]
-  float* bs = ws + O * C * K * K;               // [O]
-  float* xs = bs + O;                           // [kConvGroup][C][HP][WP], zero border
+  constexpr int KK = K * K, KKP = conv_kkp(K);
+  const int OPAIRS = (O + 1) / 2;    // a work item computes TWO output channels from one input patch
+  float* ws = sm;                                      // [2 * OPAIRS][C][KKP] (16-byte aligned rows)
+  float* bs = ws + 2 * OPAIRS * C * KKP;               // [2 * OPAIRS]
+  float* xs = bs + 2 * OPAIRS;                         // [kConvGroup][C][HP][WP], zero border
   const int img_words = C * HP * WP;
-  const float* wsrc = w + static_cast<long long>(s) * O * C * K * K;
-  for (int i = threadIdx.x; i < O * C * K * K; i += blockDim.x) ws[i] = wsrc[i];
-  for (int i = threadIdx.x; i < O; i += blockDim.x) bs[i] = b ? b[static_cast<long long>(s) * O + i] : 0.f;
+  const float* wsrc = w + static_cast<long long>(s) * O * C * KK;
+  for (int i = threadIdx.x; i < 2 * OPAIRS * C * KKP; i += blockDim.x) {
+    const int oc = i / KKP, t = i - oc * KKP;
+    ws[i] = (t < KK && oc < O * C) ? wsrc[oc * KK + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * OPAIRS; i += blockDim.x)
+    bs[i] = (b && i < O) ? b[static_cast<long long>(s) * O + i] : 0.f;
   for (int i = threadIdx.x; i < imgs * img_words; i += blockDim.x) {
     const int g = i / img_words, r = i - g * img_words;
     const int c = r / (HP * WP), r2 = r - c * HP * WP;
@@ -135,41 +143,68 @@ conv2d_fast_kernel(const float* __restrict__ in, long long in_sample_stride, con
     xs[i] = v;
   }
   __syncthreads();
-  const int per_img = O * QH * QW;
-  for (int e = threadIdx.x; e < imgs * per_img; e += blockDim.x) {
-    const int g = e / per_img, r = e - g * per_img;
-    const int o = r / (QH * QW), r2 = r - o * QH * QW;
+  const int per_pair = QH * QW, per_img = O * per_pair;
+  for (int e = threadIdx.x; e < imgs * OPAIRS * per_pair; e += blockDim.x) {
+    const int g = e / (OPAIRS * per_pair), r = e - g * OPAIRS * per_pair;
+    const int op = r / per_pair, r2 = r - op * per_pair;
     const int qy = r2 / QW, qx = r2 - qy * QW;
-    float acc[NP][NP];
+    const int o0 = 2 * op;
+    float acc[2][NP][NP];
 #pragma unroll
-    for (int dy = 0; dy < NP; ++dy)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int dx = 0; dx < NP; ++dx) acc[dy][dx] = bs[o];
+      for (int dy = 0; dy < NP; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < NP; ++dx) acc[u][dy][dx] = bs[o0 + u];
     const float* xg = xs + g * img_words + (qy * NP) * WP + qx * NP;
-    const float* wo = ws + o * C * K * K;
+    const float* wo = ws + o0 * C * KKP;
     for (int c = 0; c < C; ++c) {
       float patch[PS][PS];
+      if (POOL) {  // PS is even and the patch starts at an even word: 8-byte loads
 #pragma unroll
-      for (int y = 0; y < PS; ++y)
+        for (int y = 0; y < PS; ++y)
 #pragma unroll
-        for (int x = 0; x < PS; ++x) patch[y][x] = xg[c * HP * WP + y * WP + x];
+          for (int x = 0; x < PS; x += 2) {
+            const float2 v2 = *reinterpret_cast<const float2*>(xg + c * HP * WP + y * WP + x);
+            patch[y][x] = v2.x;
+            patch[y][x + 1] = v2.y;
+          }
+      } else {
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky)
+        for (int y = 0; y < PS; ++y)
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const float wv = wo[c * K * K + ky * K + kx];
+          for (int x = 0; x < PS; ++x) patch[y][x] = xg[c * HP * WP + y * WP + x];
+      }
 #pragma unroll
-          for (int dy = 0; dy < NP; ++dy)
+      for (int u = 0; u < 2; ++u) {
+        float wv[KKP];
 #pragma unroll
-            for (int dx = 0; dx < NP; ++dx) acc[dy][dx] = fmaf(wv, patch[ky + dy][kx + dx], acc[dy][dx]);
+        for (int t = 0; t < KKP; t += 4) {  // warp-broadcast 16-byte loads (neighbouring items share the pair)
+          const float4 q = *reinterpret_cast<const float4*>(wo + (u * C + c) * KKP + t);
+          wv[t] = q.x; wv[t + 1] = q.y; wv[t + 2] = q.z; wv[t + 3] = q.w;
         }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int dy = 0; dy < NP; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < NP; ++dx)
+                acc[u][dy][dx] = fmaf(wv[ky * K + kx], patch[ky + dy][kx + dx], acc[u][dy][dx]);
+      }
     }
-    float best = acc[0][0];
 #pragma unroll
-    for (int dy = 0; dy < NP; ++dy)
+    for (int u = 0; u < 2; ++u) {
+      if (o0 + u >= O) continue;
+      float best = acc[u][0][0];
 #pragma unroll
-      for (int dx = 0; dx < NP; ++dx) best = fmaxf(best, acc[dy][dx]);
-    out[(static_cast<long long>(s) * N + n0 + g) * per_img + r] = relu ? fmaxf(best, 0.f) : best;
+      for (int dy = 0; dy < NP; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < NP; ++dx) best = fmaxf(best, acc[u][dy][dx]);
+      out[(static_cast<long long>(s) * N + n0 + g) * per_img + (o0 + u) * per_pair + r2] =
+          relu ? fmaxf(best, 0.f) : best;
+    }
   }
 }
 
@@ -349,8 +384,9 @@ int launch_conv2d_relu_pool(const float* in, long long in_sample_stride, const f
   if (S <= 0 || N <= 0) return 0;
   if (g_conv_fast && SH == 1 && SW == 1 && KH == KW && (KH == 3 || KH == 5) && H + 2 * PH >= KH &&
       W + 2 * PW >= KW) {
-    const size_t fsmem = sizeof(float) * (static_cast<size_t>(O) * C * KH * KW + O +
-                                          static_cast<size_t>(kConvGroup) * C * (H + 2 * PH) * (W + 2 * PW));
+    const int wp = W + 2 * PW + ((W + 2 * PW) & 1), op2 = (O + 1) / 2 * 2;
+    const size_t fsmem = sizeof(float) * (static_cast<size_t>(op2) * C * conv_kkp(KH) + op2 +
+                                          static_cast<size_t>(kConvGroup) * C * (H + 2 * PH) * wp);
     if (fsmem <= 200 * 1024) {
       if (KH == 5)
         return pool ? launch_conv_fast<5, true>(in, in_sample_stride, w, b, out, S, N, C, H, W, O, PH, PW, relu, fsmem,
