@@ -211,6 +211,9 @@ conv2d_fast_kernel(const float* __restrict__ in, long long in_sample_stride, con
 // one warp per input row b.  mode 0: p = softmax(logits[s, b, :]); mode 1: p = logits[s, b, :].
 // mean[b, c] = (1/S) sum_s p ; meansq[b, c] = (1/S) sum_s p^2 (optional).  C <= 32 * kMaxPerLane.
 constexpr int kMaxPerLane = 32;
+// kPerLane = classes per lane the register arrays are sized (and the loops unrolled) for: 1 covers the 10-class nets
+// (a 32-wide unroll made every sample cost 32 x the instructions of a 10-class row: 142 us for 100 x 256 x 10 logits)
+template <int kPerLane>
 __global__ void predictive_moments_kernel(const float* __restrict__ logits, int S, int B, int Cn,
                                           int mode, float* __restrict__ mean,
                                           float* __restrict__ meansq) {
@@ -218,9 +221,9 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
   const int per = (Cn + 31) / 32;
-  float m1[kMaxPerLane], m2[kMaxPerLane];
+  float m1[kPerLane], m2[kPerLane];
 #pragma unroll
-  for (int k = 0; k < kMaxPerLane; ++k) m1[k] = m2[k] = 0.f;
+  for (int k = 0; k < kPerLane; ++k) m1[k] = m2[k] = 0.f;
   if (mode == 2) {
     // regression, CENTRED second moment (numpy std with ddof = 0, regression_sampling.py:86-88): pass 1
     // the mean, pass 2 sum (y - mean)^2.  E[y^2] - E[y]^2 in fp32 loses variances below ~1e-7 * mean^2
@@ -229,18 +232,18 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
     for (int s = 0; s < S; ++s) {
       const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
 #pragma unroll
-      for (int k = 0; k < kMaxPerLane; ++k) {
+      for (int k = 0; k < kPerLane; ++k) {
         const int c = lane + 32 * k;
         if (k < per && c < Cn) m1[k] += row[c];
       }
     }
     const float invS = 1.0f / static_cast<float>(S);
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) m1[k] *= invS;
+    for (int k = 0; k < kPerLane; ++k) m1[k] *= invS;
     for (int s = 0; s < S; ++s) {
       const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
 #pragma unroll
-      for (int k = 0; k < kMaxPerLane; ++k) {
+      for (int k = 0; k < kPerLane; ++k) {
         const int c = lane + 32 * k;
         if (k < per && c < Cn) {
           const float dv = row[c] - m1[k];
@@ -249,7 +252,7 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
       }
     }
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < kPerLane; ++k) {
       const int c = lane + 32 * k;
       if (k < per && c < Cn) {
         mean[static_cast<long long>(warp) * Cn + c] = m1[k];
@@ -260,10 +263,10 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
   }
   for (int s = 0; s < S; ++s) {
     const float* row = logits + (static_cast<long long>(s) * B + warp) * Cn;
-    float v[kMaxPerLane];
+    float v[kPerLane];
     float mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < kPerLane; ++k) {
       const int c = lane + 32 * k;
       v[k] = (k < per && c < Cn) ? row[c] : -INFINITY;
       mx = fmaxf(mx, v[k]);
@@ -273,17 +276,17 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       float sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxPerLane; ++k) {
+      for (int k = 0; k < kPerLane; ++k) {
         v[k] = (v[k] == -INFINITY) ? 0.f : expf(v[k] - mx);
         sum += v[k];
       }
       sum = warp_sum(sum);
       const float inv = 1.0f / sum;
 #pragma unroll
-      for (int k = 0; k < kMaxPerLane; ++k) v[k] *= inv;
+      for (int k = 0; k < kPerLane; ++k) v[k] *= inv;
     }
 #pragma unroll
-    for (int k = 0; k < kMaxPerLane; ++k) {
+    for (int k = 0; k < kPerLane; ++k) {
       const float pv = (v[k] == -INFINITY) ? 0.f : v[k];
       m1[k] += pv;
       m2[k] = fmaf(pv, pv, m2[k]);
@@ -291,7 +294,7 @@ __global__ void predictive_moments_kernel(const float* __restrict__ logits, int 
   }
   const float invS = 1.0f / static_cast<float>(S);
 #pragma unroll
-  for (int k = 0; k < kMaxPerLane; ++k) {
+  for (int k = 0; k < kPerLane; ++k) {
     const int c = lane + 32 * k;
     if (k < per && c < Cn) {
       mean[static_cast<long long>(warp) * Cn + c] = m1[k] * invS;
@@ -421,8 +424,13 @@ int launch_predictive_moments(const float* logits, int S, int B, int Cn, int mod
   if (Cn > 32 * kMaxPerLane) return -2;
   const int warps_per_block = 8;
   const int blocks = (B + warps_per_block - 1) / warps_per_block;
-  predictive_moments_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(logits, S, B, Cn, mode, mean,
-                                                                         meansq);
+  if (Cn <= 32)
+    predictive_moments_kernel<1><<<blocks, warps_per_block * 32, 0, stream>>>(logits, S, B, Cn, mode, mean, meansq);
+  else if (Cn <= 128)
+    predictive_moments_kernel<4><<<blocks, warps_per_block * 32, 0, stream>>>(logits, S, B, Cn, mode, mean, meansq);
+  else
+    predictive_moments_kernel<kMaxPerLane><<<blocks, warps_per_block * 32, 0, stream>>>(logits, S, B, Cn, mode, mean,
+                                                                                      meansq);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
