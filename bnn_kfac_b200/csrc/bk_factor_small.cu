@@ -48,6 +48,34 @@ struct ConvALoader {  // implicit im2col: row = (n, oy, ox), column j = (c, ky, 
     if (iy < 0 || iy >= H || ix < 0 || ix >= W) return 0.f;
     return x[((static_cast<long long>(n) * C + c) * H + iy) * W + ix];
   }
+  // The same gather with the index arithmetic hoisted: a thread of the staging loop keeps ONE patch row (n, oy, ox)
+  // per tile and walks the patch columns j = j0, j0 + 8, ...; (c, ky, kx) advance incrementally.  (Per element the
+  // generic form above costs six integer divisions - more instructions than the FMAs the element feeds.)
+  struct Row {
+    const float* base;  // image n
+    int iy0, ix0;
+  };
+  __device__ __forceinline__ Row row(long long r) const {
+    const int L = OH * OW;
+    const int n = static_cast<int>(r / L);
+    const int p = static_cast<int>(r - static_cast<long long>(n) * L);
+    const int oy = p / OW, ox = p - oy * OW;
+    return Row{x + static_cast<long long>(n) * C * H * W, oy * SH - PH, ox * SW - PW};
+  }
+  __device__ __forceinline__ float at(const Row& rw, int c, int ky, int kx) const {
+    const int iy = rw.iy0 + ky, ix = rw.ix0 + kx;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) return 0.f;
+    return rw.base[(c * H + iy) * W + ix];
+  }
+};
+
+template <class L>
+struct IsConvA {
+  static constexpr bool value = false;
+};
+template <>
+struct IsConvA<ConvALoader> {
+  static constexpr bool value = true;
 };
 
 struct ConvGLoader {  // g is [N, O, HW]; row = (n, p), column j = o
@@ -83,6 +111,35 @@ small_syrk_kernel(float* __restrict__ state, long long ld_state, Loader load, lo
   for (long long r0 = row_begin; r0 < row_end; r0 += kRowsPerTile) {
     const int nr = static_cast<int>(min(static_cast<long long>(kRowsPerTile), row_end - r0));
     // stage: consecutive threads walk whichever axis is contiguous in HBM for this loader
+    if constexpr (IsConvA<Loader>::value) {
+      // thread -> (patch row k = tid % 32, patch columns j = tid / 32 + 8 m): one row decode per tile, incremental
+      // (c, ky, kx)
+      const int k = threadIdx.x % kRowsPerTile;
+      const bool live = k < nr;
+      typename Loader::Row rw{};
+      if (live) rw = load.row(r0 + k);
+      int j = threadIdx.x / kRowsPerTile;
+      int c = j / (load.KH * load.KW);
+      int rem = j - c * load.KH * load.KW;
+      int ky = rem / load.KW, kx = rem - ky * load.KW;
+      for (; j < T * 16; j += (kTX * kTY) / kRowsPerTile) {
+        float v = 0.f;
+        if (live) {
+          if (j < d) v = load.at(rw, c, ky, kx);
+          else if (j == d && has_bias) v = 1.f;
+        }
+        xs[k * dpad + j] = v;
+        kx += (kTX * kTY) / kRowsPerTile;
+        while (kx >= load.KW) {
+          kx -= load.KW;
+          ++ky;
+        }
+        while (ky >= load.KH) {
+          ky -= load.KH;
+          ++c;
+        }
+      }
+    } else
     for (int idx = threadIdx.x; idx < kRowsPerTile * (T * 16); idx += kTX * kTY) {
       int k, j;
       if (Loader::kRowFast) {
