@@ -419,6 +419,13 @@ def main():
         reduce_state_copy(est)
         reduce_ms = best_of3(lambda: reduce_state_copy(est))
         scatter_ms = best_of3(exchange)
+        # a denser exchange schedule: 2 steps per exchange (the headline region holds `steps` steps + ONE exchange)
+        def two_steps_and_exchange():
+            step_device(resident)
+            step_device(resident)
+            exchange()
+        two_steps_and_exchange()
+        every2_ms = timed(two_steps_and_exchange, 10) / 10.0
         # the same exchange through NCCL (pack -> reduce_scatter_tensor -> unpack), for comparison
         os.environ["BK_NO_PEER"] = "1"
         exchange()
@@ -534,6 +541,10 @@ def main():
             "busbw_GBps": sent / (scatter_ms * 1e-3) / 1e9,
             "route": "peer memory" if peer else "nccl",
             "nccl_route_ms": scatter_nccl_ms,
+            "exchange_every_2_steps": {"ms_per_2_steps_and_exchange": every2_ms,
+                                       "samples_per_s": 2 * BATCH * world / (every2_ms * 1e-3),
+                                       "note": "10 x (2 steps + 1 exchange), device-timed, max over ranks; divide by "
+                                               "world x the N = 1 value for the efficiency at this schedule"},
             "note": "one per timed region (deferred: state is a plain sum of batch means); what invert_sharded issues. "
                     "peer memory: bk_tile_pack into the rank's CUDA-IPC buffer -> flags -> ONE bk_peer_tile_unpack launch "
                     "on every owner that pulls its chunk from all ranks over NVLink, adds in rank order and writes the "
