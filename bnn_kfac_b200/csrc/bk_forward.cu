@@ -133,21 +133,34 @@ conv2d_fast_kernel(const float* __restrict__ in, long long in_sample_stride, con
   }
   for (int i = threadIdx.x; i < 2 * OPAIRS; i += blockDim.x)
     bs[i] = (b && i < O) ? b[static_cast<long long>(s) * O + i] : 0.f;
-  for (int i = threadIdx.x; i < imgs * img_words; i += blockDim.x) {
-    const int g = i / img_words, r = i - g * img_words;
-    const int c = r / (HP * WP), r2 = r - c * HP * WP;
-    const int y = r2 / WP - PH, x = r2 - (r2 / WP) * WP - PW;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W)
-      v = in[s * in_sample_stride + (static_cast<long long>(n0 + g) * C + c) * H * W + y * W + x];
-    xs[i] = v;
+  {
+    // padded tiles row by row: a group of 16 or 32 lanes owns one row (g, c, y) - two integer divisions per ROW, the
+    // lanes walk x (per element the decode costs more instructions than the FMAs the element feeds in a
+    // single-channel first layer)
+    const int lpr = WP <= 16 ? 16 : 32;  // lanes per row
+    const int sub = threadIdx.x / lpr, lx = threadIdx.x - sub * lpr;
+    const int rows = imgs * C * HP;
+    for (int row = sub; row < rows; row += 256 / lpr) {
+      const int g = row / (C * HP), rc = row - g * C * HP;
+      const int c = rc / HP, y = rc - c * HP - PH;
+      const bool yin = y >= 0 && y < H;
+      const float* src = in + s * in_sample_stride + (static_cast<long long>(n0 + g) * C + c) * H * W + y * W;
+      for (int xp = lx; xp < WP; xp += lpr) {
+        const int x = xp - PW;
+        xs[row * WP + xp] = (yin && x >= 0 && x < W) ? src[x] : 0.f;
+      }
+    }
   }
   __syncthreads();
   const int per_pair = QH * QW, per_img = O * per_pair;
+  // item decode by float reciprocals (exact here: every dividend is below 2^20, the + 0.5 keeps the quotient away
+  // from the integer boundaries) - three integer divisions per item otherwise
+  const float inv_g = 1.f / static_cast<float>(OPAIRS * per_pair), inv_p = 1.f / static_cast<float>(per_pair);
+  const float inv_w = 1.f / static_cast<float>(QW);
   for (int e = threadIdx.x; e < imgs * OPAIRS * per_pair; e += blockDim.x) {
-    const int g = e / (OPAIRS * per_pair), r = e - g * OPAIRS * per_pair;
-    const int op = r / per_pair, r2 = r - op * per_pair;
-    const int qy = r2 / QW, qx = r2 - qy * QW;
+    const int g = __float2int_rz((static_cast<float>(e) + 0.5f) * inv_g), r = e - g * OPAIRS * per_pair;
+    const int op = __float2int_rz((static_cast<float>(r) + 0.5f) * inv_p), r2 = r - op * per_pair;
+    const int qy = __float2int_rz((static_cast<float>(r2) + 0.5f) * inv_w), qx = r2 - qy * QW;
     const int o0 = 2 * op;
     float acc[2][NP][NP];
 #pragma unroll
